@@ -1,0 +1,488 @@
+// Fused additive (adaptive, visual-sentinel) attention -- model_adaAttention_aic.py:103-113 -- forward and backward.
+//
+//   z_j   = tanh(key_j + hid_emb)            j < k : per-image keys;  j = k : sentinel_emb (per query)
+//   e_j   = z_j . w_alpha + b_alpha
+//   alpha = softmax over the k+1 positions   ('position'), or == 1 as the reference graph is written ('feature')
+//   ctx   = 1/(k+1) * sum_j alpha_j v_j      v_j: per-image values; v_k = sentinel          (reduce_mean, model:113)
+//
+// The reference materialises seven [B,k+1,H] tensors per step; here nothing of that size is written.
+// Forward: one CTA per (image, chunk of query rows).  The image's key and value tiles ([k,H] each, time-invariant)
+// are brought into shared memory ONCE per CTA with two 1-D TMA bulk copies (cp.async.bulk, 2 x 98 KB for bf16) and
+// every query row of the chunk (34 teacher-forced steps, or the beams of one image at inference) streams through.
+// Scores use one warp per position with 128-bit conflict-free shared loads and a shuffle reduction; the context
+// pass gives each thread 4 adjacent columns.
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+constexpr int kFwdThreads = 320;  // 10 warps: 50 positions = 5 rounds
+
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// shared-memory carve-up shared by the forward and the backward-score kernels
+struct SmemLayout {
+  int off_e, off_alpha, off_bar, off_tile0, off_tile1, total;
+};
+__host__ __device__ inline SmemLayout make_layout(int H, int k, int tile_elem_bytes, int n_tiles) {
+  SmemLayout L;
+  L.off_e = 0;
+  L.off_alpha = 128 * 4;
+  L.off_bar = 256 * 4;
+  L.off_tile0 = 256 * 4 + 64;
+  const int tile = ((k * H * tile_elem_bytes + 127) / 128) * 128;
+  L.off_tile1 = L.off_tile0 + (n_tiles > 0 ? tile : 0);
+  L.total = L.off_tile0 + n_tiles * tile;
+  return L;
+}
+
+// NV > 0: H == NV * 256, per-lane operands live in registers.  NV == 0: generic H (multiple of 8).
+template <typename T, int NV, bool STAGE>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ keys, const T* __restrict__ vals,
+                const T* __restrict__ hid_emb, const T* __restrict__ sent_emb, const T* __restrict__ sentinel,
+                const T* __restrict__ p_hid, const float* __restrict__ w_alpha, const float* __restrict__ b_alpha,
+                float* __restrict__ alpha_out, T* __restrict__ actx, T* __restrict__ ctx_out) {
+  constexpr bool F = fast_math<T>::value;
+  constexpr int RV = NV > 0 ? NV : 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int H = s.H, k = s.k, P = s.k + 1;
+  const SmemLayout L = make_layout(H, k, (int)sizeof(T), STAGE ? 2 : 0);
+  float* e_s = reinterpret_cast<float*>(smem + L.off_e);
+  float* a_s = reinterpret_cast<float*>(smem + L.off_alpha);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  const int img = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int q0 = chunk * q_per_chunk, q1 = min(s.q_per_img, q0 + q_per_chunk);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const T* Kt = keys + (long)img * k * H;
+  const T* Vt = vals + (long)img * k * H;
+  if (STAGE) {
+    const uint32_t tile_bytes = (uint32_t)(k * H * sizeof(T));
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(bar, 2 * tile_bytes);
+      tma_bulk_g2s(smem + L.off_tile0, Kt, tile_bytes, bar);
+      tma_bulk_g2s(smem + L.off_tile1, Vt, tile_bytes, bar);
+    }
+    Kt = reinterpret_cast<const T*>(smem + L.off_tile0);
+    Vt = reinterpret_cast<const T*>(smem + L.off_tile1);
+  }
+  // per-lane slice of w_alpha
+  float w[RV][8];
+  if (NV > 0) {
+#pragma unroll
+    for (int v = 0; v < RV; ++v) load8(w_alpha + v * 256 + lane * 8, w[v]);
+  }
+  const float b_a = b_alpha[0];
+  const float inv_p = 1.f / (float)P;
+  if (STAGE) {
+    __syncthreads();  // barrier init visible to all waiters
+    mbar_wait(bar, 0);
+  }
+  for (int q = q0; q < q1; ++q) {
+    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const T* he_g = hid_emb + row * H;
+    // ---- scores: one warp per position ----
+    float he[RV][8];
+    if (NV > 0) {
+#pragma unroll
+      for (int v = 0; v < RV; ++v) load8(he_g + v * 256 + lane * 8, he[v]);
+    }
+    for (int j = warp; j < P; j += nwarps) {
+      const T* kj = (j < k) ? (Kt + (long)j * H) : (sent_emb + row * H);
+      float acc = 0.f;
+      if (NV > 0) {
+#pragma unroll
+        for (int v = 0; v < RV; ++v) {
+          float kk[8];
+          load8(kj + v * 256 + lane * 8, kk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(tanh_t<F>(kk[i] + he[v][i]), w[v][i], acc);
+        }
+      } else {
+        for (int h0 = lane * 8; h0 < H; h0 += 256) {
+          float kk[8], hh[8], ww[8];
+          load8(kj + h0, kk);
+          load8(he_g + h0, hh);
+          load8(w_alpha + h0, ww);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(tanh_t<F>(kk[i] + hh[i]), ww[i], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) e_s[j] = acc + b_a;
+    }
+    __syncthreads();
+    // ---- softmax over the k+1 positions (warp 0) ----
+    if (warp == 0) {
+      if (s.position_softmax) {
+        float m = -INFINITY;
+        for (int j = lane; j < P; j += 32) m = fmaxf(m, e_s[j]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < P; j += 32) sum += __expf(e_s[j] - m);
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        for (int j = lane; j < P; j += 32) {
+          const float a = __expf(e_s[j] - m) * inv;
+          a_s[j] = a;
+          alpha_out[row * P + j] = a;
+        }
+      } else {
+        for (int j = lane; j < P; j += 32) {
+          a_s[j] = 1.f;  // softmax over a size-1 axis (model:107 as written)
+          alpha_out[row * P + j] = 1.f;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- context: each thread owns 4 adjacent columns ----
+    for (int h0 = tid * 4; h0 < H; h0 += blockDim.x * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < k; ++j) {
+        float v[4];
+        load4(Vt + (long)j * H + h0, v);
+        const float a = a_s[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]);
+      }
+      {
+        float v[4];
+        load4(sentinel + row * H + h0, v);
+        const float a = a_s[k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]) * inv_p;
+      }
+      if (ctx_out) store4(ctx_out + row * H + h0, acc);
+      if (actx) {
+        float ph[4];
+        load4(p_hid + row * H + h0, ph);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ph[i] += acc[i];
+        store4(actx + row * H + h0, ph);
+      }
+    }
+    // e_s / a_s are rewritten only after the next __syncthreads pair; the context pass reads a_s, the next
+    // score pass writes e_s only -> one barrier protects a_s before the next softmax
+    __syncthreads();
+  }
+}
+
+// ---- backward (A): d alpha_j = dctx . v_j / (k+1);  de = softmax'(alpha, d alpha);  db_alpha += sum de ----
+template <typename T, bool STAGE>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_bwd_scores_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ vals,
+                       const T* __restrict__ sentinel, const float* __restrict__ alpha, const T* __restrict__ dactx,
+                       float* __restrict__ de, float* __restrict__ db_alpha) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int H = s.H, k = s.k, P = s.k + 1;
+  const SmemLayout L = make_layout(H, k, (int)sizeof(T), STAGE ? 1 : 0);
+  float* d_s = reinterpret_cast<float*>(smem + L.off_e);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  const int img = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int q0 = chunk * q_per_chunk, q1 = min(s.q_per_img, q0 + q_per_chunk);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const T* Vt = vals + (long)img * k * H;
+  if (STAGE) {
+    const uint32_t tile_bytes = (uint32_t)(k * H * sizeof(T));
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(bar, tile_bytes);
+      tma_bulk_g2s(smem + L.off_tile0, Vt, tile_bytes, bar);
+    }
+    Vt = reinterpret_cast<const T*>(smem + L.off_tile0);
+    __syncthreads();
+    mbar_wait(bar, 0);
+  }
+  const float inv_p = 1.f / (float)P;
+  float db_acc = 0.f;
+  for (int q = q0; q < q1; ++q) {
+    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const T* dc = dactx + row * H;
+    for (int j = warp; j < P; j += nwarps) {
+      const T* vj = (j < k) ? (Vt + (long)j * H) : (sentinel + row * H);
+      float acc = 0.f;
+      for (int h0 = lane * 8; h0 < H; h0 += 256) {
+        float a[8], b[8];
+        load8(vj + h0, a);
+        load8(dc + h0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) d_s[j] = acc * inv_p;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float dot = 0.f;
+      for (int j = lane; j < P; j += 32) dot += alpha[row * P + j] * d_s[j];
+      dot = warp_sum(dot);
+      for (int j = lane; j < P; j += 32) {
+        const float v = alpha[row * P + j] * (d_s[j] - dot);
+        de[row * P + j] = v;
+        db_acc += v;
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    db_acc = warp_sum(db_acc);
+    if (lane == 0) atomicAdd(db_alpha, db_acc);
+  }
+}
+
+// dS_ctx[row, h] = alpha[row, k] * dctx[row, h] / (k+1)
+template <typename T>
+__global__ void ds_ctx_kernel(long rows, int H, int P, const float* __restrict__ alpha, const T* __restrict__ dactx,
+                              T* __restrict__ dS) {
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = rows * vec_per_row;
+  const float inv_p = 1.f / (float)P;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    const float a = alpha[r * P + (P - 1)] * inv_p;
+    float v[8];
+    load8(dactx + r * H + h0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= a;
+    store8(dS + r * H + h0, v);
+  }
+}
+
+// ---- backward (B): d values (pre-tanh).  thread = one column h of one image, accumulators over the k positions ----
+//   dV_j[h] = 1/(k+1) sum_q alpha[q,j] dctx[q,h];   d(pre) = dV * (1 - v^2)       -> dKV[img*k + j, h]
+template <typename T, int KC>
+__global__ void __launch_bounds__(256)
+attn_bwd_dv_kernel(AttnShape s, const T* __restrict__ vals, const float* __restrict__ alpha,
+                   const T* __restrict__ dactx, T* __restrict__ dKV) {
+  extern __shared__ __align__(16) float a_s[];  // [q_per_img, P]
+  const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
+  const int img = blockIdx.x, h = blockIdx.y * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < nq * P; i += blockDim.x) {
+    const int q = i / P, j = i % P;
+    a_s[i] = alpha[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j];
+  }
+  __syncthreads();
+  if (h >= H) return;
+  float acc[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) acc[j] = 0.f;
+  for (int q = 0; q < nq; ++q) {
+    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const float d = to_f(dactx[row * H + h]);
+#pragma unroll
+    for (int j = 0; j < KC; ++j)
+      if (j < k) acc[j] = fmaf(a_s[q * P + j], d, acc[j]);
+  }
+  const float inv_p = 1.f / (float)P;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    if (j < k) {
+      const float v = to_f(vals[((long)img * k + j) * H + h]);
+      dKV[((long)img * k + j) * (2 * H) + h] = from_f<T>(acc[j] * inv_p * (1.f - v * v));
+    }
+  }
+}
+
+// ---- backward (C): d keys, d hid_emb, d sentinel_emb, d w_alpha.  thread = one column h of one image ----
+//   g_j = de[q,j] * w[h] * (1 - z_j^2), z_j = tanh(key_j[h] + hid_emb[q,h]) (recomputed, never stored)
+//   dK_j[h] = sum_q g_j;  d hid_emb[q,h] = sum_j g_j;  d sentinel_emb[q,h] = g_k;  dw[h] += sum_{q,j} de[q,j] z_j
+template <typename T, int KC>
+__global__ void __launch_bounds__(256)
+attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict__ hid_emb,
+                   const T* __restrict__ sent_emb, const float* __restrict__ w_alpha, const float* __restrict__ de,
+                   T* __restrict__ dKV, T* __restrict__ dhid_emb, T* __restrict__ dsent_emb,
+                   float* __restrict__ dw_alpha) {
+  constexpr bool F = fast_math<T>::value;
+  extern __shared__ __align__(16) float de_s[];  // [q_per_img, P]
+  const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
+  const int img = blockIdx.x, h = blockIdx.y * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < nq * P; i += blockDim.x) {
+    const int q = i / P, j = i % P;
+    de_s[i] = de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j];
+  }
+  __syncthreads();
+  if (h >= H) return;
+  float kc[KC], acc[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    acc[j] = 0.f;
+    kc[j] = (j < k) ? to_f(keys[((long)img * k + j) * H + h]) : 0.f;
+  }
+  const float wh = w_alpha[h];
+  float dw = 0.f;
+  for (int q = 0; q < nq; ++q) {
+    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const float he = to_f(hid_emb[row * H + h]);
+    const float se = to_f(sent_emb[row * H + h]);
+    const float* dq = de_s + q * P;
+    float dhe = 0.f;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      if (j < k) {
+        const float z = tanh_t<F>(kc[j] + he);
+        const float d = dq[j];
+        const float g = d * wh * (1.f - z * z);
+        acc[j] += g;
+        dhe += g;
+        dw = fmaf(d, z, dw);
+      }
+    }
+    {
+      const float z = tanh_t<F>(se + he);
+      const float d = dq[k];
+      const float g = d * wh * (1.f - z * z);
+      dhe += g;
+      dw = fmaf(d, z, dw);
+      dsent_emb[row * H + h] = from_f<T>(g);
+    }
+    dhid_emb[row * H + h] = from_f<T>(dhe);
+  }
+#pragma unroll
+  for (int j = 0; j < KC; ++j)
+    if (j < k) dKV[((long)img * k + j) * (2 * H) + H + h] = from_f<T>(acc[j]);
+  atomicAdd(dw_alpha + h, dw);
+}
+
+// choose how many CTAs share one image's query rows: minimise waves x rows-per-CTA
+int pick_chunks(int n_img, int nq) {
+  int best = 1;
+  long best_cost = -1;
+  for (int c = 1; c <= nq && c <= 8; ++c) {
+    const int qpc = (nq + c - 1) / c;
+    const long waves = ((long)n_img * c + kNumSMs - 1) / kNumSMs;
+    const long cost = waves * (qpc + 2);  // +2: tile load
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+template <typename T, bool STAGE>
+void launch_fwd(LaunchCtx c, const AttnShape& s, int chunks, int qpc, size_t smem, const T* keys, const T* vals,
+                const T* hid_emb, const T* sent_emb, const T* sentinel, const T* p_hid, const float* w_alpha,
+                const float* b_alpha, float* alpha, T* actx, T* ctx_out) {
+  const int grid = s.n_img * chunks;
+#define LAUNCH_NV(NVV)                                                                                              \
+  do {                                                                                                               \
+    auto kern = attn_fwd_kernel<T, NVV, STAGE>;                                                                      \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+    kern<<<grid, kFwdThreads, smem, c.stream>>>(s, chunks, qpc, keys, vals, hid_emb, sent_emb, sentinel, p_hid,      \
+                                                w_alpha, b_alpha, alpha, actx, ctx_out);                             \
+  } while (0)
+  if (s.H == 1024) LAUNCH_NV(4);
+  else if (s.H == 512) LAUNCH_NV(2);
+  else if (s.H == 256) LAUNCH_NV(1);
+  else LAUNCH_NV(0);
+#undef LAUNCH_NV
+  if (c.launches) ++*c.launches;
+}
+
+}  // namespace
+
+template <typename T>
+void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
+                   const T* sentinel, const T* p_hid, const float* w_alpha, const float* b_alpha, float* alpha, T* actx,
+                   T* ctx_out) {
+  if (s.n_img <= 0 || s.q_per_img <= 0) return;
+  const int chunks = pick_chunks(s.n_img, s.q_per_img);
+  const int qpc = (s.q_per_img + chunks - 1) / chunks;
+  const SmemLayout Ls = make_layout(s.H, s.k, (int)sizeof(T), 2);
+  // stage both tiles in shared memory when they fit (bf16 at H=1024,k=49: 2 x 98 KB), otherwise read through L1/L2
+  const bool stage = Ls.total <= 227 * 1024 && ((size_t)s.k * s.H * sizeof(T)) % 16 == 0;
+  if (stage) {
+    launch_fwd<T, true>(c, s, chunks, qpc, Ls.total, keys, vals, hid_emb, sent_emb, sentinel, p_hid, w_alpha, b_alpha,
+                        alpha, actx, ctx_out);
+  } else {
+    const SmemLayout L0 = make_layout(s.H, s.k, (int)sizeof(T), 0);
+    launch_fwd<T, false>(c, s, chunks, qpc, L0.total, keys, vals, hid_emb, sent_emb, sentinel, p_hid, w_alpha, b_alpha,
+                         alpha, actx, ctx_out);
+  }
+}
+
+template <typename T>
+void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
+                   const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx, float* de, T* dS_ctx,
+                   T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha, float* db_alpha) {
+  if (s.n_img <= 0 || s.q_per_img <= 0) return;
+  const int H = s.H, k = s.k, P = s.k + 1;
+  const long rows = (long)s.n_img * s.q_per_img;
+  {
+    long blocks = (rows * (H / 8) + 255) / 256;
+    if (blocks > 8L * kNumSMs) blocks = 8L * kNumSMs;
+    ds_ctx_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(rows, H, P, alpha, dactx, dS_ctx);
+    if (c.launches) ++*c.launches;
+  }
+  const size_t a_bytes = (size_t)s.q_per_img * P * sizeof(float);
+  dim3 grid_cols(s.n_img, (H + 255) / 256);
+#define DISPATCH_KC(KERNEL, ...)                                                                                     \
+  do {                                                                                                               \
+    if (k == 49) KERNEL<T, 49><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                  \
+    else if (k <= 8) KERNEL<T, 8><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                               \
+    else if (k <= 16) KERNEL<T, 16><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                             \
+    else if (k <= 32) KERNEL<T, 32><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                             \
+    else KERNEL<T, 64><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                          \
+    if (c.launches) ++*c.launches;                                                                                   \
+  } while (0)
+  DISPATCH_KC(attn_bwd_dv_kernel, s, vals, alpha, dactx, dKV);
+  if (!s.position_softmax) {
+    // reference as written: alpha == 1 is constant -> no gradient reaches the scores
+    cudaMemsetAsync(de, 0, rows * P * sizeof(float), c.stream);
+    cudaMemsetAsync(dhid_emb, 0, rows * H * sizeof(T), c.stream);
+    cudaMemsetAsync(dsent_emb, 0, rows * H * sizeof(T), c.stream);
+    cudaMemset2DAsync(dKV + H, (size_t)2 * H * sizeof(T), 0, (size_t)H * sizeof(T), (size_t)s.n_img * k, c.stream);
+    return;
+  }
+  {
+    const int chunks = pick_chunks(s.n_img, s.q_per_img);
+    const int qpc = (s.q_per_img + chunks - 1) / chunks;
+    const SmemLayout L1 = make_layout(H, k, (int)sizeof(T), 1);
+    const bool stage = L1.total <= 227 * 1024 && ((size_t)k * H * sizeof(T)) % 16 == 0;
+    if (stage) {
+      auto kern = attn_bwd_scores_kernel<T, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total);
+      kern<<<s.n_img * chunks, kFwdThreads, L1.total, c.stream>>>(s, chunks, qpc, vals, sentinel, alpha, dactx, de,
+                                                                 db_alpha);
+    } else {
+      const SmemLayout L0 = make_layout(H, k, (int)sizeof(T), 0);
+      attn_bwd_scores_kernel<T, false><<<s.n_img * chunks, kFwdThreads, L0.total, c.stream>>>(
+          s, chunks, qpc, vals, sentinel, alpha, dactx, de, db_alpha);
+    }
+    if (c.launches) ++*c.launches;
+  }
+  DISPATCH_KC(attn_bwd_dk_kernel, s, keys, hid_emb, sent_emb, w_alpha, de, dKV, dhid_emb, dsent_emb, dw_alpha);
+#undef DISPATCH_KC
+}
+
+#define INSTANTIATE(T)                                                                                               \
+  template void attention_fwd<T>(LaunchCtx, const AttnShape&, const T*, const T*, const T*, const T*, const T*,      \
+                                 const T*, const float*, const float*, float*, T*, T*);                              \
+  template void attention_bwd<T>(LaunchCtx, const AttnShape&, const T*, const T*, const T*, const T*, const T*,      \
+                                 const float*, const float*, const T*, float*, T*, T*, T*, T*, float*, float*);
+INSTANTIATE(float)
+INSTANTIATE(bf16)
+
+}  // namespace capdec

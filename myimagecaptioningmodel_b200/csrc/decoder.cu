@@ -1,0 +1,790 @@
+// The decoder handle: operand layouts, workspace, and the three schedules (teacher-forced forward, backward,
+// greedy / beam inference) that replace the PaddlePaddle While-op interpreter loop of
+// model_adaAttention_aic.py:72-127 and its auto-generated while_grad.
+//
+// Training is "recurrent core + time-batched head" (SURVEY.md F7): only h_{t-1}.W_hh and the cell are
+// sequential; the word-embedding half of the gate GEMM is hoisted over all T steps and everything downstream of
+// (h_t, c_t) -- sentinel, attention, context, out, tied vocabulary projection, loss -- runs once at
+// M = B*T rows.  Rows of every [M, *] activation are time-major: m = t*B + b.
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/capdec.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace capdec {
+
+thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+#define OK(expr)                \
+  do {                          \
+    if ((expr) != 0) return -1; \
+  } while (0)
+
+// a growable device buffer owned by the handle
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, size_t* total) {
+    if (bytes <= cap) return 0;
+    if (p) { cudaFree(p); *total -= cap; p = nullptr; cap = 0; }
+    bytes = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return -1; }
+    cap = bytes;
+    *total += bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+class DecoderBase {
+ public:
+  virtual ~DecoderBase() {}
+  virtual int bind(const capdec_params* p, cudaStream_t s) = 0;
+  virtual int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
+                        cudaStream_t s) = 0;
+  virtual int train_bwd(float loss_scale, const float* inv_ntok, float* dg, float* dP, const capdec_grads* gr,
+                        cudaStream_t s) = 0;
+  virtual int decode(const float* g, const float* P, int B, int beam, int finish, int32_t* ids, float* scores,
+                     float* ids_f32, cudaStream_t s) = 0;
+  size_t ws_bytes = 0;
+  long launches = 0;
+  int device = 0;
+};
+
+template <typename T> class Decoder : public DecoderBase {
+ public:
+  explicit Decoder(const capdec_config& c) : cfg(c) {
+    H = c.hidden_dim; E = c.embedding_size; V = c.vocab_size; k = c.num_positions;
+    S = c.sentence_length; Tt = S - 1; Ti = c.infer_max_length;
+    Vp = ((V + 127) / 128) * 128;
+    const char* fs = getenv("CAPDEC_FORCE_SIMT");
+    force_simt = fs && fs[0] == '1';
+  }
+  ~Decoder() override {
+    for (DevBuf* b : all_bufs()) b->release();
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  int bind(const capdec_params* p, cudaStream_t s) override {
+    prm = *p;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const int X = E + H;
+    OK(w_v_t.ensure(e * H * H, &ws_bytes));   OK(w_k_t.ensure(e * H * H, &ws_bytes));
+    OK(w_kv_n.ensure(e * H * 2 * H, &ws_bytes));
+    OK(w_x_t.ensure(e * 5 * H * E, &ws_bytes));  OK(w_x_n.ensure(e * E * 5 * H, &ws_bytes));
+    OK(w_g_t.ensure(e * 5 * H * H, &ws_bytes));  OK(w_g_n.ensure(e * H * 5 * H, &ws_bytes));
+    OK(w_hh_t.ensure(e * 4 * H * H, &ws_bytes)); OK(w_hh_n.ensure(e * H * 4 * H, &ws_bytes));
+    OK(w_hs_t.ensure(e * H * H, &ws_bytes));  OK(w_hs_n.ensure(e * H * H, &ws_bytes));
+    OK(w_p_t.ensure(e * H * H, &ws_bytes));   OK(w_p_n.ensure(e * H * H, &ws_bytes));
+    OK(w_g2_t.ensure(e * H * H, &ws_bytes));  OK(w_g2_n.ensure(e * H * H, &ws_bytes));
+    OK(w_s_t.ensure(e * H * H, &ws_bytes));   OK(w_s_n.ensure(e * H * H, &ws_bytes));
+    OK(w_o_t.ensure(e * H * H, &ws_bytes));   OK(w_o_n.ensure(e * H * H, &ws_bytes));
+    OK(w_e_t.ensure(e * E * H, &ws_bytes));   OK(w_e_n.ensure(e * H * E, &ws_bytes));
+    OK(emb.ensure(e * (size_t)V * E, &ws_bytes)); OK(emb_t.ensure(e * (size_t)E * Vp, &ws_bytes));
+    OK(w_dec_t.ensure(e * 5 * H * (size_t)X, &ws_bytes));
+    OK(b5.ensure(4 * 5 * H, &ws_bytes)); OK(b5d.ensure(4 * 5 * H, &ws_bytes));
+
+    // forward operands: [out, in] (K-major B operand)
+    transpose_from_f32<T>(lc, p->fc_v_w, H, w_v_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_k_w, H, w_k_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_t.as<T>(), E, E, 4 * H);                       // word_emb rows
+    transpose_from_f32<T>(lc, p->fc_xs_w, H, w_x_t.as<T>() + (size_t)4 * H * E, E, E, H);
+    transpose_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_t.as<T>(), H, H, 4 * H);  // global rows
+    transpose_from_f32<T>(lc, p->fc_xs_w + (size_t)E * H, H, w_g_t.as<T>() + (size_t)4 * H * H, H, H, H);
+    transpose_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_hh_t.as<T>(), H, H, 4 * H);  // hid rows
+    transpose_from_f32<T>(lc, p->fc_hs_w, H, w_hs_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_p_w, H, w_p_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_g_w, H, w_g2_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_s_w, H, w_s_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_o_w, H, w_o_t.as<T>(), H, H, H);
+    transpose_from_f32<T>(lc, p->fc_e_w, E, w_e_t.as<T>(), H, H, E);
+    convert_from_f32<T>(lc, p->word_embedding, emb.as<T>(), (long)V * E);
+    // decode operand: [5H, E+H] = [ lstm_w(word)^T | lstm_w(hid)^T ; fc_xs(word)^T | fc_hs^T ]
+    transpose_from_f32<T>(lc, p->lstm_w, 4 * H, w_dec_t.as<T>(), X, E, 4 * H);
+    transpose_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_dec_t.as<T>() + E, X, H, 4 * H);
+    transpose_from_f32<T>(lc, p->fc_xs_w, H, w_dec_t.as<T>() + (size_t)4 * H * X, X, E, H);
+    transpose_from_f32<T>(lc, p->fc_hs_w, H, w_dec_t.as<T>() + (size_t)4 * H * X + E, X, H, H);
+    // backward-data operands: Paddle's own [in, out] layout
+    copy2d_from_f32<T>(lc, p->fc_v_w, H, w_kv_n.as<T>(), 2 * H, H, H);
+    copy2d_from_f32<T>(lc, p->fc_k_w, H, w_kv_n.as<T>() + H, 2 * H, H, H);
+    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_n.as<T>(), 5 * H, E, 4 * H);
+    copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_x_n.as<T>() + 4 * H, 5 * H, E, H);
+    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_n.as<T>(), 5 * H, H, 4 * H);
+    copy2d_from_f32<T>(lc, p->fc_xs_w + (size_t)E * H, H, w_g_n.as<T>() + 4 * H, 5 * H, H, H);
+    convert_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, w_hh_n.as<T>(), (long)H * 4 * H);
+    convert_from_f32<T>(lc, p->fc_hs_w, w_hs_n.as<T>(), (long)H * H);
+    convert_from_f32<T>(lc, p->fc_p_w, w_p_n.as<T>(), (long)H * H);
+    convert_from_f32<T>(lc, p->fc_g_w, w_g2_n.as<T>(), (long)H * H);
+    convert_from_f32<T>(lc, p->fc_s_w, w_s_n.as<T>(), (long)H * H);
+    convert_from_f32<T>(lc, p->fc_o_w, w_o_n.as<T>(), (long)H * H);
+    convert_from_f32<T>(lc, p->fc_e_w, w_e_n.as<T>(), (long)H * E);
+    CUDA_OK(cudaMemsetAsync(emb_t.p, 0, e * (size_t)E * Vp, s));
+    transpose_from_f32<T>(lc, p->word_embedding, E, emb_t.as<T>(), Vp, V, E);
+    // fused bias vectors: train [lstm_b | fc_xs_b]; decode [lstm_b | fc_xs_b + fc_hs_b]
+    CUDA_OK(cudaMemcpyAsync(b5.p, p->lstm_b, 4 * 4 * H, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b5d.p, b5.p, 4 * 5 * H, cudaMemcpyDeviceToDevice, s));
+    // b5d[4H:] += fc_hs_b  via a 1-row colsum
+    colsum_add<float>(lc, p->fc_hs_b, H, 1, H, b5d.as<float>() + 4 * H);
+    CUDA_OK(cudaGetLastError());
+    bound = true;
+    return 0;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  int image_projections(GemmContext& gc, LaunchCtx lc, const float* g, const float* P, int B) {
+    const size_t e = sizeof(T);
+    OK(gT.ensure(e * (size_t)B * H, &ws_bytes));
+    OK(PT.ensure(e * (size_t)B * k * H, &ws_bytes));
+    OK(keys.ensure(e * (size_t)B * k * H, &ws_bytes));
+    OK(vals.ensure(e * (size_t)B * k * H, &ws_bytes));
+    convert_from_f32<T>(lc, g, gT.as<T>(), (long)B * H);
+    convert_from_f32<T>(lc, P, PT.as<T>(), (long)B * k * H);
+    GemmCall c;
+    c.A = PT.p; c.lda = H; c.M = B * k; c.N = H; c.K = H; c.ldb = H; c.ldc = H;
+    c.B = w_v_t.p; c.C = vals.p; c.epi.bias = prm.fc_v_b; c.epi.act = ACT_TANH;      // model:52
+    OK(gemm<T>(gc, c));
+    c.B = w_k_t.p; c.C = keys.p; c.epi.bias = prm.fc_k_b; c.epi.act = ACT_NONE;      // model:53
+    OK(gemm<T>(gc, c));
+    return 0;
+  }
+
+  // Y[M,N] = act(X . W^T + b)  with W given as the [N,K] forward operand
+  int fc(GemmContext& gc, const void* X, long ldx, const DevBuf& Wt, const float* bias, void* Y, long ldy, int M, int N,
+         int K, int act, bool out_f32 = false) {
+    GemmCall c;
+    c.A = X; c.lda = ldx; c.B = Wt.p; c.ldb = K; c.C = Y; c.ldc = ldy; c.M = M; c.N = N; c.K = K;
+    c.epi.bias = bias; c.epi.act = act; c.epi.out_f32 = out_f32 ? 1 : 0;
+    return gemm<T>(gc, c);
+  }
+  // dW[in,out] += X[rows,in]^T . dY[rows,out]   (fp32 atomics, split-K over rows)
+  int wgrad(GemmContext& gc, const void* X, long ldx, int n_in, const void* dY, long ldy, int n_out, int rows,
+            float* dW, long ldw) {
+    if (!dW) return 0;
+    GemmCall c;
+    c.mn_major = true;
+    c.A = X; c.lda = ldx; c.B = dY; c.ldb = ldy; c.C = dW; c.ldc = ldw; c.M = n_in; c.N = n_out; c.K = rows;
+    c.epi.atomic = 1; c.epi.out_f32 = 1; c.splits = 0;
+    return gemm<T>(gc, c);
+  }
+
+  int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
+                cudaStream_t s) override {
+    if (!bound) { set_error("capdec_train_fwd: parameters not bound"); return -1; }
+    if (B <= 0) { set_error("capdec_train_fwd: empty batch"); return -1; }
+    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const long M = (long)B * Tt;
+    last_B = B; last_cap = cap;
+    OK(image_projections(gc, lc, g, P, B));
+    OK(embx.ensure(e * M * E, &ws_bytes));
+    OK(xe.ensure(e * M * 5 * H, &ws_bytes));
+    OK(g5.ensure(4 * (size_t)B * 5 * H, &ws_bytes));
+    OK(hs.ensure(e * (size_t)(Tt + 1) * B * H, &ws_bytes));
+    OK(cs.ensure(4 * (size_t)(Tt + 1) * B * H, &ws_bytes));
+    OK(gact.ensure(e * M * 4 * H, &ws_bytes));
+    OK(gpre.ensure(4 * (size_t)B * 4 * H, &ws_bytes));
+    OK(ph.ensure(e * M * H, &ws_bytes));
+    OK(sgate.ensure(e * M * H, &ws_bytes));
+    OK(sent.ensure(e * M * H, &ws_bytes));
+    OK(phid.ensure(e * M * H, &ws_bytes));
+    OK(hemb.ensure(e * M * H, &ws_bytes));
+    OK(semb.ensure(e * M * H, &ws_bytes));
+    OK(alpha.ensure(4 * M * (k + 1), &ws_bytes));
+    OK(actx.ensure(e * M * H, &ws_bytes));
+    OK(outv.ensure(e * M * H, &ws_bytes));
+    OK(proj.ensure(e * M * E, &ws_bytes));
+    OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
+    OK(lse.ensure(4 * M, &ws_bytes));
+    OK(acc.ensure(64, &ws_bytes));
+
+    // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
+    embed_gather<T>(lc, emb.as<T>(), E, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E);
+    // hoisted x-part of the gate GEMM and of p_word_emb (model:86-89): word-embedding columns for all T steps ...
+    OK(fc(gc, embx.p, E, w_x_t, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
+    // ... and the global-image columns (+ biases) once per image
+    OK(fc(gc, gT.p, H, w_g_t, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    // recurrent core (model:63, 87-88, 94-95)
+    CUDA_OK(cudaMemsetAsync(hs.p, 0, e * (size_t)B * H, s));
+    CUDA_OK(cudaMemsetAsync(cs.p, 0, 4 * (size_t)B * H, s));
+    for (int t = 0; t < Tt; ++t) {
+      OK(fc(gc, hs.as<T>() + (size_t)t * B * H, H, w_hh_t, nullptr, gpre.p, 4 * H, B, 4 * H, H, ACT_NONE, true));
+      lstm_cell_fwd<T>(lc, B, H, gpre.as<float>(), 4 * H, xe.as<T>() + (size_t)t * B * 5 * H, 5 * H, g5.as<float>(),
+                       5 * H, INT_MAX, 1, cs.as<float>() + (size_t)t * B * H, hs.as<T>() + (size_t)(t + 1) * B * H, H,
+                       cs.as<float>() + (size_t)(t + 1) * B * H, gact.as<T>() + (size_t)t * B * 4 * H);
+    }
+    const T* Hprev = hs.as<T>();
+    const T* Hcur = hs.as<T>() + (size_t)B * H;
+    const float* Ccur = cs.as<float>() + (size_t)B * H;
+    // time-batched head
+    OK(fc(gc, Hprev, H, w_hs_t, prm.fc_hs_b, ph.p, H, (int)M, H, H, ACT_NONE));                       // model:90
+    sentinel_fwd<T>(lc, M, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, g5.as<float>() + 4 * H, 5 * H, B, 1, Ccur,
+                    sgate.as<T>(), sent.as<T>());                                                     // model:91-92
+    OK(fc(gc, Hcur, H, w_p_t, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
+    OK(fc(gc, phid.p, H, w_g2_t, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
+    OK(fc(gc, sent.p, H, w_s_t, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
+    AttnShape as = train_shape(B);
+    attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
+                     prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);               // model:103-115
+    OK(fc(gc, actx.p, H, w_o_t, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
+    OK(fc(gc, outv.p, H, w_e_t, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
+    {
+      GemmCall c;                                                                                     // model:25
+      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
+      c.epi.bias = prm.out_fc_bias; c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    // masked cross entropy (model:163-171, 180-183, 205-212)
+    CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
+    ce_fwd(lc, logits.as<float>(), Vp, V, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>());
+    loss_finalize(lc, acc.as<float>());
+    if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);           // model:129-130
+    if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
+    launches += gc.launches;
+    CUDA_OK(cudaGetLastError());
+    have_fwd = true;
+    return 0;
+  }
+
+  AttnShape train_shape(int B) const {
+    AttnShape as;
+    as.H = H; as.k = k; as.n_img = B; as.q_per_img = Tt; as.row0_stride = 1; as.q_stride = B;
+    as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
+    return as;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  int train_bwd(float loss_scale, const float* inv_ntok, float* dg, float* dP, const capdec_grads* gr,
+                cudaStream_t s) override {
+    if (!have_fwd) { set_error("capdec_train_bwd: no forward pass to differentiate"); return -1; }
+    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const int B = last_B, X = E + H;
+    const long M = (long)B * Tt;
+    const int64_t* cap = last_cap;
+    const capdec_grads& G = *gr;
+    OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
+    OK(dproj.ensure(e * M * E, &ws_bytes));
+    OK(doutp.ensure(e * M * H, &ws_bytes));
+    OK(dactx.ensure(e * M * H, &ws_bytes));
+    OK(de.ensure(4 * M * (k + 1), &ws_bytes));
+    OK(dsctx.ensure(e * M * H, &ws_bytes));
+    OK(dkv.ensure(e * (size_t)B * k * 2 * H, &ws_bytes));
+    OK(dhemb.ensure(e * M * H, &ws_bytes));
+    OK(dsemb.ensure(e * M * H, &ws_bytes));
+    OK(dphp.ensure(e * M * H, &ws_bytes));
+    OK(dS.ensure(e * M * H, &ws_bytes));
+    OK(dG.ensure(e * M * 5 * H, &ws_bytes));
+    OK(dChead.ensure(4 * M * H, &ws_bytes));
+    OK(dHhead.ensure(e * M * H, &ws_bytes));
+    OK(dHprev.ensure(e * M * H, &ws_bytes));
+    OK(dhrec.ensure(4 * (size_t)B * H, &ws_bytes));
+    OK(dcrec.ensure(4 * (size_t)B * H, &ws_bytes));
+    OK(dGsum.ensure(e * (size_t)B * 5 * H, &ws_bytes));
+    OK(dembx.ensure(e * M * E, &ws_bytes));
+
+    // gradients are overwritten: start from zero, every contribution below is an fp32 atomic add
+    struct Z { float* p; size_t n; };
+    const Z zs[] = {{G.fc_v_w, (size_t)H * H}, {G.fc_v_b, (size_t)H}, {G.fc_k_w, (size_t)H * H}, {G.fc_k_b, (size_t)H},
+                    {G.lstm_w, (size_t)(X + H) * 4 * H}, {G.lstm_b, (size_t)4 * H}, {G.fc_xs_w, (size_t)X * H},
+                    {G.fc_xs_b, (size_t)H}, {G.fc_hs_w, (size_t)H * H}, {G.fc_hs_b, (size_t)H},
+                    {G.fc_p_w, (size_t)H * H}, {G.fc_p_b, (size_t)H}, {G.fc_g_w, (size_t)H * H}, {G.fc_g_b, (size_t)H},
+                    {G.fc_s_w, (size_t)H * H}, {G.fc_s_b, (size_t)H}, {G.fc_a_w, (size_t)H}, {G.fc_a_b, (size_t)1},
+                    {G.fc_o_w, (size_t)H * H}, {G.fc_o_b, (size_t)H}, {G.fc_e_w, (size_t)H * E}, {G.fc_e_b, (size_t)E},
+                    {G.word_embedding, (size_t)V * E}, {G.out_fc_bias, (size_t)V}};
+    for (const Z& z : zs) {
+      if (!z.p) { set_error("capdec_train_bwd: NULL gradient pointer"); return -1; }
+      CUDA_OK(cudaMemsetAsync(z.p, 0, z.n * 4, s));
+    }
+
+    const T* Hprev = hs.as<T>();
+    const T* Hcur = hs.as<T>() + (size_t)B * H;
+    const float* Ccur = cs.as<float>() + (size_t)B * H;
+
+    // d logits = (softmax - onehot) * mask / sum(mask)      (softmax_with_cross_entropy_grad + the mask/scale ops)
+    ce_bwd<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(),
+              inv_ntok ? inv_ntok : acc.as<float>() + 3, loss_scale, dlogits.as<T>());
+    colsum_add<T>(lc, dlogits.as<T>(), Vp, M, V, G.out_fc_bias);
+    // tied output projection (model:24-25): d proj, d Emb (output side), d fc_e
+    {
+      GemmCall c;
+      c.A = dlogits.p; c.lda = Vp; c.B = emb_t.p; c.ldb = Vp; c.C = dproj.p; c.ldc = E; c.M = (int)M; c.N = E; c.K = V;
+      OK(gemm<T>(gc, c));
+    }
+    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E));
+    colsum_add<T>(lc, dproj.as<T>(), E, M, E, G.fc_e_b);
+    OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, (int)M, G.fc_e_w, E));
+    // out = tanh(fc_o(ctx + p_hid))   (model:115)
+    {
+      GemmCall c;
+      c.A = dproj.p; c.lda = E; c.B = w_e_n.p; c.ldb = E; c.C = doutp.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = E;
+      c.epi.act = ACT_DTANH; c.epi.dact_y = outv.p; c.epi.ld_y = H;
+      OK(gemm<T>(gc, c));
+    }
+    colsum_add<T>(lc, doutp.as<T>(), H, M, H, G.fc_o_b);
+    OK(wgrad(gc, actx.p, H, H, doutp.p, H, H, (int)M, G.fc_o_w, H));
+    {
+      GemmCall c;  // d(ctx + p_hid)
+      c.A = doutp.p; c.lda = H; c.B = w_o_n.p; c.ldb = H; c.C = dactx.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      OK(gemm<T>(gc, c));
+    }
+    // attention (model:103-113)
+    AttnShape as = train_shape(B);
+    attention_bwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), prm.fc_a_w,
+                     alpha.as<float>(), dactx.as<T>(), de.as<float>(), dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(),
+                     dsemb.as<T>(), G.fc_a_w, G.fc_a_b);
+    colsum_add<T>(lc, dhemb.as<T>(), H, M, H, G.fc_g_b);
+    OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, (int)M, G.fc_g_w, H));
+    colsum_add<T>(lc, dsemb.as<T>(), H, M, H, G.fc_s_b);
+    OK(wgrad(gc, sent.p, H, H, dsemb.p, H, H, (int)M, G.fc_s_w, H));
+    {
+      GemmCall c;  // d p_hid (pre-tanh) = (d actx + d hid_emb . fc_g^T) * (1 - p_hid^2)      (model:99, 102)
+      c.A = dhemb.p; c.lda = H; c.B = w_g2_n.p; c.ldb = H; c.C = dphp.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.epi.addend = dactx.p; c.epi.ld_add = H; c.epi.act = ACT_DTANH; c.epi.dact_y = phid.p; c.epi.ld_y = H;
+      OK(gemm<T>(gc, c));
+    }
+    colsum_add<T>(lc, dphp.as<T>(), H, M, H, G.fc_p_b);
+    OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, (int)M, G.fc_p_w, H));
+    {
+      GemmCall c;  // d sentinel = alpha_k d ctx / (k+1) + d sentinel_emb . fc_s^T                (model:104, 111)
+      c.A = dsemb.p; c.lda = H; c.B = w_s_n.p; c.ldb = H; c.C = dS.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.epi.addend = dsctx.p; c.epi.ld_add = H;
+      OK(gemm<T>(gc, c));
+    }
+    // sentinel = sigmoid(p_word_emb + p_hidden) * tanh(c)     (model:89-92)
+    sentinel_bwd<T>(lc, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
+    colsum_add<T>(lc, dG.as<T>() + 4 * H, 5 * H, M, H, G.fc_hs_b);
+    CUDA_OK(cudaMemcpyAsync(G.fc_xs_b, G.fc_hs_b, 4 * H, cudaMemcpyDeviceToDevice, s));  // same pre-activation
+    OK(wgrad(gc, Hprev, H, H, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_hs_w, H));
+    {
+      GemmCall c;  // d h_t from p_hid
+      c.A = dphp.p; c.lda = H; c.B = w_p_n.p; c.ldb = H; c.C = dHhead.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      OK(gemm<T>(gc, c));
+    }
+    {
+      GemmCall c;  // d h_{t-1} from p_hidden
+      c.A = dG.as<T>() + 4 * H; c.lda = 5 * H; c.B = w_hs_n.p; c.ldb = H; c.C = dHprev.p; c.ldc = H; c.M = (int)M;
+      c.N = H; c.K = H;
+      OK(gemm<T>(gc, c));
+    }
+    // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
+    CUDA_OK(cudaMemsetAsync(dcrec.p, 0, 4 * (size_t)B * H, s));
+    for (int t = Tt - 1; t >= 0; --t) {
+      const bool last = (t == Tt - 1);
+      lstm_cell_bwd<T>(lc, B, H, dHhead.as<T>() + (size_t)t * B * H,
+                       last ? nullptr : dHprev.as<T>() + (size_t)(t + 1) * B * H, last ? nullptr : dhrec.as<float>(),
+                       dChead.as<float>() + (size_t)t * B * H, dcrec.as<float>(), gact.as<T>() + (size_t)t * B * 4 * H,
+                       cs.as<float>() + (size_t)(t + 1) * B * H, cs.as<float>() + (size_t)t * B * H,
+                       dG.as<T>() + (size_t)t * B * 5 * H, 5 * H);
+      if (t > 0) {
+        GemmCall c;  // d h_{t-1} through the gates
+        c.A = dG.as<T>() + (size_t)t * B * 5 * H; c.lda = 5 * H; c.B = w_hh_n.p; c.ldb = 4 * H; c.C = dhrec.p;
+        c.ldc = H; c.M = B; c.N = H; c.K = 4 * H; c.epi.out_f32 = 1;
+        OK(gemm<T>(gc, c));
+      }
+    }
+    // weight gradients of the gate GEMM, batched over all steps
+    OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
+    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
+    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
+    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
+    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
+    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
+    OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
+    if (dg) {
+      GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
+      c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
+      c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    {
+      GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
+      c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
+      c.K = 5 * H;
+      OK(gemm<T>(gc, c));
+    }
+    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
+    // once-per-image projections (model:52-53)
+    colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
+    colsum_add<T>(lc, dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
+    OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
+    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
+    if (dP) {
+      GemmCall c;  // d p_img_feat
+      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
+      c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    launches += gc.launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  int decode(const float* g, const float* P, int B, int beam, int finish, int32_t* ids, float* scores, float* ids_f32,
+             cudaStream_t s) override {
+    if (!bound) { set_error("capdec_decode: parameters not bound"); return -1; }
+    if (B <= 0 || beam < 1 || beam > 8) { set_error("capdec_decode: need B > 0 and 1 <= beam <= 8"); return -1; }
+    if (beam > V) { set_error("capdec_decode: beam wider than the vocabulary"); return -1; }
+    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const int R = B * beam, X = E + H;
+    have_fwd = false;  // the activation buffers of a pending train_fwd are reused below
+    OK(image_projections(gc, lc, g, P, B));
+    OK(g5.ensure(4 * (size_t)B * 5 * H, &ws_bytes));
+    OK(xin.ensure(e * (size_t)R * X, &ws_bytes));
+    OK(gpre.ensure(4 * (size_t)R * 4 * H, &ws_bytes));
+    OK(ph.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(d_hnew.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(d_cnew.ensure(4 * (size_t)R * H, &ws_bytes));
+    OK(d_ccur.ensure(4 * (size_t)R * H, &ws_bytes));
+    OK(sent.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(phid.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(hemb.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(semb.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(alpha.ensure(4 * (size_t)R * (k + 1), &ws_bytes));
+    OK(actx.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(outv.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(proj.ensure(e * (size_t)R * E, &ws_bytes));
+    OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
+    OK(d_state.ensure((size_t)R * (2 * 4 + 2 * 4 + 2 * 4 * Ti + 8) + 256, &ws_bytes));
+    // beam bookkeeping (double-buffered)
+    float* score[2]; int* fin[2]; int* hist[2]; int *tok, *src;
+    {
+      char* p = d_state.as<char>();
+      score[0] = (float*)p; p += 4 * R; score[1] = (float*)p; p += 4 * R;
+      fin[0] = (int*)p; p += 4 * R; fin[1] = (int*)p; p += 4 * R;
+      hist[0] = (int*)p; p += 4 * (size_t)R * Ti; hist[1] = (int*)p; p += 4 * (size_t)R * Ti;
+      tok = (int*)p; p += 4 * R; src = (int*)p;
+    }
+    CUDA_OK(cudaMemsetAsync(d_state.p, 0, d_state.cap, s));
+    {
+      // only prefix 0 of every image is live at step 0; every row starts from <start>, h = c = 0 (model:56-58, 63)
+      std::vector<float> sc(R, -INFINITY);
+      std::vector<int> tk(R, cfg.start_idx), sr(R, 0);
+      for (int i = 0; i < B; ++i) sc[(size_t)i * beam] = 0.f;
+      for (int r = 0; r < R; ++r) sr[r] = r % beam;
+      CUDA_OK(cudaMemcpyAsync(score[0], sc.data(), 4 * R, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(tok, tk.data(), 4 * R, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(src, sr.data(), 4 * R, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));  // the host vectors die at the end of this scope
+    }
+    CUDA_OK(cudaMemsetAsync(d_hnew.p, 0, e * (size_t)R * H, s));
+    CUDA_OK(cudaMemsetAsync(d_cnew.p, 0, 4 * (size_t)R * H, s));
+    beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
+                    xin.as<T>(), X, d_ccur.as<float>());
+    // global-image half of the gate / sentinel pre-activations, once per image
+    OK(fc(gc, gT.p, H, w_g_t, b5d.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    AttnShape as;
+    as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
+    as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
+    DevBuf w_dec_s;  // view: rows 4H..5H of w_dec_t
+    w_dec_s.p = w_dec_t.as<T>() + (size_t)4 * H * X;
+    for (int step = 0; step < Ti; ++step) {
+      const int cur = step & 1, nxt = cur ^ 1;
+      // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
+      OK(fc(gc, xin.p, X, w_dec_t, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
+      OK(fc(gc, xin.p, X, w_dec_s, nullptr, ph.p, H, R, H, X, ACT_NONE));
+      lstm_cell_fwd<T>(lc, R, H, gpre.as<float>(), 4 * H, (const T*)nullptr, 0, g5.as<float>(), 5 * H, INT_MAX, beam,
+                       d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
+      sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
+                      d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
+      OK(fc(gc, d_hnew.p, H, w_p_t, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
+      OK(fc(gc, phid.p, H, w_g2_t, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
+      OK(fc(gc, sent.p, H, w_s_t, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+      attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
+                       prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
+      OK(fc(gc, actx.p, H, w_o_t, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
+      OK(fc(gc, outv.p, H, w_e_t, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
+      {
+        GemmCall c;
+        c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
+        c.epi.bias = prm.out_fc_bias; c.epi.out_f32 = 1;
+        OK(gemm<T>(gc, c));
+      }
+      // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
+      beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
+                score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src);
+      if (step + 1 < Ti)
+        beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
+                        xin.as<T>(), X, d_ccur.as<float>());
+    }
+    const int fin_buf = Ti & 1;
+    if (ids) CUDA_OK(cudaMemcpyAsync(ids, hist[fin_buf], 4 * (size_t)R * Ti, cudaMemcpyDeviceToDevice, s));
+    if (scores) CUDA_OK(cudaMemcpyAsync(scores, score[fin_buf], 4 * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    if (ids_f32) ids_to_f32(lc, hist[fin_buf], B, beam, Ti, ids_f32);
+    launches += gc.launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  static void ids_to_f32(LaunchCtx lc, const int* hist, int B, int beam, int Ti, float* out);
+
+ private:
+  std::vector<DevBuf*> all_bufs() {
+    return {&w_v_t, &w_k_t, &w_kv_n, &w_x_t, &w_x_n, &w_g_t, &w_g_n, &w_hh_t, &w_hh_n, &w_hs_t, &w_hs_n, &w_p_t, &w_p_n,
+            &w_g2_t, &w_g2_n, &w_s_t, &w_s_n, &w_o_t, &w_o_n, &w_e_t, &w_e_n, &emb, &emb_t, &w_dec_t, &b5, &b5d, &gT, &PT,
+            &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
+            &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &d_state};
+  }
+
+  capdec_config cfg;
+  capdec_params prm{};
+  int H, E, V, Vp, k, S, Tt, Ti;
+  bool bound = false, have_fwd = false, force_simt = false;
+  int last_B = 0;
+  const int64_t* last_cap = nullptr;
+  // operands
+  DevBuf w_v_t, w_k_t, w_kv_n, w_x_t, w_x_n, w_g_t, w_g_n, w_hh_t, w_hh_n, w_hs_t, w_hs_n, w_p_t, w_p_n, w_g2_t, w_g2_n,
+      w_s_t, w_s_n, w_o_t, w_o_n, w_e_t, w_e_n, emb, emb_t, w_dec_t, b5, b5d;
+  // activations kept for the backward pass
+  DevBuf gT, PT, keys, vals, embx, xe, g5, hs, cs, gact, gpre, ph, sgate, sent, phid, hemb, semb, alpha, actx, outv, proj,
+      logits, lse, acc;
+  // backward scratch
+  DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
+      dGsum, dembx;
+  // decode state
+  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
+};
+
+namespace {
+__global__ void ids_to_f32_kernel(const int* __restrict__ hist, int B, int beam, int Ti, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ti) return;
+  const int b = i / Ti, t = i % Ti;
+  out[i] = (float)hist[((long)b * beam) * Ti + t];  // best beam, cast like model:122
+}
+}  // namespace
+template <typename T> void Decoder<T>::ids_to_f32(LaunchCtx lc, const int* hist, int B, int beam, int Ti, float* out) {
+  ids_to_f32_kernel<<<(B * Ti + 255) / 256, 256, 0, lc.stream>>>(hist, B, beam, Ti, out);
+  if (lc.launches) ++*lc.launches;
+}
+
+}  // namespace capdec
+
+// ================================================================================================================
+// C-ABI
+// ================================================================================================================
+using namespace capdec;
+
+struct capdec_handle_s {
+  DecoderBase* impl;
+};
+
+static int check_device(capdec_handle h) {
+  if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
+  cudaError_t e = cudaSetDevice(h->impl->device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->impl->device, cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+extern "C" {
+
+const char* capdec_last_error(void) { return g_err; }
+int capdec_version(void) { return 100; }
+
+int capdec_create(const capdec_config* c, int device, capdec_handle* out) {
+  if (!c || !out) { set_error("capdec_create: null argument"); return -1; }
+  if (c->hidden_dim <= 0 || c->hidden_dim % 8 || c->embedding_size <= 0 || c->embedding_size % 8) {
+    set_error("capdec_create: hidden_dim and embedding_size must be positive multiples of 8"); return -1;
+  }
+  if (c->num_positions < 1 || c->num_positions > 64) { set_error("capdec_create: num_positions must be in [1,64]"); return -1; }
+  if (c->vocab_size < 4 || c->sentence_length < 2 || c->infer_max_length < 1) {
+    set_error("capdec_create: bad vocab_size / sentence_length / infer_max_length"); return -1;
+  }
+  if (c->padding_idx < 0 || c->padding_idx >= c->vocab_size || c->start_idx < 0 || c->start_idx >= c->vocab_size ||
+      c->stop_idx < 0 || c->stop_idx >= c->vocab_size) {
+    set_error("capdec_create: special token ids out of range"); return -1;
+  }
+  if (c->softmax_axis != CAPDEC_SOFTMAX_FEATURE && c->softmax_axis != CAPDEC_SOFTMAX_POSITION) {
+    set_error("capdec_create: unsupported softmax_axis %d", c->softmax_axis); return -1;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    set_error("capdec_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e)); return -1;
+  }
+  if (device < 0 || device >= ndev) { set_error("capdec_create: device %d out of range", device); return -1; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return -1; }
+  if (prop.major != 10) {
+    set_error("capdec_create: device %d is sm_%d%d; the kernels are built for sm_100a (B200) only", device, prop.major,
+              prop.minor);
+    return -1;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return -1; }
+  DecoderBase* impl = nullptr;
+  if (c->dtype == CAPDEC_DTYPE_F32) impl = new (std::nothrow) Decoder<float>(*c);
+  else if (c->dtype == CAPDEC_DTYPE_BF16) impl = new (std::nothrow) Decoder<bf16>(*c);
+  else { set_error("capdec_create: unsupported dtype %d", c->dtype); return -1; }
+  if (!impl) { set_error("capdec_create: out of host memory"); return -1; }
+  impl->device = device;
+  capdec_handle h = new (std::nothrow) capdec_handle_s{impl};
+  if (!h) { delete impl; set_error("capdec_create: out of host memory"); return -1; }
+  *out = h;
+  return 0;
+}
+
+int capdec_destroy(capdec_handle h) {
+  if (!h) return 0;
+  if (h->impl) { cudaSetDevice(h->impl->device); delete h->impl; }
+  delete h;
+  return 0;
+}
+
+size_t capdec_workspace_bytes(capdec_handle h) { return (h && h->impl) ? h->impl->ws_bytes : 0; }
+int64_t capdec_launch_count(capdec_handle h) { return (h && h->impl) ? h->impl->launches : 0; }
+
+int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream) {
+  if (check_device(h)) return -1;
+  if (!p) { set_error("capdec_bind_params: null params"); return -1; }
+  const float* const* pp = reinterpret_cast<const float* const*>(p);
+  for (size_t i = 0; i < sizeof(capdec_params) / sizeof(float*); ++i)
+    if (!pp[i]) { set_error("capdec_bind_params: parameter pointer %zu is NULL", i); return -1; }
+  return h->impl->bind(p, (cudaStream_t)stream);
+}
+
+int capdec_train_fwd(capdec_handle h, const float* g, const float* P, const int64_t* caption, int32_t B,
+                     float* logits_out, float* loss_out, void* stream) {
+  if (check_device(h)) return -1;
+  if (!g || !P || !caption) { set_error("capdec_train_fwd: null input"); return -1; }
+  return h->impl->train_fwd(g, P, caption, B, logits_out, loss_out, (cudaStream_t)stream);
+}
+
+int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_dev, float* dg, float* dP,
+                     const capdec_grads* gr, void* stream) {
+  if (check_device(h)) return -1;
+  if (!gr) { set_error("capdec_train_bwd: null grads"); return -1; }
+  return h->impl->train_bwd(loss_scale, inv_ntok_dev, dg, dP, gr, (cudaStream_t)stream);
+}
+
+int capdec_decode(capdec_handle h, const float* g, const float* P, int32_t B, int32_t beam, int32_t finish_on_stop,
+                  int32_t* ids_out, float* scores_out, float* ids_f32_out, void* stream) {
+  if (check_device(h)) return -1;
+  if (!g || !P) { set_error("capdec_decode: null input"); return -1; }
+  return h->impl->decode(g, P, B, beam, finish_on_stop, ids_out, scores_out, ids_f32_out, (cudaStream_t)stream);
+}
+
+int capdec_gemm(int32_t dtype, int32_t mn_major, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,
+                const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t force_simt,
+                void* stream) {
+  GemmContext gc; gc.stream = (cudaStream_t)stream; gc.force_simt = force_simt != 0;
+  GemmCall c;
+  c.A = A; c.lda = lda; c.B = B; c.ldb = ldb; c.C = C; c.ldc = ldc; c.M = M; c.N = N; c.K = K; c.mn_major = mn_major != 0;
+  c.epi.bias = bias; c.epi.addend = addend; c.epi.ld_add = ld_add; c.epi.dact_y = dact_y; c.epi.ld_y = ld_y;
+  c.epi.act = act; c.epi.out_f32 = out_f32; c.epi.atomic = atomic; c.splits = atomic ? 0 : 1;
+  if (dtype == CAPDEC_DTYPE_F32) return gemm<float>(gc, c);
+  if (dtype == CAPDEC_DTYPE_BF16) return gemm<bf16>(gc, c);
+  set_error("capdec_gemm: unsupported dtype %d", dtype);
+  return -1;
+}
+
+static AttnShape make_shape(int H, int k, int n_img, int q, int64_t r0, int64_t qs, int axis) {
+  AttnShape s;
+  s.H = H; s.k = k; s.n_img = n_img; s.q_per_img = q; s.row0_stride = r0; s.q_stride = qs;
+  s.position_softmax = axis == CAPDEC_SOFTMAX_POSITION;
+  return s;
+}
+
+int capdec_attention_fwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int32_t q_per_img, int64_t row0_stride,
+                         int64_t q_stride, int32_t softmax_axis, const void* keys, const void* vals,
+                         const void* hid_emb, const void* sent_emb, const void* sentinel, const void* p_hid,
+                         const float* w_alpha, const float* b_alpha, float* alpha, void* actx, void* ctx, void* stream) {
+  if (H % 8 || k < 1 || k > 64) { set_error("capdec_attention_fwd: need H %% 8 == 0 and 1 <= k <= 64"); return -1; }
+  LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
+  if (dtype == CAPDEC_DTYPE_F32)
+    attention_fwd<float>(lc, s, (const float*)keys, (const float*)vals, (const float*)hid_emb, (const float*)sent_emb,
+                         (const float*)sentinel, (const float*)p_hid, w_alpha, b_alpha, alpha, (float*)actx, (float*)ctx);
+  else if (dtype == CAPDEC_DTYPE_BF16)
+    attention_fwd<bf16>(lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
+                        (const bf16*)sentinel, (const bf16*)p_hid, w_alpha, b_alpha, alpha, (bf16*)actx, (bf16*)ctx);
+  else { set_error("capdec_attention_fwd: unsupported dtype %d", dtype); return -1; }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("capdec_attention_fwd: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+int capdec_attention_bwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int32_t q_per_img, int64_t row0_stride,
+                         int64_t q_stride, int32_t softmax_axis, const void* keys, const void* vals,
+                         const void* hid_emb, const void* sent_emb, const void* sentinel, const float* w_alpha,
+                         const float* alpha, const void* dctx, float* de, void* dS_ctx, void* dKV, void* dhid_emb,
+                         void* dsent_emb, float* dw_alpha, float* db_alpha, void* stream) {
+  if (H % 8 || k < 1 || k > 64) { set_error("capdec_attention_bwd: need H %% 8 == 0 and 1 <= k <= 64"); return -1; }
+  LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
+  if (dtype == CAPDEC_DTYPE_F32)
+    attention_bwd<float>(lc, s, (const float*)keys, (const float*)vals, (const float*)hid_emb, (const float*)sent_emb,
+                         (const float*)sentinel, w_alpha, alpha, (const float*)dctx, de, (float*)dS_ctx, (float*)dKV,
+                         (float*)dhid_emb, (float*)dsent_emb, dw_alpha, db_alpha);
+  else if (dtype == CAPDEC_DTYPE_BF16)
+    attention_bwd<bf16>(lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
+                        (const bf16*)sentinel, w_alpha, alpha, (const bf16*)dctx, de, (bf16*)dS_ctx, (bf16*)dKV,
+                        (bf16*)dhid_emb, (bf16*)dsent_emb, dw_alpha, db_alpha);
+  else { set_error("capdec_attention_bwd: unsupported dtype %d", dtype); return -1; }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("capdec_attention_bwd: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+int capdec_lstm_cell_fwd(int32_t dtype, int32_t R, int32_t H, const float* gates_pre, const float* c_prev, void* h_out,
+                         float* c_out, void* stream) {
+  if (H % 8) { set_error("capdec_lstm_cell_fwd: H must be a multiple of 8"); return -1; }
+  LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  if (dtype == CAPDEC_DTYPE_F32)
+    lstm_cell_fwd<float>(lc, R, H, gates_pre, 4 * H, nullptr, 0, nullptr, 0, INT_MAX, 1, c_prev, (float*)h_out, H, c_out,
+                         nullptr);
+  else if (dtype == CAPDEC_DTYPE_BF16)
+    lstm_cell_fwd<bf16>(lc, R, H, gates_pre, 4 * H, nullptr, 0, nullptr, 0, INT_MAX, 1, c_prev, (bf16*)h_out, H, c_out,
+                        nullptr);
+  else { set_error("capdec_lstm_cell_fwd: unsupported dtype %d", dtype); return -1; }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("capdec_lstm_cell_fwd: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+int capdec_beam_step(const float* logits, int64_t ldl, int32_t V, int32_t n_img, int32_t beam, int32_t step,
+                     int32_t T_total, int32_t pad, int32_t stop, int32_t finish_on_stop, const float* score_in,
+                     float* score_out, const int32_t* fin_in, int32_t* fin_out, const int32_t* hist_in,
+                     int32_t* hist_out, int32_t* tok_out, int32_t* src_out, void* stream) {
+  if (beam < 1 || beam > 8) { set_error("capdec_beam_step: 1 <= beam <= 8"); return -1; }
+  LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  beam_step(lc, logits, ldl, V, n_img, beam, step, T_total, pad, stop, finish_on_stop, score_in, score_out, fin_in,
+            fin_out, hist_in, hist_out, tok_out, src_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("capdec_beam_step: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+}  // extern "C"

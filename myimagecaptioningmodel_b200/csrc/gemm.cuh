@@ -1,0 +1,79 @@
+// GEMM interface used by the decoder schedule.
+//
+//   C[M,N] (=|+=) epi( sum_k A(m,k) * B(n,k) )
+//
+// Two operand forms ("majors"):
+//   K-major  (mn_major = false): A is stored [M,K] row-major (lda), B is stored [N,K] row-major (ldb).
+//   MN-major (mn_major = true) : A is stored [K,M] row-major (lda), B is stored [K,N] row-major (ldb);
+//                                this is the weight-gradient form  dW[in,out] = X[rows,in]^T . dY[rows,out].
+// T = bf16 -> tcgen05/TMEM/TMA kernel (gemm_tc.cu); T = float -> SIMT kernel (validation precision mode).
+#pragma once
+#include "common.cuh"
+
+namespace capdec {
+
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2 };
+
+struct GemmEpi {
+  const float* bias = nullptr;   // [N] fp32, added to every row
+  const void* addend = nullptr;  // T [M, ld_add], added element-wise
+  const void* dact_y = nullptr;  // T [M, ld_y]: ACT_DTANH multiplies by (1 - y^2)
+  long ld_add = 0, ld_y = 0;
+  int act = ACT_NONE;
+  int out_f32 = 0;               // C is fp32 (otherwise T)
+  int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
+};
+
+struct GemmCall {
+  const void* A = nullptr; long lda = 0;
+  const void* B = nullptr; long ldb = 0;
+  void* C = nullptr; long ldc = 0;
+  int M = 0, N = 0, K = 0;
+  bool mn_major = false;
+  int splits = 1;                // split-K (requires epi.atomic)
+  GemmEpi epi;
+};
+
+// element-wise epilogue shared by both kernels
+template <typename T>
+__device__ __forceinline__ float epi_value(float acc, int m, int n, const GemmEpi& e) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + n);
+  if (e.addend) v += to_f(reinterpret_cast<const T*>(e.addend)[(long)m * e.ld_add + n]);
+  if (e.act == ACT_TANH) v = tanh_t<fast_math<T>::value>(v);
+  if (e.act == ACT_DTANH) {
+    float y = to_f(reinterpret_cast<const T*>(e.dact_y)[(long)m * e.ld_y + n]);
+    v *= (1.f - y * y);
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ void epi_store(float v, void* C, long ldc, int m, int n, const GemmEpi& e) {
+  if (e.atomic) {
+    atomicAdd(reinterpret_cast<float*>(C) + (long)m * ldc + n, v);
+  } else if (e.out_f32) {
+    reinterpret_cast<float*>(C)[(long)m * ldc + n] = v;
+  } else {
+    reinterpret_cast<T*>(C)[(long)m * ldc + n] = from_f<T>(v);
+  }
+}
+
+struct GemmContext {
+  cudaStream_t stream = nullptr;
+  bool force_simt = false;       // debugging: route bf16 GEMMs through the SIMT kernel
+  long launches = 0;             // number of kernels launched (bench accounting)
+};
+
+// returns cudaError_t-style int (0 ok); message via capdec::set_error
+int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c);
+template <typename T> int gemm_simt(GemmContext& ctx, const GemmCall& c);
+
+template <typename T> inline int gemm(GemmContext& ctx, const GemmCall& c);
+template <> inline int gemm<float>(GemmContext& ctx, const GemmCall& c) { return gemm_simt<float>(ctx, c); }
+template <> inline int gemm<bf16>(GemmContext& ctx, const GemmCall& c) {
+  return ctx.force_simt ? gemm_simt<bf16>(ctx, c) : gemm_bf16_tc(ctx, c);
+}
+
+void set_error(const char* fmt, ...);
+
+}  // namespace capdec

@@ -1,0 +1,350 @@
+// bf16 GEMM on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory ->
+// tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) -> fp32 accumulator in TMEM ->
+// tcgen05.ld -> fused epilogue (bias / addend / tanh / tanh' / fp32 atomics for split-K) -> global.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+// One 128 x BN output tile per CTA; a STAGES-deep mbarrier ring decouples TMA from the MMA issuer.
+//
+// Replaces the cuBLAS SGEMMs behind every layers.fc / layers.matmul on the reference's decoder path
+// (model_adaAttention_aic.py:24-25, 52-53, 87-90, 99-104, 115) and their *_grad ops.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.cuh"
+
+namespace capdec {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kThreads = 192;
+constexpr int kABytes = BM * BK * 2;  // 16 KB
+
+template <int BN> struct TcCfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// 64-bit shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1      bits [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, bool MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
+               long ldc, int M, int N, int K, int kb_per_split, int vec_ok, GemmEpi epi) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int nkb_total = (K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(nkb_total, kb0 + kb_per_split);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sA = smem + s * Cfg::kStageBytes;
+        uint8_t* sB = sA + kABytes;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        if (!MN) {
+          tma_load_2d(sA, &tmA, kb * BK, m0, &full_bar[s]);
+          tma_load_2d(sB, &tmB, kb * BK, n0, &full_bar[s]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, &full_bar[s]);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, &full_bar[s]);
+        }
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), a/b major (bits 15/16),
+      // N>>3 at [17,23), M>>4 at [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN ? 1u : 0u) << 15) | ((MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          uint64_t da, db;
+          if (!MN) {
+            // K-major SW128: rows of 128 B, 8-row groups 1024 B apart; advance 16 elements = 32 B along K
+            da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            db = make_smem_desc(b_addr + k * 32, 16, 1024);
+          } else {
+            // MN-major SW128: each k-row is 128 B (64 mn elements); 8-k groups 1024 B apart (SBO);
+            // next 64-wide mn group is one TMA box (64 rows x 128 B = 8192 B) further (LBO);
+            // advance 16 k-rows = 2048 B
+            da = make_smem_desc(a_addr + k * 2048, 8192, 1024);
+            db = make_smem_desc(b_addr + k * 2048, 8192, 1024);
+          }
+          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= N) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = nb + g * 8;
+        if (col >= N) break;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+        if (vec_ok && col + 8 <= N) {
+          if (epi.bias) {
+            float b[8];
+            load8(epi.bias + col, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += b[i];
+          }
+          if (epi.addend) {
+            float a[8];
+            load8(reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + col, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += a[i];
+          }
+          if (epi.act == ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
+          } else if (epi.act == ACT_DTANH) {
+            float y[8];
+            load8(reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + col, y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= (1.f - y[i] * y[i]);
+          }
+          if (epi.atomic) {
+            float* p = reinterpret_cast<float*>(C) + (long)row * ldc + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(p + i, v[i]);
+          } else if (epi.out_f32) {
+            store8(reinterpret_cast<float*>(C) + (long)row * ldc + col, v);
+          } else {
+            store8(reinterpret_cast<bf16*>(C) + (long)row * ldc + col, v);
+          }
+        } else {
+          for (int i = 0; i < 8 && col + i < N; ++i) {
+            float x = epi_value<bf16>(v[i], row, col + i, epi);
+            epi_store<bf16>(x, C, ldc, row, col + i, epi);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+}
+
+struct MapKey {
+  const void* p; uint64_t inner, outer, ld; uint32_t bi, bo;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.p;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.bi); mix(k.bo);
+    return h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+
+// 2-D bf16 tensor [outer, inner] with row stride ld (elements); box = [bo, bi]; 128-byte swizzle.
+int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  if (((uintptr_t)p & 15) || ((ld * 2) & 15)) {
+    set_error("gemm_tc: operand %p (ld=%llu) is not 16-byte aligned for TMA", p, (unsigned long long)ld);
+    return -1;
+  }
+  MapKey key{p, inner, outer, ld, bi, bo};
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {bi, bo};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, p,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, bi, bo);
+    return -1;
+  }
+  std::lock_guard<std::mutex> g(g_maps_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+template <int BN, bool MN>
+int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!MN) {
+    if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA)) return -1;
+    if (get_map(c.B, c.K, c.N, c.ldb, BK, BN, &tmB)) return -1;
+  } else {
+    if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA)) return -1;
+    if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB)) return -1;
+  }
+  const GemmEpi& e = c.epi;
+  const int out_elem = (e.out_f32 || e.atomic) ? 4 : 2;
+  int vec_ok = ((c.ldc % 8) == 0) && (((uintptr_t)c.C) % (out_elem * 8) == 0);
+  if (e.bias && ((uintptr_t)e.bias & 31)) vec_ok = 0;
+  if (e.addend && (((uintptr_t)e.addend & 15) || (e.ld_add % 8))) vec_ok = 0;
+  if (e.dact_y && (((uintptr_t)e.dact_y & 15) || (e.ld_y % 8))) vec_ok = 0;
+  dim3 grid((c.N + BN - 1) / BN, (c.M + BM - 1) / BM, splits);
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, c.C, c.ldc, c.M, c.N, c.K, kbps,
+                                                                         vec_ok, c.epi);
+  ctx.launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(err)); return -1; }
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
+  if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
+  const int nkb = (c.K + BK - 1) / BK;
+  const int mt = (c.M + BM - 1) / BM;
+  // split-K: 0 = auto (only with atomics)
+  int splits = c.epi.atomic ? c.splits : 1;
+  auto tiles_for = [&](int bn) { return (long)mt * ((c.N + bn - 1) / bn); };
+  // tile width: minimise (waves x (BN + fixed overhead))
+  int best_bn = 64;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (bn > 64 && c.N <= bn / 2) continue;
+    long tiles = tiles_for(bn);
+    int sp = splits;
+    if (sp == 0) sp = (int)std::max(1L, std::min<long>(nkb / 4 > 0 ? nkb / 4 : 1, (2 * kNumSMs) / std::max(1L, tiles)));
+    long waves = (tiles * sp + kNumSMs - 1) / kNumSMs;
+    double cost = (double)waves * (bn + 40) * ((double)nkb / sp + 6.0);
+    if (cost < best_cost) { best_cost = cost; best_bn = bn; }
+  }
+  if (splits == 0) {
+    long tiles = tiles_for(best_bn);
+    splits = (int)std::max(1L, std::min<long>(nkb / 4 > 0 ? nkb / 4 : 1, (2 * kNumSMs) / std::max(1L, tiles)));
+  }
+  int kbps = (nkb + splits - 1) / splits;
+  splits = (nkb + kbps - 1) / kbps;
+  if (c.mn_major) {
+    switch (best_bn) {
+      case 256: return launch<256, true>(ctx, c, splits, kbps);
+      case 128: return launch<128, true>(ctx, c, splits, kbps);
+      default: return launch<64, true>(ctx, c, splits, kbps);
+    }
+  } else {
+    switch (best_bn) {
+      case 256: return launch<256, false>(ctx, c, splits, kbps);
+      case 128: return launch<128, false>(ctx, c, splits, kbps);
+      default: return launch<64, false>(ctx, c, splits, kbps);
+    }
+  }
+}
+
+}  // namespace capdec

@@ -1,0 +1,97 @@
+// Host-side launchers of the non-GEMM kernels (templated on the storage type T in {float, bf16}).
+// Row index convention for training tensors: time-major, m = t * B + b.
+#pragma once
+#include "common.cuh"
+
+namespace capdec {
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  long* launches;
+};
+
+// ---- pointwise.cu -------------------------------------------------------------------------------
+template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* dst, long n);
+// dst[cc * ldd + r] = src[r * lds + cc]   (src fp32 [R, C])
+template <typename T> void transpose_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C);
+// dst[r * ldd + cc] = src[r * lds + cc]   (strided copy + convert)
+template <typename T> void copy2d_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C);
+// out[(t*B+b), :] = ids[b*ids_ld + t] == pad ? 0 : emb[id]      (model:28-32, 84)
+template <typename T>
+void embed_gather(LaunchCtx c, const T* emb, int E, const int64_t* ids, long ids_ld, int B, int steps, int pad, T* out,
+                  long ldo);
+// LSTM pointwise cell (Paddle lstm_unit op, gate order i,f,o,g; model:87-88).
+//   pre = gpre[r] (+ xe[r] if xe) (+ g5[(r % g5_mod) / g5_div] if g5);  c = sig(f) c_prev + sig(i) tanh(g); h = sig(o) tanh(c)
+template <typename T>
+void lstm_cell_fwd(LaunchCtx c, int R, int H, const float* gpre, long ld_gpre, const T* xe, long ld_xe, const float* g5,
+                   long ld_g5, int g5_mod, int g5_div, const float* c_prev, T* h_out, long ld_h, float* c_out,
+                   T* gates_act);
+// sentinel (model:89-92): sg = sig(ph + xe + g5);  s = sg * tanh(c)
+template <typename T>
+void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* xe, long ld_xe, const float* g5,
+                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out);
+// dsg_pre = dS * tanh(c) * sg (1 - sg)  -> dG[:, 4H:5H];   dC_head = dS * sg * (1 - tanh(c)^2)
+template <typename T>
+void sentinel_bwd(LaunchCtx c, long R, int H, const T* dS, const T* sgate, const float* cc, T* dsg_pre, long ld_dsg,
+                  float* dC_head);
+// one BPTT step of the cell (see pointwise.cu)
+template <typename T>
+void lstm_cell_bwd(LaunchCtx c, int B, int H, const T* dH_head, const T* dHprev_head, const float* dh_rec,
+                   const float* dC_head, float* dc_rec, const T* gates_act, const float* c_t, const float* c_prev,
+                   T* dgates, long ld_dg);
+// out[b, :] = sum_t x[(t*B+b), :]
+template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo);
+// out[n] += sum_m x[m, n]    (fp32 atomics)
+template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out);
+// dEmb[id] += dX[(t*B+b)]  for id != pad        (lookup_table_v2_grad, padding_idx)
+template <typename T>
+void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
+                       int pad, float* dEmb);
+void fill_f32(LaunchCtx c, float* p, float v, long n);
+
+// ---- attention.cu ------------------------------------------------------------------------------
+struct AttnShape {
+  int H, k;             // hidden size, number of image positions (k+1 attention positions)
+  int n_img;            // images
+  int q_per_img;        // query rows per image (train: T steps; decode: beam)
+  long row0_stride;     // row of query 0 of image i = i * row0_stride
+  long q_stride;        // row of query q = row0 + q * q_stride      (train: 1 / B; decode: beam / 1)
+  int position_softmax; // 1 = softmax over the k+1 positions; 0 = reference as written (alpha == 1)
+};
+// fused additive attention forward (model:103-113 + the "context + p_hid" of model:115)
+//   alpha [rows, k+1] fp32;  actx [rows, H] = mean_j(alpha_j v_j) + p_hid;  ctx_out (optional) without p_hid
+template <typename T>
+void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
+                   const T* sentinel, const T* p_hid, const float* w_alpha, const float* b_alpha, float* alpha, T* actx,
+                   T* ctx_out);
+// backward, three kernels (see attention.cu).  dactx [rows,H] is the gradient wrt context.
+//   de [rows,k+1] fp32 scratch;  dS_ctx [rows,H] = alpha_k dctx / (k+1);  dKV [n_img*k, 2H]: cols 0..H = d(values pre-tanh),
+//   cols H..2H = d keys;  dhid_emb, dsent_emb [rows,H];  dw_alpha [H], db_alpha [1] fp32 (+=)
+template <typename T>
+void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
+                   const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx, float* de, T* dS_ctx,
+                   T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha, float* db_alpha);
+
+// ---- loss.cu -----------------------------------------------------------------------------------
+// masked soft-max cross entropy (model:163-171, 180-183, 205-212): target[t*B+b] = caption[b, t+1]
+//   lse[m];  acc[0] += sum(ce * mask), acc[1] += sum(mask)
+void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* caption, long cap_ld, int B, int steps,
+            int pad, float* lse, float* acc);
+// acc[2] = acc[0] / acc[1] (the loss), acc[3] = 1 / acc[1]
+void loss_finalize(LaunchCtx c, float* acc);
+// dlogits[m, n] = (exp(l - lse) - [n == target]) * mask * (*scale) * loss_scale; columns [V, Vp) are zeroed
+template <typename T>
+void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+            int steps, int pad, const float* lse, const float* scale, float loss_scale, T* dlogits);
+// out[b, t, :V] = logits[(t*B+b), :V]
+void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out);
+// one beam-search step for every image; see loss.cu
+void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
+               int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
+               const int* hist_in, int* hist_out, int* tok_out, int* src_out);
+// next-step operands: xin[r] = [emb[tok[r]] | h_new[src_row(r)]], c_next[r] = c_new[src_row(r)]
+template <typename T>
+void beam_reorder(LaunchCtx c, int n_img, int beam, int E, int H, int pad, const T* emb, const int* tok, const int* src,
+                  const T* h_new, const float* c_new, T* xin, long ld_xin, float* c_next);
+
+}  // namespace capdec

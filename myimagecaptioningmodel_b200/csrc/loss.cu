@@ -1,0 +1,289 @@
+// Vocabulary-axis kernels: masked soft-max cross-entropy forward / backward (model:163-171, 180-183, 205-212),
+// greedy arg-max and beam-search top-k with back-pointers (model:119-123; beam spec: SURVEY.md 8c row C5).
+// One CTA per row / per image, warp-shuffle + shared-memory block reductions, 128-bit loads.
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+constexpr int kCeThreads = 256;
+
+__device__ __forceinline__ int64_t target_of(const int64_t* caption, long cap_ld, int B, long m) {
+  const long t = m / B, b = m % B;
+  return caption[b * cap_ld + t + 1];
+}
+
+__global__ void __launch_bounds__(kCeThreads)
+ce_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const int64_t* __restrict__ caption, long cap_ld, int B,
+              int pad, float* __restrict__ lse, float* __restrict__ acc) {
+  __shared__ float scratch[32];
+  const long m = blockIdx.x;
+  const float* row = logits + m * ldl;
+  const int V4 = V & ~3;
+  float mx = -INFINITY;
+  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + n);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) mx = fmaxf(mx, row[n]);
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + n);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) sum += __expf(row[n] - mx);
+  sum = block_sum(sum, scratch);
+  if (threadIdx.x == 0) {
+    const float l = mx + logf(sum);
+    lse[m] = l;
+    const int64_t tgt = target_of(caption, cap_ld, B, m);
+    if (tgt != pad) {
+      atomicAdd(acc + 0, l - row[tgt]);
+      atomicAdd(acc + 1, 1.f);
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(float* acc) {
+  acc[2] = acc[0] / acc[1];
+  acc[3] = 1.f / acc[1];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCeThreads)
+ce_bwd_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
+              long cap_ld, int B, int pad, const float* __restrict__ lse, const float* __restrict__ scale,
+              float loss_scale, T* __restrict__ dlogits) {
+  const long m = blockIdx.x;
+  const float* row = logits + m * ldl;
+  T* out = dlogits + m * (long)Vp;
+  const int64_t tgt = target_of(caption, cap_ld, B, m);
+  if (tgt == pad) {  // masked position: zero gradient row
+    for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      store8(out + n, z);
+    }
+    return;
+  }
+  const float l = lse[m];
+  const float sc = scale[0] * loss_scale;
+  for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
+    float v[8];
+    if (n + 8 <= V) {
+      load8(row + n, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (__expf(v[i] - l) - ((n + i) == tgt ? 1.f : 0.f)) * sc;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (n + i < V) ? (__expf(row[n + i] - l) - ((n + i) == tgt ? 1.f : 0.f)) * sc : 0.f;
+    }
+    store8(out + n, v);
+  }
+}
+
+__global__ void logits_bm_kernel(const float* __restrict__ logits, long ldl, int V, int B, int steps,
+                                 float* __restrict__ out) {
+  const long m = blockIdx.x;  // time-major row
+  const long t = m / B, b = m % B;
+  const float* src = logits + m * ldl;
+  float* dst = out + (b * steps + t) * (long)V;
+  for (int n = threadIdx.x; n < V; n += blockDim.x) dst[n] = src[n];
+}
+
+// ---- beam search step: one CTA per image --------------------------------------------------------------------
+struct Cand { float v; int idx; };
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+__device__ __forceinline__ Cand warp_best(Cand c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, c.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, c.idx, o);
+    if (better(ov, oi, c.v, c.idx)) { c.v = ov; c.idx = oi; }
+  }
+  return c;
+}
+
+constexpr int kBeamThreads = 512;
+constexpr int kMaxBeam = 8;
+
+__global__ void __launch_bounds__(kBeamThreads)
+beam_step_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int step, int T_total, int pad, int stop,
+                 int finish_on_stop, const float* __restrict__ score_in, float* __restrict__ score_out,
+                 const int* __restrict__ fin_in, int* __restrict__ fin_out, const int* __restrict__ hist_in,
+                 int* __restrict__ hist_out, int* __restrict__ tok_out, int* __restrict__ src_out) {
+  __shared__ float scratch[32];
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float lse_s[kMaxBeam];
+  __shared__ int sel_idx[kMaxBeam];
+  __shared__ float sel_val[kMaxBeam];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int INT_BIG = 0x7fffffff;
+  const bool greedy = (beam == 1 && !finish_on_stop);
+  // log-sum-exp of every live, unfinished prefix
+  for (int p = 0; p < beam; ++p) {
+    const float sc = score_in[img * beam + p];
+    const bool live = sc > -INFINITY;
+    const bool fin = finish_on_stop && fin_in[img * beam + p];
+    if (!live || fin) { if (tid == 0) lse_s[p] = 0.f; continue; }  // uniform branch (depends on p only)
+    const float* row = logits + ((long)img * beam + p) * ldl;
+    float mx = -INFINITY;
+    for (int n = tid; n < V; n += kBeamThreads) mx = fmaxf(mx, row[n]);
+    mx = block_max(mx, scratch);
+    float sum = 0.f;
+    for (int n = tid; n < V; n += kBeamThreads) sum += expf(row[n] - mx);
+    sum = block_sum(sum, scratch);
+    if (tid == 0) lse_s[p] = mx + logf(sum);
+  }
+  __syncthreads();
+  // `beam` rounds of block arg-max over the (prefix, token) candidates; ties -> lower flat index
+  for (int r = 0; r < beam; ++r) {
+    Cand best{-INFINITY, INT_BIG};
+    for (int p = 0; p < beam; ++p) {
+      const float sc = score_in[img * beam + p];
+      if (!(sc > -INFINITY)) continue;
+      const bool fin = finish_on_stop && fin_in[img * beam + p];
+      if (fin) {
+        // a finished prefix offers exactly one candidate: itself, emitting pad, score unchanged
+        if (tid == 0) {
+          const int idx = p * V + pad;
+          bool taken = false;
+          for (int q = 0; q < r; ++q) taken |= (sel_idx[q] == idx);
+          if (!taken && better(sc, idx, best.v, best.idx)) { best.v = sc; best.idx = idx; }
+        }
+        continue;
+      }
+      const float* row = logits + ((long)img * beam + p) * ldl;
+      const float l = lse_s[p];
+      for (int n = tid; n < V; n += kBeamThreads) {
+        // greedy (beam 1, never finishes) ranks the raw logits exactly like layers.argmax (model:120)
+        const float v = greedy ? row[n] : sc + (row[n] - l);
+        const int idx = p * V + n;
+        if (better(v, idx, best.v, best.idx)) {
+          bool taken = false;
+          for (int q = 0; q < r; ++q) taken |= (sel_idx[q] == idx);
+          if (!taken) { best.v = v; best.idx = idx; }
+        }
+      }
+    }
+    best = warp_best(best);
+    if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
+    __syncthreads();
+    if (warp == 0) {
+      Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
+      c = warp_best(c);
+      if (lane == 0) { sel_idx[r] = c.idx; sel_val[r] = c.v; }
+    }
+    __syncthreads();
+  }
+  // write-out: token, back-pointer, score, finished flag, history (one warp per selected beam)
+  if (warp < beam) {
+    const int r = warp;
+    int idx = sel_idx[r];
+    float v = sel_val[r];
+    int src, tok;
+    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }  // fewer live candidates than beams (cannot happen for V >= beam)
+    else { src = idx / V; tok = idx % V; }
+    if (greedy && idx != INT_BIG) v = score_in[img * beam] + (v - lse_s[0]);
+    const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
+    if (lane == 0) {
+      tok_out[img * beam + r] = tok;
+      src_out[img * beam + r] = src;
+      score_out[img * beam + r] = v;
+      fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
+    }
+    const int* hin = hist_in + ((long)img * beam + src) * T_total;
+    int* hout = hist_out + ((long)img * beam + r) * T_total;
+    for (int t = lane; t < T_total; t += 32) hout[t] = (t == step) ? tok : (t < step ? hin[t] : 0);
+  }
+}
+
+template <typename T>
+__global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad, const T* __restrict__ emb,
+                                    const int* __restrict__ tok, const int* __restrict__ src,
+                                    const T* __restrict__ h_new, const float* __restrict__ c_new, T* __restrict__ xin,
+                                    long ld_xin, float* __restrict__ c_next) {
+  const int ve = E / 8, vh = H / 8, per_row = ve + vh + vh;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)n_rows * per_row;
+  for (; i < n; i += stride) {
+    const int r = (int)(i / per_row);
+    const int v = (int)(i % per_row);
+    const int srow = (r / beam) * beam + src[r];
+    float x[8];
+    if (v < ve) {
+      const int id = tok[r];
+      if (id == pad) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      } else {
+        load8(emb + (long)id * E + v * 8, x);
+      }
+      store8(xin + (long)r * ld_xin + v * 8, x);
+    } else if (v < ve + vh) {
+      const int h0 = (v - ve) * 8;
+      load8(h_new + (long)srow * H + h0, x);
+      store8(xin + (long)r * ld_xin + E + h0, x);
+    } else {
+      const int h0 = (v - ve - vh) * 8;
+      load8(c_new + (long)srow * H + h0, x);
+      store8(c_next + (long)r * H + h0, x);
+    }
+  }
+}
+
+}  // namespace
+
+void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* caption, long cap_ld, int B, int steps,
+            int pad, float* lse, float* acc) {
+  ce_fwd_kernel<<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, caption, cap_ld, B, pad, lse, acc);
+  if (c.launches) ++*c.launches;
+}
+void loss_finalize(LaunchCtx c, float* acc) {
+  loss_finalize_kernel<<<1, 1, 0, c.stream>>>(acc);
+  if (c.launches) ++*c.launches;
+}
+template <typename T>
+void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+            int steps, int pad, const float* lse, const float* scale, float loss_scale, T* dlogits) {
+  ce_bwd_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, scale,
+                                                          loss_scale, dlogits);
+  if (c.launches) ++*c.launches;
+}
+void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out) {
+  logits_bm_kernel<<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
+  if (c.launches) ++*c.launches;
+}
+void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
+               int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
+               const int* hist_in, int* hist_out, int* tok_out, int* src_out) {
+  beam_step_kernel<<<n_img, kBeamThreads, 0, c.stream>>>(logits, ldl, V, beam, step, T_total, pad, stop, finish_on_stop,
+                                                        score_in, score_out, fin_in, fin_out, hist_in, hist_out,
+                                                        tok_out, src_out);
+  if (c.launches) ++*c.launches;
+}
+template <typename T>
+void beam_reorder(LaunchCtx c, int n_img, int beam, int E, int H, int pad, const T* emb, const int* tok, const int* src,
+                  const T* h_new, const float* c_new, T* xin, long ld_xin, float* c_next) {
+  const int n_rows = n_img * beam;
+  const long n = (long)n_rows * (E / 8 + 2 * (H / 8));
+  long blocks = (n + 255) / 256;
+  if (blocks > 8L * kNumSMs) blocks = 8L * kNumSMs;
+  beam_reorder_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(n_rows, beam, E, H, pad, emb, tok, src, h_new, c_new, xin,
+                                                           ld_xin, c_next);
+  if (c.launches) ++*c.launches;
+}
+
+template void ce_bwd<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, const float*,
+                            const float*, float, float*);
+template void ce_bwd<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, const float*,
+                           const float*, float, bf16*);
+template void beam_reorder<float>(LaunchCtx, int, int, int, int, int, const float*, const int*, const int*,
+                                  const float*, const float*, float*, long, float*);
+template void beam_reorder<bf16>(LaunchCtx, int, int, int, int, int, const bf16*, const int*, const int*, const bf16*,
+                                 const float*, bf16*, long, float*);
+
+}  // namespace capdec

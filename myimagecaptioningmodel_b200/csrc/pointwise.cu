@@ -1,0 +1,391 @@
+// Bandwidth-bound pointwise kernels of the decoder path: conversions, embedding gather / scatter-add,
+// the LSTM cell (Paddle lstm_unit, gate order i,f,o,g), the visual sentinel, their backward, and the small
+// reductions around them.  All are grid-stride, 128-bit vectorised (8 elements per thread per trip).
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+inline int grid_for(long work_items, int threads = 256, int max_waves = 8) {
+  long blocks = (work_items + threads - 1) / threads;
+  long cap = (long)kNumSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <typename T> __global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = from_f<T>(src[i]);
+}
+
+template <typename T>
+__global__ void transpose_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, cc = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && cc < C) ? src[(long)r * lds + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int cc = c0 + i, r = r0 + threadIdx.x;
+    if (cc < C && r < R) dst[(long)cc * ldd + r] = from_f<T>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename T>
+__global__ void copy2d_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, int R, int C) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)R * C;
+  for (; i < n; i += stride) {
+    long r = i / C, cc = i % C;
+    dst[r * ldd + cc] = from_f<T>(src[r * lds + cc]);
+  }
+}
+
+template <typename T>
+__global__ void embed_gather_kernel(const T* __restrict__ emb, int E, const int64_t* __restrict__ ids, long ids_ld,
+                                    int B, int steps, int pad, T* __restrict__ out, long ldo) {
+  const int vec_per_row = E / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)B * steps * vec_per_row;
+  for (; i < n; i += stride) {
+    const long m = i / vec_per_row;
+    const int v = (int)(i % vec_per_row);
+    const int t = (int)(m / B), b = (int)(m % B);
+    const long id = ids[(long)b * ids_ld + t];
+    float x[8];
+    if (id == pad) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    } else {
+      load8(emb + id * E + v * 8, x);
+    }
+    store8(out + m * ldo + v * 8, x);
+  }
+}
+
+template <typename T>
+__global__ void lstm_cell_fwd_kernel(int R, int H, const float* __restrict__ gpre, long ld_gpre,
+                                     const T* __restrict__ xe, long ld_xe, const float* __restrict__ g5, long ld_g5,
+                                     int g5_mod, int g5_div, const float* __restrict__ c_prev, T* __restrict__ h_out,
+                                     long ld_h, float* __restrict__ c_out, T* __restrict__ gates_act) {
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)R * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    float pre[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) load8(gpre + r * ld_gpre + g * H + h0, pre[g]);
+    if (xe) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float x[8];
+        load8(xe + r * ld_xe + g * H + h0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[g][j] += x[j];
+      }
+    }
+    if (g5) {
+      const long gr = (r % g5_mod) / g5_div;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float x[8];
+        load8(g5 + gr * ld_g5 + g * H + h0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[g][j] += x[j];
+      }
+    }
+    float cp[8], cn[8], hn[8];
+    load8(c_prev + r * H + h0, cp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ig = sigmoid_t<F>(pre[0][j]), fg = sigmoid_t<F>(pre[1][j]), og = sigmoid_t<F>(pre[2][j]);
+      const float gg = tanh_t<F>(pre[3][j]);
+      cn[j] = fg * cp[j] + ig * gg;
+      hn[j] = og * tanh_t<F>(cn[j]);
+      pre[0][j] = ig; pre[1][j] = fg; pre[2][j] = og; pre[3][j] = gg;
+    }
+    store8(c_out + r * H + h0, cn);
+    store8(h_out + r * ld_h + h0, hn);
+    if (gates_act) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) store8(gates_act + r * 4 * H + g * H + h0, pre[g]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void sentinel_fwd_kernel(long R, int H, const T* __restrict__ ph, long ld_ph, const T* __restrict__ xe,
+                                    long ld_xe, const float* __restrict__ g5, long ld_g5, int g5_mod, int g5_div,
+                                    const float* __restrict__ cc, T* __restrict__ sgate, T* __restrict__ s_out) {
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = R * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    float a[8], x[8], c8[8], sg[8], s[8];
+    load8(ph + r * ld_ph + h0, a);
+    if (xe) {
+      load8(xe + r * ld_xe + h0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += x[j];
+    }
+    if (g5) {
+      load8(g5 + ((r % g5_mod) / g5_div) * ld_g5 + h0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += x[j];
+    }
+    load8(cc + r * H + h0, c8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sg[j] = sigmoid_t<F>(a[j]);
+      s[j] = sg[j] * tanh_t<F>(c8[j]);
+    }
+    if (sgate) store8(sgate + r * H + h0, sg);
+    store8(s_out + r * H + h0, s);
+  }
+}
+
+template <typename T>
+__global__ void sentinel_bwd_kernel(long R, int H, const T* __restrict__ dS, const T* __restrict__ sgate,
+                                    const float* __restrict__ cc, T* __restrict__ dsg_pre, long ld_dsg,
+                                    float* __restrict__ dC_head) {
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = R * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    float d[8], sg[8], c8[8], o1[8], o2[8];
+    load8(dS + r * H + h0, d);
+    load8(sgate + r * H + h0, sg);
+    load8(cc + r * H + h0, c8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float tc = tanh_t<F>(c8[j]);
+      o1[j] = d[j] * tc * sg[j] * (1.f - sg[j]);
+      o2[j] = d[j] * sg[j] * (1.f - tc * tc);
+    }
+    store8(dsg_pre + r * ld_dsg + h0, o1);
+    store8(dC_head + r * H + h0, o2);
+  }
+}
+
+// One BPTT step (backward of Paddle lstm_unit + the state feedback of model:94-95):
+//   dh = dH_head[t] + dHprev_head[t+1] + dh_rec          (p_hid path, p_hidden path of step t+1, gates of step t+1)
+//   dc = dC_head[t] + dc_rec + dh * o * (1 - tanh(c_t)^2)
+//   d(pre_i) = dc g i(1-i);  d(pre_f) = dc c_prev f(1-f);  d(pre_o) = dh tanh(c_t) o(1-o);  d(pre_g) = dc i (1-g^2)
+//   dc_rec <- dc * f
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(int B, int H, const T* __restrict__ dH_head, const T* __restrict__ dHprev_head,
+                                     const float* __restrict__ dh_rec, const float* __restrict__ dC_head,
+                                     float* __restrict__ dc_rec, const T* __restrict__ gates_act,
+                                     const float* __restrict__ c_t, const float* __restrict__ c_prev,
+                                     T* __restrict__ dgates, long ld_dg) {
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)B * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    float dh[8], x[8], dc[8], ct[8], cp[8], ga[4][8], dg[4][8];
+    load8(dH_head + r * H + h0, dh);
+    if (dHprev_head) {
+      load8(dHprev_head + r * H + h0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dh[j] += x[j];
+    }
+    if (dh_rec) {
+      load8(dh_rec + r * H + h0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dh[j] += x[j];
+    }
+    load8(dC_head + r * H + h0, dc);
+    load8(dc_rec + r * H + h0, x);
+    load8(c_t + r * H + h0, ct);
+    load8(c_prev + r * H + h0, cp);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) load8(gates_act + r * 4 * H + g * H + h0, ga[g]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ig = ga[0][j], fg = ga[1][j], og = ga[2][j], gg = ga[3][j];
+      const float tc = tanh_t<F>(ct[j]);
+      const float dcj = dc[j] + x[j] + dh[j] * og * (1.f - tc * tc);
+      dg[0][j] = dcj * gg * ig * (1.f - ig);
+      dg[1][j] = dcj * cp[j] * fg * (1.f - fg);
+      dg[2][j] = dh[j] * tc * og * (1.f - og);
+      dg[3][j] = dcj * ig * (1.f - gg * gg);
+      x[j] = dcj * fg;
+    }
+    store8(dc_rec + r * H + h0, x);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store8(dgates + r * ld_dg + g * H + h0, dg[g]);
+  }
+}
+
+template <typename T>
+__global__ void sum_over_steps_kernel(const T* __restrict__ x, long ld, int B, int steps, int N, T* __restrict__ out,
+                                      long ldo) {
+  const int vec_per_row = N / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)B * vec_per_row;
+  for (; i < n; i += stride) {
+    const long b = i / vec_per_row;
+    const int n0 = (int)(i % vec_per_row) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < steps; ++t) {
+      float v[8];
+      load8(x + ((long)t * B + b) * ld + n0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    store8(out + b * ldo + n0, acc);
+  }
+}
+
+// grid (ceil(N/256), row_chunks): each thread owns one column of a row chunk
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk,
+                              float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long m0 = (long)blockIdx.y * rows_per_chunk;
+  const long m1 = (m0 + rows_per_chunk < M) ? m0 + rows_per_chunk : M;
+  float acc = 0.f;
+  for (long m = m0; m < m1; ++m) acc += to_f(x[m * ld + n]);
+  atomicAdd(out + n, acc);
+}
+
+template <typename T>
+__global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, const int64_t* __restrict__ ids,
+                                     long ids_ld, int B, int steps, int pad, float* __restrict__ dEmb) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)B * steps * E;
+  for (; i < n; i += stride) {
+    const long m = i / E;
+    const int e = (int)(i % E);
+    const int t = (int)(m / B), b = (int)(m % B);
+    const long id = ids[(long)b * ids_ld + t];
+    if (id != pad) atomicAdd(dEmb + id * E + e, to_f(dX[m * ld + e]));
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace
+
+#define BUMP(c) do { if ((c).launches) ++*(c).launches; } while (0)
+
+template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* dst, long n) {
+  if (n <= 0) return;
+  convert_kernel<T><<<grid_for(n), 256, 0, c.stream>>>(src, dst, n);
+  BUMP(c);
+}
+template <typename T> void transpose_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_kernel<T><<<grid, block, 0, c.stream>>>(src, lds, dst, ldd, R, C);
+  BUMP(c);
+}
+template <typename T> void copy2d_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C) {
+  copy2d_kernel<T><<<grid_for((long)R * C), 256, 0, c.stream>>>(src, lds, dst, ldd, R, C);
+  BUMP(c);
+}
+template <typename T>
+void embed_gather(LaunchCtx c, const T* emb, int E, const int64_t* ids, long ids_ld, int B, int steps, int pad, T* out,
+                  long ldo) {
+  embed_gather_kernel<T><<<grid_for((long)B * steps * (E / 8)), 256, 0, c.stream>>>(emb, E, ids, ids_ld, B, steps, pad,
+                                                                                 out, ldo);
+  BUMP(c);
+}
+template <typename T>
+void lstm_cell_fwd(LaunchCtx c, int R, int H, const float* gpre, long ld_gpre, const T* xe, long ld_xe, const float* g5,
+                   long ld_g5, int g5_mod, int g5_div, const float* c_prev, T* h_out, long ld_h, float* c_out,
+                   T* gates_act) {
+  lstm_cell_fwd_kernel<T><<<grid_for((long)R * (H / 8), 128), 128, 0, c.stream>>>(
+      R, H, gpre, ld_gpre, xe, ld_xe, g5, ld_g5, g5_mod, g5_div, c_prev, h_out, ld_h, c_out, gates_act);
+  BUMP(c);
+}
+template <typename T>
+void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* xe, long ld_xe, const float* g5,
+                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out) {
+  sentinel_fwd_kernel<T><<<grid_for(R * (H / 8)), 256, 0, c.stream>>>(R, H, ph, ld_ph, xe, ld_xe, g5, ld_g5, g5_mod,
+                                                                    g5_div, cc, sgate, s_out);
+  BUMP(c);
+}
+template <typename T>
+void sentinel_bwd(LaunchCtx c, long R, int H, const T* dS, const T* sgate, const float* cc, T* dsg_pre, long ld_dsg,
+                  float* dC_head) {
+  sentinel_bwd_kernel<T><<<grid_for(R * (H / 8)), 256, 0, c.stream>>>(R, H, dS, sgate, cc, dsg_pre, ld_dsg, dC_head);
+  BUMP(c);
+}
+template <typename T>
+void lstm_cell_bwd(LaunchCtx c, int B, int H, const T* dH_head, const T* dHprev_head, const float* dh_rec,
+                   const float* dC_head, float* dc_rec, const T* gates_act, const float* c_t, const float* c_prev,
+                   T* dgates, long ld_dg) {
+  lstm_cell_bwd_kernel<T><<<grid_for((long)B * (H / 8), 128), 128, 0, c.stream>>>(
+      B, H, dH_head, dHprev_head, dh_rec, dC_head, dc_rec, gates_act, c_t, c_prev, dgates, ld_dg);
+  BUMP(c);
+}
+template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo) {
+  sum_over_steps_kernel<T><<<grid_for((long)B * (N / 8), 128), 128, 0, c.stream>>>(x, ld, B, steps, N, out, ldo);
+  BUMP(c);
+}
+template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out) {
+  if (M <= 0 || N <= 0) return;
+  const int col_blocks = (N + 255) / 256;
+  long chunks = (4L * kNumSMs + col_blocks - 1) / col_blocks;
+  if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
+  if (chunks < 1) chunks = 1;
+  const long rpc = (M + chunks - 1) / chunks;
+  dim3 grid(col_blocks, (unsigned)((M + rpc - 1) / rpc));
+  colsum_kernel<T><<<grid, 256, 0, c.stream>>>(x, ld, M, N, rpc, out);
+  BUMP(c);
+}
+template <typename T>
+void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
+                       int pad, float* dEmb) {
+  embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, ids, ids_ld, B, steps, pad,
+                                                                             dEmb);
+  BUMP(c);
+}
+void fill_f32(LaunchCtx c, float* p, float v, long n) {
+  if (n <= 0) return;
+  fill_kernel<<<grid_for(n), 256, 0, c.stream>>>(p, v, n);
+  BUMP(c);
+}
+
+#define INSTANTIATE(T)                                                                                                 \
+  template void convert_from_f32<T>(LaunchCtx, const float*, T*, long);                                                \
+  template void transpose_from_f32<T>(LaunchCtx, const float*, long, T*, long, int, int);                              \
+  template void copy2d_from_f32<T>(LaunchCtx, const float*, long, T*, long, int, int);                                 \
+  template void embed_gather<T>(LaunchCtx, const T*, int, const int64_t*, long, int, int, int, T*, long);              \
+  template void lstm_cell_fwd<T>(LaunchCtx, int, int, const float*, long, const T*, long, const float*, long, int,    \
+                                 int, const float*, T*, long, float*, T*);                                             \
+  template void sentinel_fwd<T>(LaunchCtx, long, int, const T*, long, const T*, long, const float*, long, int, int,    \
+                                const float*, T*, T*);                                                                 \
+  template void sentinel_bwd<T>(LaunchCtx, long, int, const T*, const T*, const float*, T*, long, float*);             \
+  template void lstm_cell_bwd<T>(LaunchCtx, int, int, const T*, const T*, const float*, const float*, float*,          \
+                                 const T*, const float*, const float*, T*, long);                                      \
+  template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long);                                 \
+  template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*);                                           \
+  template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, const int64_t*, long, int, int, int, float*);
+
+INSTANTIATE(float)
+INSTANTIATE(bf16)
+
+}  // namespace capdec

@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference decoder interface over the C-ABI (include/capdec.h).
+
+Mirrors /root/reference/ImageCaptioning/model/model_adaAttention_aic.py:
+  * ``Decoder(hidden_size, mode='train'|'eval', rnn_layer=1).call(global_img_feat, p_img_feat, embedding_fn, words)``
+    (model:40-135): train -> logits [B,T,V] fp32 batch-major; eval -> float32 ids [B,infer_max_length];
+    an unsupported mode raises ValueError exactly like model:43-44.
+  * ``ImageCaptionModel.training_network / eval_network / loss`` from the decoder boundary on (model:161-189, 205-212).
+PyTorch is used for tensor ownership, streams and torch.distributed only; all arithmetic is in libcapdec.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _capi
+from ._capi import CapdecConfig, CapdecGrads, CapdecParams, PARAM_NAMES, check, ptr, stream_ptr
+
+
+@dataclasses.dataclass(frozen=True)
+class DecoderConfig:
+    """config.py:22-24 and config.py:51-60 of the reference, plus the two build-time choices of this library."""
+    hidden_dim: int = 1024
+    embedding_size: int = 256
+    vocab_size: int = 12295
+    num_positions: int = 49
+    sentence_length: int = 35
+    infer_max_length: int = 35
+    padding_idx: int = 0
+    start_idx: int = 2
+    stop_idx: int = 3
+    dtype: str = "bf16"             # 'bf16' (tcgen05 path) | 'fp32' (validation precision)
+    softmax_axis: str = "feature"   # 'feature' = reference as written (alpha == 1) | 'position' = intended
+
+    @property
+    def train_steps(self) -> int:
+        return self.sentence_length - 1
+
+    def to_c(self) -> CapdecConfig:
+        if self.dtype not in ("bf16", "fp32"):
+            raise ValueError("unsupported dtype {}".format(self.dtype))
+        if self.softmax_axis not in ("feature", "position"):
+            raise ValueError("unsupported softmax_axis {}".format(self.softmax_axis))
+        return CapdecConfig(self.hidden_dim, self.embedding_size, self.vocab_size, self.num_positions,
+                            self.sentence_length, self.infer_max_length, self.padding_idx, self.start_idx,
+                            self.stop_idx, _capi.DTYPE_BF16 if self.dtype == "bf16" else _capi.DTYPE_F32,
+                            _capi.SOFTMAX_POSITION if self.softmax_axis == "position" else _capi.SOFTMAX_FEATURE, 0)
+
+
+def param_shapes(cfg: DecoderConfig) -> Dict[str, tuple]:
+    """PaddlePaddle layouts ([in, out] fc weights), construction order of model:52..115, 24, 18, 23."""
+    H, E, V = cfg.hidden_dim, cfg.embedding_size, cfg.vocab_size
+    X = E + H
+    return {
+        "fc_v_w": (H, H), "fc_v_b": (H,), "fc_k_w": (H, H), "fc_k_b": (H,),
+        "lstm_w": (X + H, 4 * H), "lstm_b": (4 * H,),
+        "fc_xs_w": (X, H), "fc_xs_b": (H,), "fc_hs_w": (H, H), "fc_hs_b": (H,),
+        "fc_p_w": (H, H), "fc_p_b": (H,), "fc_g_w": (H, H), "fc_g_b": (H,), "fc_s_w": (H, H), "fc_s_b": (H,),
+        "fc_a_w": (H, 1), "fc_a_b": (1,), "fc_o_w": (H, H), "fc_o_b": (H,), "fc_e_w": (H, E), "fc_e_b": (E,),
+        "word_embedding": (V, E), "out_fc_bias": (V,),
+    }
+
+
+class ParameterStore:
+    """All decoder parameters (and their gradients) as views into two flat fp32 device buffers, so that a
+    data-parallel gradient all-reduce is a single NCCL call.  Every view starts on a 256-byte boundary."""
+
+    def __init__(self, cfg: DecoderConfig, device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.shapes = param_shapes(cfg)
+        self.offsets = {}
+        off = 0
+        for n in PARAM_NAMES:
+            self.offsets[n] = off
+            off += (math.prod(self.shapes[n]) + 63) // 64 * 64
+        self.numel_padded = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.params = {n: self._view(self.flat, n) for n in PARAM_NAMES}
+        self.grads = {n: self._view(self.flat_grad, n) for n in PARAM_NAMES}
+        self.c_params = CapdecParams(*[C.c_void_p(self.params[n].data_ptr()) for n in PARAM_NAMES])
+        self.c_grads = CapdecGrads(*[C.c_void_p(self.grads[n].data_ptr()) for n in PARAM_NAMES])
+
+    def _view(self, flat, name):
+        o = self.offsets[name]
+        return flat[o:o + math.prod(self.shapes[name])].view(self.shapes[name])
+
+    @property
+    def num_parameters(self) -> int:
+        return sum(math.prod(s) for s in self.shapes.values())
+
+    def init_reference(self, seed: int = 0, bias_scale: float = 0.0):
+        """PaddlePaddle default initialisers of the reference graph: Xavier-uniform fc weights, zero biases
+        (bias_scale > 0 draws U(-s, s) instead, used by tests), U(-1, 1) tied embedding (model:19)."""
+        gen = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for n in PARAM_NAMES:
+                shape = self.shapes[n]
+                if n == "word_embedding":
+                    t = torch.rand(shape, generator=gen) * 2 - 1
+                elif n.endswith("_w"):
+                    lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                    t = (torch.rand(shape, generator=gen) * 2 - 1) * lim
+                else:
+                    t = (torch.rand(shape, generator=gen) * 2 - 1) * bias_scale
+                self.params[n].copy_(t)
+        return self
+
+    def load(self, state: Dict[str, "torch.Tensor"]):
+        """Copy parameters given by name (torch tensors or numpy arrays, Paddle layouts)."""
+        for n in PARAM_NAMES:
+            if n not in state:
+                raise KeyError("missing parameter {}".format(n))
+            t = torch.as_tensor(state[n]).to(torch.float32)
+            if tuple(t.shape) != tuple(self.shapes[n]):
+                raise ValueError("parameter {} has shape {}, expected {}".format(n, tuple(t.shape), self.shapes[n]))
+            with torch.no_grad():
+                self.params[n].copy_(t)
+        return self
+
+    def state_dict(self):
+        return {n: self.params[n].detach().cpu().clone() for n in PARAM_NAMES}
+
+
+class CaptionDecoderEngine:
+    """One handle per (process, GPU): owns the C handle and the ParameterStore; thin, sync-free wrappers of the
+    C-ABI entry points.  This is what bench.py and the reference-shaped classes below drive."""
+
+    def __init__(self, cfg: DecoderConfig = DecoderConfig(), device=None, seed: Optional[int] = 0,
+                 bias_scale: float = 0.0):
+        if not torch.cuda.is_available():
+            raise _capi.CapdecError("no CUDA device: the caption decoder has no CPU fallback")
+        self.lib = _capi.load_library()
+        self.cfg = cfg
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        ccfg = cfg.to_c()
+        check(self.lib.capdec_create(C.byref(ccfg), self.device.index or 0, C.byref(h)), "capdec_create")
+        self.handle = h
+        self.store = ParameterStore(cfg, self.device)
+        if seed is not None:
+            self.store.init_reference(seed, bias_scale)
+        self._loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._caption_keepalive = None
+        self._bound = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.capdec_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- C-ABI wrappers --------------------------------------------------------------------------------------
+    def bind_params(self):
+        check(self.lib.capdec_bind_params(self.handle, C.byref(self.store.c_params), stream_ptr()), "capdec_bind_params")
+        self._bound = True
+
+    def _check_inputs(self, g, P, caption=None):
+        cfg = self.cfg
+        B = g.shape[0]
+        if tuple(g.shape) != (B, cfg.hidden_dim) or tuple(P.shape) != (B, cfg.num_positions, cfg.hidden_dim):
+            raise ValueError("expected global_img_feat [B,{H}] and p_img_feat [B,{k},{H}], got {} and {}".format(
+                tuple(g.shape), tuple(P.shape), H=cfg.hidden_dim, k=cfg.num_positions))
+        for t in (g, P):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("features must be contiguous float32 CUDA tensors")
+        if caption is not None:
+            if tuple(caption.shape) != (B, cfg.sentence_length) or caption.dtype != torch.int64 \
+                    or not caption.is_cuda or not caption.is_contiguous():
+                raise ValueError("caption must be a contiguous int64 CUDA tensor [B,{}]".format(cfg.sentence_length))
+        return B
+
+    def train_forward(self, g, P, caption, want_logits: bool = False):
+        """capdec_train_fwd.  Returns (loss_buf[4] device tensor, logits or None)."""
+        B = self._check_inputs(g, P, caption)
+        if not self._bound:
+            self.bind_params()
+        logits = None
+        if want_logits:
+            logits = torch.empty(B, self.cfg.train_steps, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
+        self._caption_keepalive = (g, P, caption)
+        check(self.lib.capdec_train_fwd(self.handle, ptr(g), ptr(P), ptr(caption), B, ptr(logits), ptr(self._loss_buf),
+                                        stream_ptr()), "capdec_train_fwd")
+        return self._loss_buf, logits
+
+    def train_backward(self, loss_scale: float = 1.0, inv_ntok: Optional[torch.Tensor] = None, want_dg: bool = True,
+                       want_dP: bool = True):
+        """capdec_train_bwd.  Fills store.flat_grad; returns (d_global_img_feat, d_p_img_feat)."""
+        g, P, _ = self._caption_keepalive
+        dg = torch.empty_like(g) if want_dg else None
+        dP = torch.empty_like(P) if want_dP else None
+        check(self.lib.capdec_train_bwd(self.handle, C.c_float(loss_scale), ptr(inv_ntok), ptr(dg), ptr(dP),
+                                        C.byref(self.store.c_grads), stream_ptr()), "capdec_train_bwd")
+        return dg, dP
+
+    def decode(self, g, P, beam: int = 1, finish_on_stop: bool = False, want_f32: bool = True):
+        """capdec_decode.  Returns (ids int32 [B,beam,T], scores f32 [B,beam], ids_f32 [B,T] or None)."""
+        B = self._check_inputs(g, P)
+        if not self._bound:
+            self.bind_params()
+        T = self.cfg.infer_max_length
+        ids = torch.empty(B, beam, T, dtype=torch.int32, device=self.device)
+        scores = torch.empty(B, beam, dtype=torch.float32, device=self.device)
+        ids_f32 = torch.empty(B, T, dtype=torch.float32, device=self.device) if want_f32 else None
+        check(self.lib.capdec_decode(self.handle, ptr(g), ptr(P), B, beam, 1 if finish_on_stop else 0, ptr(ids),
+                                     ptr(scores), ptr(ids_f32), stream_ptr()), "capdec_decode")
+        return ids, scores, ids_f32
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.capdec_workspace_bytes(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.capdec_launch_count(self.handle))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference-shaped interface
+# --------------------------------------------------------------------------------------------------------------
+_default_engine: Optional[CaptionDecoderEngine] = None
+
+
+def default_engine(cfg: DecoderConfig = DecoderConfig()) -> CaptionDecoderEngine:
+    """The reference keeps its parameters as global named variables of the Paddle scope; the
+    equivalent here is one process-wide engine shared by the train- and eval-mode Decoder objects
+    (cf. share_vars_from, train.py:127)."""
+    global _default_engine
+    if _default_engine is None or _default_engine.cfg != cfg:
+        _default_engine = CaptionDecoderEngine(cfg)
+    return _default_engine
+
+
+class Decoder:
+    """Drop-in for model_adaAttention_aic.Decoder (model:40-135)."""
+
+    def __init__(self, hidden_size, mode="train", rnn_layer=1, engine: Optional[CaptionDecoderEngine] = None):
+        if mode not in ["train", "eval"]:
+            raise ValueError("不支持{}".format(mode))                                  # model:43-44
+        self.engine = engine if engine is not None else default_engine()
+        if hidden_size != self.engine.cfg.hidden_dim:
+            raise ValueError("hidden_size {} does not match the engine ({})".format(hidden_size,
+                                                                                    self.engine.cfg.hidden_dim))
+        if rnn_layer != 1:
+            raise ValueError("rnn_layer must be 1 (the reference never uses another value)")
+        self.hid_size = hidden_size
+        self.rnn_layer = rnn_layer
+        self.mode = mode
+        self.start_tag = self.engine.cfg.start_idx
+
+    def call(self, global_img_feat, p_img_feat, embedding_fn=None, words=None):
+        """train: words [B,T] int64 (the source tokens caption[:, :-1]) -> logits [B,T,V] float32;
+        eval: -> float32 token ids [B,infer_max_length] (model:122, 132-133).  `embedding_fn` is accepted for
+        signature compatibility; the tied `word_embedding` table of the engine is always used (model:28-32)."""
+        eng = self.engine
+        if self.mode == "eval":
+            _, _, ids_f32 = eng.decode(global_img_feat, p_img_feat, beam=1, finish_on_stop=False)
+            return ids_f32
+        if words is None:
+            raise ValueError("train mode needs `words`")
+        cfg = eng.cfg
+        B = words.shape[0]
+        if tuple(words.shape) != (B, cfg.train_steps):
+            raise ValueError("words must be [B,{}]".format(cfg.train_steps))
+        # the C-ABI takes the full caption [B,S]; only its first S-1 columns are read as source tokens when the
+        # logits are requested, so pad one column (its value only matters for the loss, which is not returned)
+        caption = torch.cat([words.to(torch.int64), torch.full((B, 1), cfg.padding_idx, dtype=torch.int64,
+                                                               device=words.device)], dim=1).contiguous()
+        _, logits = eng.train_forward(global_img_feat, p_img_feat, caption, want_logits=True)
+        return logits
+
+
+class _TrainingLoss(torch.autograd.Function):
+    """loss = training_network(...) with the hand-written backward behind torch.autograd, so that a PyTorch
+    encoder in front and a torch optimizer behind can be used unchanged."""
+
+    @staticmethod
+    def forward(ctx, engine, g, P, caption, flat_params):
+        loss_buf, _ = engine.train_forward(g, P, caption)
+        ctx.engine = engine
+        ctx.need = (g.requires_grad, P.requires_grad)
+        return loss_buf[2].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.engine
+        scale = (eng._loss_buf[3] * grad_out.to(torch.float32)).reshape(1).contiguous()   # no host sync
+        dg, dP = eng.train_backward(1.0, inv_ntok=scale, want_dg=True, want_dP=True)
+        return None, dg, dP, None, eng.store.flat_grad.clone()
+
+
+class ImageCaptionModel:
+    """The decoder-side half of model_adaAttention_aic.ImageCaptionModel (model:138-212): everything after
+    `_img2feature` (the MobileNetV2 encoder and the feature adaptor are outside the hot path)."""
+
+    def __init__(self, engine: Optional[CaptionDecoderEngine] = None):
+        self.engine = engine if engine is not None else default_engine()
+        self._flat = self.engine.store.flat.requires_grad_(True)
+
+    def build_network(self, mode="train", **kwargs):
+        if mode not in ["train", "eval"]:
+            raise ValueError("不支持{}".format(mode))                                  # model:154-155
+        if mode == "train":
+            return self.training_network(**kwargs)
+        return self.eval_network(**kwargs)
+
+    def training_network(self, global_image_feat, image_embed, caption):
+        """model:161-183: shift, mask, decoder, masked CE -> scalar 'loss' (autograd-enabled)."""
+        self.engine.bind_params()
+        return _TrainingLoss.apply(self.engine, global_image_feat, image_embed, caption, self._flat)
+
+    def eval_network(self, global_image_feat, image_embed):
+        """model:185-189: greedy decode, float32 ids [B,35]."""
+        return Decoder(self.engine.cfg.hidden_dim, mode="eval", engine=self.engine).call(global_image_feat, image_embed)
+
+    @staticmethod
+    def loss(ground_true, prediction):
+        """model:205-212: per-position soft-max cross entropy [B,T,1] of given logits (plain torch; the fused
+        loss used for training lives inside capdec_train_fwd)."""
+        lp = torch.log_softmax(prediction, dim=-1)
+        return -torch.gather(lp, -1, ground_true.unsqueeze(-1))
+
+
+def filter_caption(ids, stop_idx=3, padding_idx=0):
+    """evaluate.py:15-25 without the id->word table: cut at <stop>, drop <pad>."""
+    out = []
+    for i in ids:
+        i = int(round(float(i)))
+        if i == stop_idx:
+            break
+        if i == padding_idx:
+            continue
+        out.append(i)
+    return out

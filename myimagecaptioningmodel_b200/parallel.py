@@ -1,0 +1,64 @@
+"""Data-parallel training and image-sharded inference over one process per GPU.
+
+Training shards along the batch; the only exchange steps are
+  (1) a 2-float all-reduce of (sum(ce*mask), sum(mask)) between forward and backward, so that every rank
+      normalises by the GLOBAL token count -- this reproduces the single-device reference at the global batch
+      (model:169, 182), not ParallelExecutor's per-device averaging (offered as `pe_semantics=True`);
+  (2) one all-reduce (sum) of the flat fp32 gradient buffer (86 MB) over NCCL / NVLink.
+Inference shards by image with no collective on the data path.
+
+The class is written against a small engine protocol (train_forward / train_backward / store.flat_grad) so the
+host logic is testable on CPU with the gloo backend (tests/test_parallel_cpu.py drives it with the oracle).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_global: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of `n_global` items owned by `rank`; earlier ranks take the remainder."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world {}/{}".format(rank, world))
+    base, rem = divmod(n_global, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DataParallelTrainer:
+    def __init__(self, engine, group: Optional["dist.ProcessGroup"] = None, pe_semantics: bool = False):
+        self.engine = engine
+        self.group = group
+        self.pe_semantics = pe_semantics
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def forward_backward(self, g, P, caption, want_input_grads: bool = False):
+        """One data-parallel forward+backward on this rank's shard.  Returns the GLOBAL loss as a device tensor
+        (no host sync).  After the call engine.store.flat_grad holds the all-reduced gradient."""
+        eng = self.engine
+        loss_buf, _ = eng.train_forward(g, P, caption)
+        if self.world == 1:
+            eng.train_backward(1.0, None, want_dg=want_input_grads, want_dP=want_input_grads)
+            return loss_buf[2]
+        if self.pe_semantics:
+            # ParallelExecutor default (CoeffNumDevice): mean over devices of per-device token means
+            eng.train_backward(1.0 / self.world, None, want_dg=want_input_grads, want_dP=want_input_grads)
+            loss = loss_buf[2].clone()
+            dist.all_reduce(loss, group=self.group)
+            loss /= self.world
+        else:
+            tot = loss_buf[:2].clone()
+            dist.all_reduce(tot, group=self.group)           # (sum ce*mask, sum mask) over all ranks
+            inv = (1.0 / tot[1]).reshape(1)
+            eng.train_backward(1.0, inv, want_dg=want_input_grads, want_dP=want_input_grads)
+            loss = tot[0] / tot[1]
+        dist.all_reduce(eng.store.flat_grad, group=self.group)
+        return loss
+
+
+def sharded_decode(engine, g, P, beam: int, finish_on_stop: bool, rank: int, world: int):
+    """Image-sharded beam search: this rank decodes images [lo, hi) of the global batch; no collective."""
+    lo, hi = shard_range(g.shape[0], rank, world)
+    return (lo, hi) + tuple(engine.decode(g[lo:hi].contiguous(), P[lo:hi].contiguous(), beam, finish_on_stop))
