@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- decoder train tokens/s (headline) and beam-search images/s on N x B200, next to the CPU oracle.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            # our arm   (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (the oracle port), rank 0 only
+
+A "step" of our arm = one teacher-forced decoder train step on one batch of synthetic features and captions at
+BASELINE.json configs[1]: B = 256 per GPU, T = 34, H = 1024, E = 256, V = 12295, k = 49, bf16 storage with fp32
+accumulation: capdec_bind_params (re-layout of the fp32 weights, as after an optimizer update) + capdec_train_fwd
++ capdec_train_bwd (+ the data-parallel exchanges at N > 1).  Inputs are resident in HBM for `value`;
+`e2e` goes through the same public calls with pinned HOST buffers (H2D of features and captions and a D2H read
+of the loss inside the timed region).  No optimizer is applied (outside the hot path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoder_train_tokens_per_sec"
+UNIT = "tokens/s"
+B_PER_GPU = 256
+BEAM_IMAGES_PER_GPU = 512
+BEAM = 3
+SOFTMAX_AXIS = "position"     # the full attention arithmetic; the parity gate also covers 'feature'
+
+
+def workload_config(n_gpus):
+    return {"workload": "teacher_forced_train_step_B256_per_gpu_T34_H1024_E256_V12295_k49", "global_batch": B_PER_GPU * n_gpus,
+            "batch_per_gpu": B_PER_GPU, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
+            "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)",
+            "l2": "per-step working set ~1.5 GB >> 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference's Paddle graph, timed on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(params, cfg, g, P, cap):
+    from oracle import decoder_ref as R
+    R.loss_and_grads(params, cfg, g, P, cap)
+
+
+def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
+    """Times the oracle (PyTorch-CPU fp32, op-for-op the reference graph incl. the materialised [B,50,H] tensors,
+    Python loop over 34 steps, autograd backward) on all host threads.  Returns tokens/s and a description."""
+    from oracle import decoder_ref as R
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = R.DecoderConfig(softmax_axis=SOFTMAX_AXIS)
+    params = R.init_params(cfg, 0, torch.float32, bias_scale=0.0)
+    g, P, cap = synth.make_batch(cfg, sample_B, 20260)
+    for _ in range(max(1, warmup)):
+        cpu_reference_step(params, cfg, g, P, cap)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        cpu_reference_step(params, cfg, g, P, cap)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": sample_B * cfg.train_steps * done / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_step": 1e3 * dt / done, "steps": done,
+            "sample": "oracle/decoder_ref.py fwd+bwd, batch %d x 34 steps, fp32, %d thread(s), %d step(s)"
+                      % (sample_B, torch.get_num_threads(), done)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res = run_cpu_reference(args.steps, args.warmup, sample_B=32)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args.gpus), sample="batch 32 per step (bounded sample of the B=256 workload)"),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "PaddlePaddle 1.8 cannot be installed (BASELINE.md section 2): the reference arm is the CPU "
+                    "oracle port of model_adaAttention_aic.py on the box's host cores"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def timed_region(fn, steps, sync, barrier):
+    """barrier + sync, K steps, sync + barrier; CUDA-event time in ms"""
+    barrier()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    sync()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def main_ours(args):
+    import torch.distributed as dist
+    import myimagecaptioningmodel_b200 as M
+    from myimagecaptioningmodel_b200 import _capi
+    from myimagecaptioningmodel_b200 import synth
+    from myimagecaptioningmodel_b200.ops import gemm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    sync = torch.cuda.synchronize
+
+    cfg = M.DecoderConfig(dtype="bf16", softmax_axis=SOFTMAX_AXIS)
+    eng = M.CaptionDecoderEngine(cfg, seed=0)           # same weights on every rank (replicated)
+    trainer = M.DataParallelTrainer(eng)
+    B = B_PER_GPU
+    g_h, P_h, cap_h = synth.make_batch(cfg, B, 20260 + rank)
+    g_h, P_h, cap_h = g_h.pin_memory(), P_h.pin_memory(), cap_h.pin_memory()
+    g_d, P_d, cap_d = g_h.cuda(), P_h.cuda(), cap_h.cuda()
+    ntok_nonpad = float((cap_h[:, 1:] != 0).sum())
+
+    def step_resident(i):
+        eng.bind_params()
+        trainer.forward_backward(g_d, P_d, cap_d)
+
+    # ---- e2e: host buffers, double-buffered upload on a side stream, loss read back every step ----
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(g_d), torch.empty_like(P_d), torch.empty_like(cap_d)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for dst, src in zip(bufs[slot], (g_h, P_h, cap_h)):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def step_e2e(i):
+        slot = i & 1
+        if i == 0:
+            upload(0)
+        upload(slot ^ 1)                                  # prefetch the next batch while this one computes
+        torch.cuda.current_stream().wait_event(ready[slot])
+        eng.bind_params()
+        loss = trainer.forward_backward(*bufs[slot])
+        consumed[slot].record()
+        losses.append(float(loss))                        # D2H read of the step's result (4 bytes, synchronises)
+
+    for c in consumed:
+        c.record()
+    for i in range(args.warmup):
+        step_resident(i)
+    sync()
+    l0 = eng.launch_count
+    with ClockSampler(local_rank) as clocks:
+        ms = timed_region(step_resident, args.steps, sync, barrier)
+    launches = eng.launch_count - l0
+    clk = clocks.summary()
+    for i in range(max(2, args.warmup // 2)):
+        step_e2e(i)
+    sync()
+    for c in consumed:
+        c.record()
+    ms_e2e = timed_region(step_e2e, args.steps, sync, barrier)
+
+    # ---- beam search (BASELINE.json configs[3], 512 images per GPU, beam 3, 35 steps): secondary number ----
+    gi, Pi, _ = synth.make_batch(cfg, BEAM_IMAGES_PER_GPU, 777 + rank)
+    gi, Pi = gi.cuda(), Pi.cuda()
+    eng.decode(gi[:8].contiguous(), Pi[:8].contiguous(), beam=BEAM, finish_on_stop=True)
+    sync()
+    beam_reps = 2
+    ms_beam = timed_region(lambda i: eng.decode(gi, Pi, beam=BEAM, finish_on_stop=True), beam_reps, sync, barrier)
+
+    # ---- roofline of the dominant kernel: the tcgen05 GEMM at the head shape (M = B*T, N = K = 1024) ----
+    Mh, Nh, Kh = B * cfg.train_steps, cfg.hidden_dim, cfg.hidden_dim
+    A = torch.randn(Mh, Kh, device="cuda").to(torch.bfloat16)
+    W = torch.randn(Nh, Kh, device="cuda").to(torch.bfloat16)
+    Cb = torch.empty(Mh, Nh, device="cuda", dtype=torch.bfloat16)
+    bias = torch.zeros(Nh, device="cuda")
+    for _ in range(3):
+        gemm(A, W, Mh, Nh, Kh, C_out=Cb, bias=bias, act=1)
+    reps = 20
+    ms_gemm = timed_region(lambda i: _capi.load_library().capdec_gemm(
+        _capi.DTYPE_BF16, 0, A.data_ptr(), Kh, W.data_ptr(), Kh, Cb.data_ptr(), Nh, Mh, Nh, Kh, bias.data_ptr(), None, 0,
+        None, 0, 1, 0, 0, 0, _capi.stream_ptr()), reps, sync, lambda: None) / reps
+    peaks = load_peaks()
+    flops = 2.0 * Mh * Nh * Kh
+    achieved = flops / (ms_gemm * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_tc_kernel<256,K-major> head GEMM M=%d N=%d K=%d bias+tanh" % (Mh, Nh, Kh),
+                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["source"] + ", burst",
+                "ms_per_launch": ms_gemm}
+    # whole-step view: algorithmic GEMM flops of one train step over the measured step time
+    step_flops = 116.7e6 * B * cfg.train_steps + 616.6e6 * B
+    step_tflops = step_flops / (ms / args.steps * 1e-3) / 1e12
+
+    # max over ranks of the device times
+    t = torch.tensor([ms, ms_e2e, ms_beam], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_beam = (float(x) for x in t.cpu())
+    tokens_per_step = world * B * cfg.train_steps
+    value = tokens_per_step * args.steps / (ms * 1e-3)
+    e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in (g_h, P_h, cap_h))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = run_cpu_reference(steps=1000, warmup=1, sample_B=32, budget_s=15.0)
+        cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+                "clocks": clk, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "extras": {"nonpad_tokens_per_sec": world * ntok_nonpad * args.steps / (ms * 1e-3),
+                           "step_gemm_tflops_algorithmic": step_tflops,
+                           "step_gemm_frac_of_sustained_peak": step_tflops / peaks["bf16_sustained"],
+                           "beam_search_images_per_sec": world * BEAM_IMAGES_PER_GPU * beam_reps / (ms_beam * 1e-3),
+                           "beam_config": "beam %d, %d steps, %d images per GPU, finish_on_stop" % (
+                               BEAM, cfg.infer_max_length, BEAM_IMAGES_PER_GPU),
+                           "workspace_gb": eng.workspace_bytes / 1e9, "last_loss": losses[-1] if losses else None}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -148,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
       const int nb = n0 + c * 32;

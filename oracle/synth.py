@@ -1,41 +1,3 @@
-"""Deterministic synthetic inputs for the decoder hot path (test/bench infrastructure).
-
-Shapes and conventions follow SURVEY.md 8d row D2:
-  P = relu(N(0,1)) [B,k,H], g = relu(N(0,1)) [B,H]   (post-ReLU like model:196-198)
-  captions [B,35] = [start, w_1..w_L, stop, pad...], L ~ U{5..33}, w ~ U{4..V-1}
-  (preprocess/ai_challenge_tokenizer.py:47, 81-86: <pad>=0 <unk>=1 <start>=2 <stop>=3)
-Only torch-CPU generators are used so the same seed gives the same bytes everywhere.
-"""
-from __future__ import annotations
-
-import torch
-
-from .decoder_ref import DecoderConfig
-
-
-def make_features(cfg: DecoderConfig, B: int, seed: int = 20260, dtype=torch.float32):
-    gen = torch.Generator().manual_seed(seed)
-    P = torch.relu(torch.randn(B, cfg.num_positions, cfg.hidden_dim, generator=gen, dtype=torch.float32))
-    g = torch.relu(torch.randn(B, cfg.hidden_dim, generator=gen, dtype=torch.float32))
-    return g.to(dtype), P.to(dtype)
-
-
-def make_captions(cfg: DecoderConfig, B: int, seed: int = 20260, min_len: int = 5, max_len=None):
-    gen = torch.Generator().manual_seed(seed + 7919)
-    S = cfg.sentence_length
-    max_len = S - 2 if max_len is None else max_len          # config.py:9: <= 33 words
-    min_len = min(min_len, max_len)
-    lens = torch.randint(min_len, max_len + 1, (B,), generator=gen)
-    words = torch.randint(4, cfg.vocab_size, (B, S), generator=gen)
-    cap = torch.zeros(B, S, dtype=torch.int64)
-    for b in range(B):
-        L = int(lens[b])
-        cap[b, 0] = cfg.start_idx
-        cap[b, 1:1 + L] = words[b, :L]
-        cap[b, 1 + L] = cfg.stop_idx
-    return cap
-
-
-def make_batch(cfg: DecoderConfig, B: int, seed: int = 20260, dtype=torch.float32):
-    g, P = make_features(cfg, B, seed, dtype)
-    return g, P, make_captions(cfg, B, seed)
+"""Synthetic inputs for the oracle-side tests: the generator itself lives in the product package
+(myimagecaptioningmodel_b200/synth.py) so that bench.py's own arm never imports oracle/."""
+from myimagecaptioningmodel_b200.synth import make_batch, make_captions, make_features  # noqa: F401

@@ -1,0 +1,132 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads and exports every symbol include/capdec.h declares;
+host-side logic (config, parameter layout, sharding, error behaviour) works without a GPU; the product path fails
+loudly when no GPU is present (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import myimagecaptioningmodel_b200 as M
+from myimagecaptioningmodel_b200 import _build, _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "capdec.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(capdec_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "libcapdec.so does not export %s" % name
+    assert sorted(_capi.EXPORTS) == declared            # the ctypes binding covers the whole header
+    assert _capi.load_library().capdec_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    text = open(os.path.join(ROOT, "include", "capdec.h")).read()
+    cfg_body = re.search(r"typedef struct capdec_config \{(.*?)\} capdec_config;", text, re.S).group(1)
+    cfg_body = re.sub(r"/\*.*?\*/", "", cfg_body, flags=re.S)
+    fields = re.findall(r"int32_t\s+(\w+);", cfg_body)
+    assert fields == [f[0] for f in _capi.CapdecConfig._fields_]
+    prm_body = re.search(r"typedef struct capdec_params \{(.*?)\} capdec_params;", text, re.S).group(1)
+    prm_body = re.sub(r"/\*.*?\*/", "", prm_body, flags=re.S)
+    names = re.findall(r"const float\*\s+(\w+);", prm_body)
+    assert names == _capi.PARAM_NAMES
+    grd_body = re.search(r"typedef struct capdec_grads \{(.*?)\} capdec_grads;", text, re.S).group(1)
+    assert re.findall(r"float\*\s+(\w+);", grd_body) == _capi.PARAM_NAMES
+    assert ctypes.sizeof(_capi.CapdecConfig) == 48
+
+
+def test_sm100_sass_is_present():
+    """the built library really contains tcgen05 / TMA code for sm_100a (not a recompiled legacy path)"""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass                     # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(M.CapdecError):
+        M.CaptionDecoderEngine()
+    lib = M.load_library()
+    h = ctypes.c_void_p()
+    cfg = M.DecoderConfig().to_c()
+    assert lib.capdec_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0
+    assert b"no CPU fallback" in lib.capdec_last_error() or b"CUDA" in lib.capdec_last_error()
+
+
+def test_create_rejects_bad_arguments():
+    lib = M.load_library()
+    h = ctypes.c_void_p()
+    assert lib.capdec_create(None, 0, ctypes.byref(h)) != 0
+    bad = M.DecoderConfig(hidden_dim=1023).to_c()
+    assert lib.capdec_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0
+    assert b"multiples of 8" in lib.capdec_last_error()
+    bad = M.DecoderConfig(num_positions=65).to_c()
+    assert lib.capdec_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0
+    assert lib.capdec_destroy(None) == 0
+    assert lib.capdec_workspace_bytes(None) == 0
+
+
+def test_config_and_parameter_layout():
+    cfg = M.DecoderConfig()
+    assert cfg.train_steps == 34                       # model:66
+    shapes = M.param_shapes(cfg)
+    assert list(shapes) == M.PARAM_NAMES
+    assert shapes["lstm_w"] == (2304, 4096) and shapes["word_embedding"] == (12295, 256)
+    n = sum(int(torch.tensor(s).prod()) for s in shapes.values())
+    assert n == 21523464                               # decoder parameter count
+    with pytest.raises(ValueError):
+        M.DecoderConfig(dtype="fp16").to_c()
+    with pytest.raises(ValueError):
+        M.DecoderConfig(softmax_axis="rows").to_c()
+    store = M.ParameterStore(M.DecoderConfig(hidden_dim=64, embedding_size=32, vocab_size=101, num_positions=5,
+                                             sentence_length=8, infer_max_length=9), "cpu").init_reference(3, 0.1)
+    assert store.num_parameters == sum(v.numel() for v in store.params.values())
+    for name, t in store.params.items():
+        # vector-load alignment of every view relative to the (512-byte aligned on CUDA) flat buffer
+        assert (t.data_ptr() - store.flat.data_ptr()) % 256 == 0, name
+    assert float(store.params["word_embedding"].abs().max()) <= 1.0
+    sd = store.state_dict()
+    store2 = M.ParameterStore(store.cfg, "cpu").load(sd)
+    assert torch.equal(store2.flat, store.flat)
+    with pytest.raises(KeyError):
+        store2.load({})
+
+
+def test_decoder_rejects_unknown_mode():
+    with pytest.raises(ValueError):
+        M.Decoder(1024, mode="test", engine=object())    # model:43-44
+
+
+def test_shard_range():
+    for n, w in [(4096, 8), (10, 3), (2, 4), (0, 2)]:
+        spans = [M.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        M.shard_range(4, 4, 4)
+
+
+def test_filter_caption():
+    assert M.filter_caption([5.0, 0.0, 7.0, 3.0, 9.0]) == [5, 7]     # evaluate.py:15-25
+    assert M.filter_caption([3.0, 4.0]) == []
