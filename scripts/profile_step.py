@@ -1,0 +1,48 @@
+"""Profiling target: warm up, then ONE train step (bind + fwd + bwd) and optionally one beam decode between
+cudaProfilerStart/Stop.  Use with  ncu --profile-from-start off ...   (see scripts/gpu_profile.sh)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import myimagecaptioningmodel_b200 as M  # noqa: E402
+from myimagecaptioningmodel_b200 import synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--decode-images", type=int, default=0)
+ap.add_argument("--beam", type=int, default=3)
+ap.add_argument("--axis", default="position")
+ap.add_argument("--no-train", action="store_true")
+args = ap.parse_args()
+
+cfg = M.DecoderConfig(dtype="bf16", softmax_axis=args.axis)
+eng = M.CaptionDecoderEngine(cfg, seed=0)
+g, P, cap = synth.make_batch(cfg, args.batch, 20260)
+g, P, cap = g.cuda(), P.cuda(), cap.cuda()
+
+
+def step():
+    eng.bind_params()
+    eng.train_forward(g, P, cap)
+    eng.train_backward(want_dg=True, want_dP=True)
+
+
+if not args.no_train:
+    for _ in range(2):
+        step()
+if args.decode_images:
+    gi, Pi, _ = synth.make_batch(cfg, args.decode_images, 777)
+    gi, Pi = gi.cuda(), Pi.cuda()
+    eng.decode(gi, Pi, beam=args.beam, finish_on_stop=True)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+if not args.no_train:
+    step()
+if args.decode_images:
+    eng.decode(gi, Pi, beam=args.beam, finish_on_stop=True)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("profiled region done; launches so far:", eng.launch_count)
