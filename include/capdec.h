@@ -123,10 +123,11 @@ int capdec_decode(capdec_handle h, const float* global_img_feat, const float* p_
 /* ---- kernel-level entry points (parity tests and micro-benchmarks) ------------------------------------------ */
 
 /* C[M,N] = act(A.B^T + bias + addend).  dtype: element type of A, B, addend, dact_y and (unless out_f32) C.
- *   mn_major = 0: A [M,K] (lda), B [N,K] (ldb);  mn_major = 1: A [K,M] (lda), B [K,N] (ldb)  (weight-grad form)
+ *   majors bit 0: A is stored [K,M] (MN-major) instead of [M,K];  bit 1: B is stored [K,N] instead of [N,K]
+ *   (0 = data-grad form, 2 = forward fc with a PaddlePaddle [in,out] weight as B, 3 = weight-grad form)
  *   act: 0 none, 1 tanh, 2 multiply by (1 - y^2) with y = dact_y;  atomic: fp32 atomicAdd into C (split-K)
  *   force_simt: route a bf16 GEMM through the SIMT kernel instead of tcgen05 (cross-check)                     */
-int capdec_gemm(int32_t dtype, int32_t mn_major, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,
                 const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t force_simt,
                 void* stream);

@@ -92,57 +92,42 @@ template <typename T> class Decoder : public DecoderBase {
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int X = E + H;
-    OK(w_v_t.ensure(e * H * H, &ws_bytes));   OK(w_k_t.ensure(e * H * H, &ws_bytes));
     OK(w_kv_n.ensure(e * H * 2 * H, &ws_bytes));
-    OK(w_x_t.ensure(e * 5 * H * E, &ws_bytes));  OK(w_x_n.ensure(e * E * 5 * H, &ws_bytes));
-    OK(w_g_t.ensure(e * 5 * H * H, &ws_bytes));  OK(w_g_n.ensure(e * H * 5 * H, &ws_bytes));
-    OK(w_hh_t.ensure(e * 4 * H * H, &ws_bytes)); OK(w_hh_n.ensure(e * H * 4 * H, &ws_bytes));
-    OK(w_hs_t.ensure(e * H * H, &ws_bytes));  OK(w_hs_n.ensure(e * H * H, &ws_bytes));
-    OK(w_p_t.ensure(e * H * H, &ws_bytes));   OK(w_p_n.ensure(e * H * H, &ws_bytes));
-    OK(w_g2_t.ensure(e * H * H, &ws_bytes));  OK(w_g2_n.ensure(e * H * H, &ws_bytes));
-    OK(w_s_t.ensure(e * H * H, &ws_bytes));   OK(w_s_n.ensure(e * H * H, &ws_bytes));
-    OK(w_o_t.ensure(e * H * H, &ws_bytes));   OK(w_o_n.ensure(e * H * H, &ws_bytes));
-    OK(w_e_t.ensure(e * E * H, &ws_bytes));   OK(w_e_n.ensure(e * H * E, &ws_bytes));
-    OK(emb.ensure(e * (size_t)V * E, &ws_bytes)); OK(emb_t.ensure(e * (size_t)E * Vp, &ws_bytes));
-    OK(w_dec_t.ensure(e * 5 * H * (size_t)X, &ws_bytes));
+    OK(w_x_n.ensure(e * E * 5 * H, &ws_bytes));
+    OK(w_g_n.ensure(e * H * 5 * H, &ws_bytes));
+    OK(w_hh_n.ensure(e * H * 4 * H, &ws_bytes));
+    OK(w_hs_n.ensure(e * H * H, &ws_bytes));
+    OK(w_p_n.ensure(e * H * H, &ws_bytes));
+    OK(w_g2_n.ensure(e * H * H, &ws_bytes));
+    OK(w_s_n.ensure(e * H * H, &ws_bytes));
+    OK(w_o_n.ensure(e * H * H, &ws_bytes));
+    OK(w_e_n.ensure(e * H * E, &ws_bytes));
+    OK(emb.ensure(e * (size_t)V * E, &ws_bytes));
+    OK(w_dec_n.ensure(e * (size_t)X * 5 * H, &ws_bytes));
     OK(b5.ensure(4 * 5 * H, &ws_bytes)); OK(b5d.ensure(4 * 5 * H, &ws_bytes));
 
-    // forward operands: [out, in] (K-major B operand)
-    transpose_from_f32<T>(lc, p->fc_v_w, H, w_v_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_k_w, H, w_k_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_t.as<T>(), E, E, 4 * H);                       // word_emb rows
-    transpose_from_f32<T>(lc, p->fc_xs_w, H, w_x_t.as<T>() + (size_t)4 * H * E, E, E, H);
-    transpose_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_t.as<T>(), H, H, 4 * H);  // global rows
-    transpose_from_f32<T>(lc, p->fc_xs_w + (size_t)E * H, H, w_g_t.as<T>() + (size_t)4 * H * H, H, H, H);
-    transpose_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_hh_t.as<T>(), H, H, 4 * H);  // hid rows
-    transpose_from_f32<T>(lc, p->fc_hs_w, H, w_hs_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_p_w, H, w_p_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_g_w, H, w_g2_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_s_w, H, w_s_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_o_w, H, w_o_t.as<T>(), H, H, H);
-    transpose_from_f32<T>(lc, p->fc_e_w, E, w_e_t.as<T>(), H, H, E);
-    convert_from_f32<T>(lc, p->word_embedding, emb.as<T>(), (long)V * E);
-    // decode operand: [5H, E+H] = [ lstm_w(word)^T | lstm_w(hid)^T ; fc_xs(word)^T | fc_hs^T ]
-    transpose_from_f32<T>(lc, p->lstm_w, 4 * H, w_dec_t.as<T>(), X, E, 4 * H);
-    transpose_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_dec_t.as<T>() + E, X, H, 4 * H);
-    transpose_from_f32<T>(lc, p->fc_xs_w, H, w_dec_t.as<T>() + (size_t)4 * H * X, X, E, H);
-    transpose_from_f32<T>(lc, p->fc_hs_w, H, w_dec_t.as<T>() + (size_t)4 * H * X + E, X, H, H);
-    // backward-data operands: Paddle's own [in, out] layout
-    copy2d_from_f32<T>(lc, p->fc_v_w, H, w_kv_n.as<T>(), 2 * H, H, H);
+    // Every weight keeps PaddlePaddle's own [in, out] layout (one storage-type copy each, no transposes):
+    //   forward  Y = X.W      reads it as the MN-major B operand,
+    //   backward dX = dY.W^T  reads the same buffer as the K-major B operand (N = in, K = out).
+    copy2d_from_f32<T>(lc, p->fc_v_w, H, w_kv_n.as<T>(), 2 * H, H, H);                              // [H, 2H] = [fc_v | fc_k]
     copy2d_from_f32<T>(lc, p->fc_k_w, H, w_kv_n.as<T>() + H, 2 * H, H, H);
-    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_n.as<T>(), 5 * H, E, 4 * H);
+    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_n.as<T>(), 5 * H, E, 4 * H);                        // word rows: [E, 5H]
     copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_x_n.as<T>() + 4 * H, 5 * H, E, H);
-    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_n.as<T>(), 5 * H, H, 4 * H);
+    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_n.as<T>(), 5 * H, H, 4 * H);    // global rows: [H, 5H]
     copy2d_from_f32<T>(lc, p->fc_xs_w + (size_t)E * H, H, w_g_n.as<T>() + 4 * H, 5 * H, H, H);
-    convert_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, w_hh_n.as<T>(), (long)H * 4 * H);
+    convert_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, w_hh_n.as<T>(), (long)H * 4 * H);         // hid rows: [H, 4H]
     convert_from_f32<T>(lc, p->fc_hs_w, w_hs_n.as<T>(), (long)H * H);
     convert_from_f32<T>(lc, p->fc_p_w, w_p_n.as<T>(), (long)H * H);
     convert_from_f32<T>(lc, p->fc_g_w, w_g2_n.as<T>(), (long)H * H);
     convert_from_f32<T>(lc, p->fc_s_w, w_s_n.as<T>(), (long)H * H);
     convert_from_f32<T>(lc, p->fc_o_w, w_o_n.as<T>(), (long)H * H);
     convert_from_f32<T>(lc, p->fc_e_w, w_e_n.as<T>(), (long)H * E);
-    CUDA_OK(cudaMemsetAsync(emb_t.p, 0, e * (size_t)E * Vp, s));
-    transpose_from_f32<T>(lc, p->word_embedding, E, emb_t.as<T>(), Vp, V, E);
+    convert_from_f32<T>(lc, p->word_embedding, emb.as<T>(), (long)V * E);
+    // inference operand [E+H, 5H]: rows = [word_emb ; h_{t-1}], cols = [lstm gates | sentinel pre-activation]
+    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_dec_n.as<T>(), 5 * H, E, 4 * H);
+    copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_dec_n.as<T>() + 4 * H, 5 * H, E, H);
+    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_dec_n.as<T>() + (size_t)E * 5 * H, 5 * H, H, 4 * H);
+    copy2d_from_f32<T>(lc, p->fc_hs_w, H, w_dec_n.as<T>() + (size_t)E * 5 * H + 4 * H, 5 * H, H, H);
     // fused bias vectors: train [lstm_b | fc_xs_b]; decode [lstm_b | fc_xs_b + fc_hs_b]
     CUDA_OK(cudaMemcpyAsync(b5.p, p->lstm_b, 4 * 4 * H, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
@@ -164,19 +149,19 @@ template <typename T> class Decoder : public DecoderBase {
     convert_from_f32<T>(lc, g, gT.as<T>(), (long)B * H);
     convert_from_f32<T>(lc, P, PT.as<T>(), (long)B * k * H);
     GemmCall c;
-    c.A = PT.p; c.lda = H; c.M = B * k; c.N = H; c.K = H; c.ldb = H; c.ldc = H;
-    c.B = w_v_t.p; c.C = vals.p; c.epi.bias = prm.fc_v_b; c.epi.act = ACT_TANH;      // model:52
+    c.A = PT.p; c.lda = H; c.M = B * k; c.N = H; c.K = H; c.ldb = 2 * H; c.b_mn = true; c.ldc = H;
+    c.B = w_kv_n.p; c.C = vals.p; c.epi.bias = prm.fc_v_b; c.epi.act = ACT_TANH;            // model:52
     OK(gemm<T>(gc, c));
-    c.B = w_k_t.p; c.C = keys.p; c.epi.bias = prm.fc_k_b; c.epi.act = ACT_NONE;      // model:53
+    c.B = w_kv_n.as<T>() + H; c.C = keys.p; c.epi.bias = prm.fc_k_b; c.epi.act = ACT_NONE;  // model:53
     OK(gemm<T>(gc, c));
     return 0;
   }
 
-  // Y[M,N] = act(X . W^T + b)  with W given as the [N,K] forward operand
-  int fc(GemmContext& gc, const void* X, long ldx, const DevBuf& Wt, const float* bias, void* Y, long ldy, int M, int N,
-         int K, int act, bool out_f32 = false) {
+  // Y[M,N] = act(X . W + b)  with W a (sub-block of a) [K = in, N = out] weight copy, row stride ldw
+  int fc(GemmContext& gc, const void* X, long ldx, const T* W, long ldw, const float* bias, void* Y, long ldy, int M,
+         int N, int K, int act, bool out_f32 = false) {
     GemmCall c;
-    c.A = X; c.lda = ldx; c.B = Wt.p; c.ldb = K; c.C = Y; c.ldc = ldy; c.M = M; c.N = N; c.K = K;
+    c.A = X; c.lda = ldx; c.B = W; c.ldb = ldw; c.b_mn = true; c.C = Y; c.ldc = ldy; c.M = M; c.N = N; c.K = K;
     c.epi.bias = bias; c.epi.act = act; c.epi.out_f32 = out_f32 ? 1 : 0;
     return gemm<T>(gc, c);
   }
@@ -185,7 +170,7 @@ template <typename T> class Decoder : public DecoderBase {
             float* dW, long ldw) {
     if (!dW) return 0;
     GemmCall c;
-    c.mn_major = true;
+    c.a_mn = true; c.b_mn = true;
     c.A = X; c.lda = ldx; c.B = dY; c.ldb = ldy; c.C = dW; c.ldc = ldw; c.M = n_in; c.N = n_out; c.K = rows;
     c.epi.atomic = 1; c.epi.out_f32 = 1; c.splits = 0;
     return gemm<T>(gc, c);
@@ -225,14 +210,15 @@ template <typename T> class Decoder : public DecoderBase {
     // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
     embed_gather<T>(lc, emb.as<T>(), E, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E);
     // hoisted x-part of the gate GEMM and of p_word_emb (model:86-89): word-embedding columns for all T steps ...
-    OK(fc(gc, embx.p, E, w_x_t, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
+    OK(fc(gc, embx.p, E, w_x_n.as<T>(), 5 * H, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
     // ... and the global-image columns (+ biases) once per image
-    OK(fc(gc, gT.p, H, w_g_t, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
     // recurrent core (model:63, 87-88, 94-95)
     CUDA_OK(cudaMemsetAsync(hs.p, 0, e * (size_t)B * H, s));
     CUDA_OK(cudaMemsetAsync(cs.p, 0, 4 * (size_t)B * H, s));
     for (int t = 0; t < Tt; ++t) {
-      OK(fc(gc, hs.as<T>() + (size_t)t * B * H, H, w_hh_t, nullptr, gpre.p, 4 * H, B, 4 * H, H, ACT_NONE, true));
+      OK(fc(gc, hs.as<T>() + (size_t)t * B * H, H, w_hh_n.as<T>(), 4 * H, nullptr, gpre.p, 4 * H, B, 4 * H, H, ACT_NONE,
+              true));
       lstm_cell_fwd<T>(lc, B, H, gpre.as<float>(), 4 * H, xe.as<T>() + (size_t)t * B * 5 * H, 5 * H, g5.as<float>(),
                        5 * H, INT_MAX, 1, cs.as<float>() + (size_t)t * B * H, hs.as<T>() + (size_t)(t + 1) * B * H, H,
                        cs.as<float>() + (size_t)(t + 1) * B * H, gact.as<T>() + (size_t)t * B * 4 * H);
@@ -241,17 +227,17 @@ template <typename T> class Decoder : public DecoderBase {
     const T* Hcur = hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
     // time-batched head
-    OK(fc(gc, Hprev, H, w_hs_t, prm.fc_hs_b, ph.p, H, (int)M, H, H, ACT_NONE));                       // model:90
+    OK(fc(gc, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, (int)M, H, H, ACT_NONE));                       // model:90
     sentinel_fwd<T>(lc, M, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, g5.as<float>() + 4 * H, 5 * H, B, 1, Ccur,
                     sgate.as<T>(), sent.as<T>());                                                     // model:91-92
-    OK(fc(gc, Hcur, H, w_p_t, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
-    OK(fc(gc, phid.p, H, w_g2_t, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
-    OK(fc(gc, sent.p, H, w_s_t, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
+    OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
+    OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
+    OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
     AttnShape as = train_shape(B);
     attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
                      prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);               // model:103-115
-    OK(fc(gc, actx.p, H, w_o_t, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
-    OK(fc(gc, outv.p, H, w_e_t, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
+    OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
+    OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
     {
       GemmCall c;                                                                                     // model:25
       c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
@@ -333,7 +319,8 @@ template <typename T> class Decoder : public DecoderBase {
     // tied output projection (model:24-25): d proj, d Emb (output side), d fc_e
     {
       GemmCall c;
-      c.A = dlogits.p; c.lda = Vp; c.B = emb_t.p; c.ldb = Vp; c.C = dproj.p; c.ldc = E; c.M = (int)M; c.N = E; c.K = V;
+      c.A = dlogits.p; c.lda = Vp; c.B = emb.p; c.ldb = E; c.b_mn = true; c.C = dproj.p; c.ldc = E; c.M = (int)M; c.N = E;
+      c.K = V;
       OK(gemm<T>(gc, c));
     }
     OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E));
@@ -404,7 +391,8 @@ template <typename T> class Decoder : public DecoderBase {
       if (t > 0) {
         GemmCall c;  // d h_{t-1} through the gates
         c.A = dG.as<T>() + (size_t)t * B * 5 * H; c.lda = 5 * H; c.B = w_hh_n.p; c.ldb = 4 * H; c.C = dhrec.p;
-        c.ldc = H; c.M = B; c.N = H; c.K = 4 * H; c.epi.out_f32 = 1;
+        c.ldc = H; c.M = B; c.N = H; c.K = 4 * H; c.epi.out_f32 = 1; c.epi.atomic = 1; c.splits = 0;  // K = 4H: split-K
+        CUDA_OK(cudaMemsetAsync(dhrec.p, 0, 4 * (size_t)B * H, s));
         OK(gemm<T>(gc, c));
       }
     }
@@ -500,28 +488,26 @@ template <typename T> class Decoder : public DecoderBase {
     beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
                     xin.as<T>(), X, d_ccur.as<float>());
     // global-image half of the gate / sentinel pre-activations, once per image
-    OK(fc(gc, gT.p, H, w_g_t, b5d.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5d.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
     as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
-    DevBuf w_dec_s;  // view: rows 4H..5H of w_dec_t
-    w_dec_s.p = w_dec_t.as<T>() + (size_t)4 * H * X;
     for (int step = 0; step < Ti; ++step) {
       const int cur = step & 1, nxt = cur ^ 1;
       // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
-      OK(fc(gc, xin.p, X, w_dec_t, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
-      OK(fc(gc, xin.p, X, w_dec_s, nullptr, ph.p, H, R, H, X, ACT_NONE));
+      OK(fc(gc, xin.p, X, w_dec_n.as<T>(), 5 * H, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
+      OK(fc(gc, xin.p, X, w_dec_n.as<T>() + 4 * H, 5 * H, nullptr, ph.p, H, R, H, X, ACT_NONE));
       lstm_cell_fwd<T>(lc, R, H, gpre.as<float>(), 4 * H, (const T*)nullptr, 0, g5.as<float>(), 5 * H, INT_MAX, beam,
                        d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
       sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
                       d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
-      OK(fc(gc, d_hnew.p, H, w_p_t, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
-      OK(fc(gc, phid.p, H, w_g2_t, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
-      OK(fc(gc, sent.p, H, w_s_t, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+      OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
+      OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
+      OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
       attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
                        prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
-      OK(fc(gc, actx.p, H, w_o_t, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
-      OK(fc(gc, outv.p, H, w_e_t, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
+      OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
+      OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
       {
         GemmCall c;
         c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
@@ -548,8 +534,7 @@ template <typename T> class Decoder : public DecoderBase {
 
  private:
   std::vector<DevBuf*> all_bufs() {
-    return {&w_v_t, &w_k_t, &w_kv_n, &w_x_t, &w_x_n, &w_g_t, &w_g_n, &w_hh_t, &w_hh_n, &w_hs_t, &w_hs_n, &w_p_t, &w_p_n,
-            &w_g2_t, &w_g2_n, &w_s_t, &w_s_n, &w_o_t, &w_o_n, &w_e_t, &w_e_n, &emb, &emb_t, &w_dec_t, &b5, &b5d, &gT, &PT,
+    return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &xin, &d_hnew, &d_cnew, &d_ccur,
@@ -563,8 +548,7 @@ template <typename T> class Decoder : public DecoderBase {
   int last_B = 0;
   const int64_t* last_cap = nullptr;
   // operands
-  DevBuf w_v_t, w_k_t, w_kv_n, w_x_t, w_x_n, w_g_t, w_g_n, w_hh_t, w_hh_n, w_hs_t, w_hs_n, w_p_t, w_p_n, w_g2_t, w_g2_n,
-      w_s_t, w_s_n, w_o_t, w_o_n, w_e_t, w_e_n, emb, emb_t, w_dec_t, b5, b5d;
+  DevBuf w_kv_n, w_x_n, w_g_n, w_hh_n, w_hs_n, w_p_n, w_g2_n, w_s_n, w_o_n, w_e_n, emb, w_dec_n, b5, b5d;
   // activations kept for the backward pass
   DevBuf gT, PT, keys, vals, embx, xe, g5, hs, cs, gact, gpre, ph, sgate, sent, phid, hemb, semb, alpha, actx, outv, proj,
       logits, lse, acc;
@@ -695,13 +679,14 @@ int capdec_decode(capdec_handle h, const float* g, const float* P, int32_t B, in
   return h->impl->decode(g, P, B, beam, finish_on_stop, ids_out, scores_out, ids_f32_out, (cudaStream_t)stream);
 }
 
-int capdec_gemm(int32_t dtype, int32_t mn_major, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,
                 const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t force_simt,
                 void* stream) {
   GemmContext gc; gc.stream = (cudaStream_t)stream; gc.force_simt = force_simt != 0;
   GemmCall c;
-  c.A = A; c.lda = lda; c.B = B; c.ldb = ldb; c.C = C; c.ldc = ldc; c.M = M; c.N = N; c.K = K; c.mn_major = mn_major != 0;
+  c.A = A; c.lda = lda; c.B = B; c.ldb = ldb; c.C = C; c.ldc = ldc; c.M = M; c.N = N; c.K = K;
+  c.a_mn = (majors & 1) != 0; c.b_mn = (majors & 2) != 0;
   c.epi.bias = bias; c.epi.addend = addend; c.epi.ld_add = ld_add; c.epi.dact_y = dact_y; c.epi.ld_y = ld_y;
   c.epi.act = act; c.epi.out_f32 = out_f32; c.epi.atomic = atomic; c.splits = atomic ? 0 : 1;
   if (dtype == CAPDEC_DTYPE_F32) return gemm<float>(gc, c);

@@ -2,10 +2,12 @@
 //
 //   C[M,N] (=|+=) epi( sum_k A(m,k) * B(n,k) )
 //
-// Two operand forms ("majors"):
-//   K-major  (mn_major = false): A is stored [M,K] row-major (lda), B is stored [N,K] row-major (ldb).
-//   MN-major (mn_major = true) : A is stored [K,M] row-major (lda), B is stored [K,N] row-major (ldb);
-//                                this is the weight-gradient form  dW[in,out] = X[rows,in]^T . dY[rows,out].
+// Operand forms ("majors"), chosen per operand:
+//   K-major  (a_mn / b_mn = false): A is stored [M,K] row-major (lda), B is stored [N,K] row-major (ldb).
+//   MN-major (a_mn / b_mn = true) : A is stored [K,M] row-major (lda), B is stored [K,N] row-major (ldb).
+//   forward fc   Y = X.W        : A = X K-major,  B = W [in,out] MN-major  (PaddlePaddle's own layout)
+//   data grad    dX = dY.W^T    : A = dY K-major, B = W [in,out] K-major   (N = in, K = out)
+//   weight grad  dW = X^T.dY    : A = X MN-major, B = dY MN-major          (contraction over the row index)
 // T = bf16 -> tcgen05/TMEM/TMA kernel (gemm_tc.cu); T = float -> SIMT kernel (validation precision mode).
 #pragma once
 #include "common.cuh"
@@ -29,8 +31,9 @@ struct GemmCall {
   const void* B = nullptr; long ldb = 0;
   void* C = nullptr; long ldc = 0;
   int M = 0, N = 0, K = 0;
-  bool mn_major = false;
-  int splits = 1;                // split-K (requires epi.atomic)
+  bool a_mn = false;             // A stored [K,M] (MN-major) instead of [M,K]
+  bool b_mn = false;             // B stored [K,N] (MN-major) instead of [N,K]
+  int splits = 1;                // split-K (requires epi.atomic); 0 = choose automatically
   GemmEpi epi;
 };
 

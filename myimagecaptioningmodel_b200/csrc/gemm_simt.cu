@@ -69,8 +69,8 @@ gemm_simt_kernel(const T* __restrict__ A, long sam, long sak, const T* __restric
 template <typename T> int gemm_simt(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
   long sam, sak, sbn, sbk;
-  if (!c.mn_major) { sam = c.lda; sak = 1; sbn = c.ldb; sbk = 1; }
-  else { sam = 1; sak = c.lda; sbn = 1; sbk = c.ldb; }
+  if (!c.a_mn) { sam = c.lda; sak = 1; } else { sam = 1; sak = c.lda; }
+  if (!c.b_mn) { sbn = c.ldb; sbk = 1; } else { sbn = 1; sbk = c.ldb; }
   int splits = 1;
   if (c.epi.atomic) {
     long tiles = (long)((c.M + TS - 1) / TS) * ((c.N + TS - 1) / TS);

@@ -1,16 +1,21 @@
-// bf16 GEMM on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory ->
-// tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) -> fp32 accumulator in TMEM ->
-// tcgen05.ld -> fused epilogue (bias / addend / tanh / tanh' / fp32 atomics for split-K) -> global.
+// bf16 GEMM on the 5th-gen tensor cores, persistent and warp-specialised:
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (cta_group::1, M=128, N=BN,
+//   K=16 per instruction) -> fp32 accumulators in TMEM (two buffers) -> tcgen05.ld -> fused epilogue -> global.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
-// One 128 x BN output tile per CTA; a STAGES-deep mbarrier ring decouples TMA from the MMA issuer.
+// One CTA per SM loops over (tile, k-split) work items.  Warp roles (192 threads): warp 0 = TMA producer (one
+// elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (warp w owns TMEM
+// lanes 32*(w%4) .. +31).  The TMEM accumulator is double-buffered, so the epilogue of tile i (bias / addend / tanh /
+// tanh' / fp32 vector reductions for split-K) overlaps the MMAs of tile i+1, and the smem ring keeps streaming
+// across tile boundaries.  Each operand is either K-major or MN-major (UMMA descriptor + instruction-descriptor
+// major bits), which covers forward fc (B = Paddle's [in,out] weight, MN-major), data-grad and weight-grad forms
+// without transposed weight copies.
 //
 // Replaces the cuBLAS SGEMMs behind every layers.fc / layers.matmul on the reference's decoder path
 // (model_adaAttention_aic.py:24-25, 52-53, 87-90, 99-104, 115) and their *_grad ops.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
 #include <unordered_map>
@@ -30,6 +35,7 @@ template <int BN> struct TcCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 32)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -45,25 +51,43 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;
   return d;
 }
+// descriptor of the k-th K=16 slice of an operand tile
+//   K-major : rows of 128 B (64 k), 8-row groups 1024 B apart (SBO); a slice is 32 B further along the row
+//   MN-major: every k-row is 128 B (64 mn elements), 8-k groups 1024 B apart (SBO), the next 64-wide mn group is one
+//             TMA box (64 k-rows x 128 B = 8192 B) further (LBO); a slice is 16 k-rows = 2048 B further
+template <bool MN> __device__ __forceinline__ uint64_t slice_desc(uint32_t tile_addr, int k) {
+  return MN ? make_smem_desc(tile_addr + k * 2048, 8192, 1024) : make_smem_desc(tile_addr + k * 32, 16, 1024);
+}
 
-template <int BN, bool MN>
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct TcShape {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split;
+  long ldc;
+  int vec_ok;
+};
+
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
-               long ldc, int M, int N, int K, int kb_per_split, int vec_ok, GemmEpi epi) {
+               TcShape sh, GemmEpi epi) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int nkb_total = (K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int kb1 = min(nkb_total, kb0 + kb_per_split);
+  const int nkb_total = (sh.K + BK - 1) / BK;
+  const int tiles = sh.tiles_m * sh.tiles_n;
+  const int total_work = tiles * sh.splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -72,10 +96,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_ptr_smem);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -86,21 +113,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sA = smem + s * Cfg::kStageBytes;
-        uint8_t* sB = sA + kABytes;
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        if (!MN) {
-          tma_load_2d(sA, &tmA, kb * BK, m0, &full_bar[s]);
-          tma_load_2d(sB, &tmB, kb * BK, n0, &full_bar[s]);
-        } else {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w % tiles, z = w / tiles;
+        const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
+        const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sA = smem + s * Cfg::kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, kb * BK, m0, &full_bar[s]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, &full_bar[s]);
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, &full_bar[s]);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, kb * BK, n0, &full_bar[s]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, &full_bar[s]);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, &full_bar[s]);
+          }
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -108,93 +143,105 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== MMA issuer =====
       // instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), a/b major (bits 15/16),
       // N>>3 at [17,23), M>>4 at [24,29)
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN ? 1u : 0u) << 15) | ((MN ? 1u : 0u) << 16) |
-                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int z = w / tiles;
+        const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
+        const int buf = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[buf], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          uint64_t da, db;
-          if (!MN) {
-            // K-major SW128: rows of 128 B, 8-row groups 1024 B apart; advance 16 elements = 32 B along K
-            da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            db = make_smem_desc(b_addr + k * 32, 16, 1024);
-          } else {
-            // MN-major SW128: each k-row is 128 B (64 mn elements); 8-k groups 1024 B apart (SBO);
-            // next 64-wide mn group is one TMA box (64 rows x 128 B = 8192 B) further (LBO);
-            // advance 16 k-rows = 2048 B
-            da = make_smem_desc(a_addr + k * 2048, 8192, 1024);
-            db = make_smem_desc(b_addr + k * 2048, 8192, 1024);
-          }
-          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, slice_desc<A_MN>(a_addr, k), slice_desc<B_MN>(b_addr, k), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int tile = w % tiles;
+      const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
+      const int buf = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < sh.M;
+      mbar_wait(&tmem_full_bar[buf], acc_ph);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= N) continue;
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
+        tmem_ld32(tmem_d + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all of this warp's TMEM reads are done: hand the accumulator back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        const int nb = n0 + c * 32;
+        if (!row_ok || nb >= sh.N) continue;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = nb + g * 8;
-        if (col >= N) break;
-        float v[8];
+        for (int g = 0; g < 4; ++g) {
+          const int col = nb + g * 8;
+          if (col >= sh.N) break;
+          float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-        if (vec_ok && col + 8 <= N) {
-          if (epi.bias) {
-            float b[8];
-            load8(epi.bias + col, b);
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+          if (sh.vec_ok && col + 8 <= sh.N) {
+            if (epi.bias) {
+              float b[8];
+              load8(epi.bias + col, b);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += b[i];
-          }
-          if (epi.addend) {
-            float a[8];
-            load8(reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + col, a);
+              for (int i = 0; i < 8; ++i) v[i] += b[i];
+            }
+            if (epi.addend) {
+              float a[8];
+              load8(reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + col, a);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += a[i];
-          }
-          if (epi.act == ACT_TANH) {
+              for (int i = 0; i < 8; ++i) v[i] += a[i];
+            }
+            if (epi.act == ACT_TANH) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
-          } else if (epi.act == ACT_DTANH) {
-            float y[8];
-            load8(reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + col, y);
+              for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
+            } else if (epi.act == ACT_DTANH) {
+              float y[8];
+              load8(reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + col, y);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= (1.f - y[i] * y[i]);
-          }
-          if (epi.atomic) {
-            float* p = reinterpret_cast<float*>(C) + (long)row * ldc + col;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(p + i, v[i]);
-          } else if (epi.out_f32) {
-            store8(reinterpret_cast<float*>(C) + (long)row * ldc + col, v);
+              for (int i = 0; i < 8; ++i) v[i] *= (1.f - y[i] * y[i]);
+            }
+            if (epi.atomic) {
+              float* p = reinterpret_cast<float*>(C) + (long)row * sh.ldc + col;
+              red_add_v4(p, v[0], v[1], v[2], v[3]);
+              red_add_v4(p + 4, v[4], v[5], v[6], v[7]);
+            } else if (epi.out_f32) {
+              store8(reinterpret_cast<float*>(C) + (long)row * sh.ldc + col, v);
+            } else {
+              store8(reinterpret_cast<bf16*>(C) + (long)row * sh.ldc + col, v);
+            }
           } else {
-            store8(reinterpret_cast<bf16*>(C) + (long)row * ldc + col, v);
-          }
-        } else {
-          for (int i = 0; i < 8 && col + i < N; ++i) {
-            float x = epi_value<bf16>(v[i], row, col + i, epi);
-            epi_store<bf16>(x, C, ldc, row, col + i, epi);
+            for (int i = 0; i < 8 && col + i < sh.N; ++i) {
+              float x = epi_value<bf16>(v[i], row, col + i, epi);
+              epi_store<bf16>(x, C, sh.ldc, row, col + i, epi);
+            }
           }
         }
       }
@@ -204,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -270,37 +317,43 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   return 0;
 }
 
-template <int BN, bool MN>
+template <int BN, bool A_MN, bool B_MN>
 int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
-  if (!MN) {
-    if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA)) return -1;
-    if (get_map(c.B, c.K, c.N, c.ldb, BK, BN, &tmB)) return -1;
-  } else {
-    if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA)) return -1;
-    if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB)) return -1;
-  }
+  if (!A_MN) { if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA)) return -1; }
+  else { if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA)) return -1; }
+  if (!B_MN) { if (get_map(c.B, c.K, c.N, c.ldb, BK, BN, &tmB)) return -1; }
+  else { if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB)) return -1; }
   const GemmEpi& e = c.epi;
   const int out_elem = (e.out_f32 || e.atomic) ? 4 : 2;
   int vec_ok = ((c.ldc % 8) == 0) && (((uintptr_t)c.C) % (out_elem * 8) == 0);
   if (e.bias && ((uintptr_t)e.bias & 31)) vec_ok = 0;
   if (e.addend && (((uintptr_t)e.addend & 15) || (e.ld_add % 8))) vec_ok = 0;
   if (e.dact_y && (((uintptr_t)e.dact_y & 15) || (e.ld_y % 8))) vec_ok = 0;
-  dim3 grid((c.N + BN - 1) / BN, (c.M + BM - 1) / BM, splits);
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, c.C, c.ldc, c.M, c.N, c.K, kbps,
-                                                                         vec_ok, c.epi);
+  TcShape sh;
+  sh.M = c.M; sh.N = c.N; sh.K = c.K;
+  sh.tiles_m = (c.M + BM - 1) / BM; sh.tiles_n = (c.N + BN - 1) / BN;
+  sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = vec_ok;
+  const long total = (long)sh.tiles_m * sh.tiles_n * splits;
+  const int grid = (int)std::min<long>(total, kNumSMs);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, c.C, sh, c.epi);
   ctx.launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(err)); return -1; }
   return 0;
+}
+
+template <int BN> int launch_majors(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
+  if (c.a_mn) return c.b_mn ? launch<BN, true, true>(ctx, c, splits, kbps) : launch<BN, true, false>(ctx, c, splits, kbps);
+  return c.b_mn ? launch<BN, false, true>(ctx, c, splits, kbps) : launch<BN, false, false>(ctx, c, splits, kbps);
 }
 
 }  // namespace
@@ -310,41 +363,34 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
   const int nkb = (c.K + BK - 1) / BK;
   const int mt = (c.M + BM - 1) / BM;
-  // split-K: 0 = auto (only with atomics)
-  int splits = c.epi.atomic ? c.splits : 1;
-  auto tiles_for = [&](int bn) { return (long)mt * ((c.N + bn - 1) / bn); };
-  // tile width: minimise (waves x (BN + fixed overhead))
-  int best_bn = 64;
-  double best_cost = 1e30;
+  // Pick the tile width and the k-split that minimise a simple cost model of the persistent kernel:
+  //   per CTA: ceil(work / 148) items, each  kb_per_split * t_kblock(BN) + t_epilogue(BN);
+  //   t_kblock ~ bytes moved per k-block (operand streaming bound), epilogue ~ BN (x3 for reductions).
+  int best_bn = 64, best_sp = 1;
+  double best_cost = 1e300;
   const int cands[3] = {256, 128, 64};
   for (int i = 0; i < 3; ++i) {
-    int bn = cands[i];
+    const int bn = cands[i];
     if (bn > 64 && c.N <= bn / 2) continue;
-    long tiles = tiles_for(bn);
-    int sp = splits;
-    if (sp == 0) sp = (int)std::max(1L, std::min<long>(nkb / 4 > 0 ? nkb / 4 : 1, (2 * kNumSMs) / std::max(1L, tiles)));
-    long waves = (tiles * sp + kNumSMs - 1) / kNumSMs;
-    double cost = (double)waves * (bn + 40) * ((double)nkb / sp + 6.0);
-    if (cost < best_cost) { best_cost = cost; best_bn = bn; }
-  }
-  if (splits == 0) {
-    long tiles = tiles_for(best_bn);
-    splits = (int)std::max(1L, std::min<long>(nkb / 4 > 0 ? nkb / 4 : 1, (2 * kNumSMs) / std::max(1L, tiles)));
-  }
-  int kbps = (nkb + splits - 1) / splits;
-  splits = (nkb + kbps - 1) / kbps;
-  if (c.mn_major) {
-    switch (best_bn) {
-      case 256: return launch<256, true>(ctx, c, splits, kbps);
-      case 128: return launch<128, true>(ctx, c, splits, kbps);
-      default: return launch<64, true>(ctx, c, splits, kbps);
+    const long tiles = (long)mt * ((c.N + bn - 1) / bn);
+    const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
+    const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
+    for (int sp = sp_min; sp <= sp_max; ++sp) {
+      const int kbps = (nkb + sp - 1) / sp;
+      const int sp_eff = (nkb + kbps - 1) / kbps;
+      const long per_cta = (tiles * sp_eff + kNumSMs - 1) / kNumSMs;
+      const double t_kb = (128.0 + bn) / 384.0;
+      const double t_epi = (bn / 256.0) * (c.epi.atomic ? 6.0 : 2.0) + 1.0;
+      const double cost = per_cta * (kbps * t_kb + t_epi) + 4.0 /*fill*/;
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; }
     }
-  } else {
-    switch (best_bn) {
-      case 256: return launch<256, false>(ctx, c, splits, kbps);
-      case 128: return launch<128, false>(ctx, c, splits, kbps);
-      default: return launch<64, false>(ctx, c, splits, kbps);
-    }
+  }
+  const int kbps = (nkb + best_sp - 1) / best_sp;
+  const int splits = (nkb + kbps - 1) / kbps;
+  switch (best_bn) {
+    case 256: return launch_majors<256>(ctx, c, splits, kbps);
+    case 128: return launch_majors<128>(ctx, c, splits, kbps);
+    default: return launch_majors<64>(ctx, c, splits, kbps);
   }
 }
 

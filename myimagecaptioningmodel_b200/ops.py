@@ -12,7 +12,7 @@ def _vp(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def gemm(A, B, M, N, K, *, mn_major=False, lda=None, ldb=None, C_out=None, ldc=None, bias=None, addend=None,
+def gemm(A, B, M, N, K, *, mn_major=False, a_mn=False, b_mn=False, lda=None, ldb=None, C_out=None, ldc=None, bias=None, addend=None,
          dact_y=None, act=0, out_f32=False, atomic=False, force_simt=False, sync=True):
     """capdec_gemm: C[M,N] = act(A.B^T + bias + addend) on CUDA tensors (A, B bf16 -> tcgen05, f32 -> SIMT)."""
     lib = _capi.load_library()
@@ -23,7 +23,8 @@ def gemm(A, B, M, N, K, *, mn_major=False, lda=None, ldb=None, C_out=None, ldc=N
         cdt = torch.float32 if (out_f32 or atomic) else A.dtype
         C_out = torch.zeros(M, N, dtype=cdt, device=A.device)
     ldc = C_out.stride(0) if ldc is None else ldc
-    _capi.check(lib.capdec_gemm(dtype, 1 if mn_major else 0, _vp(A), lda, _vp(B), ldb, _vp(C_out), ldc, M, N, K,
+    majors = 3 if mn_major else ((1 if a_mn else 0) | (2 if b_mn else 0))
+    _capi.check(lib.capdec_gemm(dtype, majors, _vp(A), lda, _vp(B), ldb, _vp(C_out), ldc, M, N, K,
                                 _vp(bias), _vp(addend), 0 if addend is None else addend.stride(0), _vp(dact_y),
                                 0 if dact_y is None else dact_y.stride(0), act, 1 if out_f32 else 0, 1 if atomic else 0,
                                 1 if force_simt else 0, _capi.stream_ptr()), "capdec_gemm")

@@ -92,6 +92,36 @@ def test_gemm_mn_major_weight_grad_form(M, N, K, simt):
     assert rel_err(out, 2 * ref) < F32_TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 200, 160), (8704, 1024, 1024), (256, 4096, 1024), (520, 12295, 256), (16, 40, 72)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_gemm_mixed_majors(M, N, K, simt):
+    """forward fc form: A = X [M,K] K-major, B = W [K,N] (PaddlePaddle [in,out]) MN-major; and the mirrored form"""
+    Np, Mp = (N + 7) // 8 * 8, (M + 7) // 8 * 8
+    X = _rand((M, K), torch.bfloat16, 20)
+    W = _rand((K, Np), torch.bfloat16, 21)
+    ref = X.float() @ W[:, :N].float()
+    out = torch.zeros(M, Np, dtype=torch.float32, device="cuda")
+    gemm(X, W, M, N, K, b_mn=True, ldb=Np, C_out=out, ldc=Np, out_f32=True, force_simt=simt)
+    assert rel_err(out[:, :N], ref) < F32_TOL, rel_err(out[:, :N], ref)
+    Xt = _rand((K, Mp), torch.bfloat16, 22)
+    Wt = _rand((N, K), torch.bfloat16, 23)
+    ref2 = Xt[:, :M].float().t() @ Wt.float().t()
+    out2 = torch.zeros(M, Np, dtype=torch.float32, device="cuda")
+    gemm(Xt, Wt, M, N, K, a_mn=True, lda=Mp, C_out=out2, ldc=Np, out_f32=True, force_simt=simt)
+    assert rel_err(out2[:, :N], ref2) < F32_TOL, rel_err(out2[:, :N], ref2)
+
+
+def test_gemm_many_tiles_per_cta():
+    """persistent scheduling: more work items than SMs, odd tile counts, both accumulator buffers reused many times"""
+    M, N, K = 128 * 37 + 5, 64 * 11 + 3, 200
+    A, B = _rand((M, K), torch.bfloat16, 30), _rand((N, K), torch.bfloat16, 31)
+    ref = A.float() @ B.float().t()
+    ldc = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldc, dtype=torch.float32, device="cuda")
+    gemm(A, B, M, N, K, C_out=out, ldc=ldc, out_f32=True)
+    assert rel_err(out[:, :N], ref) < F32_TOL
+
+
 def test_gemm_fp32_validation_path():
     M, N, K = 150, 130, 77
     A, B = _rand((M, K), torch.float32, 12), _rand((N, K), torch.float32, 13)
