@@ -105,6 +105,7 @@ template <typename T> class Decoder : public DecoderBase {
     OK(emb.ensure(e * (size_t)V * E, &ws_bytes));
     OK(w_dec_n.ensure(e * (size_t)X * 5 * H, &ws_bytes));
     OK(b5.ensure(4 * 5 * H, &ws_bytes)); OK(b5d.ensure(4 * 5 * H, &ws_bytes));
+    OK(b_vocab.ensure(4 * (size_t)Vp, &ws_bytes));
 
     // Every weight keeps PaddlePaddle's own [in, out] layout (one storage-type copy each, no transposes):
     //   forward  Y = X.W      reads it as the MN-major B operand,
@@ -128,6 +129,9 @@ template <typename T> class Decoder : public DecoderBase {
     copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_dec_n.as<T>() + 4 * H, 5 * H, E, H);
     copy2d_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_dec_n.as<T>() + (size_t)E * 5 * H, 5 * H, H, 4 * H);
     copy2d_from_f32<T>(lc, p->fc_hs_w, H, w_dec_n.as<T>() + (size_t)E * 5 * H + 4 * H, 5 * H, H, H);
+    // out_fc_bias padded to Vp columns so the GEMM epilogue may read it in whole groups of 8
+    CUDA_OK(cudaMemsetAsync(b_vocab.p, 0, 4 * (size_t)Vp, s));
+    CUDA_OK(cudaMemcpyAsync(b_vocab.p, p->out_fc_bias, 4 * (size_t)V, cudaMemcpyDeviceToDevice, s));
     // fused bias vectors: train [lstm_b | fc_xs_b]; decode [lstm_b | fc_xs_b + fc_hs_b]
     CUDA_OK(cudaMemcpyAsync(b5.p, p->lstm_b, 4 * 4 * H, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
@@ -241,7 +245,7 @@ template <typename T> class Decoder : public DecoderBase {
     {
       GemmCall c;                                                                                     // model:25
       c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
-      c.epi.bias = prm.out_fc_bias; c.epi.out_f32 = 1;
+      c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
     }
     // masked cross entropy (model:163-171, 180-183, 205-212)
@@ -511,7 +515,7 @@ template <typename T> class Decoder : public DecoderBase {
       {
         GemmCall c;
         c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
-        c.epi.bias = prm.out_fc_bias; c.epi.out_f32 = 1;
+        c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
         OK(gemm<T>(gc, c));
       }
       // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
@@ -534,7 +538,7 @@ template <typename T> class Decoder : public DecoderBase {
 
  private:
   std::vector<DevBuf*> all_bufs() {
-    return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &gT, &PT,
+    return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &xin, &d_hnew, &d_cnew, &d_ccur,
@@ -548,7 +552,7 @@ template <typename T> class Decoder : public DecoderBase {
   int last_B = 0;
   const int64_t* last_cap = nullptr;
   // operands
-  DevBuf w_kv_n, w_x_n, w_g_n, w_hh_n, w_hs_n, w_p_n, w_g2_n, w_s_n, w_o_n, w_e_n, emb, w_dec_n, b5, b5d;
+  DevBuf w_kv_n, w_x_n, w_g_n, w_hh_n, w_hs_n, w_p_n, w_g2_n, w_s_n, w_o_n, w_e_n, emb, w_dec_n, b5, b5d, b_vocab;
   // activations kept for the backward pass
   DevBuf gT, PT, keys, vals, embx, xe, g5, hs, cs, gact, gpre, ph, sgate, sent, phid, hemb, semb, alpha, actx, outv, proj,
       logits, lse, acc;
@@ -590,7 +594,12 @@ static int check_device(capdec_handle h) {
   return 0;
 }
 
+namespace capdec { void set_gemm_trace(unsigned long long* buf); }
+
 extern "C" {
+
+// debug hook (not part of include/capdec.h): device buffer of 148*32 u64 receiving per-CTA globaltimer stamps
+void capdec_debug_gemm_trace(void* buf) { capdec::set_gemm_trace(reinterpret_cast<unsigned long long*>(buf)); }
 
 const char* capdec_last_error(void) { return g_err; }
 int capdec_version(void) { return 100; }

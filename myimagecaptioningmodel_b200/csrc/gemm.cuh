@@ -24,6 +24,7 @@ struct GemmEpi {
   int act = ACT_NONE;
   int out_f32 = 0;               // C is fp32 (otherwise T)
   int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
+  int aux_padded = 0;            // bias / addend / dact_y are readable up to the next multiple of 8 columns past N
 };
 
 struct GemmCall {

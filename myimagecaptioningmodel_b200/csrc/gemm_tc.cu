@@ -29,7 +29,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter
+constexpr int kThreads = 64 + kEpiWarps * 32;    // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int kABytes = BM * BK * 2;  // 16 KB
 
 template <int BN> struct TcCfg {
@@ -37,8 +38,10 @@ template <int BN> struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 32)
-  static constexpr int kStagingBytes = 4 * 2 * 4096;  // per epilogue warp: two 32-row x 128-byte output tiles
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAlignSlack = 512;  // dynamic smem starts 1024-aligned in practice; checked at kernel entry
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte output tile
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStagingBytes + kAlignSlack + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
 
 // 64-bit shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
@@ -80,10 +83,6 @@ template <int N> __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 struct TcShape {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split;
@@ -91,35 +90,93 @@ struct TcShape {
   int vec_ok;
   int rotate_k;  // start every CTA's k-loop at a different k-block (spreads L2 hot lines among CTAs sharing a tile)
   int tma_out;   // epilogue writes through shared memory + TMA tensor stores (needs an aligned C)
+  unsigned long long* trace;  // debug timeline (capdec_debug_gemm_trace), 32 slots per CTA, or nullptr
 };
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if (sh.trace) sh.trace[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
 
-// bias / addend / activation on 8 consecutive columns of one output row
-__device__ __forceinline__ void epi_math8(float (&v)[8], const GemmEpi& epi, long row, int col, bool row_ok, int N) {
-  if (col + 8 <= N) {
-    if (epi.bias) {
-      float b[8];
-      load8(epi.bias + col, b);
+// Rare ragged-edge paths are kept out of line: the epilogue runs with ONE warp per scheduler, so its loop body has to
+// stay inside the instruction cache (an inlined scalar fallback per unrolled group made the kernel 120 KB of SASS and
+// the epilogue 3x slower than the MMAs it is supposed to hide behind).
+__device__ __noinline__ void epi_math8_tail(float* v, const GemmEpi& epi, long row, int col, bool row_ok, int N) {
+  for (int i = 0; i < 8; ++i)
+    v[i] = (row_ok && col + i < N) ? epi_value<bf16>(v[i], (int)row, col + i, epi) : 0.f;
+}
+__device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, long row, int col, int N,
+                                             const GemmEpi& epi) {
+  for (int i = 0; i < 8 && col + i < N; ++i) epi_store<bf16>(v[i], C, ldc, (int)row, col + i, epi);
+}
+
+// 32 accumulator columns of one warp's 32 rows: TMEM -> registers (tcgen05.ld) with the addend / dact_y loads in
+// flight behind it -> bias (smem) / addend / tanh / tanh' -> swizzled smem tile (16-byte chunks chunk0 .. of each
+// 128-byte row).  FULL = all 32 columns are < N: straight-line code the scheduler can interleave freely (the
+// epilogue has only two warps per scheduler, so exposed latencies are what it costs).
+template <bool OUT_F32, bool FULL>
+__device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float* bias_t, const bf16* add_p,
+                                                const bf16* y_p, bool do_tanh, int left, uint8_t* dst_row, uint32_t swz,
+                                                uint32_t chunk0) {
+  uint32_t r[32];
+  uint4 aq[4], yq[4];
+  __syncwarp();  // tcgen05.ld is .sync.aligned
+  tmem_ld32(tmem_addr, r);
+  if (add_p) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += b[i];
+    for (int g = 0; g < 4; ++g)
+      if (FULL || g * 8 < left) aq[g] = *reinterpret_cast<const uint4*>(add_p + g * 8);
+  }
+  if (y_p) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (FULL || g * 8 < left) yq[g] = *reinterpret_cast<const uint4*>(y_p + g * 8);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (FULL || g * 8 < left) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      if (bias_t) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_t + g * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_t + g * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (add_p) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aq[g]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          v[2 * i] += f.x; v[2 * i + 1] += f.y;
+        }
+      }
+      if (do_tanh) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
+      }
+      if (y_p) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yq[g]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          v[2 * i] *= (1.f - f.x * f.x); v[2 * i + 1] *= (1.f - f.y * f.y);
+        }
+      }
+      if (OUT_F32) {
+        *reinterpret_cast<float4*>(dst_row + (((chunk0 + 2 * g) ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst_row + (((chunk0 + 2 * g + 1) ^ swz) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(dst_row + (((chunk0 + g) ^ swz) << 4)) = u;
+      }
     }
-    if (epi.addend && row_ok) {
-      float a[8];
-      load8(reinterpret_cast<const bf16*>(epi.addend) + row * epi.ld_add + col, a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += a[i];
-    }
-    if (epi.act == ACT_TANH) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
-    } else if (epi.act == ACT_DTANH && row_ok) {
-      float y[8];
-      load8(reinterpret_cast<const bf16*>(epi.dact_y) + row * epi.ld_y + col, y);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= (1.f - y[i] * y[i]);
-    }
-  } else {
-    for (int i = 0; i < 8; ++i)
-      v[i] = (row_ok && col + i < N) ? epi_value<bf16>(v[i], (int)row, col + i, epi) : 0.f;
   }
 }
 
@@ -130,13 +187,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (misalign > (uint32_t)Cfg::kAlignSlack) __trap();
+  uint8_t* smem = smem_raw + misalign;
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-byte aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + 256);  // [2][BN], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb_total = (sh.K + BK - 1) / BK;
@@ -144,6 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_work = tiles * sh.splits;
 
   if (threadIdx.x == 0) {
+    TRACE(0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (sh.tma_out) tma_prefetch_desc(&tmC);
@@ -153,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -162,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -193,8 +255,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, &full_bar[s]);
           }
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+          if (w == (int)blockIdx.x && i == 0) TRACE(2);
         }
       }
+      TRACE(3);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -216,6 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
+          if (it == 0 && kb == kb0) TRACE(4);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
@@ -227,13 +292,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (it < 4) TRACE(8 + it);         // all MMAs of tile `it` issued
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int ew = warp - 2;        // epilogue warp index 0..7
+    const int half = ew >> 2;       // which of the two warps of the quarter
     int it = 0;
-    uint32_t epi_sb = 0;  // staging-buffer toggle
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int tile = w % tiles;
       const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
@@ -241,93 +308,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_ph = (it >> 1) & 1;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < sh.M;
+      const bool has_bias = epi.bias != nullptr;
+      if (sh.tma_out && has_bias) {
+        // stage this tile's bias slice (zero past the readable range) while the MMAs are still running
+        const int n_read = (sh.N + 7) & ~7;
+        for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
+          bias_s[buf * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
+      }
       mbar_wait(&tmem_full_bar[buf], acc_ph);
+      if (warp == 2 && lane == 0 && it < 4) TRACE(12 + it);   // accumulator of tile `it` complete
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
       if (sh.tma_out) {
-        // ---- coalesced path: registers -> swizzled smem tile (32 rows x 128 B) -> TMA tensor store / reduce-add ----
-        uint8_t* my_stage = staging + quarter * 8192;
+        // ---- registers -> swizzled smem tile (32 rows x 128 B) -> TMA tensor store / reduce-add ----
+        // Passes (128 bytes of output per row each) are dealt round-robin to the two warps of a lane quarter.  The
+        // host guarantees (launch()) that bias / addend / dact_y may be read in whole groups of 8 columns up to the
+        // next multiple of 8 past N; columns >= N are clipped by the TMA store, so there is no scalar edge path.
+        uint8_t* my_stage = staging + ew * 4096;
         const uint32_t swz = (uint32_t)(lane & 7);
         uint8_t* my_row = my_stage + lane * 128;
+        const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + n0
+                                                   : nullptr;
+        const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
+                              ? reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + n0 : nullptr;
+        const bool do_tanh = epi.act == ACT_TANH;
         const bool f32_out = epi.out_f32 || epi.atomic;
-        if (!f32_out) {
+        const int pw = f32_out ? 32 : 64;           // columns per pass
+        const int n_pass = BN / pw;
+        const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
+        if (half >= n_pass) {
+          // nothing to read for this warp (BN = 64, bf16): release the accumulator right away
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
 #pragma unroll 1
-          for (int c2 = 0; c2 < BN / 64; ++c2) {
-            uint32_t r0[32], r1[32];
-            __syncwarp();
-            tmem_ld32(tmem_d + (uint32_t)(c2 * 64), r0);
-            tmem_ld32(tmem_d + (uint32_t)(c2 * 64 + 32), r1);
-            tmem_ld_wait();
-            if (c2 == BN / 64 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        for (int ps = half; ps < n_pass; ps += 2) {
+          const int c0 = ps * pw;
+          const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
+          if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
+          __syncwarp();
+          const float* bt = has_bias ? bias_s + buf * BN + c0 : nullptr;
+          const bf16* ap = add_p ? add_p + c0 : nullptr;
+          const bf16* yp = y_p ? y_p + c0 : nullptr;
+          if (f32_out) {
+            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, left, my_row, swz, 0);
+            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, left, my_row, swz, 0);
+          } else {
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
+              const int o = sub * 32;
+              if (left - o >= 32)
+                epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
+                                             yp ? yp + o : nullptr, do_tanh, left - o, my_row, swz, (uint32_t)(sub * 4));
+              else
+                epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
+                                              yp ? yp + o : nullptr, do_tanh, left - o, my_row, swz, (uint32_t)(sub * 4));
             }
-            const int nb = n0 + c2 * 64;
-            if (nb >= sh.N) continue;  // warp-uniform
-            uint8_t* dst = my_row + (epi_sb & 1) * 4096;
-            if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has finished reading this buffer
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(g < 4 ? r0[g * 8 + i] : r1[(g - 4) * 8 + i]);
-              epi_math8(v, epi, row, nb + g * 8, row_ok, sh.N);
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              *reinterpret_cast<uint4*>(dst + (((uint32_t)g ^ swz) << 4)) = u;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmC, my_stage + (epi_sb & 1) * 4096, nb, m0 + quarter * 32);
-              bulk_commit();
-            }
-            ++epi_sb;
           }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
+          if (ps == my_last) {
+            // all of this warp's TMEM reads are done: hand the accumulator back to the MMA issuer
+            tc_fence_before();
             __syncwarp();
-            tmem_ld32(tmem_d + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (c == BN / 32 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-            }
-            const int nb = n0 + c * 32;
-            if (nb >= sh.N) continue;  // warp-uniform
-            uint8_t* dst = my_row + (epi_sb & 1) * 4096;
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              epi_math8(v, epi, row, nb + g * 8, row_ok, sh.N);
-              *reinterpret_cast<float4*>(dst + (((uint32_t)(2 * g) ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(dst + (((uint32_t)(2 * g + 1) ^ swz) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (epi.atomic) tma_reduce_add_2d(&tmC, my_stage + (epi_sb & 1) * 4096, nb, m0 + quarter * 32);
-              else tma_store_2d(&tmC, my_stage + (epi_sb & 1) * 4096, nb, m0 + quarter * 32);
-              bulk_commit();
-            }
-            ++epi_sb;
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+          if (left <= 0) continue;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (epi.atomic) tma_reduce_add_2d(&tmC, my_stage, n0 + c0, m0 + quarter * 32);
+            else tma_store_2d(&tmC, my_stage, n0 + c0, m0 + quarter * 32);
+            bulk_commit();
           }
         }
+        if (warp == 2 && lane == 0 && it < 4) TRACE(16 + it);   // epilogue of tile `it` issued its last store
+        continue;
+      }
+      if (half == 1) {  // the fallback path below uses one warp per lane quarter
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         continue;
       }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        // ---- fallback for outputs the TMA cannot address (unaligned base / pitch): per-thread stores ----
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
         tmem_ld32(tmem_d + (uint32_t)(c * 32), r);
@@ -340,55 +406,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (!row_ok || nb >= sh.N) continue;
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int col = nb + g * 8;
           if (col >= sh.N) break;
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-          if (sh.vec_ok && col + 8 <= sh.N) {
-            if (epi.bias) {
-              float b[8];
-              load8(epi.bias + col, b);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += b[i];
-            }
-            if (epi.addend) {
-              float a[8];
-              load8(reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + col, a);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += a[i];
-            }
-            if (epi.act == ACT_TANH) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
-            } else if (epi.act == ACT_DTANH) {
-              float y[8];
-              load8(reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + col, y);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= (1.f - y[i] * y[i]);
-            }
-            if (epi.atomic) {
-              float* p = reinterpret_cast<float*>(C) + (long)row * sh.ldc + col;
-              red_add_v4(p, v[0], v[1], v[2], v[3]);
-              red_add_v4(p + 4, v[4], v[5], v[6], v[7]);
-            } else if (epi.out_f32) {
-              store8(reinterpret_cast<float*>(C) + (long)row * sh.ldc + col, v);
-            } else {
-              store8(reinterpret_cast<bf16*>(C) + (long)row * sh.ldc + col, v);
-            }
-          } else {
-            for (int i = 0; i < 8 && col + i < sh.N; ++i) {
-              float x = epi_value<bf16>(v[i], row, col + i, epi);
-              epi_store<bf16>(x, C, sh.ldc, row, col + i, epi);
-            }
-          }
+          epi_math8_tail(v, epi, row, col, true, sh.N);
+          epi_store8_tail(v, C, sh.ldc, row, col, sh.N, epi);
         }
       }
     }
   }
   if (warp >= 2 && lane == 0 && sh.tma_out) bulk_wait<0>();  // all tensor stores of this thread have completed
+  if (warp == 2 && lane == 0) TRACE(20);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -400,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+unsigned long long* g_trace = nullptr;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
 
@@ -484,17 +517,27 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   if (e.dact_y && (((uintptr_t)e.dact_y & 15) || (e.ld_y % 8))) vec_ok = 0;
   // output through TMA tensor stores when C is 16-byte aligned with a 16-byte-multiple pitch (always true for the
   // decoder's own buffers); otherwise the direct per-thread store path is used
-  const int tma_out = (((uintptr_t)c.C & 15) == 0) && (((c.ldc * out_elem) & 15) == 0) &&
+  // TMA path: C addressable by a tensor map, aux operands 16/32-byte aligned; with aux operands the epilogue reads
+  // them in groups of 8 columns, so N must be a multiple of 8 unless the caller vouches for padded buffers
+  // (epi.aux_padded: the decoder's own buffers are padded to a multiple of 128 columns).
+  const bool has_aux = e.bias || e.addend || e.dact_y;
+  const int tma_out = (!has_aux || (c.N % 8) == 0 || e.aux_padded) &&
+                      (((uintptr_t)c.C & 15) == 0) && (((c.ldc * out_elem) & 15) == 0) &&
                       (!e.bias || ((uintptr_t)e.bias & 31) == 0) &&
                       (!e.addend || ((((uintptr_t)e.addend & 15) == 0) && (e.ld_add % 8) == 0)) &&
                       (!e.dact_y || ((((uintptr_t)e.dact_y & 15) == 0) && (e.ld_y % 8) == 0));
-  if (tma_out) {
+  // epilogue mode: 1 = swizzled smem tile + TMA tensor store / reduce-add, 0 = per-thread direct stores (unaligned C)
+  static int out_env = -1;
+  if (out_env < 0) { const char* ev = getenv("CAPDEC_GEMM_OUT"); out_env = ev ? atoi(ev) : 1; }
+  int out_mode = tma_out ? (out_env ? 1 : 0) : 0;
+  if (out_mode == 1) {
     if (get_map(c.C, c.N, c.M, c.ldc, out_elem == 2 ? 64 : 32, 32, &tmC, out_elem)) return -1;
   } else {
     tmC = tmA;
   }
   TcShape sh;
-  sh.tma_out = tma_out;
+  sh.tma_out = out_mode;
+  sh.trace = g_trace;
   sh.M = c.M; sh.N = c.N; sh.K = c.K;
   sh.tiles_m = (c.M + BM - 1) / BM; sh.tiles_n = (c.N + BN - 1) / BN;
   sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = vec_ok;
@@ -518,6 +561,8 @@ template <int BN> int launch_majors(GemmContext& ctx, const GemmCall& c, int spl
 }
 
 }  // namespace
+
+void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
