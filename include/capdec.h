@@ -35,7 +35,7 @@ typedef struct capdec_config {
   int32_t hidden_dim;       /* config.py:59  (1024) multiple of 8          */
   int32_t embedding_size;   /* config.py:56  (256)  multiple of 8          */
   int32_t vocab_size;       /* config.py:55  (12295)                       */
-  int32_t num_positions;    /* config.py:51  (49) <= 64                    */
+  int32_t num_positions;    /* config.py:51  (49) <= 63                    */
   int32_t sentence_length;  /* config.py:57  (35): train runs sentence_length-1 steps (model:66) */
   int32_t infer_max_length; /* config.py:60  (35)                          */
   int32_t padding_idx;      /* config.py:24  (0)                           */

@@ -42,21 +42,87 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
 
 // shared-memory carve-up shared by the forward and the backward-score kernels
 struct SmemLayout {
-  int off_e, off_alpha, off_bar, off_tile0, off_tile1, total;
+  int off_e, off_alpha, off_bar, off_q, off_tile0, off_tile1, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int H, int k, int tile_elem_bytes, int n_tiles) {
+// q_bytes: bytes reserved for the per-query vector ring of the forward kernel (0 for the backward kernels)
+__host__ __device__ inline SmemLayout make_layout(int H, int k, int tile_elem_bytes, int n_tiles, int q_bytes = 0) {
   SmemLayout L;
-  L.off_e = 0;
-  L.off_alpha = 128 * 4;
-  L.off_bar = 256 * 4;
-  L.off_tile0 = 256 * 4 + 64;
+  L.off_e = 0;            // 2 x 128 floats (double-buffered scores)
+  L.off_alpha = 256 * 4;  // 10 warps x 64 floats (per-warp alpha copies)
+  L.off_bar = 256 * 4 + 2560;
+  L.off_q = 256 * 4 + 2560 + 64;
+  L.off_tile0 = L.off_q + q_bytes;
   const int tile = ((k * H * tile_elem_bytes + 127) / 128) * 128;
   L.off_tile1 = L.off_tile0 + (n_tiles > 0 ? tile : 0);
   L.total = L.off_tile0 + n_tiles * tile;
   return L;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// sum_h tanh(key[h] + he[h]) * w[h] over this lane's 8-element slices (h = v*256 + lane*8 + i)
+//   bf16: packed -- one HADD2 and ONE MUFU (tanh.approx.bf16x2) per two elements, fp32 accumulation
+//   fp32: scalar tanhf (validation precision)
+template <int NV>
+__device__ __forceinline__ float score_dot(const bf16* kj, const uint32_t (&he2)[NV][4], const float (&w)[NV][8], int lane) {
+  // four independent accumulators (one per 16-byte sub-chunk): no serial FFMA chain behind the MUFU results
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  uint4 kq[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) kq[v] = *reinterpret_cast<const uint4*>(kj + v * 256 + lane * 8);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint32_t kk[4] = {kq[v].x, kq[v].y, kq[v].z, kq[v].w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint32_t s2, z2;
+      asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s2) : "r"(kk[p]), "r"(he2[v][p]));
+      asm("tanh.approx.bf16x2 %0, %1;" : "=r"(z2) : "r"(s2));
+      acc[p] = fmaf(__uint_as_float(z2 << 16), w[v][2 * p], acc[p]);
+      acc[p] = fmaf(__uint_as_float(z2 & 0xffff0000u), w[v][2 * p + 1], acc[p]);
+    }
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+template <int NV>
+__device__ __forceinline__ float score_dot(const float* kj, const float (&he)[NV][8], const float (&w)[NV][8], int lane) {
+  float acc = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float kk[8];
+    load8(kj + v * 256 + lane * 8, kk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(tanhf(kk[i] + he[v][i]), w[v][i], acc);
+  }
+  return acc;
+}
+// per-lane query slice in the form score_dot wants
+template <int NV> __device__ __forceinline__ void load_he(const bf16* he_s, uint32_t (&he2)[NV][4], int lane) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 q = *reinterpret_cast<const uint4*>(he_s + v * 256 + lane * 8);
+    he2[v][0] = q.x; he2[v][1] = q.y; he2[v][2] = q.z; he2[v][3] = q.w;
+  }
+}
+template <int NV> __device__ __forceinline__ void load_he(const float* he_s, float (&he)[NV][8], int lane) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) load8(he_s + v * 256 + lane * 8, he[v]);
+}
+template <typename T, int NV> struct HeRegs;
+template <int NV> struct HeRegs<bf16, NV> { uint32_t r[NV][4]; };
+template <int NV> struct HeRegs<float, NV> { float r[NV][8]; };
+
 // NV > 0: H == NV * 256, per-lane operands live in registers.  NV == 0: generic H (multiple of 8).
+//
+// Per query row: (1) scores, one warp per position, e -> smem (double-buffered by query parity);
+// (2) ONE block barrier; (3) every warp recomputes the (k+1)-way soft-max from smem with shuffles (no second
+// barrier, no idle warps), warp 0 writes alpha; (4) context, 4 adjacent columns per thread, alpha broadcast by
+// shuffle.  The query's four H-vectors (hid_emb, sentinel_emb, sentinel, p_hid) arrive through a 3-deep cp.async
+// ring, prefetched one query ahead, so no global-load latency is exposed inside the loop.
 template <typename T, int NV, bool STAGE>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ keys, const T* __restrict__ vals,
@@ -67,10 +133,12 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   constexpr int RV = NV > 0 ? NV : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const int H = s.H, k = s.k, P = s.k + 1;
-  const SmemLayout L = make_layout(H, k, (int)sizeof(T), STAGE ? 2 : 0);
+  const int q_bytes = 3 * 4 * H * (int)sizeof(T);
+  const SmemLayout L = make_layout(H, k, (int)sizeof(T), STAGE ? 2 : 0, q_bytes);
   float* e_s = reinterpret_cast<float*>(smem + L.off_e);
-  float* a_s = reinterpret_cast<float*>(smem + L.off_alpha);
+  float* a_s = reinterpret_cast<float*>(smem + L.off_alpha);  // [nwarps][64] per-warp alpha copies
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  T* qring = reinterpret_cast<T*>(smem + L.off_q);  // [3][4][H]: hid_emb, sent_emb, sentinel, p_hid
   const int img = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   const int q0 = chunk * q_per_chunk, q1 = min(s.q_per_img, q0 + q_per_chunk);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -88,6 +156,21 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
     Kt = reinterpret_cast<const T*>(smem + L.off_tile0);
     Vt = reinterpret_cast<const T*>(smem + L.off_tile1);
   }
+  const int vec_per_row = H / 8;  // 16-byte chunks of T=bf16 (or half-chunks of fp32) per H-vector
+  auto prefetch = [&](int q) {
+    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    T* dst = qring + (size_t)(q % 3) * 4 * H;
+    const T* src[4] = {hid_emb + row * H, sent_emb + row * H, sentinel + row * H, p_hid ? p_hid + row * H : sentinel + row * H};
+    constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte cp.async
+    const int n16 = H / EPC;
+    for (int i = tid; i < 4 * n16; i += blockDim.x) {
+      const int a = i / n16, c = i % n16;
+      cp_async16(dst + a * H + c * EPC, src[a] + c * EPC);
+    }
+    cp_async_commit();
+  };
+  (void)vec_per_row;
+  if (q0 < q1) prefetch(q0);
   // per-lane slice of w_alpha
   float w[RV][8];
   if (NV > 0) {
@@ -96,96 +179,113 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   }
   const float b_a = b_alpha[0];
   const float inv_p = 1.f / (float)P;
-  if (STAGE) {
-    __syncthreads();  // barrier init visible to all waiters
-    mbar_wait(bar, 0);
-  }
+  cp_async_wait_all();
+  __syncthreads();  // barrier init + first query vectors visible
+  if (STAGE) mbar_wait(bar, 0);
   for (int q = q0; q < q1; ++q) {
     const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
-    const T* he_g = hid_emb + row * H;
+    const T* qv = qring + (size_t)(q % 3) * 4 * H;
+    const T* he_s = qv;
+    const T* se_s = qv + H;
+    const T* sn_s = qv + 2 * H;
+    const T* ph_s = qv + 3 * H;
+    float* eq = e_s + (q & 1) * 128;
+    if (q + 1 < q1) prefetch(q + 1);  // ring slot (q+1)%3 was last read in query q-2: everyone is past it
     // ---- scores: one warp per position ----
-    float he[RV][8];
-    if (NV > 0) {
-#pragma unroll
-      for (int v = 0; v < RV; ++v) load8(he_g + v * 256 + lane * 8, he[v]);
-    }
+    HeRegs<T, RV> he;
+    if (NV > 0) load_he<RV>(he_s, he.r, lane);
     for (int j = warp; j < P; j += nwarps) {
-      const T* kj = (j < k) ? (Kt + (long)j * H) : (sent_emb + row * H);
+      const T* kj = (j < k) ? (Kt + (long)j * H) : se_s;
       float acc = 0.f;
       if (NV > 0) {
-#pragma unroll
-        for (int v = 0; v < RV; ++v) {
-          float kk[8];
-          load8(kj + v * 256 + lane * 8, kk);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fmaf(tanh_t<F>(kk[i] + he[v][i]), w[v][i], acc);
-        }
+        acc = score_dot<RV>(kj, he.r, w, lane);
       } else {
         for (int h0 = lane * 8; h0 < H; h0 += 256) {
           float kk[8], hh[8], ww[8];
           load8(kj + h0, kk);
-          load8(he_g + h0, hh);
+          load8(he_s + h0, hh);
           load8(w_alpha + h0, ww);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc = fmaf(tanh_t<F>(kk[i] + hh[i]), ww[i], acc);
         }
       }
       acc = warp_sum(acc);
-      if (lane == 0) e_s[j] = acc + b_a;
+      if (lane == 0) eq[j] = acc + b_a;
     }
+    cp_async_wait_all();  // next query's vectors have landed (this thread's part); the barrier publishes them
     __syncthreads();
-    // ---- softmax over the k+1 positions (warp 0) ----
-    if (warp == 0) {
+    // ---- soft-max over the k+1 positions, recomputed by every warp (P <= 64: two values per lane) ----
+    float a_lo, a_hi;
+    {
+      const float e0 = (lane < P) ? eq[lane] : -INFINITY;
+      const float e1 = (lane + 32 < P) ? eq[lane + 32] : -INFINITY;
       if (s.position_softmax) {
-        float m = -INFINITY;
-        for (int j = lane; j < P; j += 32) m = fmaxf(m, e_s[j]);
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int j = lane; j < P; j += 32) sum += __expf(e_s[j] - m);
-        sum = warp_sum(sum);
-        const float inv = 1.f / sum;
-        for (int j = lane; j < P; j += 32) {
-          const float a = __expf(e_s[j] - m) * inv;
-          a_s[j] = a;
-          alpha_out[row * P + j] = a;
-        }
+        const float m = warp_max(fmaxf(e0, e1));
+        const float x0 = (lane < P) ? __expf(e0 - m) : 0.f;
+        const float x1 = (lane + 32 < P) ? __expf(e1 - m) : 0.f;
+        const float inv = 1.f / warp_sum(x0 + x1);
+        a_lo = x0 * inv;
+        a_hi = x1 * inv;
       } else {
-        for (int j = lane; j < P; j += 32) {
-          a_s[j] = 1.f;  // softmax over a size-1 axis (model:107 as written)
-          alpha_out[row * P + j] = 1.f;
+        a_lo = 1.f;  // softmax over a size-1 axis (model:107 as written)
+        a_hi = 1.f;
+      }
+      if (warp == 0) {
+        if (lane < P) alpha_out[row * P + lane] = a_lo;
+        if (lane + 32 < P) alpha_out[row * P + lane + 32] = a_hi;
+      }
+    }
+    // ---- context: each thread owns 4 adjacent columns; alpha (already scaled by 1/(k+1)) sits in smem ----
+    // written redundantly (same values) by every warp for its own use -> no extra barrier; positions are processed
+    // 7 at a time with all loads issued first so that smem latency is paid once per group, not once per position
+    float* aw = a_s + warp * 64;
+    if (lane < P) aw[lane] = a_lo * inv_p;
+    if (lane + 32 < P) aw[lane + 32] = a_hi * inv_p;
+    __syncwarp();
+    for (int hb = 0; hb < H; hb += blockDim.x * 4) {
+      const int h0 = hb + tid * 4;
+      if (h0 < H) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const T* vp = Vt + h0;
+        int j = 0;
+        for (; j + 7 <= k; j += 7) {
+          float v[7][4], a[7];
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            load4(vp + (long)(j + u) * H, v[u]);
+            a[u] = aw[j + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 7; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(a[u], v[u][i], acc[i]);
+        }
+        for (; j < k; ++j) {
+          float v[4];
+          load4(vp + (long)j * H, v);
+          const float a = aw[j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]);
+        }
+        {
+          float v[4];
+          load4(sn_s + h0, v);
+          const float a = aw[k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]);
+        }
+        if (ctx_out) store4(ctx_out + row * H + h0, acc);
+        if (actx) {
+          float ph[4];
+          load4(ph_s + h0, ph);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ph[i] += acc[i];
+          store4(actx + row * H + h0, ph);
         }
       }
     }
-    __syncthreads();
-    // ---- context: each thread owns 4 adjacent columns ----
-    for (int h0 = tid * 4; h0 < H; h0 += blockDim.x * 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int j = 0; j < k; ++j) {
-        float v[4];
-        load4(Vt + (long)j * H + h0, v);
-        const float a = a_s[j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]);
-      }
-      {
-        float v[4];
-        load4(sentinel + row * H + h0, v);
-        const float a = a_s[k];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]) * inv_p;
-      }
-      if (ctx_out) store4(ctx_out + row * H + h0, acc);
-      if (actx) {
-        float ph[4];
-        load4(p_hid + row * H + h0, ph);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ph[i] += acc[i];
-        store4(actx + row * H + h0, ph);
-      }
-    }
-    // e_s / a_s are rewritten only after the next __syncthreads pair; the context pass reads a_s, the next
-    // score pass writes e_s only -> one barrier protects a_s before the next softmax
-    __syncthreads();
+    __syncwarp();  // aw is rewritten by this warp in the next query
+    // no trailing barrier: the next query writes the other score buffer and a ring slot nobody reads any more
   }
 }
 
@@ -375,7 +475,7 @@ int pick_chunks(int n_img, int nq) {
   for (int c = 1; c <= nq && c <= 8; ++c) {
     const int qpc = (nq + c - 1) / c;
     const long waves = ((long)n_img * c + kNumSMs - 1) / kNumSMs;
-    const long cost = waves * (qpc + 2);  // +2: tile load
+    const long cost = waves * (qpc + 1);  // +1: tile load
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -410,14 +510,15 @@ void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
   if (s.n_img <= 0 || s.q_per_img <= 0) return;
   const int chunks = pick_chunks(s.n_img, s.q_per_img);
   const int qpc = (s.q_per_img + chunks - 1) / chunks;
-  const SmemLayout Ls = make_layout(s.H, s.k, (int)sizeof(T), 2);
+  const int q_bytes = 3 * 4 * s.H * (int)sizeof(T);
+  const SmemLayout Ls = make_layout(s.H, s.k, (int)sizeof(T), 2, q_bytes);
   // stage both tiles in shared memory when they fit (bf16 at H=1024,k=49: 2 x 98 KB), otherwise read through L1/L2
   const bool stage = Ls.total <= 227 * 1024 && ((size_t)s.k * s.H * sizeof(T)) % 16 == 0;
   if (stage) {
     launch_fwd<T, true>(c, s, chunks, qpc, Ls.total, keys, vals, hid_emb, sent_emb, sentinel, p_hid, w_alpha, b_alpha,
                         alpha, actx, ctx_out);
   } else {
-    const SmemLayout L0 = make_layout(s.H, s.k, (int)sizeof(T), 0);
+    const SmemLayout L0 = make_layout(s.H, s.k, (int)sizeof(T), 0, q_bytes);
     launch_fwd<T, false>(c, s, chunks, qpc, L0.total, keys, vals, hid_emb, sent_emb, sentinel, p_hid, w_alpha, b_alpha,
                          alpha, actx, ctx_out);
   }

@@ -609,7 +609,7 @@ int capdec_create(const capdec_config* c, int device, capdec_handle* out) {
   if (c->hidden_dim <= 0 || c->hidden_dim % 8 || c->embedding_size <= 0 || c->embedding_size % 8) {
     set_error("capdec_create: hidden_dim and embedding_size must be positive multiples of 8"); return -1;
   }
-  if (c->num_positions < 1 || c->num_positions > 64) { set_error("capdec_create: num_positions must be in [1,64]"); return -1; }
+  if (c->num_positions < 1 || c->num_positions > 63) { set_error("capdec_create: num_positions must be in [1,63]"); return -1; }
   if (c->vocab_size < 4 || c->sentence_length < 2 || c->infer_max_length < 1) {
     set_error("capdec_create: bad vocab_size / sentence_length / infer_max_length"); return -1;
   }
@@ -715,7 +715,7 @@ int capdec_attention_fwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int
                          int64_t q_stride, int32_t softmax_axis, const void* keys, const void* vals,
                          const void* hid_emb, const void* sent_emb, const void* sentinel, const void* p_hid,
                          const float* w_alpha, const float* b_alpha, float* alpha, void* actx, void* ctx, void* stream) {
-  if (H % 8 || k < 1 || k > 64) { set_error("capdec_attention_fwd: need H %% 8 == 0 and 1 <= k <= 64"); return -1; }
+  if (H % 8 || k < 1 || k > 63) { set_error("capdec_attention_fwd: need H %% 8 == 0 and 1 <= k <= 63"); return -1; }
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
   AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
   if (dtype == CAPDEC_DTYPE_F32)
@@ -735,7 +735,7 @@ int capdec_attention_bwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int
                          const void* hid_emb, const void* sent_emb, const void* sentinel, const float* w_alpha,
                          const float* alpha, const void* dctx, float* de, void* dS_ctx, void* dKV, void* dhid_emb,
                          void* dsent_emb, float* dw_alpha, float* db_alpha, void* stream) {
-  if (H % 8 || k < 1 || k > 64) { set_error("capdec_attention_bwd: need H %% 8 == 0 and 1 <= k <= 64"); return -1; }
+  if (H % 8 || k < 1 || k > 63) { set_error("capdec_attention_bwd: need H %% 8 == 0 and 1 <= k <= 63"); return -1; }
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
   AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
   if (dtype == CAPDEC_DTYPE_F32)

@@ -79,7 +79,7 @@ def test_create_rejects_bad_arguments():
     bad = M.DecoderConfig(hidden_dim=1023).to_c()
     assert lib.capdec_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0
     assert b"multiples of 8" in lib.capdec_last_error()
-    bad = M.DecoderConfig(num_positions=65).to_c()
+    bad = M.DecoderConfig(num_positions=64).to_c()
     assert lib.capdec_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0
     assert lib.capdec_destroy(None) == 0
     assert lib.capdec_workspace_bytes(None) == 0
