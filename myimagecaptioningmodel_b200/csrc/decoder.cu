@@ -136,8 +136,7 @@ template <typename T> class Decoder : public DecoderBase {
     CUDA_OK(cudaMemcpyAsync(b5.p, p->lstm_b, 4 * 4 * H, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b5d.p, b5.p, 4 * 5 * H, cudaMemcpyDeviceToDevice, s));
-    // b5d[4H:] += fc_hs_b  via a 1-row colsum
-    colsum_add<float>(lc, p->fc_hs_b, H, 1, H, b5d.as<float>() + 4 * H);
+    add_f32(lc, b5d.as<float>() + 4 * H, p->fc_hs_b, H);
     CUDA_OK(cudaGetLastError());
     bound = true;
     return 0;
@@ -171,12 +170,12 @@ template <typename T> class Decoder : public DecoderBase {
   }
   // dW[in,out] += X[rows,in]^T . dY[rows,out]   (fp32 atomics, split-K over rows)
   int wgrad(GemmContext& gc, const void* X, long ldx, int n_in, const void* dY, long ldy, int n_out, int rows,
-            float* dW, long ldw) {
+            float* dW, long ldw, const float* alpha_dev = nullptr) {
     if (!dW) return 0;
     GemmCall c;
     c.a_mn = true; c.b_mn = true;
     c.A = X; c.lda = ldx; c.B = dY; c.ldb = ldy; c.C = dW; c.ldc = ldw; c.M = n_in; c.N = n_out; c.K = rows;
-    c.epi.atomic = 1; c.epi.out_f32 = 1; c.splits = 0;
+    c.epi.atomic = 1; c.epi.out_f32 = 1; c.splits = 0; c.epi.alpha_dev = alpha_dev;
     return gemm<T>(gc, c);
   }
 
@@ -210,6 +209,7 @@ template <typename T> class Decoder : public DecoderBase {
     OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
     OK(lse.ensure(4 * M, &ws_bytes));
     OK(acc.ensure(64, &ws_bytes));
+    OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
 
     // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
     embed_gather<T>(lc, emb.as<T>(), E, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E);
@@ -250,7 +250,9 @@ template <typename T> class Decoder : public DecoderBase {
     }
     // masked cross entropy (model:163-171, 180-183, 205-212)
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
-    ce_fwd(lc, logits.as<float>(), Vp, V, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>());
+    // ... fused with the unscaled d logits = (softmax - onehot) * mask, so the fp32 logits leave HBM only once
+    ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
+                dlogits.as<T>());
     loss_finalize(lc, acc.as<float>());
     if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);           // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
@@ -278,7 +280,6 @@ template <typename T> class Decoder : public DecoderBase {
     const long M = (long)B * Tt;
     const int64_t* cap = last_cap;
     const capdec_grads& G = *gr;
-    OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
     OK(dproj.ensure(e * M * E, &ws_bytes));
     OK(doutp.ensure(e * M * H, &ws_bytes));
     OK(dactx.ensure(e * M * H, &ws_bytes));
@@ -316,18 +317,19 @@ template <typename T> class Decoder : public DecoderBase {
     const T* Hcur = hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
 
-    // d logits = (softmax - onehot) * mask / sum(mask)      (softmax_with_cross_entropy_grad + the mask/scale ops)
-    ce_bwd<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(),
-              inv_ntok ? inv_ntok : acc.as<float>() + 3, loss_scale, dlogits.as<T>());
-    colsum_add<T>(lc, dlogits.as<T>(), Vp, M, V, G.out_fc_bias);
+    // d logits = (softmax - onehot) * mask was written by the forward pass; the factor 1/sum(mask) * loss_scale
+    // (softmax_with_cross_entropy_grad + the mask/scale ops) is applied by its three consumers
+    float* gscale = acc.as<float>() + 4;
+    scale_scalar(lc, inv_ntok ? inv_ntok : acc.as<float>() + 3, loss_scale, gscale);
+    colsum_add<T>(lc, dlogits.as<T>(), Vp, M, V, G.out_fc_bias, gscale);
     // tied output projection (model:24-25): d proj, d Emb (output side), d fc_e
     {
       GemmCall c;
       c.A = dlogits.p; c.lda = Vp; c.B = emb.p; c.ldb = E; c.b_mn = true; c.C = dproj.p; c.ldc = E; c.M = (int)M; c.N = E;
-      c.K = V;
+      c.K = V; c.epi.alpha_dev = gscale;
       OK(gemm<T>(gc, c));
     }
-    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E));
+    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E, gscale));
     colsum_add<T>(lc, dproj.as<T>(), E, M, E, G.fc_e_b);
     OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, (int)M, G.fc_e_w, E));
     // out = tanh(fc_o(ctx + p_hid))   (model:115)

@@ -25,6 +25,7 @@ struct GemmEpi {
   int out_f32 = 0;               // C is fp32 (otherwise T)
   int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
   int aux_padded = 0;            // bias / addend / dact_y are readable up to the next multiple of 8 columns past N
+  const float* alpha_dev = nullptr;  // device scalar multiplied into the accumulator before anything else
 };
 
 struct GemmCall {
@@ -41,7 +42,7 @@ struct GemmCall {
 // element-wise epilogue shared by both kernels
 template <typename T>
 __device__ __forceinline__ float epi_value(float acc, int m, int n, const GemmEpi& e) {
-  float v = acc;
+  float v = e.alpha_dev ? acc * __ldg(e.alpha_dev) : acc;
   if (e.bias) v += __ldg(e.bias + n);
   if (e.addend) v += to_f(reinterpret_cast<const T*>(e.addend)[(long)m * e.ld_add + n]);
   if (e.act == ACT_TANH) v = tanh_t<fast_math<T>::value>(v);

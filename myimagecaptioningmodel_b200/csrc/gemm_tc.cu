@@ -117,8 +117,8 @@ __device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, 
 // epilogue has only two warps per scheduler, so exposed latencies are what it costs).
 template <bool OUT_F32, bool FULL>
 __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float* bias_t, const bf16* add_p,
-                                                const bf16* y_p, bool do_tanh, int left, uint8_t* dst_row, uint32_t swz,
-                                                uint32_t chunk0) {
+                                                const bf16* y_p, bool do_tanh, float alpha, int left, uint8_t* dst_row,
+                                                uint32_t swz, uint32_t chunk0) {
   uint32_t r[32];
   uint4 aq[4], yq[4];
   __syncwarp();  // tcgen05.ld is .sync.aligned
@@ -139,7 +139,7 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
     if (FULL || g * 8 < left) {
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * alpha;
       if (bias_t) {
         const float4 b0 = *reinterpret_cast<const float4*>(bias_t + g * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias_t + g * 8 + 4);
@@ -333,6 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
                               ? reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + n0 : nullptr;
         const bool do_tanh = epi.act == ACT_TANH;
+        const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
         const bool f32_out = epi.out_f32 || epi.atomic;
         const int pw = f32_out ? 32 : 64;           // columns per pass
         const int n_pass = BN / pw;
@@ -353,18 +354,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bf16* ap = add_p ? add_p + c0 : nullptr;
           const bf16* yp = y_p ? y_p + c0 : nullptr;
           if (f32_out) {
-            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, left, my_row, swz, 0);
-            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, left, my_row, swz, 0);
+            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
           } else {
 #pragma unroll 1
             for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
               const int o = sub * 32;
               if (left - o >= 32)
                 epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
-                                             yp ? yp + o : nullptr, do_tanh, left - o, my_row, swz, (uint32_t)(sub * 4));
+                                             yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
+                                             (uint32_t)(sub * 4));
               else
                 epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
-                                              yp ? yp + o : nullptr, do_tanh, left - o, my_row, swz, (uint32_t)(sub * 4));
+                                              yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
+                                             (uint32_t)(sub * 4));
             }
           }
           if (ps == my_last) {

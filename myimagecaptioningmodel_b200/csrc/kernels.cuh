@@ -42,7 +42,9 @@ void lstm_cell_bwd(LaunchCtx c, int B, int H, const T* dH_head, const T* dHprev_
 // out[b, :] = sum_t x[(t*B+b), :]
 template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo);
 // out[n] += sum_m x[m, n]    (fp32 atomics)
-template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out);
+// out[n] += scale * sum_m x[m, n]   (fp32 atomics; scale read from a device scalar, or 1)
+template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out, const float* scale_dev = nullptr);
+void add_f32(LaunchCtx c, float* dst, const float* src, long n);
 // dEmb[id] += dX[(t*B+b)]  for id != pad        (lookup_table_v2_grad, padding_idx)
 template <typename T>
 void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
@@ -77,6 +79,13 @@ void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
 //   lse[m];  acc[0] += sum(ce * mask), acc[1] += sum(mask)
 void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* caption, long cap_ld, int B, int steps,
             int pad, float* lse, float* acc);
+// fused: the above plus the UNSCALED gradient  dlogits[m, n] = (softmax - onehot) * mask  (columns [V, Vp) zeroed);
+// the 1/sum(mask) * loss_scale factor is applied by the consumers (GemmEpi::alpha_dev, colsum_add scale)
+template <typename T>
+void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+              int steps, int pad, float* lse, float* acc, T* dlogits);
+// out[0] = in[0] * s
+void scale_scalar(LaunchCtx c, const float* in, float s, float* out);
 // acc[2] = acc[0] / acc[1] (the loss), acc[3] = 1 / acc[1]
 void loss_finalize(LaunchCtx c, float* acc);
 // dlogits[m, n] = (exp(l - lse) - [n == target]) * mask * (*scale) * loss_scale; columns [V, Vp) are zeroed

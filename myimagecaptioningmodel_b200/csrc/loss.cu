@@ -46,6 +46,62 @@ ce_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const int64_t* 
   }
 }
 
+// one pass for the online (max, sum), one L2-resident pass for the gradient: logits are read from HBM once
+template <typename T>
+__global__ void __launch_bounds__(kCeThreads)
+ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
+                long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits) {
+  __shared__ float scratch[32];
+  const long m = blockIdx.x;
+  const float* row = logits + m * ldl;
+  T* out = dlogits + m * (long)Vp;
+  const int64_t tgt = target_of(caption, cap_ld, B, m);
+  const int V4 = V & ~3;
+  float mx = -INFINITY, sum = 0.f;
+  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + n);
+    const float lm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (lm > mx) { sum *= __expf(mx - lm); mx = lm; }
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) {
+    const float x = row[n];
+    if (x > mx) { sum *= __expf(mx - x); mx = x; }
+    sum += __expf(x - mx);
+  }
+  const float gmx = block_max(mx, scratch);
+  const float gsum = block_sum(mx > -INFINITY ? sum * __expf(mx - gmx) : 0.f, scratch);
+  const float l = gmx + logf(gsum);
+  if (threadIdx.x == 0) {
+    lse[m] = l;
+    if (tgt != pad) {
+      atomicAdd(acc + 0, l - row[tgt]);
+      atomicAdd(acc + 1, 1.f);
+    }
+  }
+  if (tgt == pad) {  // masked position: zero gradient row
+    for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      store8(out + n, z);
+    }
+    return;
+  }
+  for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
+    float v[8];
+    if (n + 8 <= V) {
+      load8(row + n, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __expf(v[i] - l) - ((n + i) == tgt ? 1.f : 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (n + i < V) ? __expf(row[n + i] - l) - ((n + i) == tgt ? 1.f : 0.f) : 0.f;
+    }
+    store8(out + n, v);
+  }
+}
+
+__global__ void scale_scalar_kernel(const float* in, float s, float* out) { out[0] = in[0] * s; }
+
 __global__ void loss_finalize_kernel(float* acc) {
   acc[2] = acc[0] / acc[1];
   acc[3] = 1.f / acc[1];
@@ -109,6 +165,142 @@ __device__ __forceinline__ Cand warp_best(Cand c) {
 constexpr int kBeamThreads = 512;
 constexpr int kMaxBeam = 8;
 
+// Single pass over the logits: for every live prefix each thread keeps (a) an online log-sum-exp (running max and
+// sum) and (b) its `beam` best (logit, token) pairs in registers; within one prefix the candidate score
+// score_p + (x - lse_p) is monotone in the raw logit x, so the per-prefix top-`beam` by x contains every global
+// winner.  Block merge: the per-thread lists go to shared memory and `beam` rounds of block arg-max pick the winners
+// (ties -> lower token), then beam*beam scored candidates are merged across prefixes (ties -> lower prefix, token).
+// A finished prefix offers exactly one candidate (itself, emitting pad, score unchanged).
+template <int BEAM>
+__global__ void __launch_bounds__(kBeamThreads)
+beam_step_generic_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int step, int T_total, int pad, int stop,
+                 int finish_on_stop, const float* __restrict__ score_in, float* __restrict__ score_out,
+                 const int* __restrict__ fin_in, int* __restrict__ fin_out, const int* __restrict__ hist_in,
+                 int* __restrict__ hist_out, int* __restrict__ tok_out, int* __restrict__ src_out) {
+  __shared__ float scratch[32];
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float cand_v[kBeamThreads * BEAM];
+  __shared__ int cand_i[kBeamThreads * BEAM];
+  __shared__ float win_v[kMaxBeam * kMaxBeam];   // scored candidates of all prefixes
+  __shared__ int win_i[kMaxBeam * kMaxBeam];     // flat index p*V + token
+  __shared__ int sel_idx[kMaxBeam];
+  __shared__ float sel_val[kMaxBeam];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int INT_BIG = 0x7fffffff;
+  const bool greedy = (beam == 1 && !finish_on_stop);
+  int n_win = 0;  // number of scored candidates written so far (uniform across the block)
+  for (int p = 0; p < beam; ++p) {
+    const float sc = score_in[img * beam + p];
+    if (!(sc > -INFINITY)) continue;                       // dead prefix (uniform branch)
+    if (finish_on_stop && fin_in[img * beam + p]) {
+      if (tid == 0) { win_v[n_win] = sc; win_i[n_win] = p * V + pad; }
+      ++n_win;
+      continue;
+    }
+    const float* row = logits + ((long)img * beam + p) * ldl;
+    float bv[BEAM];
+    int bi[BEAM];
+#pragma unroll
+    for (int r = 0; r < BEAM; ++r) { bv[r] = -INFINITY; bi[r] = INT_BIG; }
+    float mx = -INFINITY, sum = 0.f;
+    for (int n = tid; n < V; n += kBeamThreads) {
+      const float x = row[n];
+      if (x > mx) { sum = sum * __expf(mx - x) + 1.f; mx = x; } else { sum += __expf(x - mx); }
+      if (better(x, n, bv[BEAM - 1], bi[BEAM - 1])) {      // sorted insertion (registers, unrolled)
+        bv[BEAM - 1] = x; bi[BEAM - 1] = n;
+#pragma unroll
+        for (int r = BEAM - 1; r > 0; --r) {
+          if (better(bv[r], bi[r], bv[r - 1], bi[r - 1])) {
+            const float tv = bv[r]; bv[r] = bv[r - 1]; bv[r - 1] = tv;
+            const int ti = bi[r]; bi[r] = bi[r - 1]; bi[r - 1] = ti;
+          }
+        }
+      }
+    }
+    // block log-sum-exp from the per-thread (max, sum) pairs
+    const float gmx = block_max(mx, scratch);
+    const float gsum = block_sum(mx > -INFINITY ? sum * __expf(mx - gmx) : 0.f, scratch);
+    const float lse = gmx + logf(gsum);
+#pragma unroll
+    for (int r = 0; r < BEAM; ++r) { cand_v[tid * BEAM + r] = bv[r]; cand_i[tid * BEAM + r] = bi[r]; }
+    __syncthreads();
+    // `beam` rounds of block arg-max over the kBeamThreads*BEAM per-thread winners
+    for (int r = 0; r < beam; ++r) {
+      Cand best{-INFINITY, INT_BIG};
+      for (int c = tid; c < kBeamThreads * BEAM; c += kBeamThreads) {
+        const float v = cand_v[c];
+        const int i = cand_i[c];
+        if (i != INT_BIG && better(v, i, best.v, best.idx)) { best.v = v; best.idx = i; }
+      }
+      best = warp_best(best);
+      if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
+      __syncthreads();
+      if (warp == 0) {
+        Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
+        c = warp_best(c);
+        if (lane == 0) {
+          // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
+          win_v[n_win + r] = (c.idx == INT_BIG) ? -INFINITY : (greedy ? c.v : sc + (c.v - lse));
+          win_i[n_win + r] = (c.idx == INT_BIG) ? INT_BIG : p * V + c.idx;
+          if (greedy) scratch[31] = sc + (c.v - lse);
+          s_i[0] = c.idx;
+        }
+      }
+      __syncthreads();
+      const int taken = s_i[0];
+      // remove the winner from the pool (token ids are unique within a prefix)
+      for (int c = tid; c < kBeamThreads * BEAM; c += kBeamThreads)
+        if (cand_i[c] == taken) cand_i[c] = INT_BIG;
+      __syncthreads();
+    }
+    n_win += beam;
+  }
+  __syncthreads();
+  // merge the scored candidates of all prefixes: `beam` winners, ties -> lower flat index
+  if (warp == 0) {
+    for (int r = 0; r < beam; ++r) {
+      Cand best{-INFINITY, INT_BIG};
+      for (int c = lane; c < n_win; c += 32) {
+        const int i = win_i[c];
+        if (i != INT_BIG && better(win_v[c], i, best.v, best.idx)) { best.v = win_v[c]; best.idx = i; }
+      }
+      best = warp_best(best);
+      if (lane == 0) { sel_idx[r] = best.idx; sel_val[r] = best.v; }
+      __syncwarp();
+      for (int c = lane; c < n_win; c += 32)
+        if (win_i[c] == best.idx) win_i[c] = INT_BIG;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // write-out: token, back-pointer, score, finished flag, history (one warp per selected beam)
+  if (warp < beam) {
+    const int r = warp;
+    int idx = sel_idx[r];
+    float v = sel_val[r];
+    int src, tok;
+    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }  // fewer live candidates than beams (V < beam only)
+    else { src = idx / V; tok = idx % V; }
+    if (greedy && idx != INT_BIG) v = scratch[31];
+    const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
+    if (lane == 0) {
+      tok_out[img * beam + r] = tok;
+      src_out[img * beam + r] = src;
+      score_out[img * beam + r] = v;
+      fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
+    }
+    const int* hin = hist_in + ((long)img * beam + src) * T_total;
+    int* hout = hist_out + ((long)img * beam + r) * T_total;
+    for (int t = lane; t < T_total; t += 32) hout[t] = (t == step) ? tok : (t < step ? hin[t] : 0);
+  }
+}
+
+
+// Fast path for V <= kBeamThreads * EPT: every thread keeps its EPT logits of the row in registers (all loads in
+// flight at once), computes the block log-sum-exp from them, and each of the `beam` rounds is a block arg-max over the
+// per-thread maxima; only the winner's owner rescans its registers.  No divergent insertion, ~6x fewer instructions.
+template <int EPT>
 __global__ void __launch_bounds__(kBeamThreads)
 beam_step_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int step, int T_total, int pad, int stop,
                  int finish_on_stop, const float* __restrict__ score_in, float* __restrict__ score_out,
@@ -117,77 +309,97 @@ beam_step_kernel(const float* __restrict__ logits, long ldl, int V, int beam, in
   __shared__ float scratch[32];
   __shared__ float s_v[32];
   __shared__ int s_i[32];
-  __shared__ float lse_s[kMaxBeam];
+  __shared__ float win_v[kMaxBeam * kMaxBeam];   // scored candidates of all prefixes
+  __shared__ int win_i[kMaxBeam * kMaxBeam];     // flat index p*V + token
   __shared__ int sel_idx[kMaxBeam];
   __shared__ float sel_val[kMaxBeam];
+  __shared__ float greedy_score;
   const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int INT_BIG = 0x7fffffff;
   const bool greedy = (beam == 1 && !finish_on_stop);
-  // log-sum-exp of every live, unfinished prefix
+  int n_win = 0;  // scored candidates written so far (uniform across the block)
   for (int p = 0; p < beam; ++p) {
     const float sc = score_in[img * beam + p];
-    const bool live = sc > -INFINITY;
-    const bool fin = finish_on_stop && fin_in[img * beam + p];
-    if (!live || fin) { if (tid == 0) lse_s[p] = 0.f; continue; }  // uniform branch (depends on p only)
+    if (!(sc > -INFINITY)) continue;                       // dead prefix (uniform branch)
+    if (finish_on_stop && fin_in[img * beam + p]) {        // finished: one candidate, itself + pad, score unchanged
+      if (tid == 0) { win_v[n_win] = sc; win_i[n_win] = p * V + pad; }
+      ++n_win;
+      continue;
+    }
     const float* row = logits + ((long)img * beam + p) * ldl;
+    float x[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int n = tid + i * kBeamThreads;
+      x[i] = (n < V) ? row[n] : -INFINITY;
+    }
     float mx = -INFINITY;
-    for (int n = tid; n < V; n += kBeamThreads) mx = fmaxf(mx, row[n]);
-    mx = block_max(mx, scratch);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) mx = fmaxf(mx, x[i]);
+    const float gmx = block_max(mx, scratch);
     float sum = 0.f;
-    for (int n = tid; n < V; n += kBeamThreads) sum += expf(row[n] - mx);
-    sum = block_sum(sum, scratch);
-    if (tid == 0) lse_s[p] = mx + logf(sum);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) sum += __expf(x[i] - gmx);   // exp(-inf) = 0 for the padding slots
+    const float lse = gmx + logf(block_sum(sum, scratch));
+    for (int r = 0; r < beam; ++r) {
+      // local arg-max over the registers (ties -> lower token = lower i)
+      float lv = -INFINITY;
+      int li = INT_BIG;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i)
+        if (x[i] > lv) { lv = x[i]; li = tid + i * kBeamThreads; }
+      Cand best = warp_best(Cand{lv, li});
+      if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
+      __syncthreads();
+      if (warp == 0) {
+        Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
+        c = warp_best(c);
+        if (lane == 0) {
+          // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
+          win_v[n_win + r] = (c.idx == INT_BIG) ? -INFINITY : (greedy ? c.v : sc + (c.v - lse));
+          win_i[n_win + r] = (c.idx == INT_BIG) ? INT_BIG : p * V + c.idx;
+          if (greedy) greedy_score = sc + (c.v - lse);
+          s_i[0] = c.idx;
+        }
+      }
+      __syncthreads();
+      const int taken = s_i[0];
+      __syncthreads();  // s_i[0] is rewritten by the next round
+      if (taken != INT_BIG && (taken % kBeamThreads) == tid) {
+        const int slot = taken / kBeamThreads;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+          if (i == slot) x[i] = -INFINITY;                  // remove the winner from this thread's pool
+      }
+    }
+    n_win += beam;
   }
   __syncthreads();
-  // `beam` rounds of block arg-max over the (prefix, token) candidates; ties -> lower flat index
-  for (int r = 0; r < beam; ++r) {
-    Cand best{-INFINITY, INT_BIG};
-    for (int p = 0; p < beam; ++p) {
-      const float sc = score_in[img * beam + p];
-      if (!(sc > -INFINITY)) continue;
-      const bool fin = finish_on_stop && fin_in[img * beam + p];
-      if (fin) {
-        // a finished prefix offers exactly one candidate: itself, emitting pad, score unchanged
-        if (tid == 0) {
-          const int idx = p * V + pad;
-          bool taken = false;
-          for (int q = 0; q < r; ++q) taken |= (sel_idx[q] == idx);
-          if (!taken && better(sc, idx, best.v, best.idx)) { best.v = sc; best.idx = idx; }
-        }
-        continue;
+  // merge the scored candidates of all prefixes: `beam` winners, ties -> lower flat index
+  if (warp == 0) {
+    for (int r = 0; r < beam; ++r) {
+      Cand best{-INFINITY, INT_BIG};
+      for (int c = lane; c < n_win; c += 32) {
+        const int i = win_i[c];
+        if (i != INT_BIG && better(win_v[c], i, best.v, best.idx)) { best.v = win_v[c]; best.idx = i; }
       }
-      const float* row = logits + ((long)img * beam + p) * ldl;
-      const float l = lse_s[p];
-      for (int n = tid; n < V; n += kBeamThreads) {
-        // greedy (beam 1, never finishes) ranks the raw logits exactly like layers.argmax (model:120)
-        const float v = greedy ? row[n] : sc + (row[n] - l);
-        const int idx = p * V + n;
-        if (better(v, idx, best.v, best.idx)) {
-          bool taken = false;
-          for (int q = 0; q < r; ++q) taken |= (sel_idx[q] == idx);
-          if (!taken) { best.v = v; best.idx = idx; }
-        }
-      }
+      best = warp_best(best);
+      if (lane == 0) { sel_idx[r] = best.idx; sel_val[r] = best.v; }
+      __syncwarp();
+      for (int c = lane; c < n_win; c += 32)
+        if (win_i[c] == best.idx) win_i[c] = INT_BIG;
+      __syncwarp();
     }
-    best = warp_best(best);
-    if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
-    __syncthreads();
-    if (warp == 0) {
-      Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
-      c = warp_best(c);
-      if (lane == 0) { sel_idx[r] = c.idx; sel_val[r] = c.v; }
-    }
-    __syncthreads();
   }
-  // write-out: token, back-pointer, score, finished flag, history (one warp per selected beam)
+  __syncthreads();
   if (warp < beam) {
     const int r = warp;
     int idx = sel_idx[r];
     float v = sel_val[r];
     int src, tok;
-    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }  // fewer live candidates than beams (cannot happen for V >= beam)
+    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }
     else { src = idx / V; tok = idx % V; }
-    if (greedy && idx != INT_BIG) v = score_in[img * beam] + (v - lse_s[0]);
+    if (greedy && idx != INT_BIG) v = greedy_score;
     const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
     if (lane == 0) {
       tok_out[img * beam + r] = tok;
@@ -242,6 +454,20 @@ void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* ca
   ce_fwd_kernel<<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, caption, cap_ld, B, pad, lse, acc);
   if (c.launches) ++*c.launches;
 }
+template <typename T>
+void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+              int steps, int pad, float* lse, float* acc, T* dlogits) {
+  ce_fused_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits);
+  if (c.launches) ++*c.launches;
+}
+template void ce_fused<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
+                              float*);
+template void ce_fused<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
+                             bf16*);
+void scale_scalar(LaunchCtx c, const float* in, float s, float* out) {
+  scale_scalar_kernel<<<1, 1, 0, c.stream>>>(in, s, out);
+  if (c.launches) ++*c.launches;
+}
 void loss_finalize(LaunchCtx c, float* acc) {
   loss_finalize_kernel<<<1, 1, 0, c.stream>>>(acc);
   if (c.launches) ++*c.launches;
@@ -260,9 +486,16 @@ void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, in
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
                const int* hist_in, int* hist_out, int* tok_out, int* src_out) {
-  beam_step_kernel<<<n_img, kBeamThreads, 0, c.stream>>>(logits, ldl, V, beam, step, T_total, pad, stop, finish_on_stop,
-                                                        score_in, score_out, fin_in, fin_out, hist_in, hist_out,
-                                                        tok_out, src_out);
+#define LAUNCH_BEAM(KERNEL)                                                                                          \
+  KERNEL<<<n_img, kBeamThreads, 0, c.stream>>>(logits, ldl, V, beam, step, T_total, pad, stop, finish_on_stop, score_in, \
+                                               score_out, fin_in, fin_out, hist_in, hist_out, tok_out, src_out)
+  if (V <= kBeamThreads * 8) LAUNCH_BEAM(beam_step_kernel<8>);
+  else if (V <= kBeamThreads * 32) LAUNCH_BEAM(beam_step_kernel<32>);
+  else if (beam <= 1) LAUNCH_BEAM(beam_step_generic_kernel<1>);
+  else if (beam <= 2) LAUNCH_BEAM(beam_step_generic_kernel<2>);
+  else if (beam <= 4) LAUNCH_BEAM(beam_step_generic_kernel<4>);
+  else LAUNCH_BEAM(beam_step_generic_kernel<8>);
+#undef LAUNCH_BEAM
   if (c.launches) ++*c.launches;
 }
 template <typename T>

@@ -5,6 +5,8 @@
 
 namespace capdec {
 
+void set_error(const char* fmt, ...);
+
 namespace {
 
 inline int grid_for(long work_items, int threads = 256, int max_waves = 8) {
@@ -254,17 +256,57 @@ __global__ void sum_over_steps_kernel(const T* __restrict__ x, long ld, int B, i
   }
 }
 
-// grid (ceil(N/256), row_chunks): each thread owns one column of a row chunk
+// grid (ceil(N/256), row_chunks), block = 32 column-threads x 16 row groups (one warp = one row group: 512
+// contiguous bytes per row).  Each thread owns 8 adjacent columns of every 16th row of the chunk with four 128-bit
+// loads in flight; the 16 row groups are reduced in shared memory and the block issues one set of fp32 atomics.
+// Same-address atomics from different SMs serialise at ~100 ns each, so the chunk count (= atomics per address) is
+// kept at <= 32 and parallelism comes from the column split instead.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk,
-                              float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+__global__ void __launch_bounds__(512)
+colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
+              const float* __restrict__ scale_dev) {
+  __shared__ float red[15][8][33];
+  const float sc = scale_dev ? __ldg(scale_dev) : 1.f;
+  const int ct = threadIdx.x & 31, rg = threadIdx.x >> 5;  // column thread, row group
+  const int n0 = (blockIdx.x * 32 + ct) * 8;
   const long m0 = (long)blockIdx.y * rows_per_chunk;
   const long m1 = (m0 + rows_per_chunk < M) ? m0 + rows_per_chunk : M;
-  float acc = 0.f;
-  for (long m = m0; m < m1; ++m) acc += to_f(x[m * ld + n]);
-  atomicAdd(out + n, acc);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n0 + 8 <= N) {
+    long m = m0 + rg;
+    for (; m + 48 < m1; m += 64) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(x + (m + 16 * u) * ld + n0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; m < m1; m += 16) {
+      float v[8];
+      load8(x + m * ld + n0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  } else if (n0 < N) {  // ragged right edge
+    for (long m = m0 + rg; m < m1; m += 16)
+      for (int j = 0; j < 8 && n0 + j < N; ++j) acc[j] += to_f(x[m * ld + n0 + j]);
+  }
+  if (rg > 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rg - 1][j][ct] = acc[j];
+  }
+  __syncthreads();
+  if (rg == 0 && n0 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[j];
+#pragma unroll
+      for (int g = 0; g < 15; ++g) v += red[g][j][ct];
+      if (n0 + j < N) atomicAdd(out + n0 + j, v * sc);
+    }
+  }
 }
 
 template <typename T>
@@ -279,6 +321,12 @@ __global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, c
     const long id = ids[(long)b * ids_ld + t];
     if (id != pad) atomicAdd(dEmb + id * E + e, to_f(dX[m * ld + e]));
   }
+}
+
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] += src[i];
 }
 
 __global__ void fill_kernel(float* p, float v, long n) {
@@ -345,15 +393,20 @@ template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int 
   sum_over_steps_kernel<T><<<grid_for((long)B * (N / 8), 128), 128, 0, c.stream>>>(x, ld, B, steps, N, out, ldo);
   BUMP(c);
 }
-template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out) {
+template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out, const float* scale_dev) {
   if (M <= 0 || N <= 0) return;
+  // 128-bit loads need 16-byte (bf16) / 32-byte (fp32) aligned rows
+  if ((ld % 8) || ((uintptr_t)x % (8 * sizeof(T)))) {
+    set_error("colsum_add: operand must have an 8-element aligned pitch and base");
+    return;
+  }
   const int col_blocks = (N + 255) / 256;
-  long chunks = (4L * kNumSMs + col_blocks - 1) / col_blocks;
-  if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
+  long chunks = 32;
+  if (chunks > (M + 15) / 16) chunks = (M + 15) / 16;
   if (chunks < 1) chunks = 1;
   const long rpc = (M + chunks - 1) / chunks;
   dim3 grid(col_blocks, (unsigned)((M + rpc - 1) / rpc));
-  colsum_kernel<T><<<grid, 256, 0, c.stream>>>(x, ld, M, N, rpc, out);
+  colsum_kernel<T><<<grid, 512, 0, c.stream>>>(x, ld, M, N, rpc, out, scale_dev);
   BUMP(c);
 }
 template <typename T>
@@ -361,6 +414,11 @@ void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* 
                        int pad, float* dEmb) {
   embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, ids, ids_ld, B, steps, pad,
                                                                              dEmb);
+  BUMP(c);
+}
+void add_f32(LaunchCtx c, float* dst, const float* src, long n) {
+  if (n <= 0) return;
+  add_f32_kernel<<<grid_for(n), 256, 0, c.stream>>>(dst, src, n);
   BUMP(c);
 }
 void fill_f32(LaunchCtx c, float* p, float v, long n) {
@@ -382,7 +440,7 @@ void fill_f32(LaunchCtx c, float* p, float v, long n) {
   template void lstm_cell_bwd<T>(LaunchCtx, int, int, const T*, const T*, const float*, const float*, float*,          \
                                  const T*, const float*, const float*, T*, long);                                      \
   template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long);                                 \
-  template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*);                                           \
+  template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*, const float*);                                           \
   template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, const int64_t*, long, int, int, int, float*);
 
 INSTANTIATE(float)
