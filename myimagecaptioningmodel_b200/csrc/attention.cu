@@ -11,6 +11,7 @@
 // every query row of the chunk (34 teacher-forced steps, or the beams of one image at inference) streams through.
 // Scores use one warp per position with 128-bit conflict-free shared loads and a shuffle reduction; the context
 // pass gives each thread 4 adjacent columns.
+#include "gemm.cuh"
 #include "kernels.cuh"
 
 namespace capdec {
@@ -289,122 +290,62 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   }
 }
 
-// ---- backward (A): d alpha_j = dctx . v_j / (k+1);  de = softmax'(alpha, d alpha);  db_alpha += sum de ----
-template <typename T, bool STAGE>
-__global__ void __launch_bounds__(kFwdThreads, 1)
-attn_bwd_scores_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ vals,
-                       const T* __restrict__ sentinel, const float* __restrict__ alpha, const T* __restrict__ dactx,
-                       float* __restrict__ de, float* __restrict__ db_alpha) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int H = s.H, k = s.k, P = s.k + 1;
-  const SmemLayout L = make_layout(H, k, (int)sizeof(T), STAGE ? 1 : 0);
-  float* d_s = reinterpret_cast<float*>(smem + L.off_e);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  const int img = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  const int q0 = chunk * q_per_chunk, q1 = min(s.q_per_img, q0 + q_per_chunk);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const T* Vt = vals + (long)img * k * H;
-  if (STAGE) {
-    const uint32_t tile_bytes = (uint32_t)(k * H * sizeof(T));
-    if (tid == 0) {
-      mbar_init(bar, 1);
-      mbar_fence_init();
-      mbar_expect_tx(bar, tile_bytes);
-      tma_bulk_g2s(smem + L.off_tile0, Vt, tile_bytes, bar);
-    }
-    Vt = reinterpret_cast<const T*>(smem + L.off_tile0);
-    __syncthreads();
-    mbar_wait(bar, 0);
-  }
+// ---- backward, row-wise part (one warp per query row) -------------------------------------------------------
+//   d alpha_j (j < k) arrives UNSCALED from the batched tensor-core GEMM  dal[row, j] = dctx[row, :] . v_j ;
+//   here: d alpha_k = dctx . sentinel,  de = alpha * (d alpha - sum alpha d alpha) / (k+1)  (soft-max backward),
+//   db_alpha += sum de,  dS_ctx = alpha_k / (k+1) * dctx,  and the storage-type copy alpha_T = alpha / (k+1)
+//   that the second batched GEMM (d values) uses as its A operand.
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const T* __restrict__ sentinel,
+                     const float* __restrict__ alpha, const T* __restrict__ dactx, const float* __restrict__ dal,
+                     int ld_dal, float* __restrict__ de, T* __restrict__ alpha_T, int ld_at, T* __restrict__ dS,
+                     float* __restrict__ db_alpha) {
+  const int lane = threadIdx.x & 31;
+  const int P = k + 1;
   const float inv_p = 1.f / (float)P;
   float db_acc = 0.f;
-  for (int q = q0; q < q1; ++q) {
-    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+  for (long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += (long)gridDim.x * (blockDim.x >> 5)) {
     const T* dc = dactx + row * H;
-    for (int j = warp; j < P; j += nwarps) {
-      const T* vj = (j < k) ? (Vt + (long)j * H) : (sentinel + row * H);
-      float acc = 0.f;
-      for (int h0 = lane * 8; h0 < H; h0 += 256) {
-        float a[8], b[8];
-        load8(vj + h0, a);
-        load8(dc + h0, b);
+    const float a0 = (lane < P) ? alpha[row * P + lane] : 0.f;
+    const float a1 = (lane + 32 < P) ? alpha[row * P + lane + 32] : 0.f;
+    if (lane < k) alpha_T[row * ld_at + lane] = from_f<T>(a0 * inv_p);
+    if (lane + 32 < k) alpha_T[row * ld_at + lane + 32] = from_f<T>(a1 * inv_p);
+    const float ak = __shfl_sync(0xffffffffu, (k < 32) ? a0 : a1, k & 31);
+    float dot_s = 0.f;
+    for (int h0 = lane * 8; h0 < H; h0 += 256) {
+      float d[8], sv[8];
+      load8(dc + h0, d);
+      if (position_softmax) {
+        load8(sentinel + row * H + h0, sv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+        for (int i = 0; i < 8; ++i) dot_s = fmaf(d[i], sv[i], dot_s);
       }
-      acc = warp_sum(acc);
-      if (lane == 0) d_s[j] = acc * inv_p;
+      const float sc = ak * inv_p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] *= sc;
+      store8(dS + row * H + h0, d);
     }
-    __syncthreads();
-    if (warp == 0) {
-      float dot = 0.f;
-      for (int j = lane; j < P; j += 32) dot += alpha[row * P + j] * d_s[j];
-      dot = warp_sum(dot);
-      for (int j = lane; j < P; j += 32) {
-        const float v = alpha[row * P + j] * (d_s[j] - dot);
-        de[row * P + j] = v;
-        db_acc += v;
-      }
+    if (position_softmax) {
+      dot_s = warp_sum(dot_s);
+      float d0 = 0.f, d1 = 0.f;  // d alpha for positions lane, lane + 32
+      if (lane < k) d0 = dal[row * ld_dal + lane];
+      if (lane + 32 < k) d1 = dal[row * ld_dal + lane + 32];
+      if (lane == k) d0 = dot_s;
+      if (lane + 32 == k) d1 = dot_s;
+      d0 *= inv_p;
+      d1 *= inv_p;
+      const float dot = warp_sum(a0 * d0 + a1 * d1);
+      const float e0 = a0 * (d0 - dot), e1 = a1 * (d1 - dot);
+      if (lane < P) de[row * P + lane] = e0;
+      if (lane + 32 < P) de[row * P + lane + 32] = e1;
+      db_acc += e0 + e1;
     }
-    __syncthreads();
   }
-  if (warp == 0) {
+  if (position_softmax) {
     db_acc = warp_sum(db_acc);
     if (lane == 0) atomicAdd(db_alpha, db_acc);
-  }
-}
-
-// dS_ctx[row, h] = alpha[row, k] * dctx[row, h] / (k+1)
-template <typename T>
-__global__ void ds_ctx_kernel(long rows, int H, int P, const float* __restrict__ alpha, const T* __restrict__ dactx,
-                              T* __restrict__ dS) {
-  const int vec_per_row = H / 8;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x, n = rows * vec_per_row;
-  const float inv_p = 1.f / (float)P;
-  for (; i < n; i += stride) {
-    const long r = i / vec_per_row;
-    const int h0 = (int)(i % vec_per_row) * 8;
-    const float a = alpha[r * P + (P - 1)] * inv_p;
-    float v[8];
-    load8(dactx + r * H + h0, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= a;
-    store8(dS + r * H + h0, v);
-  }
-}
-
-// ---- backward (B): d values (pre-tanh).  thread = one column h of one image, accumulators over the k positions ----
-//   dV_j[h] = 1/(k+1) sum_q alpha[q,j] dctx[q,h];   d(pre) = dV * (1 - v^2)       -> dKV[img*k + j, h]
-template <typename T, int KC>
-__global__ void __launch_bounds__(256)
-attn_bwd_dv_kernel(AttnShape s, const T* __restrict__ vals, const float* __restrict__ alpha,
-                   const T* __restrict__ dactx, T* __restrict__ dKV) {
-  extern __shared__ __align__(16) float a_s[];  // [q_per_img, P]
-  const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
-  const int img = blockIdx.x, h = blockIdx.y * blockDim.x + threadIdx.x;
-  for (int i = threadIdx.x; i < nq * P; i += blockDim.x) {
-    const int q = i / P, j = i % P;
-    a_s[i] = alpha[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j];
-  }
-  __syncthreads();
-  if (h >= H) return;
-  float acc[KC];
-#pragma unroll
-  for (int j = 0; j < KC; ++j) acc[j] = 0.f;
-  for (int q = 0; q < nq; ++q) {
-    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
-    const float d = to_f(dactx[row * H + h]);
-#pragma unroll
-    for (int j = 0; j < KC; ++j)
-      if (j < k) acc[j] = fmaf(a_s[q * P + j], d, acc[j]);
-  }
-  const float inv_p = 1.f / (float)P;
-#pragma unroll
-  for (int j = 0; j < KC; ++j) {
-    if (j < k) {
-      const float v = to_f(vals[((long)img * k + j) * H + h]);
-      dKV[((long)img * k + j) * (2 * H) + h] = from_f<T>(acc[j] * inv_p * (1.f - v * v));
-    }
   }
 }
 
@@ -525,18 +466,50 @@ void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
 }
 
 template <typename T>
-void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
-                   const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx, float* de, T* dS_ctx,
-                   T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha, float* db_alpha) {
-  if (s.n_img <= 0 || s.q_per_img <= 0) return;
+int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb,
+                  const T* sent_emb, const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx,
+                  float* dal, T* alpha_T, float* de, T* dS_ctx, T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha,
+                  float* db_alpha) {
+  if (s.n_img <= 0 || s.q_per_img <= 0) return 0;
   const int H = s.H, k = s.k, P = s.k + 1;
   const long rows = (long)s.n_img * s.q_per_img;
+  const long r0 = s.row0_stride, qs = s.q_stride;
+  if (s.position_softmax) {
+    // d alpha[q, j] = dctx[q, :] . v_j  for the k image positions: one [q_per_img x k x H] GEMM per image on the
+    // tensor cores (batched through 3-D tensor maps; rows of one image are q_stride apart)
+    GemmCall g;
+    g.A = dactx; g.lda = qs * H; g.batch_a = r0 * H;
+    g.B = vals; g.ldb = H; g.batch_b = (long)k * H;
+    g.C = dal; g.ldc = qs * kDalLd; g.batch_c = r0 * kDalLd;
+    g.M = s.q_per_img; g.N = k; g.K = H; g.batch = s.n_img; g.epi.out_f32 = 1;
+    if (gemm<T>(gc, g)) return -1;
+  } else {
+    // reference as written: alpha == 1 is constant -> no gradient reaches the scores (SURVEY F2)
+    cudaMemsetAsync(de, 0, rows * P * sizeof(float), c.stream);
+    cudaMemsetAsync(dhid_emb, 0, rows * H * sizeof(T), c.stream);
+    cudaMemsetAsync(dsent_emb, 0, rows * H * sizeof(T), c.stream);
+    cudaMemset2DAsync(dKV + H, (size_t)2 * H * sizeof(T), 0, (size_t)H * sizeof(T), (size_t)s.n_img * k, c.stream);
+  }
   {
-    long blocks = (rows * (H / 8) + 255) / 256;
-    if (blocks > 8L * kNumSMs) blocks = 8L * kNumSMs;
-    ds_ctx_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(rows, H, P, alpha, dactx, dS_ctx);
+    long blocks = (rows + 7) / 8;
+    if (blocks > 16L * kNumSMs) blocks = 16L * kNumSMs;
+    attn_bwd_rows_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(rows, H, k, s.position_softmax, sentinel, alpha, dactx, dal,
+                                                              kDalLd, de, alpha_T, kAlphaTLd, dS_ctx, db_alpha);
     if (c.launches) ++*c.launches;
   }
+  {
+    // d values (pre-tanh)[j, h] = (sum_q alpha[q, j] / (k+1) * dctx[q, h]) * (1 - v[j, h]^2): the weight-gradient form
+    // (contraction over the query index), one [k x H x q_per_img] GEMM per image, tanh' fused in the epilogue
+    GemmCall g;
+    g.a_mn = true; g.b_mn = true;
+    g.A = alpha_T; g.lda = qs * kAlphaTLd; g.batch_a = r0 * kAlphaTLd;
+    g.B = dactx; g.ldb = qs * H; g.batch_b = r0 * H;
+    g.C = dKV; g.ldc = 2 * H; g.batch_c = (long)k * 2 * H;
+    g.M = k; g.N = H; g.K = s.q_per_img; g.batch = s.n_img;
+    g.epi.act = ACT_DTANH; g.epi.dact_y = vals; g.epi.ld_y = H; g.epi.batch_y = (long)k * H;
+    if (gemm<T>(gc, g)) return -1;
+  }
+  if (!s.position_softmax) return 0;
   const size_t a_bytes = (size_t)s.q_per_img * P * sizeof(float);
   dim3 grid_cols(s.n_img, (H + 255) / 256);
 #define DISPATCH_KC(KERNEL, ...)                                                                                     \
@@ -548,41 +521,17 @@ void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
     else KERNEL<T, 64><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                          \
     if (c.launches) ++*c.launches;                                                                                   \
   } while (0)
-  DISPATCH_KC(attn_bwd_dv_kernel, s, vals, alpha, dactx, dKV);
-  if (!s.position_softmax) {
-    // reference as written: alpha == 1 is constant -> no gradient reaches the scores (SURVEY F2)
-    cudaMemsetAsync(de, 0, rows * P * sizeof(float), c.stream);
-    cudaMemsetAsync(dhid_emb, 0, rows * H * sizeof(T), c.stream);
-    cudaMemsetAsync(dsent_emb, 0, rows * H * sizeof(T), c.stream);
-    cudaMemset2DAsync(dKV + H, (size_t)2 * H * sizeof(T), 0, (size_t)H * sizeof(T), (size_t)s.n_img * k, c.stream);
-    return;
-  }
-  {
-    const int chunks = pick_chunks(s.n_img, s.q_per_img);
-    const int qpc = (s.q_per_img + chunks - 1) / chunks;
-    const SmemLayout L1 = make_layout(H, k, (int)sizeof(T), 1);
-    const bool stage = L1.total <= 227 * 1024 && ((size_t)k * H * sizeof(T)) % 16 == 0;
-    if (stage) {
-      auto kern = attn_bwd_scores_kernel<T, true>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total);
-      kern<<<s.n_img * chunks, kFwdThreads, L1.total, c.stream>>>(s, chunks, qpc, vals, sentinel, alpha, dactx, de,
-                                                                 db_alpha);
-    } else {
-      const SmemLayout L0 = make_layout(H, k, (int)sizeof(T), 0);
-      attn_bwd_scores_kernel<T, false><<<s.n_img * chunks, kFwdThreads, L0.total, c.stream>>>(
-          s, chunks, qpc, vals, sentinel, alpha, dactx, de, db_alpha);
-    }
-    if (c.launches) ++*c.launches;
-  }
   DISPATCH_KC(attn_bwd_dk_kernel, s, keys, hid_emb, sent_emb, w_alpha, de, dKV, dhid_emb, dsent_emb, dw_alpha);
 #undef DISPATCH_KC
+  return 0;
 }
 
 #define INSTANTIATE(T)                                                                                               \
   template void attention_fwd<T>(LaunchCtx, const AttnShape&, const T*, const T*, const T*, const T*, const T*,      \
                                  const T*, const float*, const float*, float*, T*, T*);                              \
-  template void attention_bwd<T>(LaunchCtx, const AttnShape&, const T*, const T*, const T*, const T*, const T*,      \
-                                 const float*, const float*, const T*, float*, T*, T*, T*, T*, float*, float*);
+  template int attention_bwd<T>(GemmContext&, LaunchCtx, const AttnShape&, const T*, const T*, const T*, const T*,    \
+                                const T*, const float*, const float*, const T*, float*, T*, float*, T*, T*, T*, T*,    \
+                                float*, float*);
 INSTANTIATE(float)
 INSTANTIATE(bf16)
 

@@ -348,9 +348,11 @@ template <typename T> class Decoder : public DecoderBase {
     }
     // attention (model:103-113)
     AttnShape as = train_shape(B);
-    attention_bwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), prm.fc_a_w,
-                     alpha.as<float>(), dactx.as<T>(), de.as<float>(), dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(),
-                     dsemb.as<T>(), G.fc_a_w, G.fc_a_b);
+    OK(dal.ensure(4 * M * kDalLd, &ws_bytes));
+    OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
+    OK(attention_bwd<T>(gc, lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), prm.fc_a_w,
+                        alpha.as<float>(), dactx.as<T>(), dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
+                        dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(), dsemb.as<T>(), G.fc_a_w, G.fc_a_b));
     colsum_add<T>(lc, dhemb.as<T>(), H, M, H, G.fc_g_b);
     OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, (int)M, G.fc_g_w, H));
     colsum_add<T>(lc, dsemb.as<T>(), H, M, H, G.fc_s_b);
@@ -543,7 +545,7 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
 
@@ -560,7 +562,7 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx;
+      dGsum, dembx, dal, alpha_t;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
 };
@@ -739,16 +741,33 @@ int capdec_attention_bwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int
                          void* dsent_emb, float* dw_alpha, float* db_alpha, void* stream) {
   if (H % 8 || k < 1 || k > 63) { set_error("capdec_attention_bwd: need H %% 8 == 0 and 1 <= k <= 63"); return -1; }
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  GemmContext gc; gc.stream = (cudaStream_t)stream;
   AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
+  // scratch of the two batched GEMMs (the decoder handle owns these; the stand-alone entry point allocates them)
+  const long rows = (long)n_img * q_per_img;
+  const size_t esz = dtype == CAPDEC_DTYPE_F32 ? 4 : 2;
+  void *dal = nullptr, *alpha_t = nullptr;
+  if (cudaMalloc(&dal, rows * kDalLd * 4) != cudaSuccess || cudaMalloc(&alpha_t, rows * kAlphaTLd * esz) != cudaSuccess) {
+    if (dal) cudaFree(dal);
+    set_error("capdec_attention_bwd: out of device memory");
+    return -1;
+  }
+  cudaMemsetAsync(alpha_t, 0, rows * kAlphaTLd * esz, (cudaStream_t)stream);
+  int rc = 0;
   if (dtype == CAPDEC_DTYPE_F32)
-    attention_bwd<float>(lc, s, (const float*)keys, (const float*)vals, (const float*)hid_emb, (const float*)sent_emb,
-                         (const float*)sentinel, w_alpha, alpha, (const float*)dctx, de, (float*)dS_ctx, (float*)dKV,
-                         (float*)dhid_emb, (float*)dsent_emb, dw_alpha, db_alpha);
+    rc = attention_bwd<float>(gc, lc, s, (const float*)keys, (const float*)vals, (const float*)hid_emb,
+                              (const float*)sent_emb, (const float*)sentinel, w_alpha, alpha, (const float*)dctx,
+                              (float*)dal, (float*)alpha_t, de, (float*)dS_ctx, (float*)dKV, (float*)dhid_emb,
+                              (float*)dsent_emb, dw_alpha, db_alpha);
   else if (dtype == CAPDEC_DTYPE_BF16)
-    attention_bwd<bf16>(lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
-                        (const bf16*)sentinel, w_alpha, alpha, (const bf16*)dctx, de, (bf16*)dS_ctx, (bf16*)dKV,
-                        (bf16*)dhid_emb, (bf16*)dsent_emb, dw_alpha, db_alpha);
-  else { set_error("capdec_attention_bwd: unsupported dtype %d", dtype); return -1; }
+    rc = attention_bwd<bf16>(gc, lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
+                             (const bf16*)sentinel, w_alpha, alpha, (const bf16*)dctx, (float*)dal, (bf16*)alpha_t, de,
+                             (bf16*)dS_ctx, (bf16*)dKV, (bf16*)dhid_emb, (bf16*)dsent_emb, dw_alpha, db_alpha);
+  else { set_error("capdec_attention_bwd: unsupported dtype %d", dtype); rc = -1; }
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(dal);
+  cudaFree(alpha_t);
+  if (rc) return -1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("capdec_attention_bwd: %s", cudaGetErrorString(e)); return -1; }
   return 0;

@@ -21,6 +21,7 @@ struct GemmEpi {
   const void* addend = nullptr;  // T [M, ld_add], added element-wise
   const void* dact_y = nullptr;  // T [M, ld_y]: ACT_DTANH multiplies by (1 - y^2)
   long ld_add = 0, ld_y = 0;
+  long batch_add = 0, batch_y = 0;  // element strides between batches of addend / dact_y
   int act = ACT_NONE;
   int out_f32 = 0;               // C is fp32 (otherwise T)
   int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
@@ -36,6 +37,8 @@ struct GemmCall {
   bool a_mn = false;             // A stored [K,M] (MN-major) instead of [M,K]
   bool b_mn = false;             // B stored [K,N] (MN-major) instead of [N,K]
   int splits = 1;                // split-K (requires epi.atomic); 0 = choose automatically
+  int batch = 1;                 // independent problems of the same shape; element strides between them:
+  long batch_a = 0, batch_b = 0, batch_c = 0;
   GemmEpi epi;
 };
 

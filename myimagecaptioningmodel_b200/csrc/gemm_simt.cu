@@ -12,12 +12,20 @@ constexpr int TK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, long sam, long sak, const T* __restrict__ B, long sbn, long sbk,
-                 void* __restrict__ C, long ldc, int M, int N, int K, int kchunk, GemmEpi epi) {
+                 void* __restrict__ C, long ldc, int M, int N, int K, int kchunk, int splits, long batch_a, long batch_b,
+                 long batch_c, GemmEpi epi) {
   __shared__ float sA[TK][TS + 1];
   __shared__ float sB[TK][TS + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
-  const int k_begin = blockIdx.z * kchunk, k_end = min(K, k_begin + kchunk);
+  const int bt = blockIdx.z / splits, z = blockIdx.z % splits;
+  A += bt * batch_a;
+  B += bt * batch_b;
+  if (epi.addend) epi.addend = reinterpret_cast<const T*>(epi.addend) + bt * epi.batch_add;
+  if (epi.dact_y) epi.dact_y = reinterpret_cast<const T*>(epi.dact_y) + bt * epi.batch_y;
+  C = (epi.out_f32 || epi.atomic) ? (void*)(reinterpret_cast<float*>(C) + bt * batch_c)
+                                  : (void*)(reinterpret_cast<T*>(C) + bt * batch_c);
+  const int k_begin = z * kchunk, k_end = min(K, k_begin + kchunk);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -78,10 +86,10 @@ template <typename T> int gemm_simt(GemmContext& ctx, const GemmCall& c) {
   }
   int kchunk = ((c.K + splits - 1) / splits + TK - 1) / TK * TK;
   splits = (c.K + kchunk - 1) / kchunk;
-  dim3 grid((c.N + TS - 1) / TS, (c.M + TS - 1) / TS, splits);
+  dim3 grid((c.N + TS - 1) / TS, (c.M + TS - 1) / TS, splits * c.batch);
   gemm_simt_kernel<T><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(c.A), sam, sak,
                                                    reinterpret_cast<const T*>(c.B), sbn, sbk, c.C, c.ldc, c.M, c.N,
-                                                   c.K, kchunk, c.epi);
+                                                   c.K, kchunk, splits, c.batch_a, c.batch_b, c.batch_c, c.epi);
   ctx.launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("gemm_simt launch: %s", cudaGetErrorString(err)); return -1; }

@@ -65,14 +65,22 @@ template <bool MN> __device__ __forceinline__ uint64_t slice_desc(uint32_t tile_
 }
 
 // TMA store / reduce of one [32 rows x 128 bytes] SWIZZLE_128B tile from shared memory (SASS UTMASTG / UTMAREDG)
-__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+// all tensor maps are 3-D: {innermost, row, batch}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -86,7 +94,8 @@ template <int N> __device__ __forceinline__ void bulk_wait() {
 struct TcShape {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split;
-  long ldc;
+  int batch;
+  long ldc, batch_c;
   int vec_ok;
   int rotate_k;  // start every CTA's k-loop at a different k-block (spreads L2 hot lines among CTAs sharing a tile)
   int tma_out;   // epilogue writes through shared memory + TMA tensor stores (needs an aligned C)
@@ -201,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb_total = (sh.K + BK - 1) / BK;
   const int tiles = sh.tiles_m * sh.tiles_n;
-  const int total_work = tiles * sh.splits;
+  const int tb = tiles * sh.batch;           // work item w -> (split z, batch bt, tile)
+  const int total_work = tb * sh.splits;
 
   if (threadIdx.x == 0) {
     TRACE(0);
@@ -231,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w % tiles, z = w / tiles;
+        const int z = w / tb, bt = (w % tb) / tiles, tile = w % tiles;
         const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
         const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
         const int nk = kb1 - kb0;
@@ -243,16 +253,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sB = sA + kABytes;
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
           if (!A_MN) {
-            tma_load_2d(sA, &tmA, kb * BK, m0, &full_bar[s]);
+            tma_load_3d(sA, &tmA, kb * BK, m0, bt, &full_bar[s]);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, &full_bar[s]);
+            for (int i = 0; i < BM / 64; ++i) tma_load_3d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, bt, &full_bar[s]);
           }
           if (!B_MN) {
-            tma_load_2d(sB, &tmB, kb * BK, n0, &full_bar[s]);
+            tma_load_3d(sB, &tmB, kb * BK, n0, bt, &full_bar[s]);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, &full_bar[s]);
+            for (int i = 0; i < BN / 64; ++i) tma_load_3d(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, bt, &full_bar[s]);
           }
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
           if (w == (int)blockIdx.x && i == 0) TRACE(2);
@@ -271,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       int it = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-        const int z = w / tiles;
+        const int z = w / tb;
         const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
         const int buf = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
@@ -302,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;       // which of the two warps of the quarter
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-      const int tile = w % tiles;
+      const int bt = (w % tb) / tiles, tile = w % tiles;
       const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
       const int buf = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
@@ -328,10 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* my_stage = staging + ew * 4096;
         const uint32_t swz = (uint32_t)(lane & 7);
         uint8_t* my_row = my_stage + lane * 128;
-        const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + (long)row * epi.ld_add + n0
+        const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
+                                                         (long)row * epi.ld_add + n0
                                                    : nullptr;
         const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
-                              ? reinterpret_cast<const bf16*>(epi.dact_y) + (long)row * epi.ld_y + n0 : nullptr;
+                              ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
+                              : nullptr;
         const bool do_tanh = epi.act == ACT_TANH;
         const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
         const bool f32_out = epi.out_f32 || epi.atomic;
@@ -350,22 +362,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
           if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
           __syncwarp();
-          const float* bt = has_bias ? bias_s + buf * BN + c0 : nullptr;
+          const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;
           const bf16* ap = add_p ? add_p + c0 : nullptr;
           const bf16* yp = y_p ? y_p + c0 : nullptr;
           if (f32_out) {
-            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
-            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bt, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
           } else {
 #pragma unroll 1
             for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
               const int o = sub * 32;
               if (left - o >= 32)
-                epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
+                epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
                                              yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
                                              (uint32_t)(sub * 4));
               else
-                epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bt ? bt + o : nullptr, ap ? ap + o : nullptr,
+                epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
                                               yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
                                              (uint32_t)(sub * 4));
             }
@@ -380,8 +392,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (epi.atomic) tma_reduce_add_2d(&tmC, my_stage, n0 + c0, m0 + quarter * 32);
-            else tma_store_2d(&tmC, my_stage, n0 + c0, m0 + quarter * 32);
+            if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
+            else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
             bulk_commit();
           }
         }
@@ -416,8 +428,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-          epi_math8_tail(v, epi, row, col, true, sh.N);
-          epi_store8_tail(v, C, sh.ldc, row, col, sh.N, epi);
+          GemmEpi eb = epi;
+          if (eb.addend) eb.addend = reinterpret_cast<const bf16*>(eb.addend) + bt * eb.batch_add;
+          if (eb.dact_y) eb.dact_y = reinterpret_cast<const bf16*>(eb.dact_y) + bt * eb.batch_y;
+          void* Cb = (epi.out_f32 || epi.atomic) ? (void*)(reinterpret_cast<float*>(C) + bt * sh.batch_c)
+                                                 : (void*)(reinterpret_cast<bf16*>(C) + bt * sh.batch_c);
+          epi_math8_tail(v, eb, row, col, true, sh.N);
+          epi_store8_tail(v, Cb, sh.ldc, row, col, sh.N, eb);
         }
       }
     }
@@ -447,43 +464,49 @@ void load_encode() {
 }
 
 struct MapKey {
-  const void* p; uint64_t inner, outer, ld; uint32_t bi, bo; int esize;
+  const void* p; uint64_t inner, outer, ld, nb, bs; uint32_t bi, bo; int esize;
   bool operator==(const MapKey& o) const {
-    return p == o.p && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo && esize == o.esize;
+    return p == o.p && inner == o.inner && outer == o.outer && ld == o.ld && nb == o.nb && bs == o.bs && bi == o.bi &&
+           bo == o.bo && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.p;
     auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.bi); mix(k.bo); mix((uint64_t)k.esize);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.nb); mix(k.bs); mix(k.bi); mix(k.bo); mix((uint64_t)k.esize);
     return h;
   }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// 2-D tensor [outer, inner] of bf16 (esize 2) or fp32 (esize 4) with row stride ld (elements); box = [bo, bi];
-// 128-byte swizzle.
+// 3-D tensor [nb, outer, inner] of bf16 (esize 2) or fp32 (esize 4): row stride ld, batch stride bs (elements);
+// box = [1, bo, bi]; 128-byte swizzle.
 int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
-            int esize = 2) {
+            int esize, uint64_t nb, uint64_t bs) {
+  if (nb <= 1) { nb = 1; bs = ld * (outer > 0 ? outer : 1); }
+  if ((bs * esize) & 15) {
+    set_error("gemm_tc: batch stride %llu is not a multiple of 16 bytes", (unsigned long long)bs);
+    return -1;
+  }
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
   if (((uintptr_t)p & 15) || ((ld * esize) & 15)) {
     set_error("gemm_tc: operand %p (ld=%llu) is not 16-byte aligned for TMA", p, (unsigned long long)ld);
     return -1;
   }
-  MapKey key{p, inner, outer, ld, bi, bo, esize};
+  MapKey key{p, inner, outer, ld, nb, bs, bi, bo, esize};
   {
     std::lock_guard<std::mutex> g(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
   }
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * (uint64_t)esize};
-  cuuint32_t box[2] = {bi, bo};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p), dims, strides, box, estr,
+  cuuint64_t dims[3] = {inner, outer, nb};
+  cuuint64_t strides[2] = {ld * (uint64_t)esize, bs * (uint64_t)esize};
+  cuuint32_t box[3] = {bi, bo, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(p), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -508,10 +531,10 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
     attr_set = true;
   }
   CUtensorMap tmA, tmB, tmC;
-  if (!A_MN) { if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA)) return -1; }
-  else { if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA)) return -1; }
-  if (!B_MN) { if (get_map(c.B, c.K, c.N, c.ldb, BK, BN, &tmB)) return -1; }
-  else { if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB)) return -1; }
+  if (!A_MN) { if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA, 2, c.batch, c.batch_a)) return -1; }
+  else { if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA, 2, c.batch, c.batch_a)) return -1; }
+  if (!B_MN) { if (get_map(c.B, c.K, c.N, c.ldb, BK, BN, &tmB, 2, c.batch, c.batch_b)) return -1; }
+  else { if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB, 2, c.batch, c.batch_b)) return -1; }
   const GemmEpi& e = c.epi;
   const int out_elem = (e.out_f32 || e.atomic) ? 4 : 2;
   int vec_ok = ((c.ldc % 8) == 0) && (((uintptr_t)c.C) % (out_elem * 8) == 0);
@@ -524,7 +547,8 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   // them in groups of 8 columns, so N must be a multiple of 8 unless the caller vouches for padded buffers
   // (epi.aux_padded: the decoder's own buffers are padded to a multiple of 128 columns).
   const bool has_aux = e.bias || e.addend || e.dact_y;
-  const int tma_out = (!has_aux || (c.N % 8) == 0 || e.aux_padded) &&
+  const int tma_out = (!has_aux || (c.N % 8) == 0 || e.aux_padded) && ((c.batch_c * out_elem) % 16 == 0) &&
+                      (e.batch_add % 8 == 0) && (e.batch_y % 8 == 0) &&
                       (((uintptr_t)c.C & 15) == 0) && (((c.ldc * out_elem) & 15) == 0) &&
                       (!e.bias || ((uintptr_t)e.bias & 31) == 0) &&
                       (!e.addend || ((((uintptr_t)e.addend & 15) == 0) && (e.ld_add % 8) == 0)) &&
@@ -534,7 +558,7 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   if (out_env < 0) { const char* ev = getenv("CAPDEC_GEMM_OUT"); out_env = ev ? atoi(ev) : 1; }
   int out_mode = tma_out ? (out_env ? 1 : 0) : 0;
   if (out_mode == 1) {
-    if (get_map(c.C, c.N, c.M, c.ldc, out_elem == 2 ? 64 : 32, 32, &tmC, out_elem)) return -1;
+    if (get_map(c.C, c.N, c.M, c.ldc, out_elem == 2 ? 64 : 32, 32, &tmC, out_elem, c.batch, c.batch_c)) return -1;
   } else {
     tmC = tmA;
   }
@@ -544,12 +568,13 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   sh.M = c.M; sh.N = c.N; sh.K = c.K;
   sh.tiles_m = (c.M + BM - 1) / BM; sh.tiles_n = (c.N + BN - 1) / BN;
   sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = vec_ok;
+  sh.batch = c.batch > 0 ? c.batch : 1; sh.batch_c = c.batch_c;
   {
     static int rot_env = -1;
     if (rot_env < 0) { const char* ev = getenv("CAPDEC_GEMM_ROT"); rot_env = ev ? atoi(ev) : 1; }
     sh.rotate_k = rot_env;
   }
-  const long total = (long)sh.tiles_m * sh.tiles_n * splits;
+  const long total = (long)sh.tiles_m * sh.tiles_n * splits * sh.batch;
   const int grid = (int)std::min<long>(total, kNumSMs);
   gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, tmC, c.C, sh, c.epi);
   ctx.launches++;
@@ -570,6 +595,7 @@ void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
+  if (c.batch > 1 && c.epi.atomic) { set_error("gemm_tc: batched GEMM with split-K is not supported"); return -1; }
   const int nkb = (c.K + BK - 1) / BK;
   const int mt = (c.M + BM - 1) / BM;
   // Pick the tile width and the k-split that minimise a simple cost model of the persistent kernel:
@@ -581,7 +607,7 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn > 64 && c.N <= bn / 2) continue;
-    const long tiles = (long)mt * ((c.N + bn - 1) / bn);
+    const long tiles = (long)mt * ((c.N + bn - 1) / bn) * (c.batch > 0 ? c.batch : 1);
     const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
     const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
     for (int sp = sp_min; sp <= sp_max; ++sp) {

@@ -66,13 +66,19 @@ template <typename T>
 void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
                    const T* sentinel, const T* p_hid, const float* w_alpha, const float* b_alpha, float* alpha, T* actx,
                    T* ctx_out);
-// backward, three kernels (see attention.cu).  dactx [rows,H] is the gradient wrt context.
-//   de [rows,k+1] fp32 scratch;  dS_ctx [rows,H] = alpha_k dctx / (k+1);  dKV [n_img*k, 2H]: cols 0..H = d(values pre-tanh),
+// backward (see attention.cu): two batched tensor-core GEMMs (d alpha = dctx.V^T, d values = alpha^T.dctx with tanh'
+// fused), a row-wise soft-max-backward kernel and the column-wise d keys kernel.  dactx [rows,H] = d context.
+//   scratch: dal [rows, kDalLd] fp32, alpha_T [rows, kAlphaTLd] T
+//   de [rows,k+1] fp32;  dS_ctx [rows,H] = alpha_k dctx / (k+1);  dKV [n_img*k, 2H]: cols 0..H = d(values pre-tanh),
 //   cols H..2H = d keys;  dhid_emb, dsent_emb [rows,H];  dw_alpha [H], db_alpha [1] fp32 (+=)
+constexpr int kDalLd = 68;      // >= 63 positions, 16-byte-multiple pitch in fp32
+constexpr int kAlphaTLd = 72;   // >= 63 positions, 16-byte-multiple pitch in bf16
+struct GemmContext;
 template <typename T>
-void attention_bwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
-                   const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx, float* de, T* dS_ctx,
-                   T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha, float* db_alpha);
+int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb,
+                  const T* sent_emb, const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx,
+                  float* dal, T* alpha_T, float* de, T* dS_ctx, T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha,
+                  float* db_alpha);
 
 // ---- loss.cu -----------------------------------------------------------------------------------
 // masked soft-max cross entropy (model:163-171, 180-183, 205-212): target[t*B+b] = caption[b, t+1]
