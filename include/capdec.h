@@ -94,6 +94,12 @@ size_t capdec_workspace_bytes(capdec_handle h);
 /* number of kernels launched by this handle since creation (bench accounting) */
 int64_t capdec_launch_count(capdec_handle h);
 
+/* Device-side phase timeline (profiling aid): while enabled, the schedules record CUDA events on the caller's stream
+ * at phase boundaries; capdec_profile_report synchronises on the last one and writes "phase milliseconds\n" lines
+ * (summed per phase since the previous report) into buf. */
+int capdec_profile(capdec_handle h, int32_t enable);
+int capdec_profile_report(capdec_handle h, char* buf, size_t n);
+
 /* Converts the fp32 parameters into the handle's internal operand layouts.  Call again after every optimizer
  * update.  The bias / w_alpha pointers are read directly by later calls and must stay valid. */
 int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream);

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/capdec.h"
@@ -58,9 +60,50 @@ struct DevBuf {
   template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
 
+// optional device-side phase timeline (capdec_profile): CUDA events recorded on the caller's stream at phase
+// boundaries; report() sums the elapsed time per phase name.  Costs nothing when disabled.
+struct PhaseTimer {
+  bool on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  std::vector<cudaEvent_t> pool;
+  void mark(const char* name, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    marks.emplace_back(name, e);
+  }
+  // "name ms\n" per phase (first-seen order), the time of a phase = from the previous mark to its own mark
+  std::string report() {
+    std::vector<std::pair<const char*, double>> agg;
+    if (!marks.empty()) cudaEventSynchronize(marks.back().second);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      if (marks[i].first[0] == '^') continue;  // a '^' mark only restarts the clock
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      bool found = false;
+      for (auto& a : agg)
+        if (!strcmp(a.first, marks[i].first)) { a.second += ms; found = true; break; }
+      if (!found) agg.emplace_back(marks[i].first, ms);
+    }
+    for (auto& m : marks) pool.push_back(m.second);
+    marks.clear();
+    std::string out;
+    char line[160];
+    for (auto& a : agg) { snprintf(line, sizeof line, "%s %.6f\n", a.first, a.second); out += line; }
+    return out;
+  }
+  ~PhaseTimer() {
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
 class DecoderBase {
  public:
   virtual ~DecoderBase() {}
+  PhaseTimer prof;
   virtual int bind(const capdec_params* p, cudaStream_t s) = 0;
   virtual int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
                         cudaStream_t s) = 0;
@@ -92,6 +135,7 @@ template <typename T> class Decoder : public DecoderBase {
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int X = E + H;
+    prof.mark("^bind", s);
     OK(w_kv_n.ensure(e * H * 2 * H, &ws_bytes));
     OK(w_x_n.ensure(e * E * 5 * H, &ws_bytes));
     OK(w_g_n.ensure(e * H * 5 * H, &ws_bytes));
@@ -110,25 +154,46 @@ template <typename T> class Decoder : public DecoderBase {
     // Every weight keeps PaddlePaddle's own [in, out] layout (one storage-type copy each, no transposes):
     //   forward  Y = X.W      reads it as the MN-major B operand,
     //   backward dX = dY.W^T  reads the same buffer as the K-major B operand (N = in, K = out).
-    copy2d_from_f32<T>(lc, p->fc_v_w, H, w_kv_n.as<T>(), 2 * H, H, H);                              // [H, 2H] = [fc_v | fc_k]
-    copy2d_from_f32<T>(lc, p->fc_k_w, H, w_kv_n.as<T>() + H, 2 * H, H, H);
-    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_x_n.as<T>(), 5 * H, E, 4 * H);                        // word rows: [E, 5H]
-    copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_x_n.as<T>() + 4 * H, 5 * H, E, H);
-    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)E * 4 * H, 4 * H, w_g_n.as<T>(), 5 * H, H, 4 * H);    // global rows: [H, 5H]
-    copy2d_from_f32<T>(lc, p->fc_xs_w + (size_t)E * H, H, w_g_n.as<T>() + 4 * H, 5 * H, H, H);
-    convert_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, w_hh_n.as<T>(), (long)H * 4 * H);         // hid rows: [H, 4H]
-    convert_from_f32<T>(lc, p->fc_hs_w, w_hs_n.as<T>(), (long)H * H);
-    convert_from_f32<T>(lc, p->fc_p_w, w_p_n.as<T>(), (long)H * H);
-    convert_from_f32<T>(lc, p->fc_g_w, w_g2_n.as<T>(), (long)H * H);
-    convert_from_f32<T>(lc, p->fc_s_w, w_s_n.as<T>(), (long)H * H);
-    convert_from_f32<T>(lc, p->fc_o_w, w_o_n.as<T>(), (long)H * H);
-    convert_from_f32<T>(lc, p->fc_e_w, w_e_n.as<T>(), (long)H * E);
-    convert_from_f32<T>(lc, p->word_embedding, emb.as<T>(), (long)V * E);
+    const float* lw_g = p->lstm_w + (size_t)E * 4 * H;   // global-image rows of lstm_w
+    const float* lw_h = p->lstm_w + (size_t)X * 4 * H;   // hidden rows of lstm_w
+    bool want_perm = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!force_simt && lstm_seq_fwd_supported(1, H)) {  // unit-major copy for the persistent forward recurrence
+        OK(w_hh_perm.ensure(e * H * 4 * H, &ws_bytes));
+        want_perm = true;
+      }
+    }
+    T* wd = w_dec_n.as<T>();
+    ConvertTable tab;
+    tab.add(p->fc_v_w, H, w_kv_n.as<T>(), 2 * H, H, H);                      // [H, 2H] = [fc_v | fc_k]
+    tab.add(p->fc_k_w, H, w_kv_n.as<T>() + H, 2 * H, H, H);
+    tab.add(p->lstm_w, 4 * H, w_x_n.as<T>(), 5 * H, E, 4 * H);              // word rows: [E, 5H]
+    tab.add(p->fc_xs_w, H, w_x_n.as<T>() + 4 * H, 5 * H, E, H);
+    tab.add(lw_g, 4 * H, w_g_n.as<T>(), 5 * H, H, 4 * H);                    // global rows: [H, 5H]
+    tab.add(p->fc_xs_w + (size_t)E * H, H, w_g_n.as<T>() + 4 * H, 5 * H, H, H);
+    tab.add(lw_h, 4 * H, w_hh_n.as<T>(), 4 * H, H, 4 * H);                   // hid rows: [H, 4H]
+    tab.add(p->fc_hs_w, H, w_hs_n.as<T>(), H, H, H);
+    tab.add(p->fc_p_w, H, w_p_n.as<T>(), H, H, H);
+    tab.add(p->fc_g_w, H, w_g2_n.as<T>(), H, H, H);
+    tab.add(p->fc_s_w, H, w_s_n.as<T>(), H, H, H);
+    tab.add(p->fc_o_w, H, w_o_n.as<T>(), H, H, H);
+    tab.add(p->fc_e_w, E, w_e_n.as<T>(), E, H, E);
+    tab.add(p->word_embedding, E, emb.as<T>(), E, V, E);
     // inference operand [E+H, 5H]: rows = [word_emb ; h_{t-1}], cols = [lstm gates | sentinel pre-activation]
-    copy2d_from_f32<T>(lc, p->lstm_w, 4 * H, w_dec_n.as<T>(), 5 * H, E, 4 * H);
-    copy2d_from_f32<T>(lc, p->fc_xs_w, H, w_dec_n.as<T>() + 4 * H, 5 * H, E, H);
-    copy2d_from_f32<T>(lc, p->lstm_w + (size_t)X * 4 * H, 4 * H, w_dec_n.as<T>() + (size_t)E * 5 * H, 5 * H, H, 4 * H);
-    copy2d_from_f32<T>(lc, p->fc_hs_w, H, w_dec_n.as<T>() + (size_t)E * 5 * H + 4 * H, 5 * H, H, H);
+    tab.add(p->lstm_w, 4 * H, wd, 5 * H, E, 4 * H);
+    tab.add(p->fc_xs_w, H, wd + 4 * H, 5 * H, E, H);
+    tab.add(lw_h, 4 * H, wd + (size_t)E * 5 * H, 5 * H, H, 4 * H);
+    tab.add(p->fc_hs_w, H, wd + (size_t)E * 5 * H + 4 * H, 5 * H, H, H);
+    if (want_perm) tab.add(lw_h, 4 * H, w_hh_perm.p, 4 * H, H, 4 * H, 1, H);
+    const int rc = multi_convert<T>(lc, tab);
+    if (rc < 0) return -1;
+    if (rc > 0) {  // unaligned caller buffers: per-tensor scalar kernels
+      for (int j = 0; j < tab.n; ++j) {
+        const ConvertJob& jb = tab.job[j];
+        if (jb.mode == 0) copy2d_from_f32<T>(lc, jb.src, jb.lds, reinterpret_cast<T*>(jb.dst), jb.ldd, jb.rows, jb.cols);
+        else permute_gate_cols(lc, jb.src, jb.lds, reinterpret_cast<bf16*>(jb.dst), H);
+      }
+    }
     // out_fc_bias padded to Vp columns so the GEMM epilogue may read it in whole groups of 8
     CUDA_OK(cudaMemsetAsync(b_vocab.p, 0, 4 * (size_t)Vp, s));
     CUDA_OK(cudaMemcpyAsync(b_vocab.p, p->out_fc_bias, 4 * (size_t)V, cudaMemcpyDeviceToDevice, s));
@@ -138,6 +203,7 @@ template <typename T> class Decoder : public DecoderBase {
     CUDA_OK(cudaMemcpyAsync(b5d.p, b5.p, 4 * 5 * H, cudaMemcpyDeviceToDevice, s));
     add_f32(lc, b5d.as<float>() + 4 * H, p->fc_hs_b, H);
     CUDA_OK(cudaGetLastError());
+    prof.mark("bind_params", s);
     bound = true;
     return 0;
   }
@@ -188,7 +254,9 @@ template <typename T> class Decoder : public DecoderBase {
     const size_t e = sizeof(T);
     const long M = (long)B * Tt;
     last_B = B; last_cap = cap;
+    prof.mark("^fwd", s);
     OK(image_projections(gc, lc, g, P, B));
+    prof.mark("fwd.image_kv", s);
     OK(embx.ensure(e * M * E, &ws_bytes));
     OK(xe.ensure(e * M * 5 * H, &ws_bytes));
     OK(g5.ensure(4 * (size_t)B * 5 * H, &ws_bytes));
@@ -217,16 +285,28 @@ template <typename T> class Decoder : public DecoderBase {
     OK(fc(gc, embx.p, E, w_x_n.as<T>(), 5 * H, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
     // ... and the global-image columns (+ biases) once per image
     OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    prof.mark("fwd.embed_xe_g5", s);
     // recurrent core (model:63, 87-88, 94-95)
     CUDA_OK(cudaMemsetAsync(hs.p, 0, e * (size_t)B * H, s));
     CUDA_OK(cudaMemsetAsync(cs.p, 0, 4 * (size_t)B * H, s));
-    for (int t = 0; t < Tt; ++t) {
+    bool persistent = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!force_simt && lstm_seq_fwd_supported(B, H) && w_hh_perm.p) {
+        // all T steps in one persistent kernel: W_hh resident in shared memory, cell fused into the MMA epilogue
+        OK(rec_ctr.ensure(256, &ws_bytes));
+        OK(lstm_seq_fwd(lc, B, H, Tt, w_hh_perm.as<bf16>(), xe.as<bf16>(), 5 * H, g5.as<float>(), 5 * H, hs.as<bf16>(),
+                        cs.as<float>(), gact.as<bf16>(), rec_ctr.as<unsigned>()));
+        persistent = true;
+      }
+    }
+    for (int t = 0; t < Tt && !persistent; ++t) {
       OK(fc(gc, hs.as<T>() + (size_t)t * B * H, H, w_hh_n.as<T>(), 4 * H, nullptr, gpre.p, 4 * H, B, 4 * H, H, ACT_NONE,
               true));
       lstm_cell_fwd<T>(lc, B, H, gpre.as<float>(), 4 * H, xe.as<T>() + (size_t)t * B * 5 * H, 5 * H, g5.as<float>(),
                        5 * H, INT_MAX, 1, cs.as<float>() + (size_t)t * B * H, hs.as<T>() + (size_t)(t + 1) * B * H, H,
                        cs.as<float>() + (size_t)(t + 1) * B * H, gact.as<T>() + (size_t)t * B * 4 * H);
     }
+    prof.mark("fwd.recurrence", s);
     const T* Hprev = hs.as<T>();
     const T* Hcur = hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
@@ -237,9 +317,11 @@ template <typename T> class Decoder : public DecoderBase {
     OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
     OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
     OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
+    prof.mark("fwd.head_fc", s);
     AttnShape as = train_shape(B);
     attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
                      prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);               // model:103-115
+    prof.mark("fwd.attention", s);
     OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
     OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
     {
@@ -248,6 +330,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
     }
+    prof.mark("fwd.out_proj_vocab", s);
     // masked cross entropy (model:163-171, 180-183, 205-212)
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
     // ... fused with the unscaled d logits = (softmax - onehot) * mask, so the fp32 logits leave HBM only once
@@ -256,6 +339,7 @@ template <typename T> class Decoder : public DecoderBase {
     loss_finalize(lc, acc.as<float>());
     if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);           // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
+    prof.mark("fwd.cross_entropy", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     have_fwd = true;
@@ -294,11 +378,12 @@ template <typename T> class Decoder : public DecoderBase {
     OK(dChead.ensure(4 * M * H, &ws_bytes));
     OK(dHhead.ensure(e * M * H, &ws_bytes));
     OK(dHprev.ensure(e * M * H, &ws_bytes));
-    OK(dhrec.ensure(4 * (size_t)B * H, &ws_bytes));
+    OK(dhrec.ensure(2 * 4 * (size_t)B * H, &ws_bytes));
     OK(dcrec.ensure(4 * (size_t)B * H, &ws_bytes));
     OK(dGsum.ensure(e * (size_t)B * 5 * H, &ws_bytes));
     OK(dembx.ensure(e * M * E, &ws_bytes));
 
+    prof.mark("^bwd", s);
     // gradients are overwritten: start from zero, every contribution below is an fp32 atomic add
     struct Z { float* p; size_t n; };
     const Z zs[] = {{G.fc_v_w, (size_t)H * H}, {G.fc_v_b, (size_t)H}, {G.fc_k_w, (size_t)H * H}, {G.fc_k_b, (size_t)H},
@@ -308,11 +393,13 @@ template <typename T> class Decoder : public DecoderBase {
                     {G.fc_s_w, (size_t)H * H}, {G.fc_s_b, (size_t)H}, {G.fc_a_w, (size_t)H}, {G.fc_a_b, (size_t)1},
                     {G.fc_o_w, (size_t)H * H}, {G.fc_o_b, (size_t)H}, {G.fc_e_w, (size_t)H * E}, {G.fc_e_b, (size_t)E},
                     {G.word_embedding, (size_t)V * E}, {G.out_fc_bias, (size_t)V}};
+    ZeroTable zt;
     for (const Z& z : zs) {
       if (!z.p) { set_error("capdec_train_bwd: NULL gradient pointer"); return -1; }
-      CUDA_OK(cudaMemsetAsync(z.p, 0, z.n * 4, s));
+      zt.add(z.p, (long)z.n);
     }
-
+    multi_zero(lc, zt);
+    prof.mark("bwd.zero_grads", s);
     const T* Hprev = hs.as<T>();
     const T* Hcur = hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
@@ -332,6 +419,7 @@ template <typename T> class Decoder : public DecoderBase {
     OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E, gscale));
     colsum_add<T>(lc, dproj.as<T>(), E, M, E, G.fc_e_b);
     OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, (int)M, G.fc_e_w, E));
+    prof.mark("bwd.vocab_proj", s);
     // out = tanh(fc_o(ctx + p_hid))   (model:115)
     {
       GemmCall c;
@@ -346,6 +434,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.A = doutp.p; c.lda = H; c.B = w_o_n.p; c.ldb = H; c.C = dactx.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
       OK(gemm<T>(gc, c));
     }
+    prof.mark("bwd.out_fc", s);
     // attention (model:103-113)
     AttnShape as = train_shape(B);
     OK(dal.ensure(4 * M * kDalLd, &ws_bytes));
@@ -353,6 +442,7 @@ template <typename T> class Decoder : public DecoderBase {
     OK(attention_bwd<T>(gc, lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), prm.fc_a_w,
                         alpha.as<float>(), dactx.as<T>(), dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
                         dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(), dsemb.as<T>(), G.fc_a_w, G.fc_a_b));
+    prof.mark("bwd.attention", s);
     colsum_add<T>(lc, dhemb.as<T>(), H, M, H, G.fc_g_b);
     OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, (int)M, G.fc_g_w, H));
     colsum_add<T>(lc, dsemb.as<T>(), H, M, H, G.fc_s_b);
@@ -387,9 +477,20 @@ template <typename T> class Decoder : public DecoderBase {
       c.N = H; c.K = H;
       OK(gemm<T>(gc, c));
     }
+    prof.mark("bwd.head_fc", s);
     // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
-    CUDA_OK(cudaMemsetAsync(dcrec.p, 0, 4 * (size_t)B * H, s));
-    for (int t = Tt - 1; t >= 0; --t) {
+    bool persistent = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!force_simt && lstm_seq_bwd_supported(B, H)) {
+        OK(rec_ctr.ensure(256, &ws_bytes));
+        OK(lstm_seq_bwd(lc, B, H, Tt, w_hh_n.as<bf16>(), dHhead.as<bf16>(), dHprev.as<bf16>(), dChead.as<float>(),
+                        gact.as<bf16>(), cs.as<float>(), dG.as<bf16>(), 5 * H, dhrec.as<float>(), dcrec.as<float>(),
+                        rec_ctr.as<unsigned>()));
+        persistent = true;
+      }
+    }
+    if (!persistent) CUDA_OK(cudaMemsetAsync(dcrec.p, 0, 4 * (size_t)B * H, s));
+    for (int t = Tt - 1; t >= 0 && !persistent; --t) {
       const bool last = (t == Tt - 1);
       lstm_cell_bwd<T>(lc, B, H, dHhead.as<T>() + (size_t)t * B * H,
                        last ? nullptr : dHprev.as<T>() + (size_t)(t + 1) * B * H, last ? nullptr : dhrec.as<float>(),
@@ -404,6 +505,7 @@ template <typename T> class Decoder : public DecoderBase {
         OK(gemm<T>(gc, c));
       }
     }
+    prof.mark("bwd.recurrence", s);
     // weight gradients of the gate GEMM, batched over all steps
     OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
     OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
@@ -425,6 +527,7 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
+    prof.mark("bwd.gate_wgrad_embed", s);
     // once-per-image projections (model:52-53)
     colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
     colsum_add<T>(lc, dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
@@ -436,6 +539,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
     }
+    prof.mark("bwd.image_kv", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -452,7 +556,9 @@ template <typename T> class Decoder : public DecoderBase {
     const size_t e = sizeof(T);
     const int R = B * beam, X = E + H;
     have_fwd = false;  // the activation buffers of a pending train_fwd are reused below
+    prof.mark("^dec", s);
     OK(image_projections(gc, lc, g, P, B));
+    prof.mark("dec.image_kv", s);
     OK(g5.ensure(4 * (size_t)B * 5 * H, &ws_bytes));
     OK(xin.ensure(e * (size_t)R * X, &ws_bytes));
     OK(gpre.ensure(4 * (size_t)R * 4 * H, &ws_bytes));
@@ -500,6 +606,7 @@ template <typename T> class Decoder : public DecoderBase {
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
     as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
+    prof.mark("dec.setup", s);
     for (int step = 0; step < Ti; ++step) {
       const int cur = step & 1, nxt = cur ^ 1;
       // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
@@ -509,11 +616,14 @@ template <typename T> class Decoder : public DecoderBase {
                        d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
       sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
                       d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
+      prof.mark("dec.gates_cell", s);
       OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
       OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
       OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+      prof.mark("dec.head_fc", s);
       attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
                        prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
+      prof.mark("dec.attention", s);
       OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
       OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
       {
@@ -522,12 +632,14 @@ template <typename T> class Decoder : public DecoderBase {
         c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
         OK(gemm<T>(gc, c));
       }
+      prof.mark("dec.out_proj_vocab", s);
       // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
       beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
                 score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src);
       if (step + 1 < Ti)
         beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
                         xin.as<T>(), X, d_ccur.as<float>());
+      prof.mark("dec.beam_step_reorder", s);
     }
     const int fin_buf = Ti & 1;
     if (ids) CUDA_OK(cudaMemcpyAsync(ids, hist[fin_buf], 4 * (size_t)R * Ti, cudaMemcpyDeviceToDevice, s));
@@ -545,7 +657,7 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
 
@@ -562,7 +674,7 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx, dal, alpha_t;
+      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
 };
@@ -598,11 +710,14 @@ static int check_device(capdec_handle h) {
   return 0;
 }
 
-namespace capdec { void set_gemm_trace(unsigned long long* buf); }
+namespace capdec { void set_gemm_trace(unsigned long long* buf); void set_rec_trace(unsigned long long* buf); }
 
 extern "C" {
 
 // debug hook (not part of include/capdec.h): device buffer of 148*32 u64 receiving per-CTA globaltimer stamps
+// debug hook: device buffer of n_ctas * T * 8 u64 receiving the per-step timeline of the next persistent recurrence
+// kernel (forward and backward write the same layout; trace one direction at a time)
+void capdec_debug_rec_trace(void* buf) { capdec::set_rec_trace(reinterpret_cast<unsigned long long*>(buf)); }
 void capdec_debug_gemm_trace(void* buf) { capdec::set_gemm_trace(reinterpret_cast<unsigned long long*>(buf)); }
 
 const char* capdec_last_error(void) { return g_err; }
@@ -656,6 +771,20 @@ int capdec_destroy(capdec_handle h) {
   if (!h) return 0;
   if (h->impl) { cudaSetDevice(h->impl->device); delete h->impl; }
   delete h;
+  return 0;
+}
+
+int capdec_profile(capdec_handle h, int32_t enable) {
+  if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
+  h->impl->prof.on = enable != 0;
+  if (!enable) h->impl->prof.report();
+  return 0;
+}
+int capdec_profile_report(capdec_handle h, char* buf, size_t n) {
+  if (check_device(h)) return -1;
+  if (!buf || n == 0) { set_error("capdec_profile_report: null buffer"); return -1; }
+  const std::string r = h->impl->prof.report();
+  snprintf(buf, n, "%s", r.c_str());
   return 0;
 }
 

@@ -592,6 +592,12 @@ template <int BN> int launch_majors(GemmContext& ctx, const GemmCall& c, int spl
 
 void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 
+// the tensor-map cache, for the other TMA kernels of the library (recurrent.cu)
+int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
+               int esize, uint64_t nb, uint64_t bs) {
+  return get_map(p, inner, outer, ld, bi, bo, out, esize, nb, bs);
+}
+
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }

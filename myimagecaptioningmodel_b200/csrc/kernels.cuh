@@ -11,6 +11,35 @@ struct LaunchCtx {
 };
 
 // ---- pointwise.cu -------------------------------------------------------------------------------
+// One launch for a whole list of fp32 -> T strided copies (capdec_bind_params) / of fp32 buffers to clear.
+struct ConvertJob {
+  const float* src; void* dst;
+  long lds, ldd;      // row strides (elements)
+  int rows, cols;
+  int mode;           // 0: dst[r, c] = src[r, c];  1: the gate-column permutation of recurrent.cu (cols = 4H)
+  int H;
+};
+constexpr int kMaxConvertJobs = 24;
+struct ConvertTable {
+  ConvertJob job[kMaxConvertJobs];
+  int first_block[kMaxConvertJobs + 1];
+  int n = 0;
+  void add(const float* src, long lds, void* dst, long ldd, int rows, int cols, int mode = 0, int H = 0) {
+    job[n++] = ConvertJob{src, dst, lds, ldd, rows, cols, mode, H};
+  }
+};
+// returns 0 when launched, 1 when some job is not 16-byte vectorisable (nothing was launched)
+template <typename T> int multi_convert(LaunchCtx c, ConvertTable& tab);
+constexpr int kMaxZeroJobs = 32;
+struct ZeroTable {
+  float* ptr[kMaxZeroJobs];
+  long count[kMaxZeroJobs];
+  int vec[kMaxZeroJobs];
+  int first_block[kMaxZeroJobs + 1];
+  int n = 0;
+  void add(float* p, long cnt) { ptr[n] = p; count[n] = cnt; ++n; }
+};
+void multi_zero(LaunchCtx c, ZeroTable& tab);
 template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* dst, long n);
 // dst[cc * ldd + r] = src[r * lds + cc]   (src fp32 [R, C])
 template <typename T> void transpose_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C);
@@ -79,6 +108,21 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
                   const T* sent_emb, const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx,
                   float* dal, T* alpha_T, float* de, T* dS_ctx, T* dKV, T* dhid_emb, T* dsent_emb, float* dw_alpha,
                   float* db_alpha);
+
+// ---- recurrent.cu (bf16 only) -------------------------------------------------------------------
+// The whole teacher-forced recurrence as one persistent cooperative kernel per direction (see recurrent.cu).
+//   *_supported: shape (and CAPDEC_RECURRENT != 0) allows the persistent kernel; otherwise the caller runs the
+//   per-step GEMM + cell schedule.  ctr: 64 unsigned arrival counters owned by the caller.
+bool lstm_seq_fwd_supported(int B, int H);
+bool lstm_seq_bwd_supported(int B, int H);
+// dst[k, 64*j + 4*u + gate] = src[k, gate*H + 16*j + u]: the forward kernel's unit-major weight copy
+void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H);
+int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf16* xe, long ld_xe, const float* g5,
+                 long ld_g5, bf16* hs, float* cs, bf16* gact, unsigned* ctr);
+// dhrec2 [2,B,H] and dcrec [B,H] fp32 scratch (zeroed here)
+int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16* dHhead, const bf16* dHprev,
+                 const float* dChead, const bf16* gact, const float* cs, bf16* dG, long ld_dg, float* dhrec2,
+                 float* dcrec, unsigned* ctr);
 
 // ---- loss.cu -----------------------------------------------------------------------------------
 // masked soft-max cross entropy (model:163-171, 180-183, 205-212): target[t*B+b] = caption[b, t+1]

@@ -335,9 +335,95 @@ __global__ void fill_kernel(float* p, float v, long n) {
   for (; i < n; i += stride) p[i] = v;
 }
 
+// ---- multi-tensor kernels: one launch for the whole parameter re-layout / gradient clearing ----
+constexpr int kChunk = 4096;  // elements per block
+
+template <typename T>
+__global__ void __launch_bounds__(256) multi_convert_kernel(const __grid_constant__ ConvertTable tab) {
+  int j = 0;
+  while (j + 1 < tab.n && (int)blockIdx.x >= tab.first_block[j + 1]) ++j;
+  const ConvertJob& job = tab.job[j];
+  const long total = (long)job.rows * job.cols;
+  const long base = (long)(blockIdx.x - tab.first_block[j]) * kChunk;
+  T* dst = reinterpret_cast<T*>(job.dst);
+#pragma unroll 4
+  for (int v = threadIdx.x; v < kChunk / 4; v += 256) {
+    const long e = base + (long)v * 4;
+    if (e >= total) break;
+    const long r = e / job.cols;
+    const int c = (int)(e % job.cols);
+    float4 x;
+    if (job.mode == 0) {
+      x = *reinterpret_cast<const float4*>(job.src + r * job.lds + c);
+    } else {  // gate permutation of recurrent.cu: dst col 64*jj + 4*u + gate <- src col gate*H + 16*jj + u
+      const float* sp = job.src + r * job.lds + (c >> 6) * 16 + ((c >> 2) & 15);
+      x = make_float4(sp[0], sp[job.H], sp[2 * (long)job.H], sp[3 * (long)job.H]);
+    }
+    T* d = dst + r * job.ldd + c;
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(d) = x;
+    } else {
+      uint2 u;
+      *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(x.x, x.y);
+      *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(x.z, x.w);
+      *reinterpret_cast<uint2*>(d) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) multi_zero_kernel(const __grid_constant__ ZeroTable tab) {
+  int j = 0;
+  while (j + 1 < tab.n && (int)blockIdx.x >= tab.first_block[j + 1]) ++j;
+  const long base = (long)(blockIdx.x - tab.first_block[j]) * kChunk;
+  float* p = tab.ptr[j];
+  const long n = tab.count[j];
+  if (tab.vec[j]) {
+#pragma unroll 4
+    for (int v = threadIdx.x; v < kChunk / 4; v += 256) {
+      const long e = base + (long)v * 4;
+      if (e + 4 <= n) *reinterpret_cast<float4*>(p + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else for (long i = e; i < n; ++i) p[i] = 0.f;
+    }
+  } else {
+    for (int v = threadIdx.x; v < kChunk; v += 256)
+      if (base + v < n) p[base + v] = 0.f;
+  }
+}
+
 }  // namespace
 
 #define BUMP(c) do { if ((c).launches) ++*(c).launches; } while (0)
+
+template <typename T> int multi_convert(LaunchCtx c, ConvertTable& tab) {
+  int blocks = 0;
+  for (int j = 0; j < tab.n; ++j) {
+    const ConvertJob& job = tab.job[j];
+    const size_t dst_al = sizeof(T) * 4;
+    if ((job.cols % 4) || (job.lds % 4) || (job.ldd % 4) || ((uintptr_t)job.src % 16) || ((uintptr_t)job.dst % dst_al) ||
+        (job.mode == 1 && (job.cols != 4 * job.H || job.H % 16)))
+      return 1;  // not vectorisable: the caller falls back to the per-tensor kernels
+    tab.first_block[j] = blocks;
+    blocks += (int)(((long)job.rows * job.cols + kChunk - 1) / kChunk);
+  }
+  tab.first_block[tab.n] = blocks;
+  if (blocks == 0) return 0;
+  multi_convert_kernel<T><<<blocks, 256, 0, c.stream>>>(tab);
+  BUMP(c);
+  return 0;
+}
+
+void multi_zero(LaunchCtx c, ZeroTable& tab) {
+  int blocks = 0;
+  for (int j = 0; j < tab.n; ++j) {
+    tab.vec[j] = ((uintptr_t)tab.ptr[j] % 16) == 0;
+    tab.first_block[j] = blocks;
+    blocks += (int)((tab.count[j] + kChunk - 1) / kChunk);
+  }
+  tab.first_block[tab.n] = blocks;
+  if (blocks == 0) return;
+  multi_zero_kernel<<<blocks, 256, 0, c.stream>>>(tab);
+  BUMP(c);
+}
 
 template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* dst, long n) {
   if (n <= 0) return;
@@ -426,6 +512,9 @@ void fill_f32(LaunchCtx c, float* p, float v, long n) {
   fill_kernel<<<grid_for(n), 256, 0, c.stream>>>(p, v, n);
   BUMP(c);
 }
+
+template int multi_convert<float>(LaunchCtx, ConvertTable&);
+template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
 
 #define INSTANTIATE(T)                                                                                                 \
   template void convert_from_f32<T>(LaunchCtx, const float*, T*, long);                                                \

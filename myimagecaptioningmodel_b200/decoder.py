@@ -220,6 +220,21 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
+    def profile(self, enable: bool = True) -> None:
+        """Switch the device-side phase timeline on or off (capdec_profile)."""
+        check(self.lib.capdec_profile(self.handle, 1 if enable else 0), "capdec_profile")
+
+    def profile_report(self) -> dict:
+        """{phase: milliseconds} summed since the previous report (synchronises on the last recorded event)."""
+        import ctypes
+        buf = ctypes.create_string_buffer(8192)
+        check(self.lib.capdec_profile_report(self.handle, buf, len(buf)), "capdec_profile_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(" ", 1)
+            out[name] = float(ms)
+        return out
+
 
 # --------------------------------------------------------------------------------------------------------------
 # reference-shaped interface

@@ -1,0 +1,61 @@
+"""Device-side phase timeline of one train step and one beam decode (CUDA events inside libcapdec.so, no profiler):
+where the step time goes, in stream order, warm caches.  python scripts/phase_times.py [--batch 256] [--reps 5]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import myimagecaptioningmodel_b200 as M  # noqa: E402
+from myimagecaptioningmodel_b200 import synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--decode-images", type=int, default=512)
+ap.add_argument("--beam", type=int, default=3)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--axis", default="position")
+args = ap.parse_args()
+
+cfg = M.DecoderConfig(dtype="bf16", softmax_axis=args.axis)
+eng = M.CaptionDecoderEngine(cfg, seed=0)
+g, P, cap = synth.make_batch(cfg, args.batch, 20260)
+g, P, cap = g.cuda(), P.cuda(), cap.cuda()
+
+
+def step():
+    eng.bind_params()
+    eng.train_forward(g, P, cap)
+    eng.train_backward(want_dg=True, want_dP=True)
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+eng.profile(True)
+for _ in range(args.reps):
+    step()
+rep = eng.profile_report()
+total = sum(rep.values())
+print("train step B=%d: %.3f ms (sum of phases, avg of %d)" % (args.batch, total / args.reps, args.reps))
+for k, v in rep.items():
+    print("  %-24s %8.1f us  %5.1f%%" % (k, 1e3 * v / args.reps, 100 * v / total))
+out = {"train_us": {k: 1e3 * v / args.reps for k, v in rep.items()}}
+if args.decode_images:
+    gi, Pi, _ = synth.make_batch(cfg, args.decode_images, 777)
+    gi, Pi = gi.cuda(), Pi.cuda()
+    eng.profile(False)
+    eng.decode(gi, Pi, beam=args.beam, finish_on_stop=True)
+    torch.cuda.synchronize()
+    eng.profile(True)
+    for _ in range(args.reps):
+        eng.decode(gi, Pi, beam=args.beam, finish_on_stop=True)
+    rep = eng.profile_report()
+    total = sum(rep.values())
+    print("beam decode %d images x beam %d: %.3f ms" % (args.decode_images, args.beam, total / args.reps))
+    for k, v in rep.items():
+        print("  %-24s %8.1f us  %5.1f%%" % (k, 1e3 * v / args.reps, 100 * v / total))
+    out["decode_us"] = {k: 1e3 * v / args.reps for k, v in rep.items()}
+print(json.dumps(out))

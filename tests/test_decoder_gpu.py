@@ -114,6 +114,42 @@ def test_train_step_reference_config_batch8(dtype):
     print(dtype, {k: "%.2e" % v for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("dims,B", [(MID, 9), (MID, 130), (MID, 300), ({}, 131), ({}, 300)])
+def test_persistent_recurrence_matches_per_step_schedule(dims, B, monkeypatch):
+    """The persistent cooperative recurrence kernels (recurrent.cu: W_hh resident in shared memory, one launch per
+    direction) against the per-step GEMM + cell schedule they replace, on ragged batch tiles (B % 128 != 0, more
+    batch tiles than CTA groups), and against the oracle at the small sizes."""
+    ocfg = R.DecoderConfig(softmax_axis="position", **dims)
+    params = R.init_params(ocfg, 11, torch.float32, bias_scale=0.1)
+    g, P, cap = synth.make_batch(ocfg, B, 99)
+    eng = _engine(dims, "position", "bf16", params)
+    gd, Pd, capd = g.cuda(), P.cuda(), cap.cuda()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CAPDEC_RECURRENT", mode)
+        eng.bind_params()
+        n0 = eng.launch_count
+        loss_buf, logits = eng.train_forward(gd, Pd, capd, want_logits=True)
+        dg, dP = eng.train_backward()
+        torch.cuda.synchronize()
+        out[mode] = dict(loss=float(loss_buf[2]), logits=logits.clone(), dg=dg.clone(), dP=dP.clone(),
+                         grads={k: v.clone() for k, v in eng.store.grads.items()}, launches=eng.launch_count - n0)
+    a, b = out["1"], out["0"]
+    T = ocfg.sentence_length - 1
+    assert b["launches"] - a["launches"] >= 4 * T - 8, (a["launches"], b["launches"])   # the persistent path really ran
+    assert abs(a["loss"] - b["loss"]) < 2e-3 * abs(b["loss"])
+    assert rel_err(a["logits"], b["logits"]) < 5e-3
+    assert rel_err(a["dg"], b["dg"]) < 1e-2 and rel_err(a["dP"], b["dP"]) < 1e-2
+    for name in M.PARAM_NAMES:
+        if name == "fc_a_b" or float(b["grads"][name].abs().max()) == 0.0:
+            continue
+        assert rel_err(a["grads"][name], b["grads"][name]) < 1e-2, name
+    if B <= 130 and dims:
+        p64 = {k: v.double() for k, v in params.items()}
+        monkeypatch.setenv("CAPDEC_RECURRENT", "1")
+        _check_train(eng, ocfg, p64, g.double(), P.double(), cap, TOL["bf16"])
+
+
 def _explained_by_margin(ids_gpu, ids_ref, margin, noise):
     """ids must agree up to the first step whose oracle decision margin is below the numerical noise"""
     bad = 0
