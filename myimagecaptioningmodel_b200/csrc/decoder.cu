@@ -158,8 +158,11 @@ template <typename T> class Decoder : public DecoderBase {
     const float* lw_h = p->lstm_w + (size_t)X * 4 * H;   // hidden rows of lstm_w
     bool want_perm = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (!force_simt && lstm_seq_fwd_supported(1, H)) {  // unit-major copy for the persistent forward recurrence
+      if (!force_simt && lstm_seq_supported(1, H)) {  // unit-major copy for the persistent forward recurrence
         OK(w_hh_perm.ensure(e * H * 4 * H, &ws_bytes));
+        OK(w_x_p.ensure(e * E * 5 * H, &ws_bytes));
+        OK(w_g_p.ensure(e * H * 5 * H, &ws_bytes));
+        OK(b5p.ensure(4 * 5 * H, &ws_bytes));
         want_perm = true;
       }
     }
@@ -184,7 +187,15 @@ template <typename T> class Decoder : public DecoderBase {
     tab.add(p->fc_xs_w, H, wd + 4 * H, 5 * H, E, H);
     tab.add(lw_h, 4 * H, wd + (size_t)E * 5 * H, 5 * H, H, 4 * H);
     tab.add(p->fc_hs_w, H, wd + (size_t)E * 5 * H + 4 * H, 5 * H, H, H);
-    if (want_perm) tab.add(lw_h, 4 * H, w_hh_perm.p, 4 * H, H, 4 * H, 1, H);
+    if (want_perm) {
+      // unit-major gate columns (col 4*unit + gate) for the persistent recurrence: W_hh, and the x-side weights whose
+      // GEMMs produce the pre-activation tile the kernel loads by TMA
+      tab.add(lw_h, 4 * H, w_hh_perm.p, 4 * H, H, 4 * H, 1, H);
+      tab.add(p->lstm_w, 4 * H, w_x_p.p, 5 * H, E, 4 * H, 1, H);
+      tab.add(p->fc_xs_w, H, w_x_p.as<T>() + 4 * H, 5 * H, E, H);
+      tab.add(lw_g, 4 * H, w_g_p.p, 5 * H, H, 4 * H, 1, H);
+      tab.add(p->fc_xs_w + (size_t)E * H, H, w_g_p.as<T>() + 4 * H, 5 * H, H, H);
+    }
     const int rc = multi_convert<T>(lc, tab);
     if (rc < 0) return -1;
     if (rc > 0) {  // unaligned caller buffers: per-tensor scalar kernels
@@ -202,6 +213,12 @@ template <typename T> class Decoder : public DecoderBase {
     CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b5d.p, b5.p, 4 * 5 * H, cudaMemcpyDeviceToDevice, s));
     add_f32(lc, b5d.as<float>() + 4 * H, p->fc_hs_b, H);
+    if (want_perm) {
+      ConvertTable bt;
+      bt.add(p->lstm_b, 4 * H, b5p.p, 4 * H, 1, 4 * H, 1, H);
+      if (multi_convert<float>(lc, bt) != 0) { set_error("capdec_bind_params: lstm_b must be 16-byte aligned"); return -1; }
+      CUDA_OK(cudaMemcpyAsync(b5p.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
+    }
     CUDA_OK(cudaGetLastError());
     prof.mark("bind_params", s);
     bound = true;
@@ -281,24 +298,38 @@ template <typename T> class Decoder : public DecoderBase {
 
     // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
     embed_gather<T>(lc, emb.as<T>(), E, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E);
-    // hoisted x-part of the gate GEMM and of p_word_emb (model:86-89): word-embedding columns for all T steps ...
-    OK(fc(gc, embx.p, E, w_x_n.as<T>(), 5 * H, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
-    // ... and the global-image columns (+ biases) once per image
-    OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    bool persistent = false;
+    if constexpr (std::is_same<T, bf16>::value) persistent = !force_simt && lstm_seq_supported(B, H) && w_hh_perm.p;
+    if (persistent) {
+      // Persistent recurrence: ONE activation holds the complete x-part of the gate / sentinel pre-activations,
+      //   xe[t*B+b] = emb(word).[lstm_w(word) | fc_xs(word)] + (g[b].[lstm_w(global) | fc_xs(global)] + biases),
+      // gate columns unit-major (col 4*unit + gate) so that a CTA's 16 units are one 128-byte line per row; the
+      // per-image term is added by the GEMM epilogue (row-broadcast addend, row m -> m % B).
+      OK(g5b.ensure(e * (size_t)B * 5 * H, &ws_bytes));
+      OK(fc(gc, gT.p, H, w_g_p.as<T>(), 5 * H, b5p.as<float>(), g5b.p, 5 * H, B, 5 * H, H, ACT_NONE));
+      GemmCall c;
+      c.A = embx.p; c.lda = E; c.B = w_x_p.p; c.ldb = 5 * H; c.b_mn = true; c.C = xe.p; c.ldc = 5 * H; c.M = (int)M;
+      c.N = 5 * H; c.K = E; c.epi.addend = g5b.p; c.epi.ld_add = 5 * H; c.epi.add_mod = B;
+      OK(gemm<T>(gc, c));
+    } else {
+      // hoisted x-part of the gate GEMM and of p_word_emb (model:86-89): word-embedding columns for all T steps ...
+      OK(fc(gc, embx.p, E, w_x_n.as<T>(), 5 * H, nullptr, xe.p, 5 * H, (int)M, 5 * H, E, ACT_NONE));
+      // ... and the global-image columns (+ biases) once per image
+      OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+    }
     prof.mark("fwd.embed_xe_g5", s);
     // recurrent core (model:63, 87-88, 94-95)
     CUDA_OK(cudaMemsetAsync(hs.p, 0, e * (size_t)B * H, s));
     CUDA_OK(cudaMemsetAsync(cs.p, 0, 4 * (size_t)B * H, s));
-    bool persistent = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (!force_simt && lstm_seq_fwd_supported(B, H) && w_hh_perm.p) {
+      if (persistent) {
         // all T steps in one persistent kernel: W_hh resident in shared memory, cell fused into the MMA epilogue
         OK(rec_ctr.ensure(256, &ws_bytes));
-        OK(lstm_seq_fwd(lc, B, H, Tt, w_hh_perm.as<bf16>(), xe.as<bf16>(), 5 * H, g5.as<float>(), 5 * H, hs.as<bf16>(),
-                        cs.as<float>(), gact.as<bf16>(), rec_ctr.as<unsigned>()));
-        persistent = true;
+        OK(lstm_seq_fwd(lc, B, H, Tt, w_hh_perm.as<bf16>(), xe.as<bf16>(), 5 * H, hs.as<bf16>(), cs.as<float>(),
+                        gact.as<bf16>(), rec_ctr.as<unsigned>()));
       }
     }
+    fwd_persistent = persistent;
     for (int t = 0; t < Tt && !persistent; ++t) {
       OK(fc(gc, hs.as<T>() + (size_t)t * B * H, H, w_hh_n.as<T>(), 4 * H, nullptr, gpre.p, 4 * H, B, 4 * H, H, ACT_NONE,
               true));
@@ -312,8 +343,8 @@ template <typename T> class Decoder : public DecoderBase {
     const float* Ccur = cs.as<float>() + (size_t)B * H;
     // time-batched head
     OK(fc(gc, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, (int)M, H, H, ACT_NONE));                       // model:90
-    sentinel_fwd<T>(lc, M, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, g5.as<float>() + 4 * H, 5 * H, B, 1, Ccur,
-                    sgate.as<T>(), sent.as<T>());                                                     // model:91-92
+    sentinel_fwd<T>(lc, M, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, persistent ? nullptr : g5.as<float>() + 4 * H,
+                    5 * H, B, 1, Ccur, sgate.as<T>(), sent.as<T>());                                  // model:91-92
     OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
     OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
     OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
@@ -481,7 +512,7 @@ template <typename T> class Decoder : public DecoderBase {
     // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
     bool persistent = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (!force_simt && lstm_seq_bwd_supported(B, H)) {
+      if (fwd_persistent) {  // same schedule as the forward pass (the gate-activation layouts differ)
         OK(rec_ctr.ensure(256, &ws_bytes));
         OK(lstm_seq_bwd(lc, B, H, Tt, w_hh_n.as<bf16>(), dHhead.as<bf16>(), dHprev.as<bf16>(), dChead.as<float>(),
                         gact.as<bf16>(), cs.as<float>(), dG.as<bf16>(), 5 * H, dhrec.as<float>(), dcrec.as<float>(),
@@ -657,14 +688,14 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
 
   capdec_config cfg;
   capdec_params prm{};
   int H, E, V, Vp, k, S, Tt, Ti;
-  bool bound = false, have_fwd = false, force_simt = false;
+  bool bound = false, have_fwd = false, force_simt = false, fwd_persistent = false;
   int last_B = 0;
   const int64_t* last_cap = nullptr;
   // operands
@@ -674,7 +705,7 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr;
+      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
 };

@@ -22,6 +22,8 @@ struct GemmEpi {
   const void* dact_y = nullptr;  // T [M, ld_y]: ACT_DTANH multiplies by (1 - y^2)
   long ld_add = 0, ld_y = 0;
   long batch_add = 0, batch_y = 0;  // element strides between batches of addend / dact_y
+  int add_mod = 0;               // > 0: the addend row of output row m is m % add_mod (a [add_mod, ld_add] block broadcast
+                                 // down the rows: the per-image term of a time-major [T*B, N] activation)
   int act = ACT_NONE;
   int out_f32 = 0;               // C is fp32 (otherwise T)
   int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
@@ -47,7 +49,7 @@ template <typename T>
 __device__ __forceinline__ float epi_value(float acc, int m, int n, const GemmEpi& e) {
   float v = e.alpha_dev ? acc * __ldg(e.alpha_dev) : acc;
   if (e.bias) v += __ldg(e.bias + n);
-  if (e.addend) v += to_f(reinterpret_cast<const T*>(e.addend)[(long)m * e.ld_add + n]);
+  if (e.addend) v += to_f(reinterpret_cast<const T*>(e.addend)[(long)(e.add_mod > 0 ? m % e.add_mod : m) * e.ld_add + n]);
   if (e.act == ACT_TANH) v = tanh_t<fast_math<T>::value>(v);
   if (e.act == ACT_DTANH) {
     float y = to_f(reinterpret_cast<const T*>(e.dact_y)[(long)m * e.ld_y + n]);

@@ -338,8 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* my_stage = staging + ew * 4096;
         const uint32_t swz = (uint32_t)(lane & 7);
         uint8_t* my_row = my_stage + lane * 128;
+        const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
         const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
-                                                         (long)row * epi.ld_add + n0
+                                                         add_row * epi.ld_add + n0
                                                    : nullptr;
         const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
                               ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
@@ -464,17 +465,17 @@ void load_encode() {
 }
 
 struct MapKey {
-  const void* p; uint64_t inner, outer, ld, nb, bs; uint32_t bi, bo; int esize;
+  const void* p; uint64_t inner, outer, ld, nb, bs; uint32_t bi, bo; int esize, swizzle;
   bool operator==(const MapKey& o) const {
     return p == o.p && inner == o.inner && outer == o.outer && ld == o.ld && nb == o.nb && bs == o.bs && bi == o.bi &&
-           bo == o.bo && esize == o.esize;
+           bo == o.bo && esize == o.esize && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.p;
     auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.nb); mix(k.bs); mix(k.bi); mix(k.bo); mix((uint64_t)k.esize);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.nb); mix(k.bs); mix(k.bi); mix(k.bo); mix((uint64_t)k.esize); mix((uint64_t)k.swizzle);
     return h;
   }
 };
@@ -482,9 +483,9 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
 // 3-D tensor [nb, outer, inner] of bf16 (esize 2) or fp32 (esize 4): row stride ld, batch stride bs (elements);
-// box = [1, bo, bi]; 128-byte swizzle.
+// box = [1, bo, bi]; 128-byte swizzle (or none: plain row-major box in shared memory).
 int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
-            int esize, uint64_t nb, uint64_t bs) {
+            int esize, uint64_t nb, uint64_t bs, bool swizzle = true) {
   if (nb <= 1) { nb = 1; bs = ld * (outer > 0 ? outer : 1); }
   if ((bs * esize) & 15) {
     set_error("gemm_tc: batch stride %llu is not a multiple of 16 bytes", (unsigned long long)bs);
@@ -496,7 +497,7 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
     set_error("gemm_tc: operand %p (ld=%llu) is not 16-byte aligned for TMA", p, (unsigned long long)ld);
     return -1;
   }
-  MapKey key{p, inner, outer, ld, nb, bs, bi, bo, esize};
+  MapKey key{p, inner, outer, ld, nb, bs, bi, bo, esize, swizzle ? 1 : 0};
   {
     std::lock_guard<std::mutex> g(g_maps_mu);
     auto it = g_maps.find(key);
@@ -507,7 +508,8 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   cuuint32_t box[3] = {bi, bo, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(p), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, p,
@@ -594,8 +596,8 @@ void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 
 // the tensor-map cache, for the other TMA kernels of the library (recurrent.cu)
 int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
-               int esize, uint64_t nb, uint64_t bs) {
-  return get_map(p, inner, outer, ld, bi, bo, out, esize, nb, bs);
+               int esize, uint64_t nb, uint64_t bs, bool swizzle) {
+  return get_map(p, inner, outer, ld, bi, bo, out, esize, nb, bs, swizzle);
 }
 
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {

@@ -113,12 +113,12 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
 // The whole teacher-forced recurrence as one persistent cooperative kernel per direction (see recurrent.cu).
 //   *_supported: shape (and CAPDEC_RECURRENT != 0) allows the persistent kernel; otherwise the caller runs the
 //   per-step GEMM + cell schedule.  ctr: 64 unsigned arrival counters owned by the caller.
-bool lstm_seq_fwd_supported(int B, int H);
-bool lstm_seq_bwd_supported(int B, int H);
+bool lstm_seq_supported(int B, int H);
 // dst[k, 64*j + 4*u + gate] = src[k, gate*H + 16*j + u]: the forward kernel's unit-major weight copy
 void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H);
-int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf16* xe, long ld_xe, const float* g5,
-                 long ld_g5, bf16* hs, float* cs, bf16* gact, unsigned* ctr);
+// xe [T*B, ld_xe]: complete x-part of the gate pre-activations in columns [0, 4H), unit-major (col 4*unit + gate)
+int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf16* xe, long ld_xe, bf16* hs, float* cs,
+                 bf16* gact, unsigned* ctr);
 // dhrec2 [2,B,H] and dcrec [B,H] fp32 scratch (zeroed here)
 int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16* dHhead, const bf16* dHprev,
                  const float* dChead, const bf16* gact, const float* cs, bf16* dG, long ld_dg, float* dhrec2,

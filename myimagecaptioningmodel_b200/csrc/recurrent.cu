@@ -31,7 +31,7 @@ namespace capdec {
 
 // gemm_tc.cu: cached cuTensorMapEncodeTiled wrapper, 3-D tensor {inner, outer, batch}, SWIZZLE_128B
 int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
-               int esize, uint64_t nb, uint64_t bs);
+               int esize, uint64_t nb, uint64_t bs, bool swizzle = true);
 
 namespace {
 
@@ -70,6 +70,35 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// cluster helpers: the CTAs of a cluster load disjoint row blocks of the same h tile and multicast them to each other
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// the mbarrier at the same shared-memory offset in every CTA of `mask` receives one arrival once the MMAs retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
@@ -77,6 +106,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // UMMA shared-memory descriptors, SWIZZLE_128B (same encoding as gemm_tc.cu)
@@ -108,6 +138,7 @@ struct Bars {
   uint64_t* tmem_full;
   uint64_t* tmem_empty;
   uint64_t* w_bar;
+  uint64_t* go;        // forward: the producer has passed the inter-CTA barrier of this step
   uint32_t* tmem_ptr;
 };
 template <int kStages> __device__ __forceinline__ Bars carve_bars(uint8_t* p) {
@@ -117,69 +148,90 @@ template <int kStages> __device__ __forceinline__ Bars carve_bars(uint8_t* p) {
   b.tmem_full = b.empty + kStages;
   b.tmem_empty = b.tmem_full + 2;
   b.w_bar = b.tmem_empty + 2;
-  b.tmem_ptr = reinterpret_cast<uint32_t*>(b.w_bar + 1);
+  b.go = b.w_bar + 1;
+  b.tmem_ptr = reinterpret_cast<uint32_t*>(b.go + 1);
   return b;
 }
-template <int kStages> __device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals) {
+template <int kStages>
+__device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals, uint32_t consumers = 1) {
   for (int s = 0; s < kStages; ++s) {
     mbar_init(&b.full[s], 1);
-    mbar_init(&b.empty[s], 1);
+    mbar_init(&b.empty[s], consumers);  // one MMA commit per CTA that reads the stage (cluster multicast: all of them)
   }
   for (int i = 0; i < 2; ++i) {
     mbar_init(&b.tmem_full[i], 1);
     mbar_init(&b.tmem_empty[i], epi_arrivals);
   }
   mbar_init(b.w_bar, 1);
+  mbar_init(b.go, 1);
   mbar_fence_init();
 }
 
 // ================================================================================================================
 // forward
 // ================================================================================================================
-constexpr int kFwdStages = 5;
+constexpr int kFwdStages = 4;
 constexpr int kFwdUnits = 16;            // hidden units per CTA
 constexpr int kFwdN = 4 * kFwdUnits;     // 64 gate columns
 constexpr int kFwdWTile = BK * kFwdN * 2;  // 8 KB per k-block of the resident weight slice
+constexpr int kFwdCStage = 128 * kFwdUnits * 4;  // 8 KB: c_t tile, 128 rows x 64 B, row-major
+constexpr int kFwdXStage = 128 * kFwdN * 2;      // 16 KB: 128 rows x 128 B, SWIZZLE_128B: x-part pre-activations in,
+                                                 //        gate activations out (same tile, one after the other)
 
 struct SeqFwdParams {
   int B, H, T;
   int n_mtiles;
-  const bf16* xe; long ld_xe;   // [T*B, ld_xe]  x-part of the gate pre-activations (cols gate*H + unit)
-  const float* g5; long ld_g5;  // [B, ld_g5]    global-image part + biases
   bf16* hs;                     // [(T+1)*B, H]  hs[0] = h_0 (zeros)
-  float* cs;                    // [(T+1)*B, H]  cs[0] = c_0 (zeros)
-  bf16* gact;                   // [T*B, 4H]     gate activations kept for the backward pass
+  const float* cs;              // [(T+1)*B, H]  cs[0] = c_0 (zeros); written through the tensor map
   unsigned* ctr;                // [gridDim.y]   arrival counters (zeroed by the host)
   unsigned long long* trace;    // debug timeline or nullptr
 };
 
+// Everything except h_t moves through the TMA engine in whole 128-byte lines: the per-step x-part pre-activations
+// (word-embedding and global-image terms and biases, summed by the producing GEMM; unit-major columns 4*unit + gate
+// like the weight slice) come in as one [128 x 64] tile, c_t and the gate activations go out as two tensor stores.
+// Per-lane global loads (every lane = another row = another line) were measured to cost ~3000 L1 wavefronts and
+// ~400 K sector requests per step, which either delayed the producer's polls of the arrival counter (~3 us per step)
+// or, when issued after the barrier, slowed the h tile stream by 70 %.
+//
+// CS = cluster size along the unit-slice dimension: the CS CTAs of a cluster work on the same batch tile, each loads
+// 128/CS rows of every h k-block and multicasts them.  Measured on B200: no gain over CS = 1 (474 / 468 / 469 us for
+// CS = 1 / 2 / 4) -- delivery into the SMs, not the L2 read, bounds the h stream -- so CS = 1 is the default.
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, SeqFwdParams p) {
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmCs,
+                    const __grid_constant__ CUtensorMap tmGa, SeqFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + misalign;
   const int nkb = p.H / BK;
   uint8_t* wsm = smem;                                  // nkb x 8 KB   resident weight slice
   uint8_t* stages = wsm + (size_t)nkb * kFwdWTile;      // kFwdStages x 16 KB   h tiles
-  const Bars bar = carve_bars<kFwdStages>(stages + kFwdStages * kATile);
+  uint8_t* x_stage = stages + kFwdStages * kATile;      // 16 KB (1024-aligned)
+  uint8_t* c_stage = x_stage + kFwdXStage;              // 8 KB
+  const Bars bar = carve_bars<kFwdStages>(c_stage + kFwdCStage);
+  uint64_t* x_full = bar.go;                            // the x tile of the next batch tile has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x, y = blockIdx.y, G = gridDim.x, MG = gridDim.y;
-  // All CTAs of a batch group walk the k-blocks of the same h tile in the same order: measured on B200, staggering the
-  // start (rot = slice % nkb) is SLOWER (481 vs 426 us for 34 steps) -- simultaneous requests for one line are merged
-  // by the L2, staggered ones are not.
-  const int rot = 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmW);
-    init_bars<kFwdStages>(bar, 4);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmCs);
+    tma_prefetch_desc(&tmGa);
+    init_bars<kFwdStages>(bar, 4, CS);
   }
   if (warp == 1) tmem_alloc<2 * kFwdN>(bar.tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // every CTA's barriers are initialised before a peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *bar.tmem_ptr;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -195,11 +247,14 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
         rec_trace(p.trace, p.T, t, 0);
         for (int mt = y; mt < p.n_mtiles; mt += MG) {
-          for (int i = 0; i < nkb; ++i) {
-            const int kb = (i + rot) % nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait_b(&bar.empty[s], ph ^ 1);
             mbar_expect_tx(&bar.full[s], kATile);
-            tma_load_3d(stages + s * kATile, &tmH, kb * BK, mt * 128, t, &bar.full[s]);
+            if (CS == 1)
+              tma_load_3d(stages + s * kATile, &tmH, kb * BK, mt * 128, t, &bar.full[s]);
+            else
+              tma_load_3d_mc(stages + s * kATile + crank * (kATile / CS), &tmH, kb * BK, mt * 128 + crank * (128 / CS), t,
+                             &bar.full[s], cmask);
             if (++s == kFwdStages) { s = 0; ph ^= 1; }
           }
         }
@@ -220,17 +275,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           mbar_wait_b(&bar.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kFwdN);
-          for (int i = 0; i < nkb; ++i) {
-            const int kb = (i + rot) % nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait_b(&bar.full[s], ph);
-            if (i == 0) rec_trace(p.trace, p.T, t, 2);
+            if (kb == 0) rec_trace(p.trace, p.T, t, 2);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(stages + s * kATile);
             const uint32_t b_addr = smem_u32(wsm + (size_t)kb * kFwdWTile);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d, desc_kmajor(a_addr, k), desc_mnmajor(b_addr, k), idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&bar.empty[s]);
+              umma_bf16(tmem_d, desc_kmajor(a_addr, k), desc_mnmajor(b_addr, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (CS == 1) umma_commit(&bar.empty[s]);
+            else umma_commit_mc(&bar.empty[s], cmask);
             if (++s == kFwdStages) { s = 0; ph ^= 1; }
           }
           umma_commit(&bar.tmem_full[buf]);
@@ -244,80 +299,121 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     const int et = threadIdx.x - 64;  // 0..127
     const int u0 = slice * kFwdUnits;
     const long BH = (long)p.B * p.H;
+    const int trow = quarter * 32 + lane;  // row of the 128-row tile = TMEM lane
+    uint8_t* x_row = x_stage + trow * 128;
+    uint8_t* c_row = c_stage + trow * 64;
+    const uint32_t swz = (uint32_t)(lane & 7);
+    // c_{t-1} of this thread's row: with one batch tile per CTA it is still in the c staging tile of the previous
+    // step; otherwise it is read back from global memory once the tensor stores that wrote it have completed
+    const bool single_tile = (MG >= p.n_mtiles);
+    if (et == 0) {  // x tile of the first (step, batch tile)
+      mbar_expect_tx(x_full, kFwdXStage);
+      tma_load_3d(x_stage, &tmX, 4 * u0, y * 128, 0, x_full);
+    }
     int it = 0;
     for (int t = 0; t < p.T; ++t) {
+      if (t > 0 && !single_tile) {
+        if (et == 0) {
+          bulk_wait_all();
+          fence_proxy_async_all();
+        }
+        epi_bar_sync();
+      }
       for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
         const int buf = it & 1;
-        const int row = mt * 128 + quarter * 32 + lane;
+        const int row = mt * 128 + trow;
         const bool row_ok = row < p.B;
-        // pre-activation addends and c_{t-1} do not depend on the MMA: fetch them while it runs
-        float pre[2][4][8], cp[2][8];
-        if (row_ok) {
-          const bf16* xr = p.xe + ((long)t * p.B + row) * p.ld_xe + u0;
-          const float* gr = p.g5 + (long)row * p.ld_g5 + u0;
+        float cp[2][8];
+        if (t > 0 && single_tile) {
+          load8(reinterpret_cast<const float*>(c_row), cp[0]);
+          load8(reinterpret_cast<const float*>(c_row) + 8, cp[1]);
+        } else if (row_ok) {
           const float* cr = p.cs + (long)t * BH + (long)row * p.H + u0;
+          load8(cr, cp[0]);
+          load8(cr + 8, cp[1]);
+        } else {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float a[8];
-              load8(xr + (long)g * p.H + hh * 8, a);
-              load8(gr + (long)g * p.H + hh * 8, pre[hh][g]);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pre[hh][g][i] += a[i];
-            }
-            load8(cr + hh * 8, cp[hh]);
-          }
+          for (int i = 0; i < 8; ++i) cp[0][i] = cp[1][i] = 0.f;
         }
+        // x-part pre-activations of this tile: shared memory -> registers (bf16, 8 units x 4 gates per 16 B chunk pair)
+        uint4 xq[8];
+        mbar_wait_b(x_full, (uint32_t)(it & 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xq[q] = *reinterpret_cast<const uint4*>(x_row + (((uint32_t)q ^ swz) << 4));
         mbar_wait_b(&bar.tmem_full[buf], (it >> 1) & 1);
         if (et == 0) rec_trace(p.trace, p.T, t, 4);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kFwdN) + ((uint32_t)(quarter * 32) << 16);
+        // every thread has read its x row (and its c row): the tile may now be overwritten with the gate activations
+        epi_bar_sync();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
           __syncwarp();
           tmem_ld32(tmem_d + (uint32_t)(hh * 32), r);
           tmem_ld_wait();
-          if (row_ok) {
-            float hn[8], cn[8], ga[4][8];
+          float hn[8], cn[8];
+          uint4 gq[4];  // gate activations of units 2q, 2q+1 as bf16 (i,f,o,g each)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float ig = sigmoid_t<true>(__uint_as_float(r[4 * u + 0]) + pre[hh][0][u]);
-              const float fg = sigmoid_t<true>(__uint_as_float(r[4 * u + 1]) + pre[hh][1][u]);
-              const float og = sigmoid_t<true>(__uint_as_float(r[4 * u + 2]) + pre[hh][2][u]);
-              const float gg = tanh_t<true>(__uint_as_float(r[4 * u + 3]) + pre[hh][3][u]);
-              cn[u] = fg * cp[hh][u] + ig * gg;
-              hn[u] = og * tanh_t<true>(cn[u]);
-              ga[0][u] = ig; ga[1][u] = fg; ga[2][u] = og; ga[3][u] = gg;
-            }
-            const long o = (long)(t + 1) * BH + (long)row * p.H + u0 + hh * 8;
-            store8(p.hs + o, hn);
-            store8(p.cs + o, cn);
-            bf16* gw = p.gact + ((long)t * p.B + row) * 4 * p.H + u0 + hh * 8;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) store8(gw + (long)g * p.H, ga[g]);
+          for (int u = 0; u < 8; ++u) {
+            // chunk hh*4 + u/2 of the x row holds units 2(u/2), 2(u/2)+1: (i,f,o,g) x 2
+            const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[hh * 4 + (u >> 1)]) + (u & 1) * 2;
+            const float2 x_if = __bfloat1622float2(xp[0]), x_og = __bfloat1622float2(xp[1]);
+            const float ig = sigmoid_t<true>(__uint_as_float(r[4 * u + 0]) + x_if.x);
+            const float fg = sigmoid_t<true>(__uint_as_float(r[4 * u + 1]) + x_if.y);
+            const float og = sigmoid_t<true>(__uint_as_float(r[4 * u + 2]) + x_og.x);
+            const float gg = tanh_t<true>(__uint_as_float(r[4 * u + 3]) + x_og.y);
+            cn[u] = fg * cp[hh][u] + ig * gg;
+            hn[u] = og * tanh_t<true>(cn[u]);
+            __nv_bfloat162* gp = reinterpret_cast<__nv_bfloat162*>(&gq[u >> 1]) + (u & 1) * 2;
+            gp[0] = __floats2bfloat162_rn(ig, fg);
+            gp[1] = __floats2bfloat162_rn(og, gg);
           }
+          if (row_ok) store8(p.hs + (long)(t + 1) * BH + (long)row * p.H + u0 + hh * 8, hn);
+          // rows past the batch are clipped by the tensor stores
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(x_row + (((uint32_t)(hh * 4 + q) ^ swz) << 4)) = gq[q];
+          *reinterpret_cast<float4*>(c_row + hh * 32) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(c_row + hh * 32 + 16) = make_float4(cn[4], cn[5], cn[6], cn[7]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
-      }
-      if (et == 0) rec_trace(p.trace, p.T, t, 5);
-      if (t + 1 < p.T) {
-        // h_t of this CTA's slice is written: release it to the other CTAs of the batch group
+        const bool last_tile = (mt + MG >= p.n_mtiles);
+        const bool release = (t + 1 < p.T) && last_tile;
+        if (t + 1 < p.T) __threadfence();  // this thread's h_t stores are performed at GPU scope
+        fence_proxy_async_all();            // staging writes -> async proxy
+        if (et == 0) rec_trace(p.trace, p.T, t, 5);
         epi_bar_sync();
         if (et == 0) {
-          rec_trace(p.trace, p.T, t, 6);
-          __threadfence();
-          atomicAdd(p.ctr + y, 1u);
-          rec_trace(p.trace, p.T, t, 7);
+          if (release) {
+            // release h_t of this CTA's slice to the other CTAs of the batch group
+            rec_trace(p.trace, p.T, t, 6);
+            __threadfence();
+            atomicAdd(p.ctr + y, 1u);
+            rec_trace(p.trace, p.T, t, 7);
+          }
+          tma_store_3d(&tmCs, c_stage, u0, mt * 128, t + 1);
+          tma_store_3d(&tmGa, x_stage, 4 * u0, mt * 128, t);
+          bulk_commit();
+          // next (step, batch tile) of this CTA: its x tile goes into the same buffer once the store has read it
+          int nmt = mt + MG, nt = t;
+          if (nmt >= p.n_mtiles) { nmt = y; nt = t + 1; }
+          if (nt < p.T) {
+            bulk_wait_read_all();
+            mbar_expect_tx(x_full, kFwdXStage);
+            tma_load_3d(x_stage, &tmX, 4 * u0, nmt * 128, nt, x_full);
+          }
         }
+        // the c / gate staging tiles are rewritten only after the next tile's epi_bar_sync, which thread 0 reaches
+        // after the bulk_wait_read above
       }
     }
+    if (et == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no peer still multicasts into, or signals barriers of, an exited CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<2 * kFwdN>(tmem_base);
@@ -338,7 +434,7 @@ struct SeqBwdParams {
   const bf16* dHhead;    // [T*B, H]   d loss / d h_t from the head (p_hid path)
   const bf16* dHprev;    // [T*B, H]   row block t: d loss / d h_{t-1} from step t's p_hidden
   const float* dChead;   // [T*B, H]   d loss / d c_t from the sentinel
-  const bf16* gact;      // [T*B, 4H]
+  const bf16* gact;      // [T*B, 4H]   unit-major (col 4*unit + gate), as written by lstm_seq_fwd_kernel
   const float* cs;       // [(T+1)*B, H]
   bf16* dG; long ld_dg;  // [T*B, ld_dg] cols gate*H + unit
   float* dhrec;          // [2, B, H] ping-pong d h through the gates (zeroed by the host)
@@ -348,50 +444,102 @@ struct SeqBwdParams {
   unsigned long long* trace;
 };
 
-// one BPTT step of the cell for this CTA's share of the batch tile `mt` (8 hidden units per item)
-__device__ __forceinline__ void cell_bwd_items(const SeqBwdParams& p, int t, int mt, int cta, int G, int et) {
+// ---- one BPTT step of the cell for 8 hidden units of one row ("item") ----
+// Raw operands of an item; loads of several items are issued back to back before any arithmetic.
+struct CellItem {
+  long m;        // row of the [T*B, *] activations, or -1 for "no item"
+  int row, h0;
+  uint4 dhh, dhp, ga[4];   // bf16 x 8: d h (head), d h_{t-1} (p_hidden path, step t+1); gates: 8 units x (i,f,o,g)
+  float4 dch[2], dcr[2], ct[2], cp[2], dhr[2];    // fp32 x 8: d c (head), running d c, c_t, c_{t-1}, d h through the gates
+};
+__device__ __forceinline__ void bf8_to_f(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void f4x2_to_f(const float4 (&a)[2], float (&v)[8]) {
+  v[0] = a[0].x; v[1] = a[0].y; v[2] = a[0].z; v[3] = a[0].w; v[4] = a[1].x; v[5] = a[1].y; v[6] = a[1].z; v[7] = a[1].w;
+}
+__device__ __forceinline__ void cell_load(const SeqBwdParams& p, int t, int mt, int i, bool last, CellItem& it) {
   const int vec_per_row = p.H / 8;
-  const int items = 128 * vec_per_row;
+  it.m = -1;
+  if (i >= 128 * vec_per_row) return;
+  it.row = mt * 128 + i / vec_per_row;
+  if (it.row >= p.B) return;
+  it.h0 = (i % vec_per_row) * 8;
   const long BH = (long)p.B * p.H;
-  const bool last = (t == p.T - 1);
-  float* dh_in = p.dhrec + (long)(t & 1) * BH;
-  for (int i = cta * kEpiThreads + et; i < items; i += G * kEpiThreads) {
-    const int row = mt * 128 + i / vec_per_row;
-    if (row >= p.B) continue;
-    const int h0 = (i % vec_per_row) * 8;
-    const long m = (long)t * p.B + row;
-    float dh[8], x[8], dc[8], dcr[8], ct[8], cprev[8], ga[4][8], dg[4][8];
-    load8(p.dHhead + m * p.H + h0, dh);
-    load8(p.dChead + m * p.H + h0, dc);
-    load8(p.dcrec + (long)row * p.H + h0, dcr);
-    load8(p.cs + (long)(t + 1) * BH + (long)row * p.H + h0, ct);
-    load8(p.cs + (long)t * BH + (long)row * p.H + h0, cprev);
+  it.m = (long)t * p.B + it.row;
+  const long o = (long)it.row * p.H + it.h0;
+  it.dhh = *reinterpret_cast<const uint4*>(p.dHhead + it.m * p.H + it.h0);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) load8(p.gact + m * 4 * p.H + (long)g * p.H + h0, ga[g]);
-    if (!last) {
-      load8(p.dHprev + (m + p.B) * p.H + h0, x);
-      float* hr = dh_in + (long)row * p.H + h0;
-      const float4 r0 = ldcg4(hr), r1 = ldcg4(hr + 4);  // written by other SMs (TMA reduce-add): bypass L1
-      dh[0] += x[0] + r0.x; dh[1] += x[1] + r0.y; dh[2] += x[2] + r0.z; dh[3] += x[3] + r0.w;
-      dh[4] += x[4] + r1.x; dh[5] += x[5] + r1.y; dh[6] += x[6] + r1.z; dh[7] += x[7] + r1.w;
-      // consumed: zero it for the reduce-adds of two steps from now
-      *reinterpret_cast<float4*>(hr) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(hr + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int q = 0; q < 4; ++q) it.ga[q] = *reinterpret_cast<const uint4*>(p.gact + it.m * 4 * p.H + 4 * it.h0 + 8 * q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float ig = ga[0][j], fg = ga[1][j], og = ga[2][j], gg = ga[3][j];
-      const float tc = tanh_t<true>(ct[j]);
-      const float dcj = dc[j] + dcr[j] + dh[j] * og * (1.f - tc * tc);
-      dg[0][j] = dcj * gg * ig * (1.f - ig);
-      dg[1][j] = dcj * cprev[j] * fg * (1.f - fg);
-      dg[2][j] = dh[j] * tc * og * (1.f - og);
-      dg[3][j] = dcj * ig * (1.f - gg * gg);
-      dcr[j] = dcj * fg;
-    }
-    store8(p.dcrec + (long)row * p.H + h0, dcr);
+  for (int q = 0; q < 2; ++q) {
+    it.dch[q] = *reinterpret_cast<const float4*>(p.dChead + it.m * p.H + it.h0 + 4 * q);
+    it.dcr[q] = *reinterpret_cast<const float4*>(p.dcrec + o + 4 * q);
+    it.ct[q] = *reinterpret_cast<const float4*>(p.cs + (long)(t + 1) * BH + o + 4 * q);
+    it.cp[q] = *reinterpret_cast<const float4*>(p.cs + (long)t * BH + o + 4 * q);
+  }
+  if (!last) {
+    it.dhp = *reinterpret_cast<const uint4*>(p.dHprev + (it.m + p.B) * p.H + it.h0);
+    const float* hr = p.dhrec + (long)(t & 1) * BH + o;
+    it.dhr[0] = ldcg4(hr);  // written by other SMs (TMA reduce-add): bypass L1
+    it.dhr[1] = ldcg4(hr + 4);
+  }
+}
+// d gates -> dG (needed by the other CTAs before the GEMM phase); the new running d c is left in it.dcr
+__device__ __forceinline__ void cell_compute_store_dg(const SeqBwdParams& p, bool last, CellItem& it) {
+  if (it.m < 0) return;
+  float dh[8], x[8], dc[8], dcr[8], ct[8], cprev[8], ga[4][8], dg[4][8];
+  bf8_to_f(it.dhh, dh);
+  f4x2_to_f(it.dch, dc);
+  f4x2_to_f(it.dcr, dcr);
+  f4x2_to_f(it.ct, ct);
+  f4x2_to_f(it.cp, cprev);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) store8(p.dG + m * p.ld_dg + (long)g * p.H + h0, dg[g]);
+  for (int q = 0; q < 4; ++q) {  // chunk q = units 2q, 2q+1, four gates each
+    float v[8];
+    bf8_to_f(it.ga[q], v);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { ga[g][2 * q] = v[g]; ga[g][2 * q + 1] = v[4 + g]; }
+  }
+  if (!last) {
+    float r[8];
+    bf8_to_f(it.dhp, x);
+    f4x2_to_f(it.dhr, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dh[j] += x[j] + r[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ig = ga[0][j], fg = ga[1][j], og = ga[2][j], gg = ga[3][j];
+    const float tc = tanh_t<true>(ct[j]);
+    const float dcj = dc[j] + dcr[j] + dh[j] * og * (1.f - tc * tc);
+    dg[0][j] = dcj * gg * ig * (1.f - ig);
+    dg[1][j] = dcj * cprev[j] * fg * (1.f - fg);
+    dg[2][j] = dh[j] * tc * og * (1.f - og);
+    dg[3][j] = dcj * ig * (1.f - gg * gg);
+    dcr[j] = dcj * fg;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) store8(p.dG + it.m * p.ld_dg + (long)g * p.H + it.h0, dg[g]);
+  it.dcr[0] = make_float4(dcr[0], dcr[1], dcr[2], dcr[3]);
+  it.dcr[1] = make_float4(dcr[4], dcr[5], dcr[6], dcr[7]);
+}
+// state that only this thread reads again: the running d c, and the consumed d h slot (zeroed for the reduce-adds of
+// two steps from now)
+__device__ __forceinline__ void cell_store_state(const SeqBwdParams& p, int t, bool last, const CellItem& it) {
+  if (it.m < 0) return;
+  const long o = (long)it.row * p.H + it.h0;
+  *reinterpret_cast<float4*>(p.dcrec + o) = it.dcr[0];
+  *reinterpret_cast<float4*>(p.dcrec + o + 4) = it.dcr[1];
+  if (!last) {
+    float* hr = p.dhrec + (long)(t & 1) * (long)p.B * p.H + o;
+    *reinterpret_cast<float4*>(hr) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(hr + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -403,8 +551,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + misalign;
   uint8_t* wsm = smem;                                   // 8 x 16 KB   resident W_hh slice [128 units x 512 k]
   uint8_t* stages = wsm + kBwdKb * kBwdWTile;            // kBwdStages x 16 KB   d gates tiles
-  uint8_t* staging = stages + kBwdStages * kATile;       // 4 x 4 KB    epilogue tiles (32 rows x 128 B)
-  const Bars bar = carve_bars<kBwdStages>(staging + 4 * 4096);
+  uint8_t* staging = stages + kBwdStages * kATile;       // 4 warps x 2 x 4 KB  epilogue tiles (32 rows x 128 B)
+  const Bars bar = carve_bars<kBwdStages>(staging + 8 * 4096);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = p.H / 128;  // = 4H / 512 k-slices, and H / 128 unit slices
@@ -479,8 +627,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== cell backward (phase C) and GEMM epilogue (phase G) =====
     const int quarter = warp & 3;
     const int et = threadIdx.x - 64;
-    uint8_t* my_stage = staging + (warp - 2) * 4096;
-    uint8_t* my_row = my_stage + lane * 128;
+    uint8_t* my_stage = staging + (warp - 2) * 8192;
     const uint32_t swz = (uint32_t)(lane & 7);
     int it = 0;
     for (int t = p.T - 1, i = 0; t >= 0; --t, ++i) {
@@ -493,15 +640,31 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epi_bar_sync();
       }
       if (et == 0) rec_trace(p.trace, p.T, t, 0);
-      for (int mt = y; mt < p.n_mtiles; mt += MG) cell_bwd_items(p, t, mt, cta, G, et);
-      if (et == 0) rec_trace(p.trace, p.T, t, 1);
-      if (t == 0) break;
-      epi_bar_sync();
-      if (et == 0) {
-        __threadfence();
-        atomicAdd(p.ctr_c + y, 1u);
-        rec_trace(p.trace, p.T, t, 2);
+      const bool last = (t == p.T - 1);
+      const int items = 128 * (p.H / 8);
+      CellItem ia, ib;
+      for (int mt = y; mt < p.n_mtiles; mt += MG) {
+        for (int i0 = cta * kEpiThreads + et; i0 < items; i0 += 2 * G * kEpiThreads) {
+          // two items per trip, all loads first
+          cell_load(p, t, mt, i0, last, ia);
+          cell_load(p, t, mt, i0 + G * kEpiThreads, last, ib);
+          cell_compute_store_dg(p, last, ia);
+          cell_compute_store_dg(p, last, ib);
+          cell_store_state(p, t, last, ia);
+          cell_store_state(p, t, last, ib);
+        }
       }
+      if (t > 0) {
+        __threadfence();  // every thread: its d gates (and d h zeroing) stores are performed at GPU scope
+        if (et == 0) rec_trace(p.trace, p.T, t, 1);
+        epi_bar_sync();
+        if (et == 0) {
+          __threadfence();
+          atomicAdd(p.ctr_c + y, 1u);
+          rec_trace(p.trace, p.T, t, 2);
+        }
+      }
+      if (t == 0) break;
       // ---- phase G epilogue: partial d h_{t-1} -> fp32 reduce-add into dhrec[(t-1) & 1] ----
       for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
         const int buf = it & 1;
@@ -512,13 +675,15 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
         for (int ps = 0; ps < kBwdN / 32; ++ps) {
           uint32_t r[32];
-          if (lane == 0) bulk_wait_read_all();  // the previous reduce has finished reading this warp's staging tile
+          uint8_t* st = my_stage + (ps & 1) * 4096;   // two staging tiles per warp: pass ps+1 fills one while the
+          uint8_t* st_row = st + lane * 128;          // reduce of pass ps still reads the other
+          if (lane == 0) bulk_wait_read_1();
           __syncwarp();
           tmem_ld32(tmem_d + (uint32_t)(ps * 32), r);
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(my_row + (((uint32_t)g ^ swz) << 4)) =
+            *reinterpret_cast<float4*>(st_row + (((uint32_t)g ^ swz) << 4)) =
                 make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                             __uint_as_float(r[4 * g + 3]));
           if (ps == kBwdN / 32 - 1) {
@@ -529,7 +694,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_all();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_3d(&tmC, my_stage, ns * kBwdN + ps * 32, mt * 128 + quarter * 32, (t - 1) & 1);
+            tma_reduce_add_3d(&tmC, st, ns * kBwdN + ps * 32, mt * 128 + quarter * 32, (t - 1) & 1);
             bulk_commit();
           }
         }
@@ -587,42 +752,68 @@ void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H
   if (c.launches) ++*c.launches;
 }
 
-bool lstm_seq_fwd_supported(int B, int H) {
-  if (!env_enabled() || B <= 0 || H % 64 || H > 1024) return false;
-  return H / kFwdUnits <= kNumSMs;
-}
-bool lstm_seq_bwd_supported(int B, int H) {
-  if (!env_enabled() || B <= 0 || H % 128) return false;
-  const int g = (H / 128) * (H / 128);
-  return g <= kNumSMs;
+// One condition for both directions: the persistent kernels keep the gate activations unit-major (col 4*unit + gate),
+// the per-step kernels gate-major, so a step must run entirely on one schedule.
+//   forward : W_hh slice [H x 64] bf16 resident  -> H <= 1024;  H / 16 CTAs per batch group
+//   backward: (H / 128)^2 CTAs per batch group   -> H % 128 == 0
+bool lstm_seq_supported(int B, int H) {
+  if (!env_enabled() || B <= 0 || H % 128 || H > 1024) return false;
+  return H / kFwdUnits <= kNumSMs && (H / 128) * (H / 128) <= kNumSMs;
 }
 
 // ctr: >= 2 * 64 zero-initialised-by-us unsigned counters owned by the caller
-int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf16* xe, long ld_xe, const float* g5,
-                 long ld_g5, bf16* hs, float* cs, bf16* gact, unsigned* ctr) {
+// xe: [T*B, ld_xe] bf16, columns [0, 4H) = the complete x-part of the gate pre-activations (word + global-image terms
+// + biases), unit-major (col 4*unit + gate).  gact [T*B, 4H] comes out unit-major too.
+int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf16* xe, long ld_xe, bf16* hs,
+                 float* cs_buf, bf16* gact, unsigned* ctr) {
   const int slices = H / kFwdUnits;
   const int n_mtiles = (B + 127) / 128;
   const int mg = std::max(1, std::min(n_mtiles, kNumSMs / slices));
   const int nkb = H / BK;
-  const size_t smem = (size_t)nkb * kFwdWTile + kFwdStages * kATile + 256 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const size_t smem = (size_t)nkb * kFwdWTile + kFwdStages * kATile + kFwdXStage + kFwdCStage + 256 + 1024;
+  // cluster size: CAPDEC_REC_CLUSTER in {1, 2, 4} (tuning; see the kernel's comment)
+  int cs = 1;
+  if (const char* ev = getenv("CAPDEC_REC_CLUSTER")) cs = atoi(ev);
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+  while (cs > 1 && slices % cs) cs >>= 1;
+  const void* kern = cs == 4   ? (const void*)lstm_seq_fwd_kernel<4>
+                     : cs == 2 ? (const void*)lstm_seq_fwd_kernel<2>
+                               : (const void*)lstm_seq_fwd_kernel<1>;
+  static bool attr_set[5] = {};
+  if (!attr_set[cs]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("lstm_seq_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
+    attr_set[cs] = true;
   }
-  CUtensorMap tmH, tmW;
-  if (tma_map_3d(hs, H, B, H, BK, 128, &tmH, 2, T + 1, (uint64_t)B * H)) return -1;
+  CUtensorMap tmH, tmW, tmX, tmCs, tmGa;
+  if (tma_map_3d(hs, H, B, H, BK, 128 / cs, &tmH, 2, T + 1, (uint64_t)B * H)) return -1;
   if (tma_map_3d(w_perm, 4 * H, H, 4 * H, kFwdN, BK, &tmW, 2, 1, 0)) return -1;
+  if (tma_map_3d(xe, 4 * H, B, ld_xe, kFwdN, 128, &tmX, 2, T, (uint64_t)B * ld_xe)) return -1;
+  if (tma_map_3d(cs_buf, H, B, H, kFwdUnits, 128, &tmCs, 4, T + 1, (uint64_t)B * H, false)) return -1;
+  if (tma_map_3d(gact, 4 * H, B, 4 * H, kFwdN, 128, &tmGa, 2, T, (uint64_t)B * 4 * H)) return -1;
   SeqFwdParams p;
   p.B = B; p.H = H; p.T = T; p.n_mtiles = n_mtiles;
-  p.xe = xe; p.ld_xe = ld_xe; p.g5 = g5; p.ld_g5 = ld_g5; p.hs = hs; p.cs = cs; p.gact = gact; p.ctr = ctr;
+  p.hs = hs; p.cs = cs_buf; p.ctr = ctr;
   p.trace = g_rec_trace;
   cudaError_t e = cudaMemsetAsync(ctr, 0, 64 * sizeof(unsigned), c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_fwd: memset: %s", cudaGetErrorString(e)); return -1; }
-  void* args[] = {&tmH, &tmW, &p};
-  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_fwd_kernel, dim3(slices, mg), dim3(kThreads), args, smem, c.stream);
-  if (e != cudaSuccess) { set_error("lstm_seq_fwd: cooperative launch: %s", cudaGetErrorString(e)); return -1; }
+  void* args[] = {&tmH, &tmW, &tmX, &tmCs, &tmGa, &p};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(slices, mg);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = cs;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = cs > 1 ? 2 : 1;
+  e = cudaLaunchKernelExC(&cfg, kern, args);
+  if (e != cudaSuccess) { set_error("lstm_seq_fwd: cooperative launch (cluster %d): %s", cs, cudaGetErrorString(e)); return -1; }
   if (c.launches) ++*c.launches;
   return 0;
 }
@@ -633,7 +824,7 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
   const int g = (H / 128) * (H / 128);
   const int n_mtiles = (B + 127) / 128;
   const int mg = std::max(1, std::min(n_mtiles, kNumSMs / g));
-  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + 4 * 4096 + 256 + 1024;
+  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + 8 * 4096 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
