@@ -427,6 +427,10 @@ constexpr int kBwdStages = 4;
 constexpr int kBwdN = 128;                  // output hidden units per CTA
 constexpr int kBwdKb = 8;                   // k-blocks per CTA (512 of the 4H gate columns)
 constexpr int kBwdWTile = kBwdN * BK * 2;   // 16 KB
+constexpr int kBwdEpiWarps = 8;             // two per TMEM lane quarter: half of the accumulator columns each
+constexpr int kBwdEpiThreads = kBwdEpiWarps * 32;
+constexpr int kBwdThreads = 64 + kBwdEpiThreads;
+__device__ __forceinline__ void bwd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpiThreads) : "memory"); }
 
 struct SeqBwdParams {
   int B, H, T;
@@ -543,7 +547,7 @@ __device__ __forceinline__ void cell_store_state(const SeqBwdParams& p, int t, b
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, SeqBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -551,8 +555,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + misalign;
   uint8_t* wsm = smem;                                   // 8 x 16 KB   resident W_hh slice [128 units x 512 k]
   uint8_t* stages = wsm + kBwdKb * kBwdWTile;            // kBwdStages x 16 KB   d gates tiles
-  uint8_t* staging = stages + kBwdStages * kATile;       // 4 warps x 2 x 4 KB  epilogue tiles (32 rows x 128 B)
-  const Bars bar = carve_bars<kBwdStages>(staging + 8 * 4096);
+  uint8_t* staging = stages + kBwdStages * kATile;       // 8 warps x 4 KB  epilogue tiles (32 rows x 128 B)
+  const Bars bar = carve_bars<kBwdStages>(staging + kBwdEpiWarps * 4096);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = p.H / 128;  // = 4H / 512 k-slices, and H / 128 unit slices
@@ -563,7 +567,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmC);
-    init_bars<kBwdStages>(bar, 4);
+    init_bars<kBwdStages>(bar, kBwdEpiWarps);
   }
   if (warp == 1) tmem_alloc<2 * kBwdN>(bar.tmem_ptr);
   tc_fence_before();
@@ -625,9 +629,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===== cell backward (phase C) and GEMM epilogue (phase G) =====
-    const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;
-    uint8_t* my_stage = staging + (warp - 2) * 8192;
+    const int quarter = warp & 3;          // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;      // which half of the accumulator columns
+    const int et = threadIdx.x - 64;       // 0..255
+    uint8_t* my_stage = staging + (warp - 2) * 4096;
+    uint8_t* st_row = my_stage + lane * 128;
     const uint32_t swz = (uint32_t)(lane & 7);
     int it = 0;
     for (int t = p.T - 1, i = 0; t >= 0; --t, ++i) {
@@ -637,27 +643,23 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           spin_until(p.ctr_g + y, (unsigned)i * (unsigned)G);  // every partial product of d h_t has been added
           __threadfence();
         }
-        epi_bar_sync();
+        bwd_bar_sync();
       }
       if (et == 0) rec_trace(p.trace, p.T, t, 0);
       const bool last = (t == p.T - 1);
       const int items = 128 * (p.H / 8);
-      CellItem ia, ib;
+      CellItem ia;
       for (int mt = y; mt < p.n_mtiles; mt += MG) {
-        for (int i0 = cta * kEpiThreads + et; i0 < items; i0 += 2 * G * kEpiThreads) {
-          // two items per trip, all loads first
+        for (int i0 = cta * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) {
           cell_load(p, t, mt, i0, last, ia);
-          cell_load(p, t, mt, i0 + G * kEpiThreads, last, ib);
           cell_compute_store_dg(p, last, ia);
-          cell_compute_store_dg(p, last, ib);
           cell_store_state(p, t, last, ia);
-          cell_store_state(p, t, last, ib);
         }
       }
       if (t > 0) {
         __threadfence();  // every thread: its d gates (and d h zeroing) stores are performed at GPU scope
         if (et == 0) rec_trace(p.trace, p.T, t, 1);
-        epi_bar_sync();
+        bwd_bar_sync();
         if (et == 0) {
           __threadfence();
           atomicAdd(p.ctr_c + y, 1u);
@@ -673,20 +675,20 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kBwdN) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int ps = 0; ps < kBwdN / 32; ++ps) {
+        for (int pp = 0; pp < 2; ++pp) {
+          const int ps = half * 2 + pp;  // 32-column pass of the 128-column accumulator
           uint32_t r[32];
-          uint8_t* st = my_stage + (ps & 1) * 4096;   // two staging tiles per warp: pass ps+1 fills one while the
-          uint8_t* st_row = st + lane * 128;          // reduce of pass ps still reads the other
-          if (lane == 0) bulk_wait_read_1();
           __syncwarp();
           tmem_ld32(tmem_d + (uint32_t)(ps * 32), r);
+          if (lane == 0) bulk_wait_read_all();  // the previous reduce has finished reading this warp's staging tile
           tmem_ld_wait();
+          __syncwarp();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<float4*>(st_row + (((uint32_t)g ^ swz) << 4)) =
                 make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                             __uint_as_float(r[4 * g + 3]));
-          if (ps == kBwdN / 32 - 1) {
+          if (pp == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
@@ -694,7 +696,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_all();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_3d(&tmC, st, ns * kBwdN + ps * 32, mt * 128 + quarter * 32, (t - 1) & 1);
+            tma_reduce_add_3d(&tmC, my_stage, ns * kBwdN + ps * 32, mt * 128 + quarter * 32, (t - 1) & 1);
             bulk_commit();
           }
         }
@@ -704,7 +706,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bulk_wait_all();  // this warp's reduce-adds have been performed
         fence_proxy_async_all();
       }
-      epi_bar_sync();
+      bwd_bar_sync();
       if (et == 0) {
         __threadfence();
         atomicAdd(p.ctr_g + y, 1u);
@@ -824,7 +826,7 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
   const int g = (H / 128) * (H / 128);
   const int n_mtiles = (B + 127) / 128;
   const int mg = std::max(1, std::min(n_mtiles, kNumSMs / g));
-  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + 8 * 4096 + 256 + 1024;
+  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + kBwdEpiWarps * 4096 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -845,7 +847,7 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
   if (e == cudaSuccess) e = cudaMemsetAsync(dcrec, 0, sizeof(float) * (size_t)B * H, c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_bwd: memset: %s", cudaGetErrorString(e)); return -1; }
   void* args[] = {&tmA, &tmW, &tmC, &p};
-  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_bwd_kernel, dim3(g, mg), dim3(kThreads), args, smem, c.stream);
+  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_bwd_kernel, dim3(g, mg), dim3(kBwdThreads), args, smem, c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_bwd: cooperative launch: %s", cudaGetErrorString(e)); return -1; }
   if (c.launches) ++*c.launches;
   return 0;
