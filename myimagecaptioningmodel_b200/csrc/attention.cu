@@ -11,6 +11,8 @@
 // every query row of the chunk (34 teacher-forced steps, or the beams of one image at inference) streams through.
 // Scores use one warp per position with 128-bit conflict-free shared loads and a shuffle reduction; the context
 // pass gives each thread 4 adjacent columns.
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -290,6 +292,187 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   }
 }
 
+// ---- forward, training shape (many query rows per image): scores + soft-max kernel ---------------------------
+// The score e[q,j] = sum_h w[h] tanh(key[j,h] + hid_emb[q,h]) is MUFU work (one tanh per element, 445 M per train
+// step) wrapped in a dot product.  Here the tanh runs packed (tanh.approx.bf16x2, two elements per MUFU op) and its
+// bf16x2 results ARE the A fragment of a warp-level tensor-core MMA (mma.sync m16n8k16: 16 positions x 16 columns of z
+// against a B fragment that holds w in column 0), so the multiply-accumulate with w costs 1/4 instruction per pair
+// instead of two unpacks + two FFMAs, and the kernel is MUFU-bound instead of issue-bound.
+//   CTA = one image: key tile [k, H] in shared memory (row pitch 2H + 64 B: a quarter-warp's 2 rows x 4 chunks of
+//   16 B hit all 32 banks once), 2 CTAs per SM.  Warp w owns columns [w*H/8, (w+1)*H/8) for every position and
+//   query, w fragments resident in registers; the 8 partial sums of a score meet in shared memory, one barrier per
+//   query, and one warp (rotating) finishes the soft-max while the others start the next query.
+//   Position k (the sentinel) reads its "key" row from the staged sentinel_emb row of the query.
+constexpr int kScThreads = 256;
+constexpr int kScPad = 64;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tanh_add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t s2, z2;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s2) : "r"(a), "r"(b));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(z2) : "r"(s2));
+  return z2;
+}
+
+inline size_t scores_smem_bytes(int H, int k) {
+  const int pitch = 2 * H + kScPad, Ppad = (k + 1 + 3) & ~3;
+  return (size_t)k * pitch + 4 * (size_t)pitch + 2 * 8 * Ppad * sizeof(float) + 64;
+}
+
+template <int NB>  // H = 256 * NB
+__global__ void __launch_bounds__(kScThreads, 2)
+attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __restrict__ hid_emb,
+                   const bf16* __restrict__ sent_emb, const float* __restrict__ w_alpha,
+                   const float* __restrict__ b_alpha, float* __restrict__ alpha_out, bf16* __restrict__ alpha_T,
+                   int ld_at) {
+  constexpr int H = 256 * NB;
+  constexpr int kWarpCols = 32 * NB;  // columns of one warp
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int k = s.k, P = s.k + 1, Ppad = (P + 3) & ~3;
+  const int pitch = 2 * H + kScPad;
+  uint8_t* Kt = smem;
+  uint8_t* ring = Kt + (size_t)k * pitch;                      // [2 slots][hid_emb row, sentinel_emb row]
+  float* e_part = reinterpret_cast<float*>(ring + 4 * pitch);  // [2][8 warps][Ppad]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(e_part + 2 * 8 * Ppad);
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;  // fragment row / 16-byte column chunk of this lane
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (uint32_t)(k * 2 * H));
+    const bf16* src = keys + (long)img * k * H;
+    for (int j = 0; j < k; ++j) tma_bulk_g2s(Kt + (size_t)j * pitch, src + (long)j * H, 2 * H, bar);
+  }
+  constexpr int cpr = H / 8;  // 16-byte chunks per row
+  auto prefetch = [&](int q) {
+    if (tid < 2 * cpr) {
+      const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+      const int a = tid / cpr, c = tid % cpr;
+      cp_async16(ring + (size_t)((q & 1) * 2 + a) * pitch + c * 16, (a == 0 ? hid_emb : sent_emb) + row * H + c * 8);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  // B fragments: w in column 0 (fragment lanes 0..3), zero elsewhere
+  const int col0 = warp * kWarpCols + 8 * lc;  // first column of this lane's chunk in block 0
+  uint32_t wq[NB][4];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float wv[8];
+    load8(w_alpha + col0 + 32 * b, wv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(wv[2 * i], wv[2 * i + 1]);
+      wq[b][i] = (lr == 0) ? *reinterpret_cast<uint32_t*>(&h2) : 0u;
+    }
+  }
+  const float b_a = b_alpha[0];
+  const float inv_p = 1.f / (float)P;
+  cp_async_wait_all();
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const int nq = s.q_per_img;
+  for (int q = 0; q < nq; ++q) {
+    if (q + 1 < nq) prefetch(q + 1);  // slot (q+1)&1 was last read in query q-1: everyone is past its barrier
+    const uint8_t* he_row = ring + (size_t)((q & 1) * 2) * pitch;
+    const uint8_t* se_row = he_row + pitch;
+    uint4 heq[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) heq[b] = *reinterpret_cast<const uint4*>(he_row + (col0 + 32 * b) * 2);
+    float* ep = e_part + ((q & 1) * 8 + warp) * Ppad;
+    for (int pb = 0; 16 * pb <= k; ++pb) {
+      const int jA = 16 * pb + lr, jB = jA + 8;
+      const bool half_b = (16 * pb + 8 <= k);  // warp-uniform: the upper 8 rows hold at least one valid position
+      const uint8_t* rowA = (jA < k) ? Kt + (size_t)jA * pitch : se_row;
+      const uint8_t* rowB = (jB < k) ? Kt + (size_t)jB * pitch : se_row;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint4 ka = *reinterpret_cast<const uint4*>(rowA + (col0 + 32 * b) * 2);
+        uint32_t za[4], zb[4] = {0u, 0u, 0u, 0u};
+        za[0] = tanh_add_bf16x2(ka.x, heq[b].x);
+        za[1] = tanh_add_bf16x2(ka.y, heq[b].y);
+        za[2] = tanh_add_bf16x2(ka.z, heq[b].z);
+        za[3] = tanh_add_bf16x2(ka.w, heq[b].w);
+        if (half_b) {
+          const uint4 kb = *reinterpret_cast<const uint4*>(rowB + (col0 + 32 * b) * 2);
+          zb[0] = tanh_add_bf16x2(kb.x, heq[b].x);
+          zb[1] = tanh_add_bf16x2(kb.y, heq[b].y);
+          zb[2] = tanh_add_bf16x2(kb.z, heq[b].z);
+          zb[3] = tanh_add_bf16x2(kb.w, heq[b].w);
+        }
+        // k index 2*lc + {0,1} <-> chunk elements {0,1}; k index 8 + 2*lc + {0,1} <-> elements {2,3}; then {4..7}
+        mma_bf16_16816(c, za[0], zb[0], za[1], zb[1], wq[b][0], wq[b][1]);
+        mma_bf16_16816(c, za[2], zb[2], za[3], zb[3], wq[b][2], wq[b][3]);
+      }
+      if (lc == 0) {
+        if (jA <= k) ep[jA] = c[0];
+        if (jB <= k) ep[jB] = c[2];
+      }
+    }
+    cp_async_wait_all();  // next query's rows have landed (this thread's part); the barrier publishes them
+    __syncthreads();
+    if (warp == (q & 7)) {
+      // ---- soft-max over the k+1 positions (P <= 64: two values per lane) ----
+      const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+      const float* eb = e_part + (q & 1) * 8 * Ppad;
+      float e0 = -INFINITY, e1 = -INFINITY;
+      if (lane < P) {
+        e0 = b_a;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) e0 += eb[w8 * Ppad + lane];
+      }
+      if (lane + 32 < P) {
+        e1 = b_a;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) e1 += eb[w8 * Ppad + lane + 32];
+      }
+      const float m = warp_max(fmaxf(e0, e1));
+      const float x0 = (lane < P) ? __expf(e0 - m) : 0.f;
+      const float x1 = (lane + 32 < P) ? __expf(e1 - m) : 0.f;
+      const float inv = 1.f / warp_sum(x0 + x1);
+      const float a0 = x0 * inv, a1 = x1 * inv;
+      if (lane < P) alpha_out[row * P + lane] = a0;
+      if (lane + 32 < P) alpha_out[row * P + lane + 32] = a1;
+      if (lane < k) alpha_T[row * ld_at + lane] = __float2bfloat16_rn(a0 * inv_p);
+      if (lane + 32 < k) alpha_T[row * ld_at + lane + 32] = __float2bfloat16_rn(a1 * inv_p);
+    }
+  }
+}
+
+// sadd[row, :] = p_hid[row, :] + alpha[row, k] / (k+1) * sentinel[row, :]: the two per-query terms the context GEMM
+// adds in its epilogue (p_hid may be NULL)
+__global__ void __launch_bounds__(256)
+attn_sadd_kernel(long rows, int H, int P, const float* __restrict__ alpha, const bf16* __restrict__ sentinel,
+                 const bf16* __restrict__ p_hid, bf16* __restrict__ sadd) {
+  const int vec_per_row = H / 8;
+  const float inv_p = 1.f / (float)P;
+  const long n = rows * vec_per_row;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    const float a = alpha[r * P + (P - 1)] * inv_p;
+    float v[8], ph[8];
+    load8(sentinel + r * H + h0, v);
+    if (p_hid) {
+      load8(p_hid + r * H + h0, ph);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(a, v[j], ph[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= a;
+    }
+    store8(sadd + r * H + h0, v);
+  }
+}
+
 // ---- backward, row-wise part (one warp per query row) -------------------------------------------------------
 //   d alpha_j (j < k) arrives UNSCALED from the batched tensor-core GEMM  dal[row, j] = dctx[row, :] . v_j ;
 //   here: d alpha_k = dctx . sentinel,  de = alpha * (d alpha - sum alpha d alpha) / (k+1)  (soft-max backward),
@@ -463,6 +646,61 @@ void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
     launch_fwd<T, false>(c, s, chunks, qpc, L0.total, keys, vals, hid_emb, sent_emb, sentinel, p_hid, w_alpha, b_alpha,
                          alpha, actx, ctx_out);
   }
+}
+
+bool attention_fwd_batched_supported(const AttnShape& s) {
+  if (const char* ev = getenv("CAPDEC_ATTN_BATCHED")) {
+    if (ev[0] == '0') return false;
+  }
+  if (!s.position_softmax || s.q_per_img < 8 || s.k < 1 || s.k > 63) return false;
+  if (s.H != 256 && s.H != 512 && s.H != 1024) return false;
+  return scores_smem_bytes(s.H, s.k) <= 227 * 1024;
+}
+
+// Training-shaped forward: scores + soft-max kernel (MUFU + mma.sync), then the context as one batched tcgen05 GEMM
+//   actx[q, :] = sum_j alpha[q, j] / (k+1) * v_j  +  (alpha[q, k] / (k+1) * sentinel[q] + p_hid[q])
+// per image ([q_per_img x k] . [k x H], values as the MN-major B operand, the per-query terms as the epilogue addend).
+// scratch: alpha_T [rows, kAlphaTLd] bf16 (kept: the backward pass reads it), sadd [rows, H] bf16.
+int attention_fwd_batched(GemmContext& gc, LaunchCtx c, const AttnShape& s, const bf16* keys, const bf16* vals,
+                          const bf16* hid_emb, const bf16* sent_emb, const bf16* sentinel, const bf16* p_hid,
+                          const float* w_alpha, const float* b_alpha, float* alpha, bf16* alpha_T, bf16* sadd,
+                          bf16* actx) {
+  if (s.n_img <= 0 || s.q_per_img <= 0) return 0;
+  const int H = s.H, k = s.k, P = s.k + 1;
+  const long rows = (long)s.n_img * s.q_per_img;
+  const size_t smem = scores_smem_bytes(H, k);
+#define LAUNCH_SC(NBV)                                                                                              \
+  do {                                                                                                               \
+    auto kern = attn_scores_kernel<NBV>;                                                                             \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                           \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    kern<<<s.n_img, kScThreads, smem, c.stream>>>(s, keys, hid_emb, sent_emb, w_alpha, b_alpha, alpha, alpha_T,      \
+                                                  kAlphaTLd);                                                        \
+  } while (0)
+  if (H == 1024) LAUNCH_SC(4);
+  else if (H == 512) LAUNCH_SC(2);
+  else LAUNCH_SC(1);
+#undef LAUNCH_SC
+  if (c.launches) ++*c.launches;
+  {
+    long blocks = (rows * (H / 8) + 255) / 256;
+    if (blocks > 8L * kNumSMs) blocks = 8L * kNumSMs;
+    attn_sadd_kernel<<<(int)blocks, 256, 0, c.stream>>>(rows, H, P, alpha, sentinel, p_hid, sadd);
+    if (c.launches) ++*c.launches;
+  }
+  GemmCall g;
+  g.A = alpha_T; g.lda = s.q_stride * kAlphaTLd; g.batch_a = s.row0_stride * kAlphaTLd;
+  g.B = vals; g.ldb = H; g.b_mn = true; g.batch_b = (long)k * H;
+  g.C = actx; g.ldc = s.q_stride * H; g.batch_c = s.row0_stride * H;
+  g.M = s.q_per_img; g.N = H; g.K = k; g.batch = s.n_img;
+  g.epi.addend = sadd; g.epi.ld_add = s.q_stride * H; g.epi.batch_add = s.row0_stride * H;
+  if (gemm<bf16>(gc, g)) return -1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("attention_fwd_batched: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
 }
 
 template <typename T>

@@ -350,8 +350,21 @@ template <typename T> class Decoder : public DecoderBase {
     OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
     prof.mark("fwd.head_fc", s);
     AttnShape as = train_shape(B);
-    attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
-                     prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);               // model:103-115
+    bool attn_batched = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!force_simt && attention_fwd_batched_supported(as)) {
+        // scores + soft-max on MUFU / mma.sync, context as one batched tcgen05 GEMM                  // model:103-115
+        OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
+        OK(sadd.ensure(e * M * H, &ws_bytes));
+        OK(attention_fwd_batched(gc, lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
+                                 sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
+                                 alpha_t.as<bf16>(), sadd.as<bf16>(), actx.as<bf16>()));
+        attn_batched = true;
+      }
+    }
+    if (!attn_batched)
+      attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
+                       prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);             // model:103-115
     prof.mark("fwd.attention", s);
     OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
     OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
@@ -688,7 +701,7 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
 
@@ -705,7 +718,7 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b;
+      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
 };
@@ -882,6 +895,31 @@ int capdec_attention_fwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int
   if (H % 8 || k < 1 || k > 63) { set_error("capdec_attention_fwd: need H %% 8 == 0 and 1 <= k <= 63"); return -1; }
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
   AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
+  if (dtype == CAPDEC_DTYPE_BF16 && attention_fwd_batched_supported(s) && (actx || ctx)) {
+    // the training-shaped path (scores kernel + batched context GEMM); its scratch is owned by the decoder handle in
+    // the train schedule, the stand-alone entry point allocates it
+    GemmContext gc; gc.stream = (cudaStream_t)stream;
+    const long rows = (long)n_img * q_per_img;
+    void *at = nullptr, *sa = nullptr;
+    if (cudaMalloc(&at, rows * kAlphaTLd * 2) != cudaSuccess || cudaMalloc(&sa, rows * (size_t)H * 2) != cudaSuccess) {
+      if (at) cudaFree(at);
+      set_error("capdec_attention_fwd: out of device memory");
+      return -1;
+    }
+    int rc = 0;
+    if (actx)
+      rc = attention_fwd_batched(gc, lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb,
+                                 (const bf16*)sent_emb, (const bf16*)sentinel, (const bf16*)p_hid, w_alpha, b_alpha, alpha,
+                                 (bf16*)at, (bf16*)sa, (bf16*)actx);
+    if (!rc && ctx)
+      rc = attention_fwd_batched(gc, lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb,
+                                 (const bf16*)sent_emb, (const bf16*)sentinel, nullptr, w_alpha, b_alpha, alpha, (bf16*)at,
+                                 (bf16*)sa, (bf16*)ctx);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(at);
+    cudaFree(sa);
+    return rc ? -1 : 0;
+  }
   if (dtype == CAPDEC_DTYPE_F32)
     attention_fwd<float>(lc, s, (const float*)keys, (const float*)vals, (const float*)hid_emb, (const float*)sent_emb,
                          (const float*)sentinel, (const float*)p_hid, w_alpha, b_alpha, alpha, (float*)actx, (float*)ctx);

@@ -95,6 +95,14 @@ template <typename T>
 void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb, const T* sent_emb,
                    const T* sentinel, const T* p_hid, const float* w_alpha, const float* b_alpha, float* alpha, T* actx,
                    T* ctx_out);
+struct GemmContext;
+// training-shaped forward on the tensor cores (bf16; see attention.cu): scores + soft-max kernel, then the context as a
+// batched GEMM.  scratch: alpha_T [rows, kAlphaTLd] bf16 (alpha / (k+1), reusable by the backward pass), sadd [rows, H]
+bool attention_fwd_batched_supported(const AttnShape& s);
+int attention_fwd_batched(GemmContext& gc, LaunchCtx c, const AttnShape& s, const bf16* keys, const bf16* vals,
+                          const bf16* hid_emb, const bf16* sent_emb, const bf16* sentinel, const bf16* p_hid,
+                          const float* w_alpha, const float* b_alpha, float* alpha, bf16* alpha_T, bf16* sadd,
+                          bf16* actx);
 // backward (see attention.cu): two batched tensor-core GEMMs (d alpha = dctx.V^T, d values = alpha^T.dctx with tanh'
 // fused), a row-wise soft-max-backward kernel and the column-wise d keys kernel.  dactx [rows,H] = d context.
 //   scratch: dal [rows, kDalLd] fp32, alpha_T [rows, kAlphaTLd] T
@@ -102,7 +110,6 @@ void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
 //   cols H..2H = d keys;  dhid_emb, dsent_emb [rows,H];  dw_alpha [H], db_alpha [1] fp32 (+=)
 constexpr int kDalLd = 68;      // >= 63 positions, 16-byte-multiple pitch in fp32
 constexpr int kAlphaTLd = 72;   // >= 63 positions, 16-byte-multiple pitch in bf16
-struct GemmContext;
 template <typename T>
 int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* keys, const T* vals, const T* hid_emb,
                   const T* sent_emb, const T* sentinel, const float* w_alpha, const float* alpha, const T* dactx,

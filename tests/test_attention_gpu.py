@@ -41,6 +41,9 @@ def _unrows(x, n, q, layout):
 CASES = [  # n_img, q, k, H, layout
     (5, 34, 49, 1024, "train"), (7, 3, 49, 1024, "decode"), (3, 6, 5, 64, "train"), (4, 1, 49, 512, "decode"),
     (2, 4, 16, 256, "train"), (3, 2, 7, 40, "decode"),
+    # training-shaped tensor-core path (q >= 8, H in {256, 512, 1024}): ragged position blocks, k up to 63
+    (6, 34, 49, 1024, "train"), (3, 12, 20, 256, "train"), (2, 9, 63, 512, "decode"), (4, 17, 8, 256, "train"),
+    (3, 8, 47, 1024, "train"),
 ]
 
 
