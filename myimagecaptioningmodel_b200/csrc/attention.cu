@@ -532,64 +532,86 @@ attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const T* __r
   }
 }
 
-// ---- backward (C): d keys, d hid_emb, d sentinel_emb, d w_alpha.  thread = one column h of one image ----
-//   g_j = de[q,j] * w[h] * (1 - z_j^2), z_j = tanh(key_j[h] + hid_emb[q,h]) (recomputed, never stored)
-//   dK_j[h] = sum_q g_j;  d hid_emb[q,h] = sum_j g_j;  d sentinel_emb[q,h] = g_k;  dw[h] += sum_{q,j} de[q,j] z_j
-template <typename T, int KC>
-__global__ void __launch_bounds__(256)
+// ---- backward (C): d keys, d hid_emb, d sentinel_emb, d w_alpha ----
+//   u_j = 1 - z_j^2,  z_j = tanh(key_j[h] + hid_emb[q,h])  (recomputed, never stored; z_k uses sentinel_emb[q,h])
+//   dK_j[h] = w[h] sum_q de[q,j] u_j;   d hid_emb[q,h] = w[h] sum_j de[q,j] u_j;   d sentinel_emb[q,h] = w[h] de[q,k] u_k;
+//   dw[h] += sum_{q,j} de[q,j] z_j
+// Two adjacent lanes share one column h of one image and split the k+1 positions (KH each, the sentinel is the last
+// position of the upper half), so a thread keeps KH keys + KH accumulators in registers (3 CTAs per SM instead of 2
+// with one thread per column) and the d hid_emb halves meet through one shuffle per query.  Per element: one add,
+// one MUFU tanh and four FFMAs (w[h] is applied once per output, not per element); de comes from shared memory in
+// 16-byte broadcasts.
+template <typename T, int KH>
+__global__ void __launch_bounds__(256, 3)
 attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict__ hid_emb,
                    const T* __restrict__ sent_emb, const float* __restrict__ w_alpha, const float* __restrict__ de,
                    T* __restrict__ dKV, T* __restrict__ dhid_emb, T* __restrict__ dsent_emb,
                    float* __restrict__ dw_alpha) {
   constexpr bool F = fast_math<T>::value;
-  extern __shared__ __align__(16) float de_s[];  // [q_per_img, P]
+  constexpr int KHP = (KH + 3) & ~3;  // each half of a query's de row starts 16-byte aligned
+  extern __shared__ __align__(16) float de_s[];  // [q_per_img][2 halves][KHP], zero past the valid positions
   const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
-  const int img = blockIdx.x, h = blockIdx.y * blockDim.x + threadIdx.x;
-  for (int i = threadIdx.x; i < nq * P; i += blockDim.x) {
-    const int q = i / P, j = i % P;
-    de_s[i] = de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j];
+  const int img = blockIdx.x;
+  const int h = blockIdx.y * (blockDim.x >> 1) + (threadIdx.x >> 1);
+  const int half = threadIdx.x & 1;
+  const int j0 = half * KH;  // this thread's positions: j0 .. j0 + KH - 1
+  for (int i = threadIdx.x; i < nq * 2 * KHP; i += blockDim.x) {
+    const int q = i / (2 * KHP), r = i % (2 * KHP);
+    const int hf = r / KHP, ii = r % KHP, j = hf * KH + ii;
+    de_s[i] = (ii < KH && j < P) ? de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j] : 0.f;
   }
   __syncthreads();
-  if (h >= H) return;
-  float kc[KC], acc[KC];
+  const bool active = h < H;
+  const int hc = active ? h : 0;
+  float kc[KH], acc[KH];
 #pragma unroll
-  for (int j = 0; j < KC; ++j) {
-    acc[j] = 0.f;
-    kc[j] = (j < k) ? to_f(keys[((long)img * k + j) * H + h]) : 0.f;
+  for (int i = 0; i < KH; ++i) {
+    acc[i] = 0.f;
+    kc[i] = (j0 + i < k) ? to_f(keys[((long)img * k + j0 + i) * H + hc]) : 0.f;
   }
-  const float wh = w_alpha[h];
+  const int ks = k - j0;  // index of the sentinel position within this thread's half (if 0 <= ks < KH)
+  const float wh = w_alpha[hc];
   float dw = 0.f;
-  for (int q = 0; q < nq; ++q) {
-    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
-    const float he = to_f(hid_emb[row * H + h]);
-    const float se = to_f(sent_emb[row * H + h]);
-    const float* dq = de_s + q * P;
-    float dhe = 0.f;
+  long row = (long)img * s.row0_stride;
+  float he_n = to_f(hid_emb[row * H + hc]), se_n = to_f(sent_emb[row * H + hc]);
+  for (int q = 0; q < nq; ++q, row += s.q_stride) {
+    const float he = he_n, se = se_n;
+    if (q + 1 < nq) {  // next query's operands: the loads overlap this query's arithmetic
+      he_n = to_f(hid_emb[(row + s.q_stride) * H + hc]);
+      se_n = to_f(sent_emb[(row + s.q_stride) * H + hc]);
+    }
+    const float4* dq4 = reinterpret_cast<const float4*>(de_s + (q * 2 + half) * KHP);
+    float dhe = 0.f, g_s = 0.f;
 #pragma unroll
-    for (int j = 0; j < KC; ++j) {
-      if (j < k) {
-        const float z = tanh_t<F>(kc[j] + he);
-        const float d = dq[j];
-        const float g = d * wh * (1.f - z * z);
-        acc[j] += g;
-        dhe += g;
-        dw = fmaf(d, z, dw);
+    for (int i4 = 0; i4 < (KH + 3) / 4; ++i4) {
+      const float4 d4 = dq4[i4];
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i4 * 4 + u;
+        if (i < KH) {
+          const float kv = (i == ks) ? se : kc[i];   // positions past the sentinel have de == 0
+          const float z = tanh_t<F>(kv + he);
+          const float uu = fmaf(-z, z, 1.f);
+          acc[i] = fmaf(dd[u], uu, acc[i]);
+          dhe = fmaf(dd[u], uu, dhe);
+          dw = fmaf(dd[u], z, dw);
+          if (i == ks) g_s = dd[u] * uu;
+        }
       }
     }
-    {
-      const float z = tanh_t<F>(se + he);
-      const float d = dq[k];
-      const float g = d * wh * (1.f - z * z);
-      dhe += g;
-      dw = fmaf(d, z, dw);
-      dsent_emb[row * H + h] = from_f<T>(g);
+    dhe += __shfl_xor_sync(0xffffffffu, dhe, 1);
+    if (active) {
+      if (half == 0) dhid_emb[row * H + h] = from_f<T>(dhe * wh);
+      if (ks >= 0 && ks < KH) dsent_emb[row * H + h] = from_f<T>(g_s * wh);
     }
-    dhid_emb[row * H + h] = from_f<T>(dhe);
   }
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < KC; ++j)
-    if (j < k) dKV[((long)img * k + j) * (2 * H) + H + h] = from_f<T>(acc[j]);
-  atomicAdd(dw_alpha + h, dw);
+    for (int i = 0; i < KH; ++i)
+      if (j0 + i < k) dKV[((long)img * k + j0 + i) * (2 * H) + H + h] = from_f<T>(acc[i] * wh);
+    atomicAdd(dw_alpha + h, dw);
+  }
 }
 
 // choose how many CTAs share one image's query rows: minimise waves x rows-per-CTA
@@ -748,15 +770,17 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
     if (gemm<T>(gc, g)) return -1;
   }
   if (!s.position_softmax) return 0;
-  const size_t a_bytes = (size_t)s.q_per_img * P * sizeof(float);
-  dim3 grid_cols(s.n_img, (H + 255) / 256);
+  // KH = positions per thread (two threads per column): the smallest instantiated size with 2 * KH >= k + 1
+  dim3 grid_cols(s.n_img, (H + 127) / 128);
 #define DISPATCH_KC(KERNEL, ...)                                                                                     \
   do {                                                                                                               \
-    if (k == 49) KERNEL<T, 49><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                  \
-    else if (k <= 8) KERNEL<T, 8><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                               \
-    else if (k <= 16) KERNEL<T, 16><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                             \
-    else if (k <= 32) KERNEL<T, 32><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                             \
-    else KERNEL<T, 64><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                          \
+    const int kh = P <= 8 ? 4 : P <= 16 ? 8 : P <= 32 ? 16 : P <= 50 ? 25 : 32;                                      \
+    const size_t a_bytes = (size_t)s.q_per_img * 2 * ((kh + 3) & ~3) * sizeof(float);                                \
+    if (kh == 25) KERNEL<T, 25><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                 \
+    else if (kh == 4) KERNEL<T, 4><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                              \
+    else if (kh == 8) KERNEL<T, 8><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                              \
+    else if (kh == 16) KERNEL<T, 16><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                            \
+    else KERNEL<T, 32><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                          \
     if (c.launches) ++*c.launches;                                                                                   \
   } while (0)
   DISPATCH_KC(attn_bwd_dk_kernel, s, keys, hid_emb, sent_emb, w_alpha, de, dKV, dhid_emb, dsent_emb, dw_alpha);

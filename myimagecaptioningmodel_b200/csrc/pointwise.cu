@@ -487,7 +487,7 @@ template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, 
     return;
   }
   const int col_blocks = (N + 255) / 256;
-  long chunks = 32;
+  long chunks = 32;  // measured: 4x more (smaller) chunks is slower in stream order (+80 us per train step)
   if (chunks > (M + 15) / 16) chunks = (M + 15) / 16;
   if (chunks < 1) chunks = 1;
   const long rpc = (M + chunks - 1) / chunks;
