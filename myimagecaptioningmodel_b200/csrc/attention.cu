@@ -554,11 +554,14 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
   const int img = blockIdx.x;
   const int h = blockIdx.y * (blockDim.x >> 1) + (threadIdx.x >> 1);
   const int half = threadIdx.x & 1;
-  const int j0 = half * KH;  // this thread's positions: j0 .. j0 + KH - 1
+  // positions of this thread: the upper half owns the LAST KH positions, so the sentinel (position k) always sits in
+  // its slot KH - 1 (a compile-time register); the lower half owns [0, P - KH) and pads
+  const int j0 = half ? P - KH : 0;
+  const int nv = half ? KH : P - KH;  // valid slots
   for (int i = threadIdx.x; i < nq * 2 * KHP; i += blockDim.x) {
     const int q = i / (2 * KHP), r = i % (2 * KHP);
-    const int hf = r / KHP, ii = r % KHP, j = hf * KH + ii;
-    de_s[i] = (ii < KH && j < P) ? de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j] : 0.f;
+    const int hf = r / KHP, ii = r % KHP, j = (hf ? P - KH : 0) + ii;
+    de_s[i] = (ii < (hf ? KH : P - KH)) ? de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j] : 0.f;
   }
   __syncthreads();
   const bool active = h < H;
@@ -567,9 +570,8 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
 #pragma unroll
   for (int i = 0; i < KH; ++i) {
     acc[i] = 0.f;
-    kc[i] = (j0 + i < k) ? to_f(keys[((long)img * k + j0 + i) * H + hc]) : 0.f;
+    kc[i] = (i < nv && j0 + i < k) ? to_f(keys[((long)img * k + j0 + i) * H + hc]) : 0.f;
   }
-  const int ks = k - j0;  // index of the sentinel position within this thread's half (if 0 <= ks < KH)
   const float wh = w_alpha[hc];
   float dw = 0.f;
   long row = (long)img * s.row0_stride;
@@ -590,26 +592,26 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
       for (int u = 0; u < 4; ++u) {
         const int i = i4 * 4 + u;
         if (i < KH) {
-          const float kv = (i == ks) ? se : kc[i];   // positions past the sentinel have de == 0
+          const float kv = (i == KH - 1 && half) ? se : kc[i];   // padded slots have de == 0
           const float z = tanh_t<F>(kv + he);
           const float uu = fmaf(-z, z, 1.f);
           acc[i] = fmaf(dd[u], uu, acc[i]);
           dhe = fmaf(dd[u], uu, dhe);
           dw = fmaf(dd[u], z, dw);
-          if (i == ks) g_s = dd[u] * uu;
+          if (i == KH - 1) g_s = dd[u] * uu;
         }
       }
     }
     dhe += __shfl_xor_sync(0xffffffffu, dhe, 1);
     if (active) {
       if (half == 0) dhid_emb[row * H + h] = from_f<T>(dhe * wh);
-      if (ks >= 0 && ks < KH) dsent_emb[row * H + h] = from_f<T>(g_s * wh);
+      if (half) dsent_emb[row * H + h] = from_f<T>(g_s * wh);
     }
   }
   if (active) {
 #pragma unroll
     for (int i = 0; i < KH; ++i)
-      if (j0 + i < k) dKV[((long)img * k + j0 + i) * (2 * H) + H + h] = from_f<T>(acc[i] * wh);
+      if (i < nv && j0 + i < k) dKV[((long)img * k + j0 + i) * (2 * H) + H + h] = from_f<T>(acc[i] * wh);
     atomicAdd(dw_alpha + h, dw);
   }
 }
