@@ -27,17 +27,22 @@ namespace capdec {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;  // rows of one UMMA; a CTA tile is MT of them stacked (MT = 1 or 2)
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter
 constexpr int kThreads = 64 + kEpiWarps * 32;    // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int kABytes = BM * BK * 2;  // 16 KB
 
-template <int BN> struct TcCfg {
+// MT = 2: a 256-row CTA tile (two UMMA row blocks sharing every B k-block).  The decoder's big GEMMs are bound by the
+// L2 -> shared-memory operand stream (all 148 SMs pull (BM + BN) * 128 B per k-block, ~7 TB/s chip-wide), not by the
+// tensor pipe, and a 256 x 256 tile moves 1/3 less operand data per flop than 128 x 256.
+template <int BN, int MT> struct TcCfg {
+  static constexpr int kABytesT = MT * kABytes;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 32)
+  static constexpr int kStageBytes = kABytesT + kBBytes;
+  static constexpr int kStages = (MT == 2) ? (BN == 256 ? 3 : 4) : (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kAccBufs = (2 * MT * BN <= 512) ? 2 : 1;  // accumulator buffers that fit the 512 TMEM columns
+  static constexpr int kTmemCols = kAccBufs * MT * BN;           // power of two >= 32
   static constexpr int kAlignSlack = 512;  // dynamic smem starts 1024-aligned in practice; checked at kernel entry
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte output tile
   static constexpr int kSmemBytes =
@@ -189,11 +194,13 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, void* __restrict__ C, TcShape sh, GemmEpi epi) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
+  constexpr int BMT = BM * MT;          // rows of the CTA tile
+  constexpr int NB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -242,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int z = w / tb, bt = (w % tb) / tiles, tile = w % tiles;
-        const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
+        const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BMT;
         const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
         const int nk = kb1 - kb0;
         const int rot = sh.rotate_k ? (int)((blockIdx.x / sh.tiles_n) % nk) : 0;
@@ -250,13 +257,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kb = kb0 + (i + rot < nk ? i + rot : i + rot - nk);
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sA = smem + s * Cfg::kStageBytes;
-          uint8_t* sB = sA + kABytes;
+          uint8_t* sB = sA + Cfg::kABytesT;
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
           if (!A_MN) {
-            tma_load_3d(sA, &tmA, kb * BK, m0, bt, &full_bar[s]);
+#pragma unroll
+            for (int mh = 0; mh < MT; ++mh) tma_load_3d(sA + mh * kABytes, &tmA, kb * BK, m0 + mh * BM, bt, &full_bar[s]);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_3d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, bt, &full_bar[s]);
+            for (int i = 0; i < BMT / 64; ++i) tma_load_3d(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, bt, &full_bar[s]);
           }
           if (!B_MN) {
             tma_load_3d(sB, &tmB, kb * BK, n0, bt, &full_bar[s]);
@@ -283,21 +291,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
         const int z = w / tb;
         const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
-        const int buf = it & 1;
-        const uint32_t acc_ph = (it >> 1) & 1;
+        const int buf = it % NB;
+        const uint32_t acc_ph = (it / NB) & 1;
         mbar_wait(&tmem_empty_bar[buf], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * MT * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           if (it == 0 && kb == kb0) TRACE(4);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t b_addr = a_addr + Cfg::kABytesT;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, slice_desc<A_MN>(a_addr, k), slice_desc<B_MN>(b_addr, k), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int mh = 0; mh < MT; ++mh)  // the row blocks share the B slice
+              umma_bf16(tmem_d + (uint32_t)(mh * BN), slice_desc<A_MN>(a_addr + mh * kABytes, k),
+                        slice_desc<B_MN>(b_addr, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
@@ -313,131 +323,138 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int bt = (w % tb) / tiles, tile = w % tiles;
-      const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BM;
-      const int buf = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < sh.M;
+      const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * BMT;
+      const int buf = it % NB;
+      const uint32_t acc_ph = (it / NB) & 1;
       const bool has_bias = epi.bias != nullptr;
       if (sh.tma_out && has_bias) {
         // stage this tile's bias slice (zero past the readable range) while the MMAs are still running
         const int n_read = (sh.N + 7) & ~7;
         for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
-          bias_s[buf * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
+          bias_s[(it & 1) * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
       }
       mbar_wait(&tmem_full_bar[buf], acc_ph);
       if (warp == 2 && lane == 0 && it < 4) TRACE(12 + it);   // accumulator of tile `it` complete
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
-      if (sh.tma_out) {
-        // ---- registers -> swizzled smem tile (32 rows x 128 B) -> TMA tensor store / reduce-add ----
-        // Passes (128 bytes of output per row each) are dealt round-robin to the two warps of a lane quarter.  The
-        // host guarantees (launch()) that bias / addend / dact_y may be read in whole groups of 8 columns up to the
-        // next multiple of 8 past N; columns >= N are clipped by the TMA store, so there is no scalar edge path.
-        uint8_t* my_stage = staging + ew * 4096;
-        const uint32_t swz = (uint32_t)(lane & 7);
-        uint8_t* my_row = my_stage + lane * 128;
-        const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
-        const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
-                                                         add_row * epi.ld_add + n0
-                                                   : nullptr;
-        const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
-                              ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
-                              : nullptr;
-        const bool do_tanh = epi.act == ACT_TANH;
-        const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
-        const bool f32_out = epi.out_f32 || epi.atomic;
-        const int pw = f32_out ? 32 : 64;           // columns per pass
-        const int n_pass = BN / pw;
-        const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
-        if (half >= n_pass) {
-          // nothing to read for this warp (BN = 64, bf16): release the accumulator right away
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        }
 #pragma unroll 1
-        for (int ps = half; ps < n_pass; ps += 2) {
-          const int c0 = ps * pw;
-          const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
-          if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
-          __syncwarp();
-          const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;
-          const bf16* ap = add_p ? add_p + c0 : nullptr;
-          const bf16* yp = y_p ? y_p + c0 : nullptr;
-          if (f32_out) {
-            if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
-            else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
-          } else {
+      for (int mh = 0; mh < MT; ++mh) {  // the 128-row blocks of the CTA tile, one after the other
+        const bool last_block = (mh == MT - 1);
+        const int row = m0 + mh * BM + quarter * 32 + lane;
+        const bool row_ok = row < sh.M;
+        const uint32_t tmem_d =
+            tmem_base + (uint32_t)(buf * MT * BN + mh * BN) + ((uint32_t)(quarter * 32) << 16);
+        if (sh.tma_out) {
+          // ---- registers -> swizzled smem tile (32 rows x 128 B) -> TMA tensor store / reduce-add ----
+          // Passes (128 bytes of output per row each) are dealt round-robin to the two warps of a lane quarter.  The
+          // host guarantees (launch()) that bias / addend / dact_y may be read in whole groups of 8 columns up to the
+          // next multiple of 8 past N; columns >= N are clipped by the TMA store, so there is no scalar edge path.
+          uint8_t* my_stage = staging + ew * 4096;
+          const uint32_t swz = (uint32_t)(lane & 7);
+          uint8_t* my_row = my_stage + lane * 128;
+          const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
+          const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
+                                                           add_row * epi.ld_add + n0
+                                                     : nullptr;
+          const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
+                                ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
+                                : nullptr;
+          const bool do_tanh = epi.act == ACT_TANH;
+          const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
+          const bool f32_out = epi.out_f32 || epi.atomic;
+          const int pw = f32_out ? 32 : 64;           // columns per pass
+          const int n_pass = BN / pw;
+          const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
+          if (half >= n_pass && last_block) {
+            // nothing to read for this warp (BN = 64, bf16): release the accumulator right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
-              const int o = sub * 32;
-              if (left - o >= 32)
-                epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
-                                             yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                             (uint32_t)(sub * 4));
-              else
-                epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
-                                              yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                             (uint32_t)(sub * 4));
+          for (int ps = half; ps < n_pass; ps += 2) {
+            const int c0 = ps * pw;
+            const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
+            if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
+            __syncwarp();
+            const float* bsp = has_bias ? bias_s + (it & 1) * BN + c0 : nullptr;
+            const bf16* ap = add_p ? add_p + c0 : nullptr;
+            const bf16* yp = y_p ? y_p + c0 : nullptr;
+            if (f32_out) {
+              if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+              else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+            } else {
+#pragma unroll 1
+              for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
+                const int o = sub * 32;
+                if (left - o >= 32)
+                  epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                                               yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
+                                               (uint32_t)(sub * 4));
+                else
+                  epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                                                yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
+                                               (uint32_t)(sub * 4));
+              }
+            }
+            if (ps == my_last && last_block) {
+              // all of this warp's TMEM reads are done: hand the accumulator back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            }
+            if (left <= 0) continue;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
+              else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
+              bulk_commit();
             }
           }
-          if (ps == my_last) {
+          continue;
+        }
+        if (half == 1) {  // the fallback path below uses one warp per lane quarter
+          if (last_block) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+          continue;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          // ---- fallback for outputs the TMA cannot address (unaligned base / pitch): per-thread stores ----
+          uint32_t r[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
+          tmem_ld32(tmem_d + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1 && last_block) {
             // all of this warp's TMEM reads are done: hand the accumulator back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
           }
-          if (left <= 0) continue;
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
-            else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
-            bulk_commit();
+          const int nb = n0 + c * 32;
+          if (!row_ok || nb >= sh.N) continue;
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            const int col = nb + g * 8;
+            if (col >= sh.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+            GemmEpi eb = epi;
+            if (eb.addend) eb.addend = reinterpret_cast<const bf16*>(eb.addend) + bt * eb.batch_add;
+            if (eb.dact_y) eb.dact_y = reinterpret_cast<const bf16*>(eb.dact_y) + bt * eb.batch_y;
+            void* Cb = (epi.out_f32 || epi.atomic) ? (void*)(reinterpret_cast<float*>(C) + bt * sh.batch_c)
+                                                   : (void*)(reinterpret_cast<bf16*>(C) + bt * sh.batch_c);
+            epi_math8_tail(v, eb, row, col, true, sh.N);
+            epi_store8_tail(v, Cb, sh.ldc, row, col, sh.N, eb);
           }
         }
-        if (warp == 2 && lane == 0 && it < 4) TRACE(16 + it);   // epilogue of tile `it` issued its last store
-        continue;
       }
-      if (half == 1) {  // the fallback path below uses one warp per lane quarter
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        continue;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        // ---- fallback for outputs the TMA cannot address (unaligned base / pitch): per-thread stores ----
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous trip
-        tmem_ld32(tmem_d + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          // all of this warp's TMEM reads are done: hand the accumulator back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        const int nb = n0 + c * 32;
-        if (!row_ok || nb >= sh.N) continue;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          const int col = nb + g * 8;
-          if (col >= sh.N) break;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-          GemmEpi eb = epi;
-          if (eb.addend) eb.addend = reinterpret_cast<const bf16*>(eb.addend) + bt * eb.batch_add;
-          if (eb.dact_y) eb.dact_y = reinterpret_cast<const bf16*>(eb.dact_y) + bt * eb.batch_y;
-          void* Cb = (epi.out_f32 || epi.atomic) ? (void*)(reinterpret_cast<float*>(C) + bt * sh.batch_c)
-                                                 : (void*)(reinterpret_cast<bf16*>(C) + bt * sh.batch_c);
-          epi_math8_tail(v, eb, row, col, true, sh.N);
-          epi_store8_tail(v, Cb, sh.ldc, row, col, sh.N, eb);
-        }
-      }
+      if (warp == 2 && lane == 0 && it < 4) TRACE(16 + it);   // epilogue of tile `it` issued its last store
     }
   }
   if (warp >= 2 && lane == 0 && sh.tma_out) bulk_wait<0>();  // all tensor stores of this thread have completed
@@ -522,12 +539,12 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MT>
 int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
@@ -568,7 +585,7 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   sh.tma_out = out_mode;
   sh.trace = g_trace;
   sh.M = c.M; sh.N = c.N; sh.K = c.K;
-  sh.tiles_m = (c.M + BM - 1) / BM; sh.tiles_n = (c.N + BN - 1) / BN;
+  sh.tiles_m = (c.M + BM * MT - 1) / (BM * MT); sh.tiles_n = (c.N + BN - 1) / BN;
   sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = vec_ok;
   sh.batch = c.batch > 0 ? c.batch : 1; sh.batch_c = c.batch_c;
   {
@@ -578,16 +595,17 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   }
   const long total = (long)sh.tiles_m * sh.tiles_n * splits * sh.batch;
   const int grid = (int)std::min<long>(total, kNumSMs);
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, tmC, c.C, sh, c.epi);
+  gemm_tc_kernel<BN, A_MN, B_MN, MT><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, tmC, c.C, sh, c.epi);
   ctx.launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(err)); return -1; }
   return 0;
 }
 
-template <int BN> int launch_majors(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
-  if (c.a_mn) return c.b_mn ? launch<BN, true, true>(ctx, c, splits, kbps) : launch<BN, true, false>(ctx, c, splits, kbps);
-  return c.b_mn ? launch<BN, false, true>(ctx, c, splits, kbps) : launch<BN, false, false>(ctx, c, splits, kbps);
+template <int BN, int MT> int launch_majors(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
+  if (c.a_mn)
+    return c.b_mn ? launch<BN, true, true, MT>(ctx, c, splits, kbps) : launch<BN, true, false, MT>(ctx, c, splits, kbps);
+  return c.b_mn ? launch<BN, false, true, MT>(ctx, c, splits, kbps) : launch<BN, false, false, MT>(ctx, c, splits, kbps);
 }
 
 }  // namespace
@@ -605,39 +623,59 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
   if (c.batch > 1 && c.epi.atomic) { set_error("gemm_tc: batched GEMM with split-K is not supported"); return -1; }
   const int nkb = (c.K + BK - 1) / BK;
-  const int mt = (c.M + BM - 1) / BM;
-  // Pick the tile width and the k-split that minimise a simple cost model of the persistent kernel:
-  //   per CTA: ceil(work / 148) items, each  kb_per_split * t_kblock(BN) + t_epilogue(BN);
-  //   t_kblock ~ bytes moved per k-block (operand streaming bound), epilogue ~ BN (x3 for reductions).
-  int best_bn = 64, best_sp = 1;
+  // Pick the tile (rows 128 or 256, width 64 / 128 / 256) and the k-split that minimise a simple cost model of the
+  // persistent kernel:
+  //   per CTA: ceil(work / 148) items, each  kb_per_split * t_kblock + t_epilogue;
+  //   t_kblock ~ operand bytes moved per k-block (the L2 -> smem stream bounds the mainloop), epilogue ~ tile area
+  //   (x3 for reductions).
+  int best_bn = 64, best_sp = 1, best_mt = 1;
   double best_cost = 1e300;
   const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && c.N <= bn / 2) continue;
-    const long tiles = (long)mt * ((c.N + bn - 1) / bn) * (c.batch > 0 ? c.batch : 1);
-    const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
-    const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
-    for (int sp = sp_min; sp <= sp_max; ++sp) {
-      const int kbps = (nkb + sp - 1) / sp;
-      const int sp_eff = (nkb + kbps - 1) / kbps;
-      const long per_cta = (tiles * sp_eff + kNumSMs - 1) / kNumSMs;
-      const double t_kb = (128.0 + bn) / 384.0;
-      const double t_epi = (bn / 256.0) * (c.epi.atomic ? 6.0 : 2.0) + 1.0;
-      const double cost = per_cta * (kbps * t_kb + t_epi) + 4.0 /*fill*/;
-      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; }
+  int mt_env = 0;  // CAPDEC_GEMM_MT = 1 / 2 forces the tile height (tests, tuning); read at every call
+  if (const char* ev = getenv("CAPDEC_GEMM_MT")) mt_env = atoi(ev);
+  for (int mtile = 1; mtile <= 2; ++mtile) {
+    // Measured on B200: the 256-row tile is NOT faster (head fc 25.8 vs 25.5 us, key/value projection 43.9 vs 32.1 us):
+    // the mainloop is bound by the shared-memory operand reads of the UMMAs (12 KB per 128x256x16), which a taller
+    // CTA tile does not reduce, and its single accumulator buffer exposes the epilogue.  It is kept selectable
+    // (CAPDEC_GEMM_MT=2) for the tests; auto-selection uses 128-row tiles.
+    if (mtile != (mt_env > 0 ? mt_env : 1)) continue;
+    if (mtile == 2 && c.M <= BM) continue;
+    const int mt = (c.M + BM * mtile - 1) / (BM * mtile);
+    for (int i = 0; i < 3; ++i) {
+      const int bn = cands[i];
+      if (bn > 64 && c.N <= bn / 2) continue;
+      if (mtile == 2 && bn == 64) continue;  // not instantiated: a 256 x 64 tile has no use
+      const long tiles = (long)mt * ((c.N + bn - 1) / bn) * (c.batch > 0 ? c.batch : 1);
+      const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
+      const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
+      for (int sp = sp_min; sp <= sp_max; ++sp) {
+        const int kbps = (nkb + sp - 1) / sp;
+        const int sp_eff = (nkb + kbps - 1) / kbps;
+        const long per_cta = (tiles * sp_eff + kNumSMs - 1) / kNumSMs;
+        const double t_kb = (128.0 * mtile + bn) / 384.0;
+        const double t_epi = mtile * ((bn / 256.0) * (c.epi.atomic ? 6.0 : 2.0) + 1.0);
+        const double cost = per_cta * (kbps * t_kb + t_epi) + 4.0 /*fill*/;
+        if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; best_mt = mtile; }
+      }
     }
   }
   if (const char* ev = getenv("CAPDEC_GEMM_BN")) {  // tuning / profiling override
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256) best_bn = v;
+    if (best_bn == 64) best_mt = 1;
   }
   const int kbps = (nkb + best_sp - 1) / best_sp;
   const int splits = (nkb + kbps - 1) / kbps;
+  if (best_mt == 2) {
+    switch (best_bn) {
+      case 256: return launch_majors<256, 2>(ctx, c, splits, kbps);
+      default: return launch_majors<128, 2>(ctx, c, splits, kbps);
+    }
+  }
   switch (best_bn) {
-    case 256: return launch_majors<256>(ctx, c, splits, kbps);
-    case 128: return launch_majors<128>(ctx, c, splits, kbps);
-    default: return launch_majors<64>(ctx, c, splits, kbps);
+    case 256: return launch_majors<256, 1>(ctx, c, splits, kbps);
+    case 128: return launch_majors<128, 1>(ctx, c, splits, kbps);
+    default: return launch_majors<64, 1>(ctx, c, splits, kbps);
   }
 }
 

@@ -146,3 +146,34 @@ def test_gemm_linearity_at_full_size():
     c12 = gemm((A1.float() + A2.float()).to(torch.bfloat16), B, M, N, K, out_f32=True)
     assert torch.equal(c1 + c2, c12)                       # small integers: exact in fp32
     assert torch.equal(c1, A1.float() @ B.float().t())
+
+
+@pytest.mark.parametrize("mt", ["1", "2"])
+@pytest.mark.parametrize("majors", [0, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(304, 520, 192), (264, 136, 64), (8704, 1024, 1024), (1024, 1024, 8704), (136, 72, 40),
+                                   (640, 12295, 256)])
+def test_gemm_tile_heights(M, N, K, majors, mt, monkeypatch):
+    """Both CTA tile heights (128 rows, and 256 rows = two UMMA row blocks sharing every B k-block) on ragged and
+    full-size shapes, every operand-major form, bf16 output with the fused epilogue and fp32 split-K reduction."""
+    monkeypatch.setenv("CAPDEC_GEMM_MT", mt)
+    a_mn, b_mn = bool(majors & 1), bool(majors & 2)
+    if b_mn and N % 8:
+        pytest.skip("an MN-major operand needs a 16-byte row pitch")
+    A = _rand((K, M) if a_mn else (M, K), torch.bfloat16, 11)
+    B = _rand((K, N) if b_mn else (N, K), torch.bfloat16, 12)
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float() if b_mn else B.float().t()
+    ref = Af @ Bf
+    ldc = (N + 7) // 8 * 8
+    if majors == 3:   # weight-gradient form: fp32 accumulation into C (split-K, TMA reduce-add)
+        Cbuf = torch.ones(M, ldc, dtype=torch.float32, device="cuda")
+        out = gemm(A, B, M, N, K, a_mn=True, b_mn=True, C_out=Cbuf, ldc=ldc, atomic=True)[:, :N]
+        assert rel_err(out - 1.0, ref) < 5e-5, rel_err(out - 1.0, ref)
+    else:
+        bias = _rand((ldc,), torch.float32, 13)
+        addend = _rand((M, ldc), torch.bfloat16, 14)
+        Cbuf = torch.zeros(M, ldc, dtype=torch.bfloat16, device="cuda")
+        out = gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, C_out=Cbuf, ldc=ldc, bias=bias, addend=addend,
+                   act=1)[:, :N]
+        ref2 = torch.tanh(ref + bias[:N] + addend[:, :N].float())
+        assert rel_err(out.float(), ref2) < BF16_TOL, rel_err(out.float(), ref2)
