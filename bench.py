@@ -97,6 +97,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu --set full
+    capture (profiles/r01_head_gemm_ncu.json, written by scripts/ncu_traffic.py); None if no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r01_head_gemm_ncu.json")
+    try:
+        return float(json.load(open(path))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port of the reference's Paddle graph, timed on the host cores
 # ------------------------------------------------------------------------------------------------------------------
@@ -241,34 +251,55 @@ def main_ours(args):
     # ---- beam search (BASELINE.json configs[3], 512 images per GPU, beam 3, 35 steps): secondary number ----
     gi, Pi, _ = synth.make_batch(cfg, BEAM_IMAGES_PER_GPU, 777 + rank)
     gi, Pi = gi.cuda(), Pi.cuda()
-    eng.decode(gi[:8].contiguous(), Pi[:8].contiguous(), beam=BEAM, finish_on_stop=True)
+    for _ in range(2):   # warm-up at the full size: the handle's decode workspace is allocated here, not in the timed region
+        eng.decode(gi, Pi, beam=BEAM, finish_on_stop=True)
     sync()
-    beam_reps = 2
+    beam_reps = 3
     ms_beam = timed_region(lambda i: eng.decode(gi, Pi, beam=BEAM, finish_on_stop=True), beam_reps, sync, barrier)
 
+    # ---- batch-1 greedy decode latency (BASELINE.json configs[4]) ----
+    g1, P1 = gi[:1].contiguous(), Pi[:1].contiguous()
+    for _ in range(3):
+        eng.decode(g1, P1, beam=1)
+    sync()
+    lat = []
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.decode(g1, P1, beam=1)
+        e1.record()
+        sync()
+        lat.append(e0.elapsed_time(e1))
+    lat.sort()
+
     # ---- roofline of the dominant kernel: the tcgen05 GEMM at the head shape (M = B*T, N = K = 1024) ----
+    # Timed live with CUDA events on the launching stream; the launches rotate over 8 activation / output buffer pairs
+    # (8 x 35.6 MB = 285 MB > the 126 MB L2), so every launch streams its A operand from HBM as it does inside a step.
     Mh, Nh, Kh = B * cfg.train_steps, cfg.hidden_dim, cfg.hidden_dim
-    A = torch.randn(Mh, Kh, device="cuda").to(torch.bfloat16)
+    NBUF = 8
+    As = [torch.randn(Mh, Kh, device="cuda").to(torch.bfloat16) for _ in range(NBUF)]
     W = torch.randn(Kh, Nh, device="cuda").to(torch.bfloat16)      # PaddlePaddle [in,out] weight = MN-major B operand
-    Cb = torch.empty(Mh, Nh, device="cuda", dtype=torch.bfloat16)
+    Cs = [torch.empty(Mh, Nh, device="cuda", dtype=torch.bfloat16) for _ in range(NBUF)]
     bias = torch.zeros(Nh, device="cuda")
     lib = _capi.load_library()
 
     def head_gemm(i):
+        A, Cb = As[i % NBUF], Cs[i % NBUF]
         _capi.check(lib.capdec_gemm(_capi.DTYPE_BF16, 2, A.data_ptr(), Kh, W.data_ptr(), Nh, Cb.data_ptr(), Nh, Mh, Nh, Kh,
                                     bias.data_ptr(), None, 0, None, 0, 1, 0, 0, 0, _capi.stream_ptr()), "capdec_gemm")
 
-    for i in range(3):
+    for i in range(NBUF):
         head_gemm(i)
-    reps = 20
+    reps = 3 * NBUF
     ms_gemm = timed_region(head_gemm, reps, sync, lambda: None) / reps
     peaks = load_peaks()
     flops = 2.0 * Mh * Nh * Kh
     achieved = flops / (ms_gemm * 1e-3) / 1e12
     roofline = {"kernel": "gemm_tc_kernel<256,A K-major,B MN-major> head fc M=%d N=%d K=%d bias+tanh" % (Mh, Nh, Kh),
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["source"] + ", burst",
-                "ms_per_launch": ms_gemm}
+                "frac": achieved / peaks["bf16_burst"], "traffic": load_ncu_traffic(),
+                "peak_source": peaks["source"] + ", burst", "ms_per_launch": ms_gemm,
+                "algorithmic_flops_per_launch": flops, "l2": "8 rotating A/C buffer pairs, 285 MB > L2"}
     # whole-step view: algorithmic GEMM flops of one train step over the measured step time
     step_flops = 116.7e6 * B * cfg.train_steps + 616.6e6 * B
     step_tflops = step_flops / (ms / args.steps * 1e-3) / 1e12
@@ -302,6 +333,9 @@ def main_ours(args):
                            "beam_search_images_per_sec": world * BEAM_IMAGES_PER_GPU * beam_reps / (ms_beam * 1e-3),
                            "beam_config": "beam %d, %d steps, %d images per GPU, finish_on_stop" % (
                                BEAM, cfg.infer_max_length, BEAM_IMAGES_PER_GPU),
+                           "batch1_greedy_latency_ms": {"median": lat[len(lat) // 2], "p95": lat[int(0.95 * (len(lat) - 1))],
+                                                        "per_step_median": lat[len(lat) // 2] / cfg.infer_max_length,
+                                                        "config": "1 image, beam 1, %d steps" % cfg.infer_max_length},
                            "workspace_gb": eng.workspace_bytes / 1e9, "last_loss": losses[-1] if losses else None}}
         print(json.dumps(line), flush=True)
     if world > 1:
