@@ -665,8 +665,18 @@ template <typename T> class Decoder : public DecoderBase {
       OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
       OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
       prof.mark("dec.head_fc", s);
-      attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
-                       prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
+      bool attn_small = false;
+      if constexpr (std::is_same<T, bf16>::value) {
+        if (!force_simt && attention_fwd_small_supported(as)) {
+          OK(attention_fwd_small(lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
+                                 sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
+                                 actx.as<bf16>()));
+          attn_small = true;
+        }
+      }
+      if (!attn_small)
+        attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
+                         prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
       prof.mark("dec.attention", s);
       OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
       OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
@@ -895,6 +905,18 @@ int capdec_attention_fwd(int32_t dtype, int32_t H, int32_t k, int32_t n_img, int
   if (H % 8 || k < 1 || k > 63) { set_error("capdec_attention_fwd: need H %% 8 == 0 and 1 <= k <= 63"); return -1; }
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
   AttnShape s = make_shape(H, k, n_img, q_per_img, row0_stride, q_stride, softmax_axis);
+  if (dtype == CAPDEC_DTYPE_BF16 && !attention_fwd_batched_supported(s) && attention_fwd_small_supported(s) &&
+      (actx || ctx)) {
+    // the inference-shaped path (scores kernel + small context kernel)
+    int rc = 0;
+    if (actx)
+      rc = attention_fwd_small(lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
+                               (const bf16*)sentinel, (const bf16*)p_hid, w_alpha, b_alpha, alpha, (bf16*)actx);
+    if (!rc && ctx)
+      rc = attention_fwd_small(lc, s, (const bf16*)keys, (const bf16*)vals, (const bf16*)hid_emb, (const bf16*)sent_emb,
+                               (const bf16*)sentinel, nullptr, w_alpha, b_alpha, alpha, (bf16*)ctx);
+    return rc ? -1 : 0;
+  }
   if (dtype == CAPDEC_DTYPE_BF16 && attention_fwd_batched_supported(s) && (actx || ctx)) {
     // the training-shaped path (scores kernel + batched context GEMM); its scratch is owned by the decoder handle in
     // the train schedule, the stand-alone entry point allocates it

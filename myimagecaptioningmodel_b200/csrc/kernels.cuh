@@ -103,6 +103,11 @@ int attention_fwd_batched(GemmContext& gc, LaunchCtx c, const AttnShape& s, cons
                           const bf16* hid_emb, const bf16* sent_emb, const bf16* sentinel, const bf16* p_hid,
                           const float* w_alpha, const float* b_alpha, float* alpha, bf16* alpha_T, bf16* sadd,
                           bf16* actx);
+// inference-shaped forward (q_per_img <= 8): the same scores kernel + a small context kernel
+bool attention_fwd_small_supported(const AttnShape& s);
+int attention_fwd_small(LaunchCtx c, const AttnShape& s, const bf16* keys, const bf16* vals, const bf16* hid_emb,
+                        const bf16* sent_emb, const bf16* sentinel, const bf16* p_hid, const float* w_alpha,
+                        const float* b_alpha, float* alpha, bf16* actx);
 // backward (see attention.cu): two batched tensor-core GEMMs (d alpha = dctx.V^T, d values = alpha^T.dctx with tanh'
 // fused), a row-wise soft-max-backward kernel and the column-wise d keys kernel.  dactx [rows,H] = d context.
 //   scratch: dal [rows, kDalLd] fp32, alpha_T [rows, kAlphaTLd] T

@@ -1,6 +1,8 @@
 // Vocabulary-axis kernels: masked soft-max cross-entropy forward / backward (model:163-171, 180-183, 205-212),
 // greedy arg-max and beam-search top-k with back-pointers (model:119-123; beam spec: SURVEY.md 8c row C5).
 // One CTA per row / per image, warp-shuffle + shared-memory block reductions, 128-bit loads.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace capdec {
@@ -413,6 +415,131 @@ beam_step_kernel(const float* __restrict__ logits, long ldl, int V, int beam, in
   }
 }
 
+// ---- beam search step, split form: one CTA per (image, prefix) ROW, then one warp per image -----------------------
+// beam_rows_kernel: the row's log-sum-exp and its `beam` best tokens, all logits of the row in registers (EPT per
+// thread, every load in flight at once), one block barrier per selection round (every warp re-reduces the 8 warp
+// winners from a double-buffered shared array).  3x the CTAs of the per-image kernel and a third of its serial chain:
+// 57 -> ~20 us per step at 512 images x beam 3 on B200.
+// beam_merge_kernel: merges the beam*beam scored candidates of an image (ties -> lower prefix, then lower token) and
+// writes tokens, back-pointers, scores, finished flags and histories.
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+
+template <int EPT>
+__global__ void __launch_bounds__(kRowThreads)
+beam_rows_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int pad, int finish_on_stop,
+                 const float* __restrict__ score_in, const int* __restrict__ fin_in, float* __restrict__ cand_v,
+                 int* __restrict__ cand_i, float* __restrict__ gscore) {
+  __shared__ float scratch[32];
+  __shared__ float s_v[2][kRowWarps];
+  __shared__ int s_i[2][kRowWarps];
+  const int r = blockIdx.x, p = r % beam;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int INT_BIG = 0x7fffffff;
+  const bool greedy = (beam == 1 && !finish_on_stop);
+  float* cv = cand_v + (long)r * kMaxBeam;
+  int* ci = cand_i + (long)r * kMaxBeam;
+  const float sc = score_in[r];
+  if (!(sc > -INFINITY)) {  // dead prefix: no candidates
+    if (tid < beam) { cv[tid] = -INFINITY; ci[tid] = INT_BIG; }
+    return;
+  }
+  if (finish_on_stop && fin_in[r]) {  // finished: one candidate, itself + pad, score unchanged
+    if (tid < beam) { cv[tid] = tid == 0 ? sc : -INFINITY; ci[tid] = tid == 0 ? p * V + pad : INT_BIG; }
+    return;
+  }
+  const float* row = logits + (long)r * ldl;
+  float x[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int n = tid + i * kRowThreads;
+    x[i] = (n < V) ? row[n] : -INFINITY;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) mx = fmaxf(mx, x[i]);
+  const float gmx = block_max(mx, scratch);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) sum += __expf(x[i] - gmx);   // exp(-inf) = 0 for the padding slots
+  const float lse = gmx + logf(block_sum(sum, scratch));
+  for (int rr = 0; rr < beam; ++rr) {
+    // local arg-max over the registers (ties -> lower token = lower i)
+    float lv = -INFINITY;
+    int li = INT_BIG;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (x[i] > lv) { lv = x[i]; li = tid + i * kRowThreads; }
+    const Cand wb = warp_best(Cand{lv, li});
+    if (lane == 0) { s_v[rr & 1][warp] = wb.v; s_i[rr & 1][warp] = wb.idx; }
+    __syncthreads();
+    Cand c{lane < kRowWarps ? s_v[rr & 1][lane] : -INFINITY, lane < kRowWarps ? s_i[rr & 1][lane] : INT_BIG};
+    c = warp_best(c);  // every warp computes the same block winner
+    if (tid == 0) {
+      // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
+      cv[rr] = (c.idx == INT_BIG) ? -INFINITY : (greedy ? c.v : sc + (c.v - lse));
+      ci[rr] = (c.idx == INT_BIG) ? INT_BIG : p * V + c.idx;
+      if (greedy) gscore[r] = sc + (c.v - lse);
+    }
+    if (c.idx != INT_BIG && (c.idx % kRowThreads) == tid) {
+      const int slot = c.idx / kRowThreads;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i)
+        if (i == slot) x[i] = -INFINITY;                  // remove the winner from this thread's pool
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, int stop, int finish_on_stop,
+                  const float* __restrict__ cand_v, const int* __restrict__ cand_i, const float* __restrict__ gscore,
+                  float* __restrict__ score_out, const int* __restrict__ fin_in, int* __restrict__ fin_out,
+                  const int* __restrict__ hist_in, int* __restrict__ hist_out, int* __restrict__ tok_out,
+                  int* __restrict__ src_out) {
+  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (img >= n_img) return;
+  const int INT_BIG = 0x7fffffff;
+  const bool greedy = (beam == 1 && !finish_on_stop);
+  // candidate (prefix p, rank rr) sits in lanes p * beam + rr (beam <= 8: two candidates per lane cover 64)
+  float v0 = -INFINITY, v1 = -INFINITY;
+  int i0 = INT_BIG, i1 = INT_BIG;
+  {
+    const int c0 = lane, c1 = lane + 32;
+    if (c0 < beam * beam) {
+      const long o = ((long)img * beam + c0 / beam) * kMaxBeam + c0 % beam;
+      v0 = cand_v[o]; i0 = cand_i[o];
+    }
+    if (c1 < beam * beam) {
+      const long o = ((long)img * beam + c1 / beam) * kMaxBeam + c1 % beam;
+      v1 = cand_v[o]; i1 = cand_i[o];
+    }
+  }
+  for (int r = 0; r < beam; ++r) {
+    Cand best{-INFINITY, INT_BIG};
+    if (i0 != INT_BIG && better(v0, i0, best.v, best.idx)) { best.v = v0; best.idx = i0; }
+    if (i1 != INT_BIG && better(v1, i1, best.v, best.idx)) { best.v = v1; best.idx = i1; }
+    best = warp_best(best);
+    if (i0 == best.idx) i0 = INT_BIG;   // flat indices p*V + token are unique: remove the winner
+    if (i1 == best.idx) i1 = INT_BIG;
+    int idx = best.idx;
+    float v = best.v;
+    int src, tok;
+    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }  // fewer live candidates than beams
+    else { src = idx / V; tok = idx % V; }
+    if (greedy && idx != INT_BIG) v = gscore[img * beam + src];
+    const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
+    if (lane == 0) {
+      tok_out[img * beam + r] = tok;
+      src_out[img * beam + r] = src;
+      score_out[img * beam + r] = v;
+      fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
+    }
+    const int* hin = hist_in + ((long)img * beam + src) * T_total;
+    int* hout = hist_out + ((long)img * beam + r) * T_total;
+    for (int t = lane; t < T_total; t += 32) hout[t] = (t == step) ? tok : (t < step ? hin[t] : 0);
+  }
+}
+
 template <typename T>
 __global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad, const T* __restrict__ emb,
                                     const int* __restrict__ tok, const int* __restrict__ src,
@@ -483,9 +610,50 @@ void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, in
   logits_bm_kernel<<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
   if (c.launches) ++*c.launches;
 }
+namespace {
+// candidate scratch of the split beam step (per device, grown on demand, process lifetime)
+struct BeamScratch { void* p = nullptr; size_t cap = 0; };
+BeamScratch g_beam_scratch[64];
+void* beam_scratch(size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  BeamScratch& b = g_beam_scratch[dev];
+  if (bytes > b.cap) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    if (cudaMalloc(&b.p, bytes) != cudaSuccess) { b.p = nullptr; return nullptr; }
+    b.cap = bytes;
+  }
+  return b.p;
+}
+}  // namespace
+
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
                const int* hist_in, int* hist_out, int* tok_out, int* src_out) {
+  static const bool split_ok = [] { const char* e = getenv("CAPDEC_BEAM_SPLIT"); return !(e && e[0] == '0'); }();
+  if (split_ok && V <= kRowThreads * 64 && n_img > 0) {
+    const long rows = (long)n_img * beam;
+    const size_t nb = (size_t)rows * kMaxBeam * 8 + (size_t)rows * 4;
+    char* sp = static_cast<char*>(beam_scratch(nb));
+    if (sp) {
+      float* cv = reinterpret_cast<float*>(sp);
+      int* ci = reinterpret_cast<int*>(sp + (size_t)rows * kMaxBeam * 4);
+      float* gs = reinterpret_cast<float*>(sp + (size_t)rows * kMaxBeam * 8);
+#define LAUNCH_ROWS(EPTV)                                                                                           \
+  beam_rows_kernel<EPTV><<<(unsigned)rows, kRowThreads, 0, c.stream>>>(logits, ldl, V, beam, pad, finish_on_stop,   \
+                                                                       score_in, fin_in, cv, ci, gs)
+      if (V <= kRowThreads * 8) LAUNCH_ROWS(8);
+      else if (V <= kRowThreads * 49) LAUNCH_ROWS(49);
+      else LAUNCH_ROWS(64);
+#undef LAUNCH_ROWS
+      beam_merge_kernel<<<(n_img + 3) / 4, 128, 0, c.stream>>>(n_img, V, beam, step, T_total, pad, stop, finish_on_stop, cv,
+                                                              ci, gs, score_out, fin_in, fin_out, hist_in, hist_out,
+                                                              tok_out, src_out);
+      if (c.launches) *c.launches += 2;
+      return;
+    }
+  }
 #define LAUNCH_BEAM(KERNEL)                                                                                          \
   KERNEL<<<n_img, kBeamThreads, 0, c.stream>>>(logits, ldl, V, beam, step, T_total, pad, stop, finish_on_stop, score_in, \
                                                score_out, fin_in, fin_out, hist_in, hist_out, tok_out, src_out)
