@@ -295,7 +295,8 @@ def main_ours(args):
     peaks = load_peaks()
     flops = 2.0 * Mh * Nh * Kh
     achieved = flops / (ms_gemm * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_tc_kernel<256,A K-major,B MN-major> head fc M=%d N=%d K=%d bias+tanh" % (Mh, Nh, Kh),
+    roofline = {"kernel": "gemm_tc_pair_kernel<A K-major,B MN-major> (tcgen05 cta_group::2, 256x256 tile per CTA pair) "
+                          "head fc M=%d N=%d K=%d bias+tanh" % (Mh, Nh, Kh),
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_burst"], "traffic": load_ncu_traffic(),
                 "peak_source": peaks["source"] + ", burst", "ms_per_launch": ms_gemm,

@@ -467,6 +467,289 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): one 256 x 256 tile per pair of CTAs on the two SMs of a TPC.
+//
+// The single-CTA mainloop above is bound by shared-memory ports, not by the tensor pipe: per 128x256x16 UMMA it reads
+// 12 KB of operands while TMA writes the next k-block into the same shared memory (0.37 us per 48 KB k-block against
+// 0.27 us of MMA time).  In a pair, CTA r keeps rows [128r, 128r+128) of A and columns [128r, 128r+128) of B: the
+// leader's UMMA (M = 256, N = 256) reads each SM's A half from that SM's shared memory and the two B halves from
+// both, so an SM reads 8 KB and receives 32 KB per k-block for the same 128x256x16 of work, and both the read and
+// the fill traffic per flop drop by a third.
+//   leader (cluster rank 0): issues every UMMA; its full[] barriers count the bytes of BOTH CTAs' TMA loads
+//   both CTAs              : TMA producer for their own halves, epilogue for their own 128 accumulator rows
+//   tcgen05.commit multicast: frees the stage in both CTAs / publishes the accumulator to both epilogues
+//   tmem_empty (leader)    : 2 x 8 epilogue warps arrive (the peer's through the cluster shared window)
+// ================================================================================================================
+constexpr int kPairBN = 256;
+struct PairCfg {
+  static constexpr int kBHalfBytes = (kPairBN / 2) * BK * 2;    // 16 KB
+  static constexpr int kStageBytes = kABytes + kBHalfBytes;     // 32 KB per CTA and stage
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 2 * kPairBN;                 // two accumulator buffers
+  static constexpr int kAlignSlack = 512;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAlignSlack + 256 + 2 * kPairBN * 4;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted by a barrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, int cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, int cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// bounded wait: a protocol error traps (the launch fails loudly) instead of hanging both SMs
+__device__ __forceinline__ void mbar_wait_bd(uint64_t* bar, uint32_t parity) {
+  unsigned n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 24)) __trap();
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, TcShape sh, GemmEpi epi) {
+  using Cfg = PairCfg;
+  constexpr int BN = kPairBN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (misalign > (uint32_t)Cfg::kAlignSlack) __trap();
+  uint8_t* smem = smem_raw + misalign;
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]  (used in the leader only)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + 256);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int nkb_total = (sh.K + BK - 1) / BK;
+  const int tiles = sh.tiles_m * sh.tiles_n;
+  const int tb = tiles * sh.batch;
+  const int total_work = tb * sh.splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps);  // the epilogue warps of both CTAs
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  cluster_barrier();  // barriers of both CTAs are initialised before anyone signals across
+  if (warp == 1) tmem_alloc_pair(tmem_ptr_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): my 128 rows of A, my 128 columns of B; bytes counted by the LEADER's barrier =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = pair; w < total_work; w += n_pairs) {
+        const int z = w / tb, bt = (w % tb) / tiles, tile = w % tiles;
+        const int n0 = (tile % sh.tiles_n) * BN + (int)rank * (BN / 2);
+        const int m0 = (tile / sh.tiles_n) * (2 * BM) + (int)rank * BM;
+        const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_bd(&empty_bar[s], ph ^ 1);
+          uint8_t* sA = smem + s * Cfg::kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          const uint32_t fb = map_to_rank(&full_bar[s], 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_3d_pair(sA, &tmA, kb * BK, m0, bt, fb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_3d_pair(sA + i * 8192, &tmA, m0 + i * 64, kb * BK, bt, fb);
+          }
+          if (!B_MN) {
+            tma_load_3d_pair(sB, &tmB, kb * BK, n0, bt, fb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < (BN / 2) / 64; ++i) tma_load_3d_pair(sB + i * 8192, &tmB, n0 + i * 64, kb * BK, bt, fb);
+          }
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader only): D[256 x 256] += A[256 x 16] . B[256 x 16]^T per instruction =====
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int w = pair; w < total_work; w += n_pairs, ++it) {
+        const int z = w / tb;
+        const int kb0 = z * sh.kb_per_split, kb1 = min(nkb_total, kb0 + sh.kb_per_split);
+        const int buf = it & 1;
+        mbar_wait_bd(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_bd(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_pair(tmem_d, slice_desc<A_MN>(a_addr, k), slice_desc<B_MN>(b_addr, k), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);  // frees the stage in both CTAs once these MMAs retire
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(&tmem_full_bar[buf]);  // accumulator complete: both epilogues may read their rows
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): my 128 accumulator rows, all 256 columns =====
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    int it = 0;
+    for (int w = pair; w < total_work; w += n_pairs, ++it) {
+      const int bt = (w % tb) / tiles, tile = w % tiles;
+      const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * (2 * BM) + (int)rank * BM;
+      const int buf = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < sh.M;
+      const bool has_bias = epi.bias != nullptr;
+      if (has_bias) {
+        const int n_read = (sh.N + 7) & ~7;
+        for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
+          bias_s[buf * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
+      mbar_wait_bd(&tmem_full_bar[buf], acc_ph);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
+      uint8_t* my_stage = staging + ew * 4096;
+      const uint32_t swz = (uint32_t)(lane & 7);
+      uint8_t* my_row = my_stage + lane * 128;
+      const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
+      const bf16* add_p = (epi.addend && row_ok)
+                              ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add + add_row * epi.ld_add + n0
+                              : nullptr;
+      const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
+                            ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
+                            : nullptr;
+      const bool do_tanh = epi.act == ACT_TANH;
+      const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
+      const bool f32_out = epi.out_f32 || epi.atomic;
+      const int pw = f32_out ? 32 : 64;
+      const int n_pass = BN / pw;
+      const int my_last = ((n_pass - 1 - half) & ~1) + half;
+      const uint32_t empty_leader = map_to_rank(&tmem_empty_bar[buf], 0);
+#pragma unroll 1
+      for (int ps = half; ps < n_pass; ps += 2) {
+        const int c0 = ps * pw;
+        const int left = sh.N - (n0 + c0);
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;
+        const bf16* ap = add_p ? add_p + c0 : nullptr;
+        const bf16* yp = y_p ? y_p + c0 : nullptr;
+        if (f32_out) {
+          if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+          else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+        } else {
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            const int o = sub * 32;
+            if (left - o >= 32)
+              epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                                           yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
+            else
+              epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
+          }
+        }
+        if (ps == my_last) {
+          // all of this warp's TMEM reads are done: hand the accumulator back to the leader's MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(empty_leader);
+        }
+        if (left <= 0) continue;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
+          else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
+          bulk_commit();
+        }
+      }
+    }
+  }
+  if (warp >= 2 && lane == 0) bulk_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();  // the peer no longer signals my barriers / reads my shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -608,6 +891,62 @@ template <int BN, int MT> int launch_majors(GemmContext& ctx, const GemmCall& c,
   return c.b_mn ? launch<BN, false, true, MT>(ctx, c, splits, kbps) : launch<BN, false, false, MT>(ctx, c, splits, kbps);
 }
 
+template <bool A_MN, bool B_MN>
+int launch_pair(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
+  using Cfg = PairCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("gemm_tc pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB, tmC;
+  if (!A_MN) { if (get_map(c.A, c.K, c.M, c.lda, BK, BM, &tmA, 2, c.batch, c.batch_a)) return -1; }
+  else { if (get_map(c.A, c.M, c.K, c.lda, 64, BK, &tmA, 2, c.batch, c.batch_a)) return -1; }
+  if (!B_MN) { if (get_map(c.B, c.K, c.N, c.ldb, BK, kPairBN / 2, &tmB, 2, c.batch, c.batch_b)) return -1; }
+  else { if (get_map(c.B, c.N, c.K, c.ldb, 64, BK, &tmB, 2, c.batch, c.batch_b)) return -1; }
+  const GemmEpi& e = c.epi;
+  const int out_elem = (e.out_f32 || e.atomic) ? 4 : 2;
+  if (get_map(c.C, c.N, c.M, c.ldc, out_elem == 2 ? 64 : 32, 32, &tmC, out_elem, c.batch, c.batch_c)) return -1;
+  TcShape sh;
+  sh.tma_out = 1;
+  sh.trace = nullptr;
+  sh.M = c.M; sh.N = c.N; sh.K = c.K;
+  sh.tiles_m = (c.M + 2 * BM - 1) / (2 * BM); sh.tiles_n = (c.N + kPairBN - 1) / kPairBN;
+  sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = 1;
+  sh.batch = c.batch > 0 ? c.batch : 1; sh.batch_c = c.batch_c;
+  sh.rotate_k = 0;
+  const long total = (long)sh.tiles_m * sh.tiles_n * splits * sh.batch;
+  const int pairs = (int)std::min<long>(total, kNumSMs / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN>, tmA, tmB, tmC, sh, c.epi);
+  ctx.launches++;
+  if (err != cudaSuccess) { set_error("gemm_tc pair launch: %s", cudaGetErrorString(err)); return -1; }
+  return 0;
+}
+
+// the pair kernel writes through TMA only: same alignment conditions as the single-CTA TMA epilogue
+bool pair_eligible(const GemmCall& c) {
+  const GemmEpi& e = c.epi;
+  const int out_elem = (e.out_f32 || e.atomic) ? 4 : 2;
+  const bool has_aux = e.bias || e.addend || e.dact_y;
+  return c.M > BM && c.N > kPairBN / 2 && (!has_aux || (c.N % 8) == 0 || e.aux_padded) &&
+         ((c.batch_c * out_elem) % 16 == 0) && (e.batch_add % 8 == 0) && (e.batch_y % 8 == 0) &&
+         (((uintptr_t)c.C & 15) == 0) && (((c.ldc * out_elem) & 15) == 0) && (!e.bias || ((uintptr_t)e.bias & 31) == 0) &&
+         (!e.addend || ((((uintptr_t)e.addend & 15) == 0) && (e.ld_add % 8) == 0)) &&
+         (!e.dact_y || ((((uintptr_t)e.dact_y & 15) == 0) && (e.ld_y % 8) == 0));
+}
+
 }  // namespace
 
 void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
@@ -658,6 +997,32 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
         if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; best_mt = mtile; }
       }
     }
+  }
+  // CTA-pair 256 x 256 tiles (cta_group::2): 74 pairs, a k-block costs ~0.27 us instead of 0.37 us (see the kernel)
+  int pair_env = -1;  // CAPDEC_GEMM_PAIR = 0 / 1 forces the choice (tests, tuning); default: the cost model decides
+  if (const char* ev = getenv("CAPDEC_GEMM_PAIR")) pair_env = atoi(ev);
+  bool use_pair = false;
+  int pair_sp = 1;
+  if (pair_env != 0 && pair_eligible(c)) {
+    const long tiles = (long)((c.M + 2 * BM - 1) / (2 * BM)) * ((c.N + kPairBN - 1) / kPairBN) * (c.batch > 0 ? c.batch : 1);
+    const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
+    const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
+    double pair_cost = 1e300;
+    for (int sp = sp_min; sp <= sp_max; ++sp) {
+      const int kbps = (nkb + sp - 1) / sp;
+      const int sp_eff = (nkb + kbps - 1) / kbps;
+      const long per_pair = (tiles * sp_eff + kNumSMs / 2 - 1) / (kNumSMs / 2);
+      const double t_epi = (c.epi.atomic ? 6.0 : 2.0) + 1.0;
+      const double cost = per_pair * (kbps * 0.75 + t_epi) + 5.0;
+      if (cost < pair_cost) { pair_cost = cost; pair_sp = sp_eff; }
+    }
+    use_pair = pair_env == 1 || pair_cost < best_cost;
+  }
+  if (use_pair) {
+    const int kbps2 = (nkb + pair_sp - 1) / pair_sp;
+    const int splits2 = (nkb + kbps2 - 1) / kbps2;
+    if (c.a_mn) return c.b_mn ? launch_pair<true, true>(ctx, c, splits2, kbps2) : launch_pair<true, false>(ctx, c, splits2, kbps2);
+    return c.b_mn ? launch_pair<false, true>(ctx, c, splits2, kbps2) : launch_pair<false, false>(ctx, c, splits2, kbps2);
   }
   if (const char* ev = getenv("CAPDEC_GEMM_BN")) {  // tuning / profiling override
     const int v = atoi(ev);

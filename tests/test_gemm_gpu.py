@@ -148,14 +148,17 @@ def test_gemm_linearity_at_full_size():
     assert torch.equal(c1, A1.float() @ B.float().t())
 
 
-@pytest.mark.parametrize("mt", ["1", "2"])
+@pytest.mark.parametrize("mt", ["1", "2", "pair"])
 @pytest.mark.parametrize("majors", [0, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(304, 520, 192), (264, 136, 64), (8704, 1024, 1024), (1024, 1024, 8704), (136, 72, 40),
                                    (640, 12295, 256)])
 def test_gemm_tile_heights(M, N, K, majors, mt, monkeypatch):
     """Both CTA tile heights (128 rows, and 256 rows = two UMMA row blocks sharing every B k-block) on ragged and
     full-size shapes, every operand-major form, bf16 output with the fused epilogue and fp32 split-K reduction."""
-    monkeypatch.setenv("CAPDEC_GEMM_MT", mt)
+    if mt == "pair":   # CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) wherever eligible
+        monkeypatch.setenv("CAPDEC_GEMM_PAIR", "1")
+    else:
+        monkeypatch.setenv("CAPDEC_GEMM_MT", mt)
     a_mn, b_mn = bool(majors & 1), bool(majors & 2)
     if b_mn and N % 8:
         pytest.skip("an MN-major operand needs a 16-byte row pitch")
