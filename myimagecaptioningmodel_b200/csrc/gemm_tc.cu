@@ -365,14 +365,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int pw = f32_out ? 32 : 64;           // columns per pass
           const int n_pass = BN / pw;
           const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
-          if (half >= n_pass && last_block) {
+          // none of this warp's 32 rows exists (small-M problems, e.g. the per-image attention GEMMs with M = 34 / 49):
+          // nothing to read, convert or store
+          const bool warp_empty = (m0 + mh * BM + quarter * 32) >= sh.M;
+          if ((half >= n_pass || warp_empty) && last_block) {
             // nothing to read for this warp (BN = 64, bf16): release the accumulator right away
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
           }
 #pragma unroll 1
-          for (int ps = half; ps < n_pass; ps += 2) {
+          for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
             const int c0 = ps * pw;
             const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
             if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
@@ -699,8 +702,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_pass = BN / pw;
       const int my_last = ((n_pass - 1 - half) & ~1) + half;
       const uint32_t empty_leader = map_to_rank(&tmem_empty_bar[buf], 0);
+      const bool warp_empty = (m0 + quarter * 32) >= sh.M;  // none of this warp's rows exists: nothing to read or store
+      if (warp_empty) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(empty_leader);
+      }
 #pragma unroll 1
-      for (int ps = half; ps < n_pass; ps += 2) {
+      for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
         if (lane == 0) bulk_wait_read<0>();

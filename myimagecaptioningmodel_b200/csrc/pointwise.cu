@@ -309,6 +309,61 @@ colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chu
   }
 }
 
+// Narrow variant for N <= 4096: 64 columns per CTA (8 column threads x 64 row groups), so a [8704 x 1024] sum runs on
+// 16 x 32 = 512 CTAs with every load of a thread in flight at once, while each output address still receives only
+// 32 atomics (see above).  Row groups meet through two shuffles and one shared-memory step.
+template <typename T>
+__global__ void __launch_bounds__(512)
+colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
+                     const float* __restrict__ scale_dev) {
+  __shared__ float red[16][8][9];
+  const float sc = scale_dev ? __ldg(scale_dev) : 1.f;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + ct) * 8;
+  const long m0 = (long)blockIdx.y * rows_per_chunk;
+  const long m1 = (m0 + rows_per_chunk < M) ? m0 + rows_per_chunk : M;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n0 + 8 <= N) {
+    long m = m0 + rg;
+    for (; m + 192 < m1; m += 256) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(x + (m + 64 * u) * ld + n0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; m < m1; m += 64) {
+      float v[8];
+      load8(x + m * ld + n0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  } else if (n0 < N) {  // ragged right edge
+    for (long m = m0 + rg; m < m1; m += 64)
+      for (int j = 0; j < 8 && n0 + j < N; ++j) acc[j] += to_f(x[m * ld + n0 + j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][j][ct] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) v += red[w][j][c];
+    const int n = (blockIdx.x * 8 + c) * 8 + j;
+    if (n < N) atomicAdd(out + n, v * sc);
+  }
+}
+
 template <typename T>
 __global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, const int64_t* __restrict__ ids,
                                      long ids_ld, int B, int steps, int pad, float* __restrict__ dEmb) {
@@ -491,8 +546,13 @@ template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, 
   if (chunks > (M + 15) / 16) chunks = (M + 15) / 16;
   if (chunks < 1) chunks = 1;
   const long rpc = (M + chunks - 1) / chunks;
-  dim3 grid(col_blocks, (unsigned)((M + rpc - 1) / rpc));
-  colsum_kernel<T><<<grid, 512, 0, c.stream>>>(x, ld, M, N, rpc, out, scale_dev);
+  if (N <= 4096 && M >= 2048) {
+    dim3 grid((N + 63) / 64, (unsigned)((M + rpc - 1) / rpc));
+    colsum_narrow_kernel<T><<<grid, 512, 0, c.stream>>>(x, ld, M, N, rpc, out, scale_dev);
+  } else {
+    dim3 grid(col_blocks, (unsigned)((M + rpc - 1) / rpc));
+    colsum_kernel<T><<<grid, 512, 0, c.stream>>>(x, ld, M, N, rpc, out, scale_dev);
+  }
   BUMP(c);
 }
 template <typename T>
