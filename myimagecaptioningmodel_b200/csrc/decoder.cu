@@ -291,7 +291,6 @@ template <typename T> class Decoder : public DecoderBase {
     OK(actx.ensure(e * M * H, &ws_bytes));
     OK(outv.ensure(e * M * H, &ws_bytes));
     OK(proj.ensure(e * M * E, &ws_bytes));
-    OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
     OK(lse.ensure(4 * M, &ws_bytes));
     OK(acc.ensure(64, &ws_bytes));
     OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
@@ -368,18 +367,53 @@ template <typename T> class Decoder : public DecoderBase {
     prof.mark("fwd.attention", s);
     OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
     OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
-    {
-      GemmCall c;                                                                                     // model:25
-      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
-      c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
-      OK(gemm<T>(gc, c));
-    }
-    prof.mark("fwd.out_proj_vocab", s);
-    // masked cross entropy (model:163-171, 180-183, 205-212)
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
-    // ... fused with the unscaled d logits = (softmax - onehot) * mask, so the fp32 logits leave HBM only once
-    ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
-                dlogits.as<T>());
+    bool ce_in_gemm = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+      // Off by default: measured on B200 the two epilogue-bound K = 256 passes cost 289 + 202 us against 161 us (GEMM
+      // with fp32 logits) + 118 us (cross-entropy kernel) for the separate form; CAPDEC_CE_FUSED=1 selects it.
+      const char* ev = getenv("CAPDEC_CE_FUSED");
+      ce_in_gemm = ev && ev[0] == '1' && !force_simt && !logits_out && (E % 8) == 0;
+    }
+    if (ce_in_gemm) {
+      // The logits are never written: pass 1 of the tied projection (model:25) leaves only per-row soft-max statistics,
+      // ce_merge turns them into lse / loss (model:163-171, 180-183, 205-212), pass 2 recomputes the tile and writes the
+      // unscaled d logits = (softmax - onehot) * mask directly.  1.08 GB of HBM traffic (fp32 logits written + read,
+      // bf16 gradient written) becomes 0.23 GB at the price of a second K = 256 GEMM.
+      const int S = (V + 63) / 64;
+      const long sld = (S + 7) & ~7;
+      OK(ce_stats.ensure(2 * 4 * (size_t)M * sld, &ws_bytes));
+      OK(ce_rows.ensure(8 * (size_t)M, &ws_bytes));
+      float* st_m = ce_stats.as<float>();
+      float* st_s = st_m + (size_t)M * sld;
+      float* lse_eff = ce_rows.as<float>();
+      int* tgt = reinterpret_cast<int*>(lse_eff + M);
+      GemmCall c;
+      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = dlogits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
+      c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1;
+      c.epi.act = ACT_ROWSTATS; c.epi.stats_m = st_m; c.epi.stats_s = st_s; c.epi.stats_ld = sld;
+      OK(gemm<T>(gc, c));
+      if constexpr (std::is_same<T, bf16>::value)
+        ce_merge(lc, M, S, st_m, st_s, sld, proj.as<bf16>(), E, emb.as<bf16>(), b_vocab.as<float>(), cap, S_len(), B,
+                 cfg.padding_idx, lse.as<float>(), lse_eff, tgt, acc.as<float>());
+      c.epi.act = ACT_SOFTMAX_GRAD; c.epi.stats_m = nullptr; c.epi.stats_s = nullptr; c.epi.row_lse = lse_eff;
+      c.epi.row_tgt = tgt;
+      OK(gemm<T>(gc, c));
+      prof.mark("fwd.out_proj_vocab", s);
+    } else {
+      OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
+      {
+        GemmCall c;                                                                                   // model:25
+        c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
+        c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
+        OK(gemm<T>(gc, c));
+      }
+      prof.mark("fwd.out_proj_vocab", s);
+      // masked cross entropy (model:163-171, 180-183, 205-212)
+      // ... fused with the unscaled d logits = (softmax - onehot) * mask, so the fp32 logits leave HBM only once
+      ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
+                  dlogits.as<T>());
+    }
     loss_finalize(lc, acc.as<float>());
     if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);           // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
@@ -390,6 +424,7 @@ template <typename T> class Decoder : public DecoderBase {
     return 0;
   }
 
+  long S_len() const { return S; }
   AttnShape train_shape(int B) const {
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = Tt; as.row0_stride = 1; as.q_stride = B;
@@ -711,7 +746,7 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &ce_stats, &ce_rows, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
 
@@ -728,7 +763,7 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd;
+      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd, ce_stats, ce_rows;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
 };

@@ -14,7 +14,12 @@
 
 namespace capdec {
 
-enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2 };
+// ACT_ROWSTATS / ACT_SOFTMAX_GRAD (tensor-core kernels only): the two passes of a soft-max cross entropy fused into the
+// vocabulary GEMM, so the [M, V] logits are never written:
+//   ACT_ROWSTATS     no C output; per (row, 64-column group g) the partial max and sum exp(x - max) of x = acc + bias go to
+//                    stats_m / stats_s [M, stats_ld] at column g
+//   ACT_SOFTMAX_GRAD C = exp(x - row_lse[m]) - [n == row_tgt[m]]   (row_lse = +inf gives an all-zero row: masked position)
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_SOFTMAX_GRAD = 4 };
 
 struct GemmEpi {
   const float* bias = nullptr;   // [N] fp32, added to every row
@@ -29,6 +34,11 @@ struct GemmEpi {
   int atomic = 0;                // fp32 atomicAdd into C (split-K / gradient accumulation)
   int aux_padded = 0;            // bias / addend / dact_y are readable up to the next multiple of 8 columns past N
   const float* alpha_dev = nullptr;  // device scalar multiplied into the accumulator before anything else
+  float* stats_m = nullptr;      // ACT_ROWSTATS outputs
+  float* stats_s = nullptr;
+  long stats_ld = 0;
+  const float* row_lse = nullptr;  // ACT_SOFTMAX_GRAD inputs
+  const int* row_tgt = nullptr;
 };
 
 struct GemmCall {

@@ -132,7 +132,8 @@ __device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, 
 template <bool OUT_F32, bool FULL>
 __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float* bias_t, const bf16* add_p,
                                                 const bf16* y_p, bool do_tanh, float alpha, int left, uint8_t* dst_row,
-                                                uint32_t swz, uint32_t chunk0) {
+                                                uint32_t swz, uint32_t chunk0, bool sm_grad = false, float lse_row = 0.f,
+                                                int tgt_rel = -1) {
   uint32_t r[32];
   uint4 aq[4], yq[4];
   __syncwarp();  // tcgen05.ld is .sync.aligned
@@ -172,6 +173,10 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
       }
+      if (sm_grad) {  // soft-max cross-entropy gradient; tgt_rel = target column relative to this 32-column chunk
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __expf(v[i] - lse_row) - ((g * 8 + i) == tgt_rel ? 1.f : 0.f);
+      }
       if (y_p) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yq[g]);
 #pragma unroll
@@ -191,6 +196,26 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
         *reinterpret_cast<uint4*>(dst_row + (((chunk0 + g) ^ swz) << 4)) = u;
       }
     }
+  }
+}
+
+// ACT_ROWSTATS: running (max, sum exp(x - max)) of x = acc + bias over 32 accumulator columns of this thread's row
+__device__ __forceinline__ void epilogue_stats32(uint32_t tmem_addr, const float* bias_t, int left, float& m, float& s) {
+  uint32_t r[32];
+  __syncwarp();
+  tmem_ld32(tmem_addr, r);
+  tmem_ld_wait();
+  float x[32];
+  float cm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    x[i] = (i < left) ? __uint_as_float(r[i]) + (bias_t ? bias_t[i] : 0.f) : -INFINITY;
+    cm = fmaxf(cm, x[i]);
+  }
+  if (cm > m) { s *= __expf(m - cm); m = cm; }   // m == -inf initially: s == 0, exp(-inf) = 0
+  if (m > -INFINITY) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += __expf(x[i] - m);
   }
 }
 
@@ -362,6 +387,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool do_tanh = epi.act == ACT_TANH;
           const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
           const bool f32_out = epi.out_f32 || epi.atomic;
+          const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;
+          const float lse_row = (sm_grad && row_ok) ? __ldg(epi.row_lse + row) : 0.f;
+          const int tgt_row = (sm_grad && row_ok) ? __ldg(epi.row_tgt + row) : -1;
           const int pw = f32_out ? 32 : 64;           // columns per pass
           const int n_pass = BN / pw;
           const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
@@ -383,6 +411,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float* bsp = has_bias ? bias_s + (it & 1) * BN + c0 : nullptr;
             const bf16* ap = add_p ? add_p + c0 : nullptr;
             const bf16* yp = y_p ? y_p + c0 : nullptr;
+            if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
+              float rm = -INFINITY, rs = 0.f;
+              epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+              epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+              if (row_ok && left > 0) {
+                const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+                epi.stats_m[o] = rm;
+                epi.stats_s[o] = rs;
+              }
+              if (ps == my_last && last_block) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+              }
+              continue;
+            }
             if (f32_out) {
               if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
               else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
@@ -393,11 +437,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (left - o >= 32)
                   epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
                                                yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                               (uint32_t)(sub * 4));
+                                               (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
                 else
                   epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
                                                 yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                               (uint32_t)(sub * 4));
+                                               (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
               }
             }
             if (ps == my_last && last_block) {
@@ -491,6 +535,8 @@ struct PairCfg {
   static constexpr int kStages = 6;
   static constexpr int kTmemCols = 2 * kPairBN;                 // two accumulator buffers
   static constexpr int kAlignSlack = 512;
+  // one 32-row x 128-byte output tile per epilogue warp.  (Measured: two tiles per warp with 5 instead of 6 stages is
+  // slower -- 3.01 vs 2.91 ms per train step -- the epilogue does not wait on its previous store.)
   static constexpr int kStagingBytes = kEpiWarps * 4096;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAlignSlack + 256 + 2 * kPairBN * 4;
 };
@@ -685,9 +731,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait_bd(&tmem_full_bar[buf], acc_ph);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
-      uint8_t* my_stage = staging + ew * 4096;
       const uint32_t swz = (uint32_t)(lane & 7);
-      uint8_t* my_row = my_stage + lane * 128;
       const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
       const bf16* add_p = (epi.addend && row_ok)
                               ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add + add_row * epi.ld_add + n0
@@ -698,6 +742,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool do_tanh = epi.act == ACT_TANH;
       const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
       const bool f32_out = epi.out_f32 || epi.atomic;
+      const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;
+      const float lse_row = (sm_grad && row_ok) ? __ldg(epi.row_lse + row) : 0.f;
+      const int tgt_row = (sm_grad && row_ok) ? __ldg(epi.row_tgt + row) : -1;
       const int pw = f32_out ? 32 : 64;
       const int n_pass = BN / pw;
       const int my_last = ((n_pass - 1 - half) & ~1) + half;
@@ -712,11 +759,29 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
-        if (lane == 0) bulk_wait_read<0>();
+        uint8_t* my_stage = staging + ew * 4096;
+        uint8_t* my_row = my_stage + lane * 128;
+        if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
         __syncwarp();
         const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;
         const bf16* ap = add_p ? add_p + c0 : nullptr;
         const bf16* yp = y_p ? y_p + c0 : nullptr;
+        if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
+          float rm = -INFINITY, rs = 0.f;
+          epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+          epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+          if (row_ok && left > 0) {
+            const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+            epi.stats_m[o] = rm;
+            epi.stats_s[o] = rs;
+          }
+          if (ps == my_last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty_leader);
+          }
+          continue;
+        }
         if (f32_out) {
           if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
           else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
@@ -726,10 +791,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int o = sub * 32;
             if (left - o >= 32)
               epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
-                                           yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
+                                           yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
+                                           sm_grad, lse_row, tgt_row - (n0 + c0 + o));
             else
               epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
-                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
+                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
+                                            sm_grad, lse_row, tgt_row - (n0 + c0 + o));
           }
         }
         if (ps == my_last) {
@@ -968,6 +1035,14 @@ int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint3
 
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
+  if (c.epi.act == ACT_ROWSTATS || c.epi.act == ACT_SOFTMAX_GRAD) {
+    const GemmEpi& e = c.epi;
+    const bool ok = !e.out_f32 && !e.atomic && c.batch <= 1 && !e.addend && !e.dact_y && (!e.bias || e.aux_padded) &&
+                    (((uintptr_t)c.C & 15) == 0) && ((c.ldc * 2) % 16 == 0) &&
+                    (e.act == ACT_ROWSTATS ? (e.stats_m && e.stats_s && e.stats_ld >= (c.N + 63) / 64)
+                                           : (e.row_lse && e.row_tgt));
+    if (!ok) { set_error("gemm_tc: unsupported arguments for the fused soft-max epilogue"); return -1; }
+  }
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
   if (c.batch > 1 && c.epi.atomic) { set_error("gemm_tc: batched GEMM with split-K is not supported"); return -1; }
   const int nkb = (c.K + BK - 1) / BK;

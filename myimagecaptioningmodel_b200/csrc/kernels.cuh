@@ -146,6 +146,11 @@ void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* ca
 template <typename T>
 void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
               int steps, int pad, float* lse, float* acc, T* dlogits);
+// cross entropy fused into the vocabulary GEMM (gemm.cuh ACT_ROWSTATS / ACT_SOFTMAX_GRAD): merge of the row statistics,
+// target logit, loss sums and the per-row operands (lse_eff, tgt) of the gradient pass; E % 8 == 0
+void ce_merge(LaunchCtx c, long M, int S, const float* stats_m, const float* stats_s, long ld, const bf16* proj, int E,
+              const bf16* emb, const float* bias, const int64_t* caption, long cap_ld, int B, int pad, float* lse,
+              float* lse_eff, int* tgt, float* acc);
 // out[0] = in[0] * s
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out);
 // acc[2] = acc[0] / acc[1] (the loss), acc[3] = 1 / acc[1]

@@ -102,6 +102,62 @@ ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const
   }
 }
 
+// Second half of the cross entropy that is fused into the vocabulary GEMM (gemm.cuh: ACT_ROWSTATS / ACT_SOFTMAX_GRAD):
+// merges the per-(row, 64-column group) partial (max, sum) pairs of the first GEMM pass into lse[row], computes the
+// target logit directly ( proj[row] . Emb[target] + bias[target], the same bf16 products the GEMM accumulates ) and
+// the masked loss sums, and writes the per-row operands of the second GEMM pass:
+//   lse_eff[row] = lse or +inf for a masked (padding) target -> exp(x - inf) = 0: an all-zero gradient row
+//   tgt[row]     = target id or -1
+// One warp per row.
+__global__ void __launch_bounds__(256)
+ce_merge_kernel(long M, int S, const float* __restrict__ sm, const float* __restrict__ ss, long ld,
+                const bf16* __restrict__ proj, int E, const bf16* __restrict__ emb, const float* __restrict__ bias,
+                const int64_t* __restrict__ caption, long cap_ld, int B, int pad, float* __restrict__ lse_out,
+                float* __restrict__ lse_eff, int* __restrict__ tgt_out, float* __restrict__ acc) {
+  __shared__ float part[8][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + warp;
+  float loss = 0.f, cnt = 0.f;
+  if (row < M) {
+    float m = -INFINITY;
+    for (int g = lane; g < S; g += 32) m = fmaxf(m, sm[row * ld + g]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int g = lane; g < S; g += 32) sum += ss[row * ld + g] * __expf(sm[row * ld + g] - m);
+    sum = warp_sum(sum);
+    const float l = m + logf(sum);
+    const int64_t tgt = target_of(caption, cap_ld, B, row);
+    if (tgt != pad) {
+      float dot = 0.f;
+      for (int e0 = lane * 8; e0 < E; e0 += 256) {
+        float a[8], b[8];
+        load8(proj + row * E + e0, a);
+        load8(emb + tgt * E + e0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(a[i], b[i], dot);
+      }
+      dot = warp_sum(dot) + bias[tgt];
+      loss = l - dot;
+      cnt = 1.f;
+    }
+    if (lane == 0) {
+      lse_out[row] = l;
+      lse_eff[row] = (tgt != pad) ? l : INFINITY;
+      tgt_out[row] = (tgt != pad) ? (int)tgt : -1;
+    }
+  }
+  if (lane == 0) { part[warp][0] = loss; part[warp][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += part[w][0]; b += part[w][1]; }
+    if (b > 0.f) {
+      atomicAdd(acc + 0, a);
+      atomicAdd(acc + 1, b);
+    }
+  }
+}
+
 __global__ void scale_scalar_kernel(const float* in, float s, float* out) { out[0] = in[0] * s; }
 
 __global__ void loss_finalize_kernel(float* acc) {
@@ -591,6 +647,13 @@ template void ce_fused<float>(LaunchCtx, const float*, long, int, int, const int
                               float*);
 template void ce_fused<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
                              bf16*);
+void ce_merge(LaunchCtx c, long M, int S, const float* stats_m, const float* stats_s, long ld, const bf16* proj, int E,
+              const bf16* emb, const float* bias, const int64_t* caption, long cap_ld, int B, int pad, float* lse,
+              float* lse_eff, int* tgt, float* acc) {
+  ce_merge_kernel<<<(unsigned)((M + 7) / 8), 256, 0, c.stream>>>(M, S, stats_m, stats_s, ld, proj, E, emb, bias, caption,
+                                                               cap_ld, B, pad, lse, lse_eff, tgt, acc);
+  if (c.launches) ++*c.launches;
+}
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out) {
   scale_scalar_kernel<<<1, 1, 0, c.stream>>>(in, s, out);
   if (c.launches) ++*c.launches;
