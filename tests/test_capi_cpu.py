@@ -56,9 +56,21 @@ def test_sm100_sass_is_present():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM"):
+    # tcgen05.mma (single CTA and cta_group::2), TMA tensor loads / stores / reduce-adds (+ the 2-CTA and multicast forms),
+    # TMA bulk copies, tcgen05.ld
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.3D", "UTMALDG.3D.2CTA", "UTMASTG.3D", "UTMAREDG.3D.ADD",
+                     "UTCBAR.2CTA.MULTICAST", "UBLKCP", "LDTM"):
         assert mnemonic in sass, mnemonic
-    assert "HMMA.16816" not in sass                     # no legacy mma.sync path
+    # no GEMM runs on the legacy mma.sync path: the only HMMA in the library is the matrix-VECTOR product inside the
+    # attention score kernel (tanh results as the A fragment, w_alpha as one B column; attention.cu)
+    func = None
+    hmma_funcs = set()
+    for line in sass.splitlines():
+        if "Function :" in line:
+            func = line.split("Function :")[1].strip()
+        elif "HMMA." in line and "UTCHMMA" not in line:
+            hmma_funcs.add(func)
+    assert hmma_funcs and all("attn_scores_kernel" in f for f in hmma_funcs), hmma_funcs
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
