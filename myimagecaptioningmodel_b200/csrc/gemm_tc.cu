@@ -96,6 +96,13 @@ template <int N> __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Programmatic dependent launch: a GEMM launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still draining; everything up to pdl_wait() (barrier init, TMEM allocation, tensor-map
+// prefetch) touches no global memory, so the launch latency and the prologue of GEMM n+1 hide behind the tail of
+// kernel n.  pdl_wait() returns once the prerequisite grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct TcShape {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split;
@@ -266,6 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) TRACE(1);
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -646,6 +655,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -898,6 +909,11 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   return 0;
 }
 
+bool pdl_enabled() {  // CAPDEC_GEMM_PDL=0 switches programmatic dependent launch off (A/B measurements)
+  static const bool on = [] { const char* e = getenv("CAPDEC_GEMM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int BN, bool A_MN, bool B_MN, int MT>
 int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   using Cfg = TcCfg<BN, MT>;
@@ -954,9 +970,19 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   }
   const long total = (long)sh.tiles_m * sh.tiles_n * splits * sh.batch;
   const int grid = (int)std::min<long>(total, kNumSMs);
-  gemm_tc_kernel<BN, A_MN, B_MN, MT><<<grid, kThreads, Cfg::kSmemBytes, ctx.stream>>>(tmA, tmB, tmC, c.C, sh, c.epi);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  void* Cp = c.C;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, MT>, tmA, tmB, tmC, Cp, sh, c.epi);
   ctx.launches++;
-  cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("gemm_tc launch: %s", cudaGetErrorString(err)); return -1; }
   return 0;
 }
@@ -1000,11 +1026,13 @@ int launch_pair(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = ctx.stream;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
   cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN>, tmA, tmB, tmC, sh, c.epi);
   ctx.launches++;
   if (err != cudaSuccess) { set_error("gemm_tc pair launch: %s", cudaGetErrorString(err)); return -1; }
