@@ -331,6 +331,7 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
                    const bf16* __restrict__ sent_emb, const float* __restrict__ w_alpha,
                    const float* __restrict__ b_alpha, float* __restrict__ alpha_out, bf16* __restrict__ alpha_T,
                    int ld_at) {
+  pdl_trigger();
   constexpr int H = 256 * NB;
   constexpr int kWarpCols = 32 * NB;  // columns of one warp
   extern __shared__ __align__(128) uint8_t smem[];
@@ -454,6 +455,7 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
 __global__ void __launch_bounds__(256)
 attn_sadd_kernel(long rows, int H, int P, const float* __restrict__ alpha, const bf16* __restrict__ sentinel,
                  const bf16* __restrict__ p_hid, bf16* __restrict__ sadd) {
+  pdl_trigger();
   const int vec_per_row = H / 8;
   const float inv_p = 1.f / (float)P;
   const long n = rows * vec_per_row;
@@ -483,6 +485,7 @@ template <int QMAX>
 __global__ void __launch_bounds__(256)
 attn_ctx_small_kernel(AttnShape s, const bf16* __restrict__ vals, const bf16* __restrict__ sentinel,
                       const bf16* __restrict__ p_hid, const float* __restrict__ alpha, bf16* __restrict__ actx) {
+  pdl_trigger();
   extern __shared__ __align__(16) float aw[];  // [q_per_img][P], already scaled by 1/(k+1)
   const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
   const int img = blockIdx.x;
@@ -539,6 +542,7 @@ attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const T* __r
                      const float* __restrict__ alpha, const T* __restrict__ dactx, const float* __restrict__ dal,
                      int ld_dal, float* __restrict__ de, T* __restrict__ alpha_T, int ld_at, T* __restrict__ dS,
                      float* __restrict__ db_alpha) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int P = k + 1;
   const float inv_p = 1.f / (float)P;
@@ -602,6 +606,7 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
                    const T* __restrict__ sent_emb, const float* __restrict__ w_alpha, const float* __restrict__ de,
                    T* __restrict__ dKV, T* __restrict__ dhid_emb, T* __restrict__ dsent_emb,
                    float* __restrict__ dw_alpha) {
+  pdl_trigger();
   constexpr bool F = fast_math<T>::value;
   constexpr int KHP = (KH + 3) & ~3;  // each half of a query's de row starts 16-byte aligned
   extern __shared__ __align__(16) float de_s[];  // [q_per_img][2 halves][KHP], zero past the valid positions

@@ -166,6 +166,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// Programmatic dependent launch, primary side: lets a dependent kernel that was launched with the programmatic-stream-
+// serialization attribute (the GEMMs) start its prologue while this grid is still running.  The dependent blocks in
+// griddepcontrol.wait until this grid has completed, so calling this first thing in a kernel is always safe.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -53,6 +53,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCeThreads)
 ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
                 long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits) {
+  pdl_trigger();
   __shared__ float scratch[32];
   const long m = blockIdx.x;
   const float* row = logits + m * ldl;
@@ -114,6 +115,7 @@ ce_merge_kernel(long M, int S, const float* __restrict__ sm, const float* __rest
                 const bf16* __restrict__ proj, int E, const bf16* __restrict__ emb, const float* __restrict__ bias,
                 const int64_t* __restrict__ caption, long cap_ld, int B, int pad, float* __restrict__ lse_out,
                 float* __restrict__ lse_eff, int* __restrict__ tgt_out, float* __restrict__ acc) {
+  pdl_trigger();
   __shared__ float part[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * 8 + warp;
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(kRowThreads)
 beam_rows_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int pad, int finish_on_stop,
                  const float* __restrict__ score_in, const int* __restrict__ fin_in, float* __restrict__ cand_v,
                  int* __restrict__ cand_i, float* __restrict__ gscore) {
+  pdl_trigger();
   __shared__ float scratch[32];
   __shared__ float s_v[2][kRowWarps];
   __shared__ int s_i[2][kRowWarps];
@@ -552,6 +555,7 @@ beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, in
                   float* __restrict__ score_out, const int* __restrict__ fin_in, int* __restrict__ fin_out,
                   const int* __restrict__ hist_in, int* __restrict__ hist_out, int* __restrict__ tok_out,
                   int* __restrict__ src_out) {
+  pdl_trigger();
   const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (img >= n_img) return;
   const int INT_BIG = 0x7fffffff;
@@ -601,6 +605,7 @@ __global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad,
                                     const int* __restrict__ tok, const int* __restrict__ src,
                                     const T* __restrict__ h_new, const float* __restrict__ c_new, T* __restrict__ xin,
                                     long ld_xin, float* __restrict__ c_next) {
+  pdl_trigger();
   const int ve = E / 8, vh = H / 8, per_row = ve + vh + vh;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x, n = (long)n_rows * per_row;

@@ -18,6 +18,7 @@ inline int grid_for(long work_items, int threads = 256, int max_waves = 8) {
 }
 
 template <typename T> __global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, long n) {
+  pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = from_f<T>(src[i]);
@@ -40,6 +41,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, long lds, T* __r
 
 template <typename T>
 __global__ void copy2d_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, int R, int C) {
+  pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x, n = (long)R * C;
   for (; i < n; i += stride) {
@@ -51,6 +53,7 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long lds, T* __rest
 template <typename T>
 __global__ void embed_gather_kernel(const T* __restrict__ emb, int E, const int64_t* __restrict__ ids, long ids_ld,
                                     int B, int steps, int pad, T* __restrict__ out, long ldo) {
+  pdl_trigger();
   const int vec_per_row = E / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x, n = (long)B * steps * vec_per_row;
@@ -127,6 +130,7 @@ template <typename T>
 __global__ void sentinel_fwd_kernel(long R, int H, const T* __restrict__ ph, long ld_ph, const T* __restrict__ xe,
                                     long ld_xe, const float* __restrict__ g5, long ld_g5, int g5_mod, int g5_div,
                                     const float* __restrict__ cc, T* __restrict__ sgate, T* __restrict__ s_out) {
+  pdl_trigger();
   constexpr bool F = fast_math<T>::value;
   const int vec_per_row = H / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +165,7 @@ template <typename T>
 __global__ void sentinel_bwd_kernel(long R, int H, const T* __restrict__ dS, const T* __restrict__ sgate,
                                     const float* __restrict__ cc, T* __restrict__ dsg_pre, long ld_dsg,
                                     float* __restrict__ dC_head) {
+  pdl_trigger();
   constexpr bool F = fast_math<T>::value;
   const int vec_per_row = H / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,6 +244,7 @@ __global__ void lstm_cell_bwd_kernel(int B, int H, const T* __restrict__ dH_head
 template <typename T>
 __global__ void sum_over_steps_kernel(const T* __restrict__ x, long ld, int B, int steps, int N, T* __restrict__ out,
                                       long ldo) {
+  pdl_trigger();
   const int vec_per_row = N / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x, n = (long)B * vec_per_row;
@@ -265,6 +271,7 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
               const float* __restrict__ scale_dev) {
+  pdl_trigger();
   __shared__ float red[15][8][33];
   const float sc = scale_dev ? __ldg(scale_dev) : 1.f;
   const int ct = threadIdx.x & 31, rg = threadIdx.x >> 5;  // column thread, row group
@@ -316,6 +323,7 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
                      const float* __restrict__ scale_dev) {
+  pdl_trigger();
   __shared__ float red[16][8][9];
   const float sc = scale_dev ? __ldg(scale_dev) : 1.f;
   const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -367,6 +375,7 @@ colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_
 template <typename T>
 __global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, const int64_t* __restrict__ ids,
                                      long ids_ld, int B, int steps, int pad, float* __restrict__ dEmb) {
+  pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x, n = (long)B * steps * E;
   for (; i < n; i += stride) {
@@ -395,6 +404,7 @@ constexpr int kChunk = 4096;  // elements per block
 
 template <typename T>
 __global__ void __launch_bounds__(256) multi_convert_kernel(const __grid_constant__ ConvertTable tab) {
+  pdl_trigger();
   int j = 0;
   while (j + 1 < tab.n && (int)blockIdx.x >= tab.first_block[j + 1]) ++j;
   const ConvertJob& job = tab.job[j];
@@ -427,6 +437,7 @@ __global__ void __launch_bounds__(256) multi_convert_kernel(const __grid_constan
 }
 
 __global__ void __launch_bounds__(256) multi_zero_kernel(const __grid_constant__ ZeroTable tab) {
+  pdl_trigger();
   int j = 0;
   while (j + 1 < tab.n && (int)blockIdx.x >= tab.first_block[j + 1]) ++j;
   const long base = (long)(blockIdx.x - tab.first_block[j]) * kChunk;

@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmCs,
                     const __grid_constant__ CUtensorMap tmGa, SeqFwdParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + misalign;
@@ -550,6 +551,7 @@ __device__ __forceinline__ void cell_store_state(const SeqBwdParams& p, int t, b
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, SeqBwdParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + misalign;
