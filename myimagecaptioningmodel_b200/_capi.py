@@ -17,7 +17,7 @@ EXPORTS = [
     "capdec_last_error", "capdec_version", "capdec_create", "capdec_destroy", "capdec_workspace_bytes",
     "capdec_launch_count", "capdec_bind_params", "capdec_train_fwd", "capdec_train_bwd", "capdec_decode",
     "capdec_gemm", "capdec_attention_fwd", "capdec_attention_bwd", "capdec_lstm_cell_fwd", "capdec_beam_step",
-    "capdec_profile", "capdec_profile_report",
+    "capdec_profile", "capdec_profile_report", "capdec_set_grad_ready_events",
 ]
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
@@ -70,6 +70,7 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_workspace_bytes.argtypes = [vp]
     lib.capdec_launch_count.restype = C.c_int64
     lib.capdec_launch_count.argtypes = [vp]
+    lib.capdec_set_grad_ready_events.argtypes = [vp, vp, vp, vp]
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.capdec_bind_params.argtypes = [vp, C.POINTER(CapdecParams), vp]

@@ -114,6 +114,11 @@ class DecoderBase {
   size_t ws_bytes = 0;
   long launches = 0;
   int device = 0;
+  // caller-owned events recorded by train_bwd when a group of gradients is final (capdec_set_grad_ready_events)
+  cudaEvent_t grad_ready[3] = {nullptr, nullptr, nullptr};
+  void mark_ready(int i, cudaStream_t s) {
+    if (grad_ready[i]) cudaEventRecord(grad_ready[i], s);
+  }
 };
 
 template <typename T> class Decoder : public DecoderBase {
@@ -557,6 +562,7 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     prof.mark("bwd.head_fc", s);
+    mark_ready(0, s);  // fc_hs .. fc_e (and fc_a) are final: their all-reduce may overlap the BPTT
     // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
     bool persistent = false;
     if constexpr (std::is_same<T, bf16>::value) {
@@ -593,6 +599,7 @@ template <typename T> class Decoder : public DecoderBase {
     sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
     OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
     OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
+    mark_ready(1, s);  // lstm_w, lstm_b, fc_xs_w, fc_xs_b are final
     if (dg) {
       GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
@@ -606,6 +613,7 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
+    mark_ready(2, s);  // word_embedding, out_fc_bias are final (fc_v / fc_k follow: final when the call's work is done)
     prof.mark("bwd.gate_wgrad_embed", s);
     // once-per-image projections (model:52-53)
     colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
@@ -860,6 +868,14 @@ int capdec_destroy(capdec_handle h) {
   if (!h) return 0;
   if (h->impl) { cudaSetDevice(h->impl->device); delete h->impl; }
   delete h;
+  return 0;
+}
+
+int capdec_set_grad_ready_events(capdec_handle h, void* head_ready, void* gates_ready, void* embedding_ready) {
+  if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
+  h->impl->grad_ready[0] = (cudaEvent_t)head_ready;
+  h->impl->grad_ready[1] = (cudaEvent_t)gates_ready;
+  h->impl->grad_ready[2] = (cudaEvent_t)embedding_ready;
   return 0;
 }
 

@@ -220,6 +220,30 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
+    # the gradient groups of capdec_set_grad_ready_events, in the order they become final during train_backward, as
+    # [first, last] parameter names: contiguous ranges of store.flat_grad
+    GRAD_GROUPS = (("fc_hs_w", "fc_e_b"), ("lstm_w", "fc_xs_b"), ("word_embedding", "out_fc_bias"), ("fc_v_w", "fc_k_b"))
+
+    def grad_group_slices(self):
+        """[(lo, hi)] element ranges of store.flat_grad for GRAD_GROUPS"""
+        st = self.store
+        out = []
+        for first, last in self.GRAD_GROUPS:
+            lo = st.offsets[first]
+            hi = st.offsets[last] + (math.prod(st.shapes[last]) + 63) // 64 * 64
+            out.append((lo, hi))
+        return out
+
+    def set_grad_ready_events(self, events) -> None:
+        """events: three recorded torch.cuda.Event (head, gates, embedding) or None to switch the marks off"""
+        if events is None:
+            check(self.lib.capdec_set_grad_ready_events(self.handle, None, None, None), "capdec_set_grad_ready_events")
+            self._grad_events = None
+            return
+        ptrs = [C.c_void_p(int(e.cuda_event)) for e in events]
+        check(self.lib.capdec_set_grad_ready_events(self.handle, *ptrs), "capdec_set_grad_ready_events")
+        self._grad_events = list(events)   # keep them alive
+
     def profile(self, enable: bool = True) -> None:
         """Switch the device-side phase timeline on or off (capdec_profile)."""
         check(self.lib.capdec_profile(self.handle, 1 if enable else 0), "capdec_profile")

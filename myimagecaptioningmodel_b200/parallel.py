@@ -54,8 +54,43 @@ class DataParallelTrainer:
             inv = (1.0 / tot[1]).reshape(1)
             eng.train_backward(1.0, inv, want_dg=want_input_grads, want_dP=want_input_grads)
             loss = tot[0] / tot[1]
-        dist.all_reduce(eng.store.flat_grad, group=self.group)
+        self._all_reduce_grads()
         return loss
+
+    def _setup_overlap(self):
+        """Bucketed gradient exchange overlapped with the backward pass: engines that can signal when a group of
+        gradients is final (CaptionDecoderEngine.set_grad_ready_events) get three events and a communication stream."""
+        eng = self.engine
+        self._overlap = False
+        if self.world == 1 or not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
+            return
+        self._comm = torch.cuda.Stream()
+        self._events = [torch.cuda.Event() for _ in range(3)]
+        for e in self._events:
+            e.record()                      # creates the underlying cudaEvent_t
+        eng.set_grad_ready_events(self._events)
+        self._slices = eng.grad_group_slices()
+        self._done = torch.cuda.Event()
+        self._overlap = True
+
+    def _all_reduce_grads(self):
+        eng = self.engine
+        if not getattr(self, "_overlap_ready", False):
+            self._setup_overlap()
+            self._overlap_ready = True
+        if not self._overlap:
+            dist.all_reduce(eng.store.flat_grad, group=self.group)
+            return
+        main = torch.cuda.current_stream()
+        self._done.record(main)             # everything train_backward enqueued
+        flat = eng.store.flat_grad
+        with torch.cuda.stream(self._comm):
+            for i, (lo, hi) in enumerate(self._slices):
+                # groups 0..2 wait for their own event (recorded in the middle of the backward pass), the last one
+                # (fc_v / fc_k) for the end of the call
+                self._comm.wait_event(self._events[i] if i < 3 else self._done)
+                dist.all_reduce(flat[lo:hi], group=self.group)
+        main.wait_stream(self._comm)
 
 
 def sharded_decode(engine, g, P, beam: int, finish_on_stop: bool, rank: int, world: int):
