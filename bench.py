@@ -40,6 +40,8 @@ def workload_config(n_gpus):
     return {"workload": "teacher_forced_train_step_B256_per_gpu_T34_H1024_E256_V12295_k49", "global_batch": B_PER_GPU * n_gpus,
             "batch_per_gpu": B_PER_GPU, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
             "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)",
+            "e2e": "pinned host buffers, H2D of the next batch prefetched on a copy stream, loss D2H every step (read by the "
+                   "host one step later)",
             "l2": "per-step working set ~1.5 GB >> 126 MB L2 (no flush needed)"}
 
 
@@ -47,45 +49,73 @@ def workload_config(n_gpus):
 # clocks sampling (nvidia-smi) during the timed region
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """One long-running `nvidia-smi -lms 20` process (a timed region of K train steps lasts tens of milliseconds: spawning
+    nvidia-smi per sample would give one sample at best).  Every line is time-stamped on arrival; summary() keeps the
+    samples that fall inside the marked windows (the device-timed regions)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.stop = threading.Event()
+        self.samples = []      # (t, fields)
+        self.windows = []      # [t0, t1]
+        self.proc = None
         self.thread = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        try:
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+                    self.samples.append((time.perf_counter(), parts))
+        except Exception:
+            pass
 
     def __enter__(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
         return self
 
+    def window(self):
+        """context manager marking a device-timed region"""
+        sampler = self
+
+        class _W:
+            def __enter__(self_w):
+                self_w.t0 = time.perf_counter()
+
+            def __exit__(self_w, *a):
+                sampler.windows.append((self_w.t0, time.perf_counter()))
+        return _W()
+
     def __exit__(self, *a):
-        self.stop.set()
-        self.thread.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
 
     def summary(self):
-        if not self.samples:
+        inside = [f for (t, f) in self.samples if any(t0 <= t <= t1 + 0.02 for t0, t1 in self.windows)]
+        if not inside:
+            inside = [f for (_, f) in self.samples]      # regions shorter than the sampling period: all samples of the run
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        sm = [float(s[0]) for s in inside if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in inside if s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in inside)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(inside), "period_ms": 20}
 
 
 def load_peaks():
@@ -220,6 +250,23 @@ def main_ours(args):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
+    # the loss of every step is copied to pinned host memory inside the step (4 bytes D2H) and read by the host one step
+    # later, when its copy event has fired -- the way a training loop logs it -- so the GPU is never idle while the host
+    # enqueues the next step; the last value is read after the closing synchronisation of the timed region
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    pending = []
+
+    def drain(block, only=None):
+        while pending and (block or loss_evt[pending[0]].query()):
+            if only is not None and pending[0] != only:
+                break
+            k = pending.pop(0)
+            loss_evt[k].synchronize()
+            losses.append(float(loss_host[k][0]))
+            if only is not None:
+                break
+
     def step_e2e(i):
         slot = i & 1
         if i == 0:
@@ -229,7 +276,13 @@ def main_ours(args):
         eng.bind_params()
         loss = trainer.forward_backward(*bufs[slot])
         consumed[slot].record()
-        losses.append(float(loss))                        # D2H read of the step's result (4 bytes, synchronises)
+        k = i & 1
+        if k in pending:                                  # the buffer about to be reused (written two steps ago)
+            drain(True, only=k)
+        loss_host[k].copy_(loss.reshape(1), non_blocking=True)   # D2H read of the step's result
+        loss_evt[k].record()
+        pending.append(k)
+        drain(False)
 
     for c in consumed:
         c.record()
@@ -238,15 +291,20 @@ def main_ours(args):
     sync()
     l0 = eng.launch_count
     with ClockSampler(local_rank) as clocks:
-        ms = timed_region(step_resident, args.steps, sync, barrier)
-    launches = eng.launch_count - l0
+        time.sleep(0.05)                                  # first nvidia-smi line
+        with clocks.window():
+            ms = timed_region(step_resident, args.steps, sync, barrier)
+        launches = eng.launch_count - l0
+        for i in range(max(2, args.warmup // 2)):
+            step_e2e(i)
+        sync()
+        drain(True)
+        for c in consumed:
+            c.record()
+        with clocks.window():
+            ms_e2e = timed_region(step_e2e, args.steps, sync, barrier)
+        drain(True)
     clk = clocks.summary()
-    for i in range(max(2, args.warmup // 2)):
-        step_e2e(i)
-    sync()
-    for c in consumed:
-        c.record()
-    ms_e2e = timed_region(step_e2e, args.steps, sync, barrier)
 
     # ---- beam search (BASELINE.json configs[3], 512 images per GPU, beam 3, 35 steps): secondary number ----
     gi, Pi, _ = synth.make_batch(cfg, BEAM_IMAGES_PER_GPU, 777 + rank)
