@@ -143,8 +143,8 @@ void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* ca
             int pad, float* lse, float* acc);
 // fused: the above plus the UNSCALED gradient  dlogits[m, n] = (softmax - onehot) * mask  (columns [V, Vp) zeroed);
 // the 1/sum(mask) * loss_scale factor is applied by the consumers (GemmEpi::alpha_dev, colsum_add scale)
-template <typename T>
-void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+template <typename T, typename L>
+void ce_fused(LaunchCtx c, const L* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
               int steps, int pad, float* lse, float* acc, T* dlogits);
 // cross entropy fused into the vocabulary GEMM (gemm.cuh ACT_ROWSTATS / ACT_SOFTMAX_GRAD): merge of the row statistics,
 // target logit, loss sums and the per-row operands (lse_eff, tgt) of the gradient pass; E % 8 == 0
@@ -160,7 +160,8 @@ template <typename T>
 void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
             int steps, int pad, const float* lse, const float* scale, float loss_scale, T* dlogits);
 // out[b, t, :V] = logits[(t*B+b), :V]
-void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out);
+template <typename L>
+void logits_to_batch_major(LaunchCtx c, const L* logits, long ldl, int V, int B, int steps, float* out);
 // one beam-search step for every image; see loss.cu
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,

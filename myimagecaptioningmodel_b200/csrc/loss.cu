@@ -48,27 +48,33 @@ ce_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const int64_t* 
   }
 }
 
-// one pass for the online (max, sum), one L2-resident pass for the gradient: logits are read from HBM once
-template <typename T>
+// one pass for the online (max, sum), one L2-resident pass for the gradient: logits are read from HBM once.
+// L = storage type of the logits (fp32, or bf16 on the bf16 path: half the bytes of the [M, V] round trip; every
+// reduction is fp32)
+template <typename T, typename L>
 __global__ void __launch_bounds__(kCeThreads)
-ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
+ce_fused_kernel(const L* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
                 long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits) {
   pdl_trigger();
   __shared__ float scratch[32];
   const long m = blockIdx.x;
-  const float* row = logits + m * ldl;
+  const L* row = logits + m * ldl;
   T* out = dlogits + m * (long)Vp;
   const int64_t tgt = target_of(caption, cap_ld, B, m);
-  const int V4 = V & ~3;
+  const int V8 = V & ~7;
   float mx = -INFINITY, sum = 0.f;
-  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + n);
-    const float lm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+  for (int n = threadIdx.x * 8; n < V8; n += kCeThreads * 8) {
+    float v[8];
+    load8(row + n, v);
+    float lm = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) lm = fmaxf(lm, v[i]);
     if (lm > mx) { sum *= __expf(mx - lm); mx = lm; }
-    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += __expf(v[i] - mx);
   }
-  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) {
-    const float x = row[n];
+  for (int n = V8 + threadIdx.x; n < V; n += kCeThreads) {
+    const float x = to_f(row[n]);
     if (x > mx) { sum *= __expf(mx - x); mx = x; }
     sum += __expf(x - mx);
   }
@@ -78,7 +84,7 @@ ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const
   if (threadIdx.x == 0) {
     lse[m] = l;
     if (tgt != pad) {
-      atomicAdd(acc + 0, l - row[tgt]);
+      atomicAdd(acc + 0, l - to_f(row[tgt]));
       atomicAdd(acc + 1, 1.f);
     }
   }
@@ -97,7 +103,7 @@ ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const
       for (int i = 0; i < 8; ++i) v[i] = __expf(v[i] - l) - ((n + i) == tgt ? 1.f : 0.f);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (n + i < V) ? __expf(row[n + i] - l) - ((n + i) == tgt ? 1.f : 0.f) : 0.f;
+      for (int i = 0; i < 8; ++i) v[i] = (n + i < V) ? __expf(to_f(row[n + i]) - l) - ((n + i) == tgt ? 1.f : 0.f) : 0.f;
     }
     store8(out + n, v);
   }
@@ -200,13 +206,14 @@ ce_bwd_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const i
   }
 }
 
-__global__ void logits_bm_kernel(const float* __restrict__ logits, long ldl, int V, int B, int steps,
+template <typename L>
+__global__ void logits_bm_kernel(const L* __restrict__ logits, long ldl, int V, int B, int steps,
                                  float* __restrict__ out) {
   const long m = blockIdx.x;  // time-major row
   const long t = m / B, b = m % B;
-  const float* src = logits + m * ldl;
+  const L* src = logits + m * ldl;
   float* dst = out + (b * steps + t) * (long)V;
-  for (int n = threadIdx.x; n < V; n += blockDim.x) dst[n] = src[n];
+  for (int n = threadIdx.x; n < V; n += blockDim.x) dst[n] = to_f(src[n]);
 }
 
 // ---- beam search step: one CTA per image --------------------------------------------------------------------
@@ -642,16 +649,18 @@ void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* ca
   ce_fwd_kernel<<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, caption, cap_ld, B, pad, lse, acc);
   if (c.launches) ++*c.launches;
 }
-template <typename T>
-void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+template <typename T, typename L>
+void ce_fused(LaunchCtx c, const L* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
               int steps, int pad, float* lse, float* acc, T* dlogits) {
-  ce_fused_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits);
+  ce_fused_kernel<T, L><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits);
   if (c.launches) ++*c.launches;
 }
-template void ce_fused<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
-                              float*);
-template void ce_fused<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
-                             bf16*);
+template void ce_fused<float, float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*,
+                                     float*, float*);
+template void ce_fused<bf16, float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*,
+                                    float*, bf16*);
+template void ce_fused<bf16, bf16>(LaunchCtx, const bf16*, long, int, int, const int64_t*, long, int, int, int, float*,
+                                   float*, bf16*);
 void ce_merge(LaunchCtx c, long M, int S, const float* stats_m, const float* stats_s, long ld, const bf16* proj, int E,
               const bf16* emb, const float* bias, const int64_t* caption, long cap_ld, int B, int pad, float* lse,
               float* lse_eff, int* tgt, float* acc) {
@@ -674,10 +683,13 @@ void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int
                                                           loss_scale, dlogits);
   if (c.launches) ++*c.launches;
 }
-void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out) {
-  logits_bm_kernel<<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
+template <typename L>
+void logits_to_batch_major(LaunchCtx c, const L* logits, long ldl, int V, int B, int steps, float* out) {
+  logits_bm_kernel<L><<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
   if (c.launches) ++*c.launches;
 }
+template void logits_to_batch_major<float>(LaunchCtx, const float*, long, int, int, int, float*);
+template void logits_to_batch_major<bf16>(LaunchCtx, const bf16*, long, int, int, int, float*);
 namespace {
 // candidate scratch of the split beam step (per device, grown on demand, process lifetime)
 struct BeamScratch { void* p = nullptr; size_t cap = 0; };

@@ -171,6 +171,10 @@ __device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals, 
 // forward
 // ================================================================================================================
 constexpr int kFwdStages = 4;
+constexpr int kFwdEpiWarps = 8;   // two per TMEM lane quarter: 8 of the CTA's 16 hidden units each
+constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
+constexpr int kFwdThreads = 64 + kFwdEpiThreads;
+__device__ __forceinline__ void fwd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFwdEpiThreads) : "memory"); }
 constexpr int kFwdUnits = 16;            // hidden units per CTA
 constexpr int kFwdN = 4 * kFwdUnits;     // 64 gate columns
 constexpr int kFwdWTile = BK * kFwdN * 2;  // 8 KB per k-block of the resident weight slice
@@ -185,6 +189,7 @@ struct SeqFwdParams {
   const float* cs;              // [(T+1)*B, H]  cs[0] = c_0 (zeros); written through the tensor map
   unsigned* ctr;                // [gridDim.y]   arrival counters (zeroed by the host)
   unsigned long long* trace;    // debug timeline or nullptr
+  int stagger_ns;               // start offset between batch groups (0 = none)
 };
 
 // Everything except h_t moves through the TMA engine in whole 128-byte lines: the per-step x-part pre-activations
@@ -198,7 +203,7 @@ struct SeqFwdParams {
 // 128/CS rows of every h k-block and multicasts them.  Measured on B200: no gain over CS = 1 (474 / 468 / 469 us for
 // CS = 1 / 2 / 4) -- delivery into the SMs, not the L2 read, bounds the h stream -- so CS = 1 is the default.
 template <int CS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmCs,
                     const __grid_constant__ CUtensorMap tmGa, SeqFwdParams p) {
@@ -223,7 +228,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmCs);
     tma_prefetch_desc(&tmGa);
-    init_bars<kFwdStages>(bar, 4, CS);
+    init_bars<kFwdStages>(bar, kFwdEpiWarps, CS);
   }
   if (warp == 1) tmem_alloc<2 * kFwdN>(bar.tmem_ptr);
   tc_fence_before();
@@ -241,6 +246,16 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       for (int kb = 0; kb < nkb; ++kb) tma_load_3d(wsm + (size_t)kb * kFwdWTile, &tmW, slice * kFwdN, kb * BK, 0, bar.w_bar);
       int s = 0;
       uint32_t ph = 0;
+      if (p.stagger_ns > 0 && y > 0) {
+        // The batch groups are independent chains that all stream through the same L2 at the same moment; starting group
+        // y half a step late lets each group's h stream run while the others are in their epilogue / barrier phase.
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+          __nanosleep(200);
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < (unsigned long long)p.stagger_ns * (unsigned)y / (unsigned)MG);
+      }
       for (int t = 0; t < p.T; ++t) {
         if (t > 0) {
           spin_until(p.ctr + y, (unsigned)t * (unsigned)G);  // every CTA of this batch group has written its h_t slice
@@ -296,13 +311,15 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     }
   } else {
     // ===== epilogue: the LSTM cell applied to the accumulator (Paddle lstm_unit, gates i,f,o,g) =====
+    // 8 warps: warp (quarter, hh) owns TMEM lanes [32*quarter, +32) and accumulator columns [32*hh, +32) = 8 units
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int hh = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
     const int u0 = slice * kFwdUnits;
     const long BH = (long)p.B * p.H;
     const int trow = quarter * 32 + lane;  // row of the 128-row tile = TMEM lane
     uint8_t* x_row = x_stage + trow * 128;
-    uint8_t* c_row = c_stage + trow * 64;
+    uint8_t* c_row = c_stage + trow * 64 + hh * 32;
     const uint32_t swz = (uint32_t)(lane & 7);
     // c_{t-1} of this thread's row: with one batch tile per CTA it is still in the c staging tile of the previous
     // step; otherwise it is read back from global memory once the tensor stores that wrote it have completed
@@ -318,53 +335,48 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           bulk_wait_all();
           fence_proxy_async_all();
         }
-        epi_bar_sync();
+        fwd_bar_sync();
       }
       for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
         const int buf = it & 1;
         const int row = mt * 128 + trow;
         const bool row_ok = row < p.B;
-        float cp[2][8];
+        float cp[8];
         if (t > 0 && single_tile) {
-          load8(reinterpret_cast<const float*>(c_row), cp[0]);
-          load8(reinterpret_cast<const float*>(c_row) + 8, cp[1]);
+          load8(reinterpret_cast<const float*>(c_row), cp);
         } else if (row_ok) {
-          const float* cr = p.cs + (long)t * BH + (long)row * p.H + u0;
-          load8(cr, cp[0]);
-          load8(cr + 8, cp[1]);
+          load8(p.cs + (long)t * BH + (long)row * p.H + u0 + hh * 8, cp);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cp[0][i] = cp[1][i] = 0.f;
+          for (int i = 0; i < 8; ++i) cp[i] = 0.f;
         }
-        // x-part pre-activations of this tile: shared memory -> registers (bf16, 8 units x 4 gates per 16 B chunk pair)
-        uint4 xq[8];
+        // x-part pre-activations of this thread's 8 units: shared memory -> registers (bf16, (i,f,o,g) per unit)
+        uint4 xq[4];
         mbar_wait_b(x_full, (uint32_t)(it & 1));
 #pragma unroll
-        for (int q = 0; q < 8; ++q) xq[q] = *reinterpret_cast<const uint4*>(x_row + (((uint32_t)q ^ swz) << 4));
+        for (int q = 0; q < 4; ++q) xq[q] = *reinterpret_cast<const uint4*>(x_row + (((uint32_t)(hh * 4 + q)) ^ swz) * 16);
         mbar_wait_b(&bar.tmem_full[buf], (it >> 1) & 1);
         if (et == 0) rec_trace(p.trace, p.T, t, 4);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kFwdN) + ((uint32_t)(quarter * 32) << 16);
-        // every thread has read its x row (and its c row): the tile may now be overwritten with the gate activations
-        epi_bar_sync();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kFwdN + hh * 32) + ((uint32_t)(quarter * 32) << 16);
+        // every thread has read its x chunks (and its c values): the tile may now be overwritten with the gate activations
+        fwd_bar_sync();
+        {
           uint32_t r[32];
           __syncwarp();
-          tmem_ld32(tmem_d + (uint32_t)(hh * 32), r);
+          tmem_ld32(tmem_d, r);
           tmem_ld_wait();
           float hn[8], cn[8];
           uint4 gq[4];  // gate activations of units 2q, 2q+1 as bf16 (i,f,o,g each)
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            // chunk hh*4 + u/2 of the x row holds units 2(u/2), 2(u/2)+1: (i,f,o,g) x 2
-            const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[hh * 4 + (u >> 1)]) + (u & 1) * 2;
+            const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[u >> 1]) + (u & 1) * 2;
             const float2 x_if = __bfloat1622float2(xp[0]), x_og = __bfloat1622float2(xp[1]);
             const float ig = sigmoid_t<true>(__uint_as_float(r[4 * u + 0]) + x_if.x);
             const float fg = sigmoid_t<true>(__uint_as_float(r[4 * u + 1]) + x_if.y);
             const float og = sigmoid_t<true>(__uint_as_float(r[4 * u + 2]) + x_og.x);
             const float gg = tanh_t<true>(__uint_as_float(r[4 * u + 3]) + x_og.y);
-            cn[u] = fg * cp[hh][u] + ig * gg;
+            cn[u] = fg * cp[u] + ig * gg;
             hn[u] = og * tanh_t<true>(cn[u]);
             __nv_bfloat162* gp = reinterpret_cast<__nv_bfloat162*>(&gq[u >> 1]) + (u & 1) * 2;
             gp[0] = __floats2bfloat162_rn(ig, fg);
@@ -373,9 +385,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           if (row_ok) store8(p.hs + (long)(t + 1) * BH + (long)row * p.H + u0 + hh * 8, hn);
           // rows past the batch are clipped by the tensor stores
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(x_row + (((uint32_t)(hh * 4 + q) ^ swz) << 4)) = gq[q];
-          *reinterpret_cast<float4*>(c_row + hh * 32) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(c_row + hh * 32 + 16) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(x_row + (((uint32_t)(hh * 4 + q)) ^ swz) * 16) = gq[q];
+          *reinterpret_cast<float4*>(c_row) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(c_row + 16) = make_float4(cn[4], cn[5], cn[6], cn[7]);
         }
         tc_fence_before();
         __syncwarp();
@@ -385,7 +397,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         if (t + 1 < p.T) __threadfence();  // this thread's h_t stores are performed at GPU scope
         fence_proxy_async_all();            // staging writes -> async proxy
         if (et == 0) rec_trace(p.trace, p.T, t, 5);
-        epi_bar_sync();
+        fwd_bar_sync();
         if (et == 0) {
           if (release) {
             // release h_t of this CTA's slice to the other CTAs of the batch group
@@ -406,7 +418,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
             tma_load_3d(x_stage, &tmX, 4 * u0, nmt * 128, nt, x_full);
           }
         }
-        // the c / gate staging tiles are rewritten only after the next tile's epi_bar_sync, which thread 0 reaches
+        // the c / gate staging tiles are rewritten only after the next tile's fwd_bar_sync, which thread 0 reaches
         // after the bulk_wait_read above
       }
     }
@@ -799,12 +811,14 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
   p.B = B; p.H = H; p.T = T; p.n_mtiles = n_mtiles;
   p.hs = hs; p.cs = cs_buf; p.ctr = ctr;
   p.trace = g_rec_trace;
+  p.stagger_ns = 0;
+  if (const char* ev = getenv("CAPDEC_REC_STAGGER_NS")) p.stagger_ns = atoi(ev);
   cudaError_t e = cudaMemsetAsync(ctr, 0, 64 * sizeof(unsigned), c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_fwd: memset: %s", cudaGetErrorString(e)); return -1; }
   void* args[] = {&tmH, &tmW, &tmX, &tmCs, &tmGa, &p};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(slices, mg);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kFwdThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c.stream;
   cudaLaunchAttribute attrs[2];
