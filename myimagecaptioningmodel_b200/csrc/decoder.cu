@@ -42,6 +42,9 @@ void set_error(const char* fmt, ...) {
     if ((expr) != 0) return -1; \
   } while (0)
 
+// bumped whenever a workspace buffer is (re)allocated: captured decode graphs hold raw pointers and are dropped then
+static unsigned long g_ws_epoch = 0;
+
 // a growable device buffer owned by the handle
 struct DevBuf {
   void* p = nullptr;
@@ -54,6 +57,7 @@ struct DevBuf {
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return -1; }
     cap = bytes;
     *total += bytes;
+    ++g_ws_epoch;
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -131,12 +135,15 @@ template <typename T> class Decoder : public DecoderBase {
     force_simt = fs && fs[0] == '1';
   }
   ~Decoder() override {
+    dgraph.reset();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (DevBuf* b : all_bufs()) b->release();
   }
 
   // ------------------------------------------------------------------------------------------------------------
   int bind(const capdec_params* p, cudaStream_t s) override {
     prm = *p;
+    ++g_ws_epoch;  // the caller's bias / w_alpha pointers are baked into captured decode graphs
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int X = E + H;
@@ -694,72 +701,119 @@ template <typename T> class Decoder : public DecoderBase {
       hist[0] = (int*)p; p += 4 * (size_t)R * Ti; hist[1] = (int*)p; p += 4 * (size_t)R * Ti;
       tok = (int*)p; p += 4 * R; src = (int*)p;
     }
-    CUDA_OK(cudaMemsetAsync(d_state.p, 0, d_state.cap, s));
-    {
-      // only prefix 0 of every image is live at step 0; every row starts from <start>, h = c = 0 (model:56-58, 63)
-      std::vector<float> sc(R, -INFINITY);
-      std::vector<int> tk(R, cfg.start_idx), sr(R, 0);
-      for (int i = 0; i < B; ++i) sc[(size_t)i * beam] = 0.f;
-      for (int r = 0; r < R; ++r) sr[r] = r % beam;
-      CUDA_OK(cudaMemcpyAsync(score[0], sc.data(), 4 * R, cudaMemcpyHostToDevice, s));
-      CUDA_OK(cudaMemcpyAsync(tok, tk.data(), 4 * R, cudaMemcpyHostToDevice, s));
-      CUDA_OK(cudaMemcpyAsync(src, sr.data(), 4 * R, cudaMemcpyHostToDevice, s));
-      CUDA_OK(cudaStreamSynchronize(s));  // the host vectors die at the end of this scope
-    }
-    CUDA_OK(cudaMemsetAsync(d_hnew.p, 0, e * (size_t)R * H, s));
-    CUDA_OK(cudaMemsetAsync(d_cnew.p, 0, 4 * (size_t)R * H, s));
-    beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
-                    xin.as<T>(), X, d_ccur.as<float>());
-    // global-image half of the gate / sentinel pre-activations, once per image
-    OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5d.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
     as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
-    prof.mark("dec.setup", s);
-    for (int step = 0; step < Ti; ++step) {
-      const int cur = step & 1, nxt = cur ^ 1;
-      // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
-      OK(fc(gc, xin.p, X, w_dec_n.as<T>(), 5 * H, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
-      OK(fc(gc, xin.p, X, w_dec_n.as<T>() + 4 * H, 5 * H, nullptr, ph.p, H, R, H, X, ACT_NONE));
-      lstm_cell_fwd<T>(lc, R, H, gpre.as<float>(), 4 * H, (const T*)nullptr, 0, g5.as<float>(), 5 * H, INT_MAX, beam,
-                       d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
-      sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
-                      d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
-      prof.mark("dec.gates_cell", s);
-      OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
-      OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
-      OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
-      prof.mark("dec.head_fc", s);
-      bool attn_small = false;
-      if constexpr (std::is_same<T, bf16>::value) {
-        if (!force_simt && attention_fwd_small_supported(as)) {
-          OK(attention_fwd_small(lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
-                                 sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
-                                 actx.as<bf16>()));
-          attn_small = true;
+    // everything from here to the end of the step loop touches handle-owned memory only
+    cudaStream_t rs = s;  // stream the step loop is enqueued on (a private stream while it is being captured)
+    auto run_steps = [&]() -> int {
+      CUDA_OK(cudaMemsetAsync(d_state.p, 0, d_state.cap, rs));
+      // only prefix 0 of every image is live at step 0; every row starts from <start>, h = c = 0 (model:56-58, 63)
+      beam_init(lc, R, beam, cfg.start_idx, score[0], tok, src);
+      CUDA_OK(cudaMemsetAsync(d_hnew.p, 0, e * (size_t)R * H, rs));
+      CUDA_OK(cudaMemsetAsync(d_cnew.p, 0, 4 * (size_t)R * H, rs));
+      beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
+                      xin.as<T>(), X, d_ccur.as<float>());
+      // global-image half of the gate / sentinel pre-activations, once per image
+      OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5d.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
+      prof.mark("dec.setup", rs);
+      for (int step = 0; step < Ti; ++step) {
+        const int cur = step & 1, nxt = cur ^ 1;
+        // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
+        OK(fc(gc, xin.p, X, w_dec_n.as<T>(), 5 * H, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
+        OK(fc(gc, xin.p, X, w_dec_n.as<T>() + 4 * H, 5 * H, nullptr, ph.p, H, R, H, X, ACT_NONE));
+        lstm_cell_fwd<T>(lc, R, H, gpre.as<float>(), 4 * H, (const T*)nullptr, 0, g5.as<float>(), 5 * H, INT_MAX, beam,
+                         d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
+        sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
+                        d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
+        prof.mark("dec.gates_cell", rs);
+        OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
+        OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
+        OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+        prof.mark("dec.head_fc", rs);
+        bool attn_small = false;
+        if constexpr (std::is_same<T, bf16>::value) {
+          if (!force_simt && attention_fwd_small_supported(as)) {
+            OK(attention_fwd_small(lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
+                                   sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
+                                   actx.as<bf16>()));
+            attn_small = true;
+          }
+        }
+        if (!attn_small)
+          attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
+                           prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
+        prof.mark("dec.attention", rs);
+        OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
+        OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
+        {
+          GemmCall c;
+          c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
+          c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
+          OK(gemm<T>(gc, c));
+        }
+        prof.mark("dec.out_proj_vocab", rs);
+        // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
+        beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
+                  score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src);
+        if (step + 1 < Ti)
+          beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
+                          xin.as<T>(), X, d_ccur.as<float>());
+        prof.mark("dec.beam_step_reorder", rs);
+      }
+      return 0;
+    };
+    // Small batches are launch-latency bound (14 dependent launches per step, ~9 us each at one image): the step loop
+    // is captured once into a CUDA graph per (images, beam, finish) and replayed.  The first call of a shape runs
+    // eagerly (it allocates the workspace and warms the tensor-map cache), the second captures.
+    static const bool graph_ok = [] { const char* ev = getenv("CAPDEC_DECODE_GRAPH"); return !(ev && ev[0] == '0'); }();
+    const bool want_graph = graph_ok && R <= 96 && !prof.on;
+    bool done = false;
+    if (want_graph) {
+      const unsigned long key_epoch = g_ws_epoch;
+      if (dgraph.exec && dgraph.B == B && dgraph.beam == beam && dgraph.finish == finish && dgraph.epoch == key_epoch &&
+          dgraph.stream == s) {
+        CUDA_OK(cudaGraphLaunch(dgraph.exec, s));
+        launches += dgraph.launches;
+        done = true;
+      } else if (dgraph.seen_B == B && dgraph.seen_beam == beam && dgraph.seen_finish == finish &&
+                 dgraph.seen_epoch == key_epoch) {
+        dgraph.reset();
+        const long l0 = launches + gc.launches;
+        set_gemm_pdl(false);  // programmatic edges are not captured: plain launches inside the graph
+        cudaGraph_t graph = nullptr;
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); the graph
+        // itself is launched into the caller's stream
+        if (!cap_stream && cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess) cap_stream = nullptr;
+        if (cap_stream && cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          rs = cap_stream; gc.stream = cap_stream; lc.stream = cap_stream;
+          const int rc = run_steps();
+          const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+          rs = s; gc.stream = s; lc.stream = s;
+          if (getenv("CAPDEC_DEBUG"))
+            fprintf(stderr, "[capdec] decode graph capture: rc=%d (%s) end=%s\n", rc, rc ? g_err : "", cudaGetErrorString(ce));
+          if (rc == 0 && ce == cudaSuccess && graph &&
+              cudaGraphInstantiate(&dgraph.exec, graph, 0) == cudaSuccess) {
+            dgraph.B = B; dgraph.beam = beam; dgraph.finish = finish; dgraph.epoch = key_epoch; dgraph.stream = s;
+            dgraph.launches = (launches + gc.launches) - l0;
+          } else {
+            dgraph.exec = nullptr;
+            cudaGetLastError();
+          }
+          if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();  // a refused capture must not leave its error behind for the eager path
+        set_gemm_pdl(true);
+        launches = l0 - gc.launches;  // the capture enqueued nothing; the replay below is what runs
+        if (dgraph.exec) {
+          CUDA_OK(cudaGraphLaunch(dgraph.exec, s));
+          launches += dgraph.launches;
+          done = true;
         }
       }
-      if (!attn_small)
-        attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
-                         prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);
-      prof.mark("dec.attention", s);
-      OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
-      OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
-      {
-        GemmCall c;
-        c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
-        c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
-        OK(gemm<T>(gc, c));
-      }
-      prof.mark("dec.out_proj_vocab", s);
-      // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
-      beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
-                score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src);
-      if (step + 1 < Ti)
-        beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
-                        xin.as<T>(), X, d_ccur.as<float>());
-      prof.mark("dec.beam_step_reorder", s);
+      dgraph.seen_B = B; dgraph.seen_beam = beam; dgraph.seen_finish = finish; dgraph.seen_epoch = g_ws_epoch;
     }
+    if (!done) OK(run_steps());
     const int fin_buf = Ti & 1;
     if (ids) CUDA_OK(cudaMemcpyAsync(ids, hist[fin_buf], 4 * (size_t)R * Ti, cudaMemcpyDeviceToDevice, s));
     if (scores) CUDA_OK(cudaMemcpyAsync(scores, score[fin_buf], 4 * (size_t)R, cudaMemcpyDeviceToDevice, s));
@@ -779,6 +833,22 @@ template <typename T> class Decoder : public DecoderBase {
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &ce_stats, &ce_rows, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state};
   }
+
+  // captured step loop of capdec_decode for small batches
+  struct DecodeGraph {
+    cudaGraphExec_t exec = nullptr;
+    int B = 0, beam = 0, finish = 0;
+    unsigned long epoch = 0;
+    cudaStream_t stream = nullptr;
+    long launches = 0;
+    int seen_B = -1, seen_beam = -1, seen_finish = -1;
+    unsigned long seen_epoch = 0;
+    void reset() {
+      if (exec) cudaGraphExecDestroy(exec);
+      exec = nullptr;
+    }
+  } dgraph;
+  cudaStream_t cap_stream = nullptr;
 
   capdec_config cfg;
   capdec_params prm{};

@@ -909,9 +909,10 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   return 0;
 }
 
+thread_local bool t_pdl_on = true;
 bool pdl_enabled() {  // CAPDEC_GEMM_PDL=0 switches programmatic dependent launch off (A/B measurements)
   static const bool on = [] { const char* e = getenv("CAPDEC_GEMM_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  return on && t_pdl_on;
 }
 
 template <int BN, bool A_MN, bool B_MN, int MT>
@@ -1054,6 +1055,7 @@ bool pair_eligible(const GemmCall& c) {
 }  // namespace
 
 void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
+void set_gemm_pdl(bool on) { t_pdl_on = on; }
 
 // the tensor-map cache, for the other TMA kernels of the library (recurrent.cu)
 int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,

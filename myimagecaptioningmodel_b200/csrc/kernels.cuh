@@ -166,6 +166,8 @@ void logits_to_batch_major(LaunchCtx c, const L* logits, long ldl, int V, int B,
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
                const int* hist_in, int* hist_out, int* tok_out, int* src_out);
+// initial beam state: score = 0 for prefix 0 of every image, -inf for the others; tok = start; src = r % beam
+void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src);
 // next-step operands: xin[r] = [emb[tok[r]] | h_new[src_row(r)]], c_next[r] = c_new[src_row(r)]
 template <typename T>
 void beam_reorder(LaunchCtx c, int n_img, int beam, int E, int H, int pad, const T* emb, const int* tok, const int* src,

@@ -607,6 +607,16 @@ beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, in
   }
 }
 
+// initial beam state: only prefix 0 of every image is live, every row starts from <start> (model:56-58)
+__global__ void beam_init_kernel(int R, int beam, int start, float* __restrict__ score, int* __restrict__ tok,
+                                 int* __restrict__ src) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  score[r] = (r % beam == 0) ? 0.f : -INFINITY;
+  tok[r] = start;
+  src[r] = r % beam;
+}
+
 template <typename T>
 __global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad, const T* __restrict__ emb,
                                     const int* __restrict__ tok, const int* __restrict__ src,
@@ -744,6 +754,10 @@ void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int
   else if (beam <= 4) LAUNCH_BEAM(beam_step_generic_kernel<4>);
   else LAUNCH_BEAM(beam_step_generic_kernel<8>);
 #undef LAUNCH_BEAM
+  if (c.launches) ++*c.launches;
+}
+void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src) {
+  beam_init_kernel<<<(R + 255) / 256, 256, 0, c.stream>>>(R, beam, start, score, tok, src);
   if (c.launches) ++*c.launches;
 }
 template <typename T>

@@ -181,6 +181,36 @@ def test_cross_entropy_fused_into_vocab_gemm(dims, B, monkeypatch):
         assert rel_err(ga[name], eng.store.grads[name]) < 5e-3, name
 
 
+@pytest.mark.parametrize("B,beam,finish", [(1, 1, False), (4, 3, True), (20, 2, True)])
+def test_small_batch_decode_graph_replay(B, beam, finish):
+    """Small decodes replay a captured CUDA graph of the step loop from the second call of a shape on: eager run, capture +
+    replay, replay and a re-capture after new parameters were bound must all give bit-identical ids and scores; a
+    different input through the same graph must match its own eager result."""
+    ocfg = R.DecoderConfig(softmax_axis="position", **MID)
+    params = R.init_params(ocfg, 21, torch.float32, bias_scale=0.1)
+    g, P, _ = synth.make_batch(ocfg, B, 5)
+    g2, P2, _ = synth.make_batch(ocfg, B, 6)
+    eng = _engine(MID, "position", "bf16", params)
+    gd, Pd, g2d, P2d = g.cuda(), P.cuda(), g2.cuda(), P2.cuda()
+    n0 = eng.launch_count
+    ids0, sc0, f0 = eng.decode(gd, Pd, beam=beam, finish_on_stop=finish)          # eager
+    n1 = eng.launch_count
+    ids1, sc1, f1 = eng.decode(gd, Pd, beam=beam, finish_on_stop=finish)          # captured + replayed
+    ids2, sc2, f2 = eng.decode(gd, Pd, beam=beam, finish_on_stop=finish)          # replayed
+    torch.cuda.synchronize()
+    n3 = eng.launch_count
+    assert n1 - n0 > 100 and abs((n3 - n1) - 2 * (n1 - n0)) <= 8                  # the launch accounting covers replays
+    for a, b in ((ids0, ids1), (ids0, ids2), (sc0, sc1), (sc0, sc2), (f0, f1), (f0, f2)):
+        assert torch.equal(a, b)
+    idsB, scB, _ = eng.decode(g2d, P2d, beam=beam, finish_on_stop=finish)         # other images through the same graph
+    eng.bind_params()                                                             # drops the graph
+    idsC, scC, _ = eng.decode(g2d, P2d, beam=beam, finish_on_stop=finish)         # eager again
+    idsD, scD, _ = eng.decode(g2d, P2d, beam=beam, finish_on_stop=finish)         # re-captured
+    torch.cuda.synchronize()
+    assert torch.equal(idsB, idsC) and torch.equal(scB, scC) and torch.equal(idsC, idsD) and torch.equal(scC, scD)
+    assert not torch.equal(idsB, ids0) or B == 1
+
+
 def _explained_by_margin(ids_gpu, ids_ref, margin, noise):
     """ids must agree up to the first step whose oracle decision margin is below the numerical noise"""
     bad = 0
