@@ -23,7 +23,10 @@ import sys
 import threading
 import time
 
-import torch
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"                   # keep NCCL's version banner off stdout: one JSON line only
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

@@ -122,10 +122,10 @@ int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_de
 /* Data-parallel callers (the reference's ParallelExecutor wrapper, train.py:119-127): three optional
  * cudaEvent_t (as void*, NULL = none) that every following capdec_train_bwd records on its stream as soon as a group of
  * gradients is final, so that the caller can all-reduce that group while the rest of the backward pass still runs:
- *   head_ready      fc_hs_w .. fc_e_b (incl. fc_p, fc_g, fc_s, fc_a, fc_o) -- before the BPTT kernel starts
+ *   head_ready      fc_hs_w .. fc_e_b (incl. fc_p, fc_g, fc_s, fc_a, fc_o) and fc_v_w .. fc_k_b
+ *                                                                           -- before the BPTT kernel starts
  *   gates_ready     lstm_w, lstm_b, fc_xs_w, fc_xs_b                        -- after the batched gate weight gradients
- *   embedding_ready word_embedding, out_fc_bias                             -- after the lookup scatter-add
- * fc_v_w .. fc_k_b are final when all work of the call has completed. */
+ *   embedding_ready word_embedding, out_fc_bias                             -- after the lookup scatter-add (last work) */
 int capdec_set_grad_ready_events(capdec_handle h, void* head_ready, void* gates_ready, void* embedding_ready);
 
 /* Inference: Decoder(mode='eval').call (model:55-58, 66-69, 119-123, 132-133) generalised to beam search

@@ -591,7 +591,22 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     prof.mark("bwd.head_fc", s);
-    mark_ready(0, s);  // fc_hs .. fc_e (and fc_a) are final: their all-reduce may overlap the BPTT
+    // once-per-image projections (model:52-53)
+    colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
+    colsum_add<T>(lc, dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
+    OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
+    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
+    if (dP) {
+      GemmCall c;  // d p_img_feat
+      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
+      c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    prof.mark("bwd.image_kv", s);
+    // fc_hs .. fc_e (incl. fc_a) and fc_v, fc_k are final: their all-reduce overlaps the BPTT.  (The per-image
+    // projections depend on the attention gradients only, so they run here rather than at the end of the pass, where
+    // their gradients would be exchanged with nothing left to hide behind.)
+    mark_ready(0, s);
     // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
     bool persistent = false;
     if constexpr (std::is_same<T, bf16>::value) {
@@ -642,20 +657,8 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
-    mark_ready(2, s);  // word_embedding, out_fc_bias are final (fc_v / fc_k follow: final when the call's work is done)
+    mark_ready(2, s);  // word_embedding, out_fc_bias are final: nothing is left
     prof.mark("bwd.gate_wgrad_embed", s);
-    // once-per-image projections (model:52-53)
-    colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
-    colsum_add<T>(lc, dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
-    OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
-    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
-    if (dP) {
-      GemmCall c;  // d p_img_feat
-      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
-      c.epi.out_f32 = 1;
-      OK(gemm<T>(gc, c));
-    }
-    prof.mark("bwd.image_kv", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     return 0;

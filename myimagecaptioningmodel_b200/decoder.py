@@ -220,18 +220,19 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
-    # the gradient groups of capdec_set_grad_ready_events, in the order they become final during train_backward, as
-    # [first, last] parameter names: contiguous ranges of store.flat_grad
-    GRAD_GROUPS = (("fc_hs_w", "fc_e_b"), ("lstm_w", "fc_xs_b"), ("word_embedding", "out_fc_bias"), ("fc_v_w", "fc_k_b"))
+    # the gradient groups of capdec_set_grad_ready_events as (event index, first, last parameter name): contiguous
+    # ranges of store.flat_grad, in the order they become final during train_backward
+    GRAD_GROUPS = ((0, "fc_hs_w", "fc_e_b"), (0, "fc_v_w", "fc_k_b"), (1, "lstm_w", "fc_xs_b"),
+                   (2, "word_embedding", "out_fc_bias"))
 
     def grad_group_slices(self):
-        """[(lo, hi)] element ranges of store.flat_grad for GRAD_GROUPS"""
+        """[(event index, lo, hi)] element ranges of store.flat_grad for GRAD_GROUPS"""
         st = self.store
         out = []
-        for first, last in self.GRAD_GROUPS:
+        for ev, first, last in self.GRAD_GROUPS:
             lo = st.offsets[first]
             hi = st.offsets[last] + (math.prod(st.shapes[last]) + 63) // 64 * 64
-            out.append((lo, hi))
+            out.append((ev, lo, hi))
         return out
 
     def set_grad_ready_events(self, events) -> None:

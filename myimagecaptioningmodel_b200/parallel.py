@@ -70,7 +70,6 @@ class DataParallelTrainer:
             e.record()                      # creates the underlying cudaEvent_t
         eng.set_grad_ready_events(self._events)
         self._slices = eng.grad_group_slices()
-        self._done = torch.cuda.Event()
         self._overlap = True
 
     def _all_reduce_grads(self):
@@ -82,13 +81,11 @@ class DataParallelTrainer:
             dist.all_reduce(eng.store.flat_grad, group=self.group)
             return
         main = torch.cuda.current_stream()
-        self._done.record(main)             # everything train_backward enqueued
         flat = eng.store.flat_grad
         with torch.cuda.stream(self._comm):
-            for i, (lo, hi) in enumerate(self._slices):
-                # groups 0..2 wait for their own event (recorded in the middle of the backward pass), the last one
-                # (fc_v / fc_k) for the end of the call
-                self._comm.wait_event(self._events[i] if i < 3 else self._done)
+            for ev, lo, hi in self._slices:
+                # every group waits for its own event, recorded by capdec_train_bwd in the middle of the backward pass
+                self._comm.wait_event(self._events[ev])
                 dist.all_reduce(flat[lo:hi], group=self.group)
         main.wait_stream(self._comm)
 
