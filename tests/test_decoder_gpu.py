@@ -261,6 +261,83 @@ def test_greedy_and_beam_decode(axis, dtype):
         assert M.filter_caption(a) == M.filter_caption(b)
 
 
+@pytest.mark.parametrize("B,beam", [(1, 8), (3, 5), (2, 1)])
+def test_beam_search_edge_cases_bit_exact_fp32(B, beam):
+    """fp32 path against the oracle's beam search on the shapes the domain makes awkward: one image, the widest beam the
+    kernels accept (8), beams that finish early (stop token) and keep emitting padding, and scores sorted per image.
+    Rows whose oracle selection margin exceeds the fp32 noise must match bit for bit (ids) and to 1e-3 (scores)."""
+    ocfg = R.DecoderConfig(softmax_axis="position", **MID)
+    params = R.init_params(ocfg, 17, torch.float32, bias_scale=0.1)
+    # make <stop> likely so that finished-prefix handling is exercised: raise its output bias
+    params["out_fc_bias"][ocfg.stop_idx] += 4.0
+    g, P, _ = synth.make_batch(ocfg, B, 71)
+    p64 = {k: v.double() for k, v in params.items()}
+    eng = _engine(MID, "position", "fp32", params)
+    ref_ids, ref_sc, margin = R.beam_search(p64, ocfg, g.double(), P.double(), beam, return_margin=True)
+    ids, sc, ids_f32 = eng.decode(g.cuda(), P.cuda(), beam=beam, finish_on_stop=True)
+    ids, sc = ids.cpu().long(), sc.cpu()
+    assert ids.shape == (B, beam, ocfg.infer_max_length) and sc.shape == (B, beam)
+    assert (sc[:, :-1] >= sc[:, 1:]).all()
+    ok = margin.min(dim=1).values > 1e-3
+    assert ok.any()
+    assert torch.equal(ids[ok], ref_ids[ok])
+    assert float((sc[ok] - ref_sc[ok].float()).abs().max()) < 1e-3
+    # a finished beam emits padding from the step after <stop> on
+    stops = (ids == ocfg.stop_idx)
+    assert stops.any()
+    for b in range(B):
+        for r in range(beam):
+            pos = stops[b, r].nonzero()
+            if len(pos):
+                assert (ids[b, r, int(pos[0]) + 1:] == ocfg.padding_idx).all()
+    assert torch.equal(ids_f32.cpu().long(), ids[:, 0])            # the reference's float32 return = best beam
+
+
+def test_beam_wider_than_live_candidates_and_tiny_vocab():
+    """vocabulary of 5 tokens with beam 3: step 0 has one live prefix and 5 candidates, later steps at most 15; the
+    kernels must never emit an out-of-range token or a duplicate hypothesis."""
+    dims = dict(hidden_dim=128, embedding_size=32, vocab_size=5, num_positions=6, sentence_length=6, infer_max_length=7)
+    ocfg = R.DecoderConfig(softmax_axis="position", **dims)
+    params = R.init_params(ocfg, 3, torch.float32, bias_scale=0.3)
+    g, P, _ = synth.make_batch(ocfg, 5, 9)
+    p64 = {k: v.double() for k, v in params.items()}
+    eng = _engine(dims, "position", "fp32", params)
+    ref_ids, ref_sc, margin = R.beam_search(p64, ocfg, g.double(), P.double(), 3, finish_on_stop=False, return_margin=True)
+    ids, sc, _ = eng.decode(g.cuda(), P.cuda(), beam=3, finish_on_stop=False)
+    ids = ids.cpu().long()
+    assert int(ids.min()) >= 0 and int(ids.max()) < 5
+    ok = margin.min(dim=1).values > 1e-4
+    assert torch.equal(ids[ok], ref_ids[ok])
+    for b in range(5):
+        hyps = {tuple(ids[b, r].tolist()) for r in range(3)}
+        assert len(hyps) == 3
+    with pytest.raises(M.CapdecError):
+        eng.decode(g.cuda(), P.cuda(), beam=9)                       # beam > 8 is rejected, not truncated
+
+
+def test_single_caption_and_degenerate_captions():
+    """B = 1 and captions at the extremes of the tokenizer's layout ([2, 3, 0...]: no word at all; 33 words, no
+    padding): the masked loss normalises by the true token count and padded steps contribute no gradient."""
+    ocfg = R.DecoderConfig(softmax_axis="position", **MID)
+    params = R.init_params(ocfg, 23, torch.float32, bias_scale=0.1)
+    p64 = {k: v.double() for k, v in params.items()}
+    for B in (1, 3):
+        g, P, cap = synth.make_batch(ocfg, B, 100 + B)
+        cap[0, :] = 0
+        cap[0, 0], cap[0, 1] = ocfg.start_idx, ocfg.stop_idx          # empty caption: a single target token
+        if B > 1:
+            cap[1, 0] = ocfg.start_idx
+            cap[1, 1:-1] = torch.arange(4, 4 + ocfg.sentence_length - 2)
+            cap[1, -1] = ocfg.stop_idx                                 # full-length caption: no padding at all
+        for dtype in ("fp32", "bf16"):
+            eng = _engine(MID, "position", dtype, params)
+            # with a handful of target tokens nothing averages the bf16 rounding of the activations: the small gradients
+            # of the sentinel path (fc_s) sit at 2.6e-2 for B = 1 (one target token), so the bf16 gradient bound is 5e-2
+            # here; loss and logits keep the 2e-2 bound, fp32 keeps 1e-3 throughout
+            _check_train(eng, ocfg, p64, g.double(), P.double(), cap, TOL[dtype],
+                         grad_tol=5e-2 if dtype == "bf16" else None)
+
+
 def test_reference_shaped_interface():
     """Decoder.call / ImageCaptionModel mirror model:40-135, 161-189 (shapes, dtypes, errors, autograd)."""
     ocfg = R.DecoderConfig(softmax_axis="position", **SMALL)
