@@ -70,7 +70,7 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_workspace_bytes.argtypes = [vp]
     lib.capdec_launch_count.restype = C.c_int64
     lib.capdec_launch_count.argtypes = [vp]
-    lib.capdec_set_grad_ready_events.argtypes = [vp, vp, vp, vp]
+    lib.capdec_set_grad_ready_events.argtypes = [vp, C.POINTER(vp), i32]
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.capdec_bind_params.argtypes = [vp, C.POINTER(CapdecParams), vp]

@@ -119,7 +119,7 @@ class DecoderBase {
   long launches = 0;
   int device = 0;
   // caller-owned events recorded by train_bwd when a group of gradients is final (capdec_set_grad_ready_events)
-  cudaEvent_t grad_ready[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t grad_ready[4] = {nullptr, nullptr, nullptr, nullptr};
   void mark_ready(int i, cudaStream_t s) {
     if (grad_ready[i]) cudaEventRecord(grad_ready[i], s);
   }
@@ -636,14 +636,16 @@ template <typename T> class Decoder : public DecoderBase {
     }
     prof.mark("bwd.recurrence", s);
     // weight gradients of the gate GEMM, batched over all steps
+    // ordered so that the two 16 MB row blocks of d lstm_w are final first: their all-reduce runs behind the rest
     OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
-    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
-    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
-    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
+    mark_ready(1, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
     sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
     OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
+    mark_ready(2, s);  // lstm_w rows [E, E+H) (global-image rows) are final
+    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
+    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
     OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
-    mark_ready(1, s);  // lstm_w, lstm_b, fc_xs_w, fc_xs_b are final
+    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
     if (dg) {
       GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
@@ -657,7 +659,7 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
-    mark_ready(2, s);  // word_embedding, out_fc_bias are final: nothing is left
+    mark_ready(3, s);  // lstm_w word rows, lstm_b, fc_xs_w, fc_xs_b, word_embedding, out_fc_bias: everything is final
     prof.mark("bwd.gate_wgrad_embed", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
@@ -966,11 +968,10 @@ int capdec_destroy(capdec_handle h) {
   return 0;
 }
 
-int capdec_set_grad_ready_events(capdec_handle h, void* head_ready, void* gates_ready, void* embedding_ready) {
+int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n) {
   if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
-  h->impl->grad_ready[0] = (cudaEvent_t)head_ready;
-  h->impl->grad_ready[1] = (cudaEvent_t)gates_ready;
-  h->impl->grad_ready[2] = (cudaEvent_t)embedding_ready;
+  if (n < 0 || n > 4 || (n > 0 && !events)) { set_error("capdec_set_grad_ready_events: need 0 <= n <= 4 events"); return -1; }
+  for (int i = 0; i < 4; ++i) h->impl->grad_ready[i] = (i < n) ? (cudaEvent_t)events[i] : nullptr;
   return 0;
 }
 

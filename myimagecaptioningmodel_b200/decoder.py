@@ -220,29 +220,34 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
-    # the gradient groups of capdec_set_grad_ready_events as (event index, first, last parameter name): contiguous
-    # ranges of store.flat_grad, in the order they become final during train_backward
-    GRAD_GROUPS = ((0, "fc_hs_w", "fc_e_b"), (0, "fc_v_w", "fc_k_b"), (1, "lstm_w", "fc_xs_b"),
-                   (2, "word_embedding", "out_fc_bias"))
+    N_GRAD_EVENTS = 4
 
     def grad_group_slices(self):
-        """[(event index, lo, hi)] element ranges of store.flat_grad for GRAD_GROUPS"""
-        st = self.store
-        out = []
-        for ev, first, last in self.GRAD_GROUPS:
-            lo = st.offsets[first]
-            hi = st.offsets[last] + (math.prod(st.shapes[last]) + 63) // 64 * 64
-            out.append((ev, lo, hi))
+        """[(event index, lo, hi)]: element ranges of store.flat_grad in the order capdec_train_bwd finalises them
+        (include/capdec.h, capdec_set_grad_ready_events); together they cover every parameter exactly once."""
+        st, cfg = self.store, self.cfg
+        E, H = cfg.embedding_size, cfg.hidden_dim
+
+        def span(first, last):
+            return st.offsets[first], st.offsets[last] + (math.prod(st.shapes[last]) + 63) // 64 * 64
+
+        lw = st.offsets["lstm_w"]
+        row = 4 * H
+        out = [(0,) + span("fc_hs_w", "fc_e_b"), (0,) + span("fc_v_w", "fc_k_b"),
+               (1, lw + (E + H) * row, lw + (E + 2 * H) * row),          # hidden-state rows
+               (2, lw + E * row, lw + (E + H) * row),                    # global-image rows
+               (3, lw, lw + E * row),                                    # word rows
+               (3,) + span("lstm_b", "fc_xs_b"), (3,) + span("word_embedding", "out_fc_bias")]
         return out
 
     def set_grad_ready_events(self, events) -> None:
-        """events: three recorded torch.cuda.Event (head, gates, embedding) or None to switch the marks off"""
+        """events: N_GRAD_EVENTS recorded torch.cuda.Event, or None to switch the marks off"""
         if events is None:
-            check(self.lib.capdec_set_grad_ready_events(self.handle, None, None, None), "capdec_set_grad_ready_events")
+            check(self.lib.capdec_set_grad_ready_events(self.handle, None, 0), "capdec_set_grad_ready_events")
             self._grad_events = None
             return
-        ptrs = [C.c_void_p(int(e.cuda_event)) for e in events]
-        check(self.lib.capdec_set_grad_ready_events(self.handle, *ptrs), "capdec_set_grad_ready_events")
+        arr = (C.c_void_p * len(events))(*[C.c_void_p(int(e.cuda_event)) for e in events])
+        check(self.lib.capdec_set_grad_ready_events(self.handle, arr, len(events)), "capdec_set_grad_ready_events")
         self._grad_events = list(events)   # keep them alive
 
     def profile(self, enable: bool = True) -> None:

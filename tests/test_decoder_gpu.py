@@ -338,6 +338,27 @@ def test_single_caption_and_degenerate_captions():
                          grad_tol=5e-2 if dtype == "bf16" else None)
 
 
+def test_gradient_groups_cover_the_flat_buffer_once():
+    """the ranges the data-parallel trainer all-reduces as train_bwd finalises them tile store.flat_grad exactly"""
+    eng = M.CaptionDecoderEngine(M.DecoderConfig(dtype="bf16", **MID), seed=0)
+    sl = sorted((lo, hi, ev) for ev, lo, hi in eng.grad_group_slices())
+    assert sl[0][0] == 0 and sl[-1][1] == eng.store.numel_padded
+    for (lo0, hi0, _), (lo1, hi1, _) in zip(sl[:-1], sl[1:]):
+        assert hi0 == lo1 and lo0 < hi0
+    assert {ev for _, _, ev in sl} == set(range(eng.N_GRAD_EVENTS))
+    evs = [torch.cuda.Event() for _ in range(eng.N_GRAD_EVENTS)]
+    for e in evs:
+        e.record()
+    eng.set_grad_ready_events(evs)
+    ocfg = R.DecoderConfig(softmax_axis="position", **MID)
+    g, P, cap = synth.make_batch(ocfg, 5, 3)
+    eng.train_forward(g.cuda(), P.cuda(), cap.cuda())
+    eng.train_backward()
+    torch.cuda.synchronize()
+    assert all(e.query() for e in evs)
+    eng.set_grad_ready_events(None)
+
+
 def test_reference_shaped_interface():
     """Decoder.call / ImageCaptionModel mirror model:40-135, 161-189 (shapes, dtypes, errors, autograd)."""
     ocfg = R.DecoderConfig(softmax_axis="position", **SMALL)
