@@ -289,12 +289,11 @@ def main_ours(args):
 
     for c in consumed:
         c.record()
-    for i in range(args.warmup):
-        step_resident(i)
-    sync()
-    l0 = eng.launch_count
-    with ClockSampler(local_rank) as clocks:
-        time.sleep(0.05)                                  # first nvidia-smi line
+    with ClockSampler(local_rank) as clocks:              # started before the warm-up: nvidia-smi needs a moment
+        for i in range(args.warmup):
+            step_resident(i)
+        sync()
+        l0 = eng.launch_count
         with clocks.window():
             ms = timed_region(step_resident, args.steps, sync, barrier)
         launches = eng.launch_count - l0

@@ -64,6 +64,15 @@ def param_shapes(cfg: DecoderConfig) -> Dict[str, tuple]:
     }
 
 
+# Order of the tensors inside the flat buffers (the C structs address every tensor by name, so any order works): the
+# order in which capdec_train_bwd finalises the gradients, so that each group of capdec_set_grad_ready_events is ONE
+# contiguous range = one all-reduce call; lstm_w comes last because its word rows (the first rows) are final last.
+FLAT_ORDER = ["fc_hs_w", "fc_hs_b", "fc_p_w", "fc_p_b", "fc_g_w", "fc_g_b", "fc_s_w", "fc_s_b", "fc_a_w", "fc_a_b",
+              "fc_o_w", "fc_o_b", "fc_e_w", "fc_e_b", "fc_v_w", "fc_v_b", "fc_k_w", "fc_k_b",
+              "lstm_b", "fc_xs_w", "fc_xs_b", "word_embedding", "out_fc_bias", "lstm_w"]
+assert sorted(FLAT_ORDER) == sorted(PARAM_NAMES)
+
+
 class ParameterStore:
     """All decoder parameters (and their gradients) as views into two flat fp32 device buffers, so that a
     data-parallel gradient all-reduce is a single NCCL call.  Every view starts on a 256-byte boundary."""
@@ -74,7 +83,7 @@ class ParameterStore:
         self.shapes = param_shapes(cfg)
         self.offsets = {}
         off = 0
-        for n in PARAM_NAMES:
+        for n in FLAT_ORDER:
             self.offsets[n] = off
             off += (math.prod(self.shapes[n]) + 63) // 64 * 64
         self.numel_padded = off
@@ -233,11 +242,10 @@ class CaptionDecoderEngine:
 
         lw = st.offsets["lstm_w"]
         row = 4 * H
-        out = [(0,) + span("fc_hs_w", "fc_e_b"), (0,) + span("fc_v_w", "fc_k_b"),
-               (1, lw + (E + H) * row, lw + (E + 2 * H) * row),          # hidden-state rows
-               (2, lw + E * row, lw + (E + H) * row),                    # global-image rows
-               (3, lw, lw + E * row),                                    # word rows
-               (3,) + span("lstm_b", "fc_xs_b"), (3,) + span("word_embedding", "out_fc_bias")]
+        out = [(0,) + span("fc_hs_w", "fc_k_b"),                         # head parameters and fc_v, fc_k
+               (1, lw + (E + H) * row, lw + (E + 2 * H) * row),          # lstm_w hidden-state rows
+               (2, lw + E * row, lw + (E + H) * row),                    # lstm_w global-image rows
+               (3, st.offsets["lstm_b"], lw + E * row)]                  # lstm_b .. out_fc_bias and the lstm_w word rows
         return out
 
     def set_grad_ready_events(self, events) -> None:
