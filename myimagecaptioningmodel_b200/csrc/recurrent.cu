@@ -507,6 +507,24 @@ __device__ __forceinline__ void cell_load(const SeqBwdParams& p, int t, int mt, 
     it.dhr[1] = ldcg4(hr + 4);
   }
 }
+// L2 prefetch of the operands of item i at step t that come from HBM (everything except the running state): issued while
+// the epilogue warps wait for the GEMM phase of step t+1, so that the cell phase finds them in L2 (no register cost)
+__device__ __forceinline__ void cell_prefetch(const SeqBwdParams& p, int t, int mt, int i) {
+  const int vec_per_row = p.H / 8;
+  if (i >= 128 * vec_per_row) return;
+  const int row = mt * 128 + i / vec_per_row;
+  if (row >= p.B) return;
+  const int h0 = (i % vec_per_row) * 8;
+  const long BH = (long)p.B * p.H;
+  const long m = (long)t * p.B + row;
+  const long o = (long)row * p.H + h0;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gact + m * 4 * p.H + 4 * h0));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dHhead + m * p.H + h0));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dChead + m * p.H + h0));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cs + (long)t * BH + o));   // c_{t-1}; c_t was this step's c_{t-1}
+  if (t + 1 < p.T) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dHprev + (m + p.B) * p.H + h0));
+}
+
 // d gates -> dG (needed by the other CTAs before the GEMM phase); the new running d c is left in it.dcr
 __device__ __forceinline__ void cell_compute_store_dg(const SeqBwdParams& p, bool last, CellItem& it) {
   if (it.m < 0) return;
@@ -681,6 +699,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (t == 0) break;
+      // next step's cell operands on their way from HBM to L2 while the GEMM phase runs
+      for (int mt = y; mt < p.n_mtiles; mt += MG)
+        for (int i0 = cta * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) cell_prefetch(p, t - 1, mt, i0);
       // ---- phase G epilogue: partial d h_{t-1} -> fp32 reduce-add into dhrec[(t-1) & 1] ----
       for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
         const int buf = it & 1;
