@@ -119,7 +119,7 @@ class DecoderBase {
   long launches = 0;
   int device = 0;
   // caller-owned events recorded by train_bwd when a group of gradients is final (capdec_set_grad_ready_events)
-  cudaEvent_t grad_ready[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t grad_ready[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void mark_ready(int i, cudaStream_t s) {
     if (grad_ready[i]) cudaEventRecord(grad_ready[i], s);
   }
@@ -635,23 +635,8 @@ template <typename T> class Decoder : public DecoderBase {
       }
     }
     prof.mark("bwd.recurrence", s);
-    // weight gradients of the gate GEMM, batched over all steps
-    // ordered so that the two 16 MB row blocks of d lstm_w are final first: their all-reduce runs behind the rest
-    OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
-    mark_ready(1, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
-    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
-    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
-    mark_ready(2, s);  // lstm_w rows [E, E+H) (global-image rows) are final
-    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
-    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
-    OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
-    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
-    if (dg) {
-      GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
-      c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
-      c.epi.out_f32 = 1;
-      OK(gemm<T>(gc, c));
-    }
+    // After the BPTT everything left is independent; it is ordered so that the gradients become final in large groups
+    // early and a small one last (capdec_set_grad_ready_events): each group's all-reduce runs behind the remaining work.
     {
       GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
       c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
@@ -659,7 +644,24 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
-    mark_ready(3, s);  // lstm_w word rows, lstm_b, fc_xs_w, fc_xs_b, word_embedding, out_fc_bias: everything is final
+    mark_ready(1, s);  // word_embedding, out_fc_bias are final
+    // weight gradients of the gate GEMM, batched over all steps
+    OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
+    mark_ready(2, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
+    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
+    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
+    mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
+    if (dg) {
+      GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
+      c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
+      c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
+    OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
+    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
+    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
+    mark_ready(4, s);  // lstm_b, fc_xs_w, fc_xs_b and the lstm_w word rows: everything is final
     prof.mark("bwd.gate_wgrad_embed", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
@@ -970,8 +972,8 @@ int capdec_destroy(capdec_handle h) {
 
 int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n) {
   if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
-  if (n < 0 || n > 4 || (n > 0 && !events)) { set_error("capdec_set_grad_ready_events: need 0 <= n <= 4 events"); return -1; }
-  for (int i = 0; i < 4; ++i) h->impl->grad_ready[i] = (i < n) ? (cudaEvent_t)events[i] : nullptr;
+  if (n < 0 || n > 5 || (n > 0 && !events)) { set_error("capdec_set_grad_ready_events: need 0 <= n <= 5 events"); return -1; }
+  for (int i = 0; i < 5; ++i) h->impl->grad_ready[i] = (i < n) ? (cudaEvent_t)events[i] : nullptr;
   return 0;
 }
 

@@ -69,7 +69,7 @@ def param_shapes(cfg: DecoderConfig) -> Dict[str, tuple]:
 # contiguous range = one all-reduce call; lstm_w comes last because its word rows (the first rows) are final last.
 FLAT_ORDER = ["fc_hs_w", "fc_hs_b", "fc_p_w", "fc_p_b", "fc_g_w", "fc_g_b", "fc_s_w", "fc_s_b", "fc_a_w", "fc_a_b",
               "fc_o_w", "fc_o_b", "fc_e_w", "fc_e_b", "fc_v_w", "fc_v_b", "fc_k_w", "fc_k_b",
-              "lstm_b", "fc_xs_w", "fc_xs_b", "word_embedding", "out_fc_bias", "lstm_w"]
+              "word_embedding", "out_fc_bias", "lstm_b", "fc_xs_w", "fc_xs_b", "lstm_w"]
 assert sorted(FLAT_ORDER) == sorted(PARAM_NAMES)
 
 
@@ -229,7 +229,7 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
-    N_GRAD_EVENTS = 4
+    N_GRAD_EVENTS = 5
 
     def grad_group_slices(self):
         """[(event index, lo, hi)]: element ranges of store.flat_grad in the order capdec_train_bwd finalises them
@@ -243,9 +243,10 @@ class CaptionDecoderEngine:
         lw = st.offsets["lstm_w"]
         row = 4 * H
         out = [(0,) + span("fc_hs_w", "fc_k_b"),                         # head parameters and fc_v, fc_k
-               (1, lw + (E + H) * row, lw + (E + 2 * H) * row),          # lstm_w hidden-state rows
-               (2, lw + E * row, lw + (E + H) * row),                    # lstm_w global-image rows
-               (3, st.offsets["lstm_b"], lw + E * row)]                  # lstm_b .. out_fc_bias and the lstm_w word rows
+               (1,) + span("word_embedding", "out_fc_bias"),
+               (2, lw + (E + H) * row, lw + (E + 2 * H) * row),          # lstm_w hidden-state rows
+               (3, lw + E * row, lw + (E + H) * row),                    # lstm_w global-image rows
+               (4, st.offsets["lstm_b"], lw + E * row)]                  # lstm_b, fc_xs_* and the lstm_w word rows
         return out
 
     def set_grad_ready_events(self, events) -> None:

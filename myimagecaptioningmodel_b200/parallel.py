@@ -65,7 +65,7 @@ class DataParallelTrainer:
         if self.world == 1 or not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
             return
         self._comm = torch.cuda.Stream()
-        self._events = [torch.cuda.Event() for _ in range(getattr(eng, "N_GRAD_EVENTS", 4))]
+        self._events = [torch.cuda.Event() for _ in range(getattr(eng, "N_GRAD_EVENTS", 5))]
         for e in self._events:
             e.record()                      # creates the underlying cudaEvent_t
         eng.set_grad_ready_events(self._events)
