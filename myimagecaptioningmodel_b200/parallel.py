@@ -12,6 +12,7 @@ host logic is testable on CPU with the gloo backend (tests/test_parallel_cpu.py 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -48,13 +49,46 @@ class DataParallelTrainer:
             loss = loss_buf[2].clone()
             dist.all_reduce(loss, group=self.group)
             loss /= self.world
-        else:
-            tot = loss_buf[:2].clone()
-            dist.all_reduce(tot, group=self.group)           # (sum ce*mask, sum mask) over all ranks
-            inv = (1.0 / tot[1]).reshape(1)
-            eng.train_backward(1.0, inv, want_dg=want_input_grads, want_dP=want_input_grads)
-            loss = tot[0] / tot[1]
+            self._all_reduce_grads()
+            return loss
+        if not getattr(self, "_overlap_ready", False):
+            self._setup_overlap()
+            self._overlap_ready = True
+        if self._overlap and not want_input_grads:
+            return self._forward_backward_overlapped(loss_buf)
+        tot = loss_buf[:2].clone()
+        dist.all_reduce(tot, group=self.group)               # (sum ce*mask, sum mask) over all ranks
+        inv = (1.0 / tot[1]).reshape(1)
+        eng.train_backward(1.0, inv, want_dg=want_input_grads, want_dP=want_input_grads)
+        loss = tot[0] / tot[1]
         self._all_reduce_grads()
+        return loss
+
+    def _forward_backward_overlapped(self, loss_buf):
+        """Global token normalisation without a synchronisation point between forward and backward: the backward pass
+        runs with the LOCAL normaliser 1 / n_r straight away; the (sum ce*mask, sum mask) exchange runs beside it on the
+        communication stream, and every gradient group is multiplied by n_r / n_global there before its all-reduce:
+        sum_r (n_r / n) * (g_r / n_r) = (sum_r g_r) / n, the single-device gradient at the global batch."""
+        eng = self.engine
+        main = torch.cuda.current_stream()
+        self._fwd_done.record(main)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._fwd_done)
+            tot = loss_buf[:2].clone()
+            n_local = tot[1].clone()
+            dist.all_reduce(tot, group=self.group)
+            weight = n_local / tot[1]
+            loss = tot[0] / tot[1]
+        eng.train_backward(1.0, None, want_dg=False, want_dP=False)
+        if os.environ.get("CAPDEC_DP_DEBUG_SYNC") == "1":
+            torch.cuda.synchronize()
+        flat = eng.store.flat_grad
+        with torch.cuda.stream(self._comm):
+            for ev, lo, hi in self._slices:
+                self._comm.wait_event(self._events[ev])
+                flat[lo:hi].mul_(weight)
+                dist.all_reduce(flat[lo:hi], group=self.group)
+        main.wait_stream(self._comm)
         return loss
 
     def _setup_overlap(self):
@@ -70,6 +104,7 @@ class DataParallelTrainer:
             e.record()                      # creates the underlying cudaEvent_t
         eng.set_grad_ready_events(self._events)
         self._slices = eng.grad_group_slices()
+        self._fwd_done = torch.cuda.Event()
         self._overlap = True
 
     def _all_reduce_grads(self):

@@ -32,16 +32,18 @@ lb, _ = ref.train_forward(g, P, cap)
 ref.train_backward()
 torch.cuda.synchronize()
 a, b = eng.store.flat_grad.double(), ref.store.flat_grad.double()
-worst = 0.0
+worst, worst_name = 0.0, ""
 for name in M.PARAM_NAMES:
     x, y = eng.store.grads[name].double(), ref.store.grads[name].double()
     if float(y.abs().max()) == 0.0 or name == "fc_a_b":
         continue
-    worst = max(worst, float((x - y).norm() / y.norm()))
+    e = float((x - y).norm() / y.norm())
+    if e > worst:
+        worst, worst_name = e, name
 err = float((a - b).norm() / b.norm())
 dl = abs(float(loss) - float(lb[2])) / abs(float(lb[2]))
-print("rank %d: overlap=%s  loss rel diff %.2e  flat grad rel err %.2e  worst tensor %.2e" % (
-    rank, getattr(trainer, "_overlap", None), dl, err, worst), flush=True)
+print("rank %d: overlap=%s  loss rel diff %.2e  flat grad rel err %.2e  worst tensor %.2e (%s)" % (
+    rank, getattr(trainer, "_overlap", None), dl, err, worst, worst_name), flush=True)
 assert dl < 1e-3 and err < 1e-2 and worst < 2e-2
 dist.barrier()
 if rank == 0:
