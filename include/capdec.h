@@ -81,6 +81,18 @@ typedef struct capdec_grads {
   float* out_fc_bias;
 } capdec_grads;
 
+/* The feature adaptor between the encoder and the decoder: ImageCaptionModel._img2feature from the encoder output on
+ * (model:193-199).  fp32, PaddlePaddle [in, out] layouts, X = encoder_channel
+ * (config.py:52, 1280). */
+typedef struct capdec_adaptor_params {
+  const float* fc_img_w;  const float* fc_img_b;   /* model:197 [X,H],[H]  img_embed  = relu(fc(map^T))          */
+  const float* fc_glob_w; const float* fc_glob_b;  /* model:199 [X,H],[H]  img_global = relu(fc(mean_k(map^T)))  */
+} capdec_adaptor_params;
+typedef struct capdec_adaptor_grads {
+  float* fc_img_w;  float* fc_img_b;
+  float* fc_glob_w; float* fc_glob_b;
+} capdec_adaptor_grads;
+
 typedef struct capdec_handle_s* capdec_handle;
 
 const char* capdec_last_error(void);
@@ -106,6 +118,7 @@ int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream);
 
 /* Teacher-forced forward: Decoder(mode='train').call + training_network loss wiring (model:50-130, 161-183).
  *   global_img_feat [B,H] f32, p_img_feat [B,k,H] f32, caption [B,sentence_length] int64
+ *   (both feature pointers NULL: use the features staged in the handle by capdec_img2feature for the same B)
  *   logits_out      [B,T,V] f32 batch-major (model:129-130) or NULL when only the loss is wanted
  *   loss_out        4 floats on the device: {sum(ce*mask), sum(mask), loss = ratio, 1/sum(mask)}            */
 int capdec_train_fwd(capdec_handle h, const float* global_img_feat, const float* p_img_feat, const int64_t* caption,
@@ -137,12 +150,40 @@ int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n
 int capdec_decode(capdec_handle h, const float* global_img_feat, const float* p_img_feat, int32_t B, int32_t beam,
                   int32_t finish_on_stop, int32_t* ids_out, float* scores_out, float* ids_f32_out, void* stream);
 
+/* ---- the callers either side of the decoder ---------------------------------------------------- */
+
+/* Converts the adaptor's fp32 parameters into the handle's operand layout (call again after every optimizer update).
+ * The bias pointers are read directly by later calls and must stay valid. */
+int capdec_bind_adaptor(capdec_handle h, int32_t encoder_channel, const capdec_adaptor_params* p, void* stream);
+
+/* ImageCaptionModel._img2feature after the encoder (model:195-199):
+ *   enc_map [B, X, k] f32 = the encoder output [B,1280,7,7] reshaped (model:195; cast model:194 is a no-op for f32)
+ *   -> p_img_feat [B,k,H] = relu(fc(transpose(enc_map)))  and  global_img_feat [B,H] = relu(fc(mean over k)).
+ * The results are STAGED in the handle in its storage type: a following capdec_train_fwd / capdec_decode called with
+ * NULL feature pointers and the same B consumes them without a round trip through fp32.  p_img_feat_out /
+ * global_img_feat_out (f32, either may be NULL) receive copies for callers that want to look at them. */
+int capdec_img2feature(capdec_handle h, const float* enc_map, int32_t B, float* p_img_feat_out,
+                       float* global_img_feat_out, void* stream);
+
+/* Backward of the staged adaptor, after capdec_img2feature -> capdec_train_fwd(NULL, NULL, ..) -> capdec_train_bwd:
+ * the four parameter gradients are overwritten; d_enc_map [B, X, k] f32 (or NULL) is the gradient handed to the encoder
+ * (config.py:50 encoder_trainable). */
+int capdec_img2feature_bwd(capdec_handle h, float* d_enc_map, const capdec_adaptor_grads* g, void* stream);
+
+/* One step of fluid.optimizer.Adam behind opt.minimize(loss) (train.py:26-31, 44-45) over a flat fp32 buffer of n
+ * elements, PaddlePaddle 1.8 update rule:
+ *   lr_t = lr * sqrt(1 - beta2_pow) / (1 - beta1_pow)       beta?_pow = beta?^t of THIS step (t = 1, 2, ..)
+ *   m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;  param -= lr_t * m / (sqrt(v) + epsilon)
+ * clip_value > 0 applies GradientClipByValue(clip_value) to g first (train.py:41-42); 0 = off (config.py:36). */
+int capdec_adam_step(float* param, const float* grad, float* moment1, float* moment2, int64_t n, float lr, float beta1,
+                     float beta2, float epsilon, float beta1_pow, float beta2_pow, float clip_value, void* stream);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks) ------------------------------------------ */
 
 /* C[M,N] = act(A.B^T + bias + addend).  dtype: element type of A, B, addend, dact_y and (unless out_f32) C.
  *   majors bit 0: A is stored [K,M] (MN-major) instead of [M,K];  bit 1: B is stored [K,N] instead of [N,K]
  *   (0 = data-grad form, 2 = forward fc with a PaddlePaddle [in,out] weight as B, 3 = weight-grad form)
- *   act: 0 none, 1 tanh, 2 multiply by (1 - y^2) with y = dact_y;  atomic: fp32 atomicAdd into C (split-K)
+ *   act: 0 none, 1 tanh, 2 multiply by (1 - y^2) with y = dact_y, 5 relu, 6 multiply by [y > 0];  atomic: fp32 atomicAdd into C (split-K)
  *   force_simt: route a bf16 GEMM through the SIMT kernel instead of tcgen05 (cross-check)                     */
 int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,

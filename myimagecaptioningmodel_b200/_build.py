@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcapdec.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "pointwise.cu", "attention.cu", "loss.cu", "recurrent.cu", "decoder.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "pointwise.cu", "attention.cu", "loss.cu", "recurrent.cu", "adaptor.cu", "decoder.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", os.path.join("..", "..", "include", "capdec.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -13,11 +13,14 @@ PARAM_NAMES = [
     "fc_e_w", "fc_e_b", "word_embedding", "out_fc_bias",
 ]
 
+ADAPTOR_NAMES = ["fc_img_w", "fc_img_b", "fc_glob_w", "fc_glob_b"]     # model:197, 199
+
 EXPORTS = [
     "capdec_last_error", "capdec_version", "capdec_create", "capdec_destroy", "capdec_workspace_bytes",
     "capdec_launch_count", "capdec_bind_params", "capdec_train_fwd", "capdec_train_bwd", "capdec_decode",
     "capdec_gemm", "capdec_attention_fwd", "capdec_attention_bwd", "capdec_lstm_cell_fwd", "capdec_beam_step",
     "capdec_profile", "capdec_profile_report", "capdec_set_grad_ready_events",
+    "capdec_bind_adaptor", "capdec_img2feature", "capdec_img2feature_bwd", "capdec_adam_step",
 ]
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
@@ -36,6 +39,14 @@ class CapdecParams(C.Structure):
 
 class CapdecGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_NAMES]
+
+
+class CapdecAdaptorParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ADAPTOR_NAMES]
+
+
+class CapdecAdaptorGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ADAPTOR_NAMES]
 
 
 class CapdecError(RuntimeError):
@@ -77,6 +88,10 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_train_fwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     lib.capdec_train_bwd.argtypes = [vp, f32, vp, vp, vp, C.POINTER(CapdecGrads), vp]
     lib.capdec_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.capdec_bind_adaptor.argtypes = [vp, i32, C.POINTER(CapdecAdaptorParams), vp]
+    lib.capdec_img2feature.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.capdec_img2feature_bwd.argtypes = [vp, vp, C.POINTER(CapdecAdaptorGrads), vp]
+    lib.capdec_adam_step.argtypes = [vp, vp, vp, vp, i64] + [f32] * 7 + [vp]
     lib.capdec_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, i32, i32,
                                 i32, i32, vp]
     lib.capdec_attention_fwd.argtypes = [i32, i32, i32, i32, i32, i64, i64, i32] + [vp] * 12

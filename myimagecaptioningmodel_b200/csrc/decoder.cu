@@ -115,6 +115,9 @@ class DecoderBase {
                         cudaStream_t s) = 0;
   virtual int decode(const float* g, const float* P, int B, int beam, int finish, int32_t* ids, float* scores,
                      float* ids_f32, cudaStream_t s) = 0;
+  virtual int bind_adaptor(int X, const capdec_adaptor_params* p, cudaStream_t s) = 0;
+  virtual int img2feature(const float* enc_map, int B, float* P_out, float* g_out, cudaStream_t s) = 0;
+  virtual int img2feature_bwd(float* d_enc_map, const capdec_adaptor_grads* gr, cudaStream_t s) = 0;
   size_t ws_bytes = 0;
   long launches = 0;
   int device = 0;
@@ -240,12 +243,25 @@ template <typename T> class Decoder : public DecoderBase {
   // ------------------------------------------------------------------------------------------------------------
   int image_projections(GemmContext& gc, LaunchCtx lc, const float* g, const float* P, int B) {
     const size_t e = sizeof(T);
+    if (!g && !P) {
+      // features staged by capdec_img2feature: gT / PT already hold them in the storage type
+      if (!staged || staged_B != B) {
+        set_error("no staged features for %d images: call capdec_img2feature first (or pass the features)", B);
+        return -1;
+      }
+    } else if (!g || !P) {
+      set_error("global_img_feat and p_img_feat must both be given, or both be NULL (staged features)");
+      return -1;
+    }
     OK(gT.ensure(e * (size_t)B * H, &ws_bytes));
     OK(PT.ensure(e * (size_t)B * k * H, &ws_bytes));
     OK(keys.ensure(e * (size_t)B * k * H, &ws_bytes));
     OK(vals.ensure(e * (size_t)B * k * H, &ws_bytes));
-    convert_from_f32<T>(lc, g, gT.as<T>(), (long)B * H);
-    convert_from_f32<T>(lc, P, PT.as<T>(), (long)B * k * H);
+    if (g) {
+      convert_from_f32<T>(lc, g, gT.as<T>(), (long)B * H);
+      convert_from_f32<T>(lc, P, PT.as<T>(), (long)B * k * H);
+      staged = false;
+    }
     GemmCall c;
     c.A = PT.p; c.lda = H; c.M = B * k; c.N = H; c.K = H; c.ldb = 2 * H; c.b_mn = true; c.ldc = H;
     c.B = w_kv_n.p; c.C = vals.p; c.epi.bias = prm.fc_v_b; c.epi.act = ACT_TANH;            // model:52
@@ -274,6 +290,91 @@ template <typename T> class Decoder : public DecoderBase {
     return gemm<T>(gc, c);
   }
 
+  // ------------------------------------------------------------------------------------------------------------
+  // Feature adaptor, ImageCaptionModel._img2feature from the encoder map on (model:193-199)
+  int bind_adaptor(int X, const capdec_adaptor_params* p, cudaStream_t s) override {
+    if (X <= 0 || X % 8) { set_error("capdec_bind_adaptor: encoder_channel must be a positive multiple of 8"); return -1; }
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    Xc = X; aprm = *p;
+    OK(w_img_n.ensure(e * (size_t)X * H, &ws_bytes));
+    OK(w_glob_n.ensure(e * (size_t)X * H, &ws_bytes));
+    ConvertTable tab;   // [in = X, out = H] kept as is: MN-major B operand forward, K-major B operand backward
+    tab.add(p->fc_img_w, H, w_img_n.as<T>(), H, X, H);
+    tab.add(p->fc_glob_w, H, w_glob_n.as<T>(), H, X, H);
+    const int rc = multi_convert<T>(lc, tab);
+    if (rc < 0) return -1;
+    if (rc > 0)
+      for (int j = 0; j < tab.n; ++j)
+        copy2d_from_f32<T>(lc, tab.job[j].src, tab.job[j].lds, reinterpret_cast<T*>(tab.job[j].dst), tab.job[j].ldd,
+                           tab.job[j].rows, tab.job[j].cols);
+    CUDA_OK(cudaGetLastError());
+    adaptor_bound = true;
+    return 0;
+  }
+
+  int img2feature(const float* enc_map, int B, float* P_out, float* g_out, cudaStream_t s) override {
+    if (!adaptor_bound) { set_error("capdec_img2feature: adaptor parameters not bound"); return -1; }
+    if (B <= 0) { set_error("capdec_img2feature: empty batch"); return -1; }
+    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const int X = Xc;
+    prof.mark("^adaptor", s);
+    OK(gT.ensure(e * (size_t)B * H, &ws_bytes));
+    OK(PT.ensure(e * (size_t)B * k * H, &ws_bytes));
+    OK(imgT.ensure(e * (size_t)B * k * X, &ws_bytes));
+    OK(meanT.ensure(e * (size_t)B * X, &ws_bytes));
+    // reshape + transpose (model:195-196) and reduce_mean over the positions (model:198): the map is read once
+    OK(map_to_rows<T>(lc, enc_map, B, X, k, imgT.as<T>(), meanT.as<T>()));
+    OK(fc(gc, imgT.p, X, w_img_n.as<T>(), H, aprm.fc_img_b, PT.p, H, B * k, H, X, ACT_RELU));      // model:197
+    OK(fc(gc, meanT.p, X, w_glob_n.as<T>(), H, aprm.fc_glob_b, gT.p, H, B, H, X, ACT_RELU));       // model:199
+    if (P_out) convert_to_f32<T>(lc, PT.as<T>(), P_out, (long)B * k * H);
+    if (g_out) convert_to_f32<T>(lc, gT.as<T>(), g_out, (long)B * H);
+    prof.mark("adaptor.fwd", s);
+    launches += gc.launches;
+    CUDA_OK(cudaGetLastError());
+    staged = true; staged_B = B; have_dz = false;
+    return 0;
+  }
+
+  int img2feature_bwd(float* d_enc_map, const capdec_adaptor_grads* gr, cudaStream_t s) override {
+    if (!have_dz || !staged) {
+      set_error("capdec_img2feature_bwd: needs capdec_img2feature -> capdec_train_fwd(NULL features) -> capdec_train_bwd first");
+      return -1;
+    }
+    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    LaunchCtx lc{s, &launches};
+    const size_t e = sizeof(T);
+    const int X = Xc, B = staged_B;
+    const capdec_adaptor_grads& G = *gr;
+    prof.mark("^adaptor_bwd", s);
+    ZeroTable zt;
+    zt.add(G.fc_img_w, (long)X * H); zt.add(G.fc_img_b, H); zt.add(G.fc_glob_w, (long)X * H); zt.add(G.fc_glob_b, H);
+    multi_zero(lc, zt);
+    colsum_add<T>(lc, dzp.as<T>(), H, (long)B * k, H, G.fc_img_b);
+    OK(wgrad(gc, imgT.p, X, X, dzp.p, H, H, B * k, G.fc_img_w, H));
+    colsum_add<T>(lc, dzg.as<T>(), H, (long)B, H, G.fc_glob_b);
+    OK(wgrad(gc, meanT.p, X, X, dzg.p, H, H, B, G.fc_glob_w, H));
+    if (d_enc_map) {
+      // gradient handed to the encoder (config.py:50 encoder_trainable): through both fc layers, then back to [B, X, k]
+      OK(dimg.ensure(e * (size_t)B * k * X, &ws_bytes));
+      OK(dmean.ensure(4 * (size_t)B * X, &ws_bytes));
+      GemmCall c;
+      c.A = dzp.p; c.lda = H; c.B = w_img_n.p; c.ldb = H; c.C = dimg.p; c.ldc = X; c.M = B * k; c.N = X; c.K = H;
+      OK(gemm<T>(gc, c));
+      GemmCall d;
+      d.A = dzg.p; d.lda = H; d.B = w_glob_n.p; d.ldb = H; d.C = dmean.p; d.ldc = X; d.M = B; d.N = X; d.K = H;
+      d.epi.out_f32 = 1;
+      OK(gemm<T>(gc, d));
+      OK(rows_to_map<T>(lc, dimg.as<T>(), dmean.as<float>(), B, X, k, d_enc_map));
+    }
+    prof.mark("adaptor.bwd", s);
+    launches += gc.launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
   int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
                 cudaStream_t s) override {
     if (!bound) { set_error("capdec_train_fwd: parameters not bound"); return -1; }
@@ -283,6 +384,7 @@ template <typename T> class Decoder : public DecoderBase {
     const size_t e = sizeof(T);
     const long M = (long)B * Tt;
     last_B = B; last_cap = cap;
+    fwd_staged = (g == nullptr); have_dz = false;
     prof.mark("^fwd", s);
     OK(image_projections(gc, lc, g, P, B));
     prof.mark("fwd.image_kv", s);
@@ -602,6 +704,15 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
     }
+    if (fwd_staged) {
+      // the features came from the adaptor (capdec_img2feature): leave d(pre-ReLU img_embed) = d p_img_feat * [P > 0]
+      // in the handle for capdec_img2feature_bwd (model:197)
+      OK(dzp.ensure(e * (size_t)B * k * H, &ws_bytes));
+      GemmCall c;
+      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dzp.p; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
+      c.epi.act = ACT_DRELU; c.epi.dact_y = PT.p; c.epi.ld_y = H;
+      OK(gemm<T>(gc, c));
+    }
     prof.mark("bwd.image_kv", s);
     // fc_hs .. fc_e (incl. fc_a) and fc_v, fc_k are final: their all-reduce overlaps the BPTT.  (The per-image
     // projections depend on the attention gradients only, so they run here rather than at the end of the pass, where
@@ -656,6 +767,14 @@ template <typename T> class Decoder : public DecoderBase {
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
       c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
+    }
+    if (fwd_staged) {  // d(pre-ReLU img_global) for capdec_img2feature_bwd (model:199)
+      OK(dzg.ensure(e * (size_t)B * H, &ws_bytes));
+      GemmCall c;
+      c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dzg.p; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
+      c.epi.act = ACT_DRELU; c.epi.dact_y = gT.p; c.epi.ld_y = H;
+      OK(gemm<T>(gc, c));
+      have_dz = true;
     }
     OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
     OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
@@ -838,7 +957,7 @@ template <typename T> class Decoder : public DecoderBase {
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &ce_stats, &ce_rows, &xin, &d_hnew, &d_cnew, &d_ccur,
-            &d_state};
+            &d_state, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
   // captured step loop of capdec_decode for small batches
@@ -873,6 +992,11 @@ template <typename T> class Decoder : public DecoderBase {
       dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd, ce_stats, ce_rows;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
+  // feature adaptor (capdec_img2feature)
+  capdec_adaptor_params aprm{};
+  int Xc = 0, staged_B = 0;
+  bool adaptor_bound = false, staged = false, fwd_staged = false, have_dz = false;
+  DevBuf w_img_n, w_glob_n, imgT, meanT, dzp, dzg, dimg, dmean;
 };
 
 namespace {
@@ -1006,7 +1130,7 @@ int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream) {
 int capdec_train_fwd(capdec_handle h, const float* g, const float* P, const int64_t* caption, int32_t B,
                      float* logits_out, float* loss_out, void* stream) {
   if (check_device(h)) return -1;
-  if (!g || !P || !caption) { set_error("capdec_train_fwd: null input"); return -1; }
+  if (!caption) { set_error("capdec_train_fwd: null caption"); return -1; }
   return h->impl->train_fwd(g, P, caption, B, logits_out, loss_out, (cudaStream_t)stream);
 }
 
@@ -1020,8 +1144,41 @@ int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_de
 int capdec_decode(capdec_handle h, const float* g, const float* P, int32_t B, int32_t beam, int32_t finish_on_stop,
                   int32_t* ids_out, float* scores_out, float* ids_f32_out, void* stream) {
   if (check_device(h)) return -1;
-  if (!g || !P) { set_error("capdec_decode: null input"); return -1; }
   return h->impl->decode(g, P, B, beam, finish_on_stop, ids_out, scores_out, ids_f32_out, (cudaStream_t)stream);
+}
+
+int capdec_bind_adaptor(capdec_handle h, int32_t encoder_channel, const capdec_adaptor_params* p, void* stream) {
+  if (check_device(h)) return -1;
+  if (!p || !p->fc_img_w || !p->fc_img_b || !p->fc_glob_w || !p->fc_glob_b) {
+    set_error("capdec_bind_adaptor: null parameter pointer"); return -1;
+  }
+  return h->impl->bind_adaptor(encoder_channel, p, (cudaStream_t)stream);
+}
+
+int capdec_img2feature(capdec_handle h, const float* enc_map, int32_t B, float* p_img_feat_out,
+                       float* global_img_feat_out, void* stream) {
+  if (check_device(h)) return -1;
+  if (!enc_map) { set_error("capdec_img2feature: null encoder map"); return -1; }
+  return h->impl->img2feature(enc_map, B, p_img_feat_out, global_img_feat_out, (cudaStream_t)stream);
+}
+
+int capdec_img2feature_bwd(capdec_handle h, float* d_enc_map, const capdec_adaptor_grads* gr, void* stream) {
+  if (check_device(h)) return -1;
+  if (!gr || !gr->fc_img_w || !gr->fc_img_b || !gr->fc_glob_w || !gr->fc_glob_b) {
+    set_error("capdec_img2feature_bwd: null gradient pointer"); return -1;
+  }
+  return h->impl->img2feature_bwd(d_enc_map, gr, (cudaStream_t)stream);
+}
+
+int capdec_adam_step(float* param, const float* grad, float* moment1, float* moment2, int64_t n, float lr, float beta1,
+                     float beta2, float epsilon, float beta1_pow, float beta2_pow, float clip_value, void* stream) {
+  if (n < 0 || (n > 0 && (!param || !grad || !moment1 || !moment2))) { set_error("capdec_adam_step: null buffer"); return -1; }
+  if (!(beta1_pow < 1.f) || !(beta2_pow < 1.f)) { set_error("capdec_adam_step: beta powers must be < 1 (step >= 1)"); return -1; }
+  if (adam_step((cudaStream_t)stream, param, grad, moment1, moment2, (long)n, lr, beta1, beta2, epsilon, beta1_pow,
+                beta2_pow, clip_value)) {
+    set_error("capdec_adam_step: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -1;
+  }
+  return 0;
 }
 
 int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,

@@ -19,7 +19,9 @@ namespace capdec {
 //   ACT_ROWSTATS     no C output; per (row, 64-column group g) the partial max and sum exp(x - max) of x = acc + bias go to
 //                    stats_m / stats_s [M, stats_ld] at column g
 //   ACT_SOFTMAX_GRAD C = exp(x - row_lse[m]) - [n == row_tgt[m]]   (row_lse = +inf gives an all-zero row: masked position)
-enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_SOFTMAX_GRAD = 4 };
+//   ACT_RELU         max(x, 0)            (the feature adaptor, model:196-198)
+//   ACT_DRELU        x * [y > 0] with y = dact_y, the ReLU output
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_SOFTMAX_GRAD = 4, ACT_RELU = 5, ACT_DRELU = 6 };
 
 struct GemmEpi {
   const float* bias = nullptr;   // [N] fp32, added to every row
@@ -61,9 +63,14 @@ __device__ __forceinline__ float epi_value(float acc, int m, int n, const GemmEp
   if (e.bias) v += __ldg(e.bias + n);
   if (e.addend) v += to_f(reinterpret_cast<const T*>(e.addend)[(long)(e.add_mod > 0 ? m % e.add_mod : m) * e.ld_add + n]);
   if (e.act == ACT_TANH) v = tanh_t<fast_math<T>::value>(v);
+  if (e.act == ACT_RELU) v = fmaxf(v, 0.f);
   if (e.act == ACT_DTANH) {
     float y = to_f(reinterpret_cast<const T*>(e.dact_y)[(long)m * e.ld_y + n]);
     v *= (1.f - y * y);
+  }
+  if (e.act == ACT_DRELU) {
+    float y = to_f(reinterpret_cast<const T*>(e.dact_y)[(long)m * e.ld_y + n]);
+    v = y > 0.f ? v : 0.f;
   }
   return v;
 }

@@ -138,7 +138,7 @@ __device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, 
 // epilogue has only two warps per scheduler, so exposed latencies are what it costs).
 template <bool OUT_F32, bool FULL>
 __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float* bias_t, const bf16* add_p,
-                                                const bf16* y_p, bool do_tanh, float alpha, int left, uint8_t* dst_row,
+                                                const bf16* y_p, int fact, float alpha, int left, uint8_t* dst_row,
                                                 uint32_t swz, uint32_t chunk0, bool sm_grad = false, float lse_row = 0.f,
                                                 int tgt_rel = -1) {
   uint32_t r[32];
@@ -176,9 +176,12 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
           v[2 * i] += f.x; v[2 * i + 1] += f.y;
         }
       }
-      if (do_tanh) {
+      if (fact & 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
+      } else if (fact & 2) {  // ACT_RELU
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (sm_grad) {  // soft-max cross-entropy gradient; tgt_rel = target column relative to this 32-column chunk
 #pragma unroll
@@ -189,7 +192,11 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 f = __bfloat1622float2(h[i]);
-          v[2 * i] *= (1.f - f.x * f.x); v[2 * i + 1] *= (1.f - f.y * f.y);
+          if (fact & 4) {  // ACT_DRELU: y is the ReLU output
+            v[2 * i] = f.x > 0.f ? v[2 * i] : 0.f; v[2 * i + 1] = f.y > 0.f ? v[2 * i + 1] : 0.f;
+          } else {
+            v[2 * i] *= (1.f - f.x * f.x); v[2 * i + 1] *= (1.f - f.y * f.y);
+          }
         }
       }
       if (OUT_F32) {
@@ -390,10 +397,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
                                                            add_row * epi.ld_add + n0
                                                      : nullptr;
-          const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
+          const bf16* y_p = ((epi.act == ACT_DTANH || epi.act == ACT_DRELU) && row_ok)
                                 ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
                                 : nullptr;
-          const bool do_tanh = epi.act == ACT_TANH;
+          const int do_tanh = (epi.act == ACT_TANH ? 1 : 0) | (epi.act == ACT_RELU ? 2 : 0) | (epi.act == ACT_DRELU ? 4 : 0);
           const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
           const bool f32_out = epi.out_f32 || epi.atomic;
           const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;
@@ -747,10 +754,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bf16* add_p = (epi.addend && row_ok)
                               ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add + add_row * epi.ld_add + n0
                               : nullptr;
-      const bf16* y_p = (epi.act == ACT_DTANH && row_ok)
+      const bf16* y_p = ((epi.act == ACT_DTANH || epi.act == ACT_DRELU) && row_ok)
                             ? reinterpret_cast<const bf16*>(epi.dact_y) + bt * epi.batch_y + (long)row * epi.ld_y + n0
                             : nullptr;
-      const bool do_tanh = epi.act == ACT_TANH;
+      const int do_tanh = (epi.act == ACT_TANH ? 1 : 0) | (epi.act == ACT_RELU ? 2 : 0) | (epi.act == ACT_DRELU ? 4 : 0);
       const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
       const bool f32_out = epi.out_f32 || epi.atomic;
       const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;

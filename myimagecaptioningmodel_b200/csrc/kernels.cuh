@@ -80,6 +80,16 @@ void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* 
                        int pad, float* dEmb);
 void fill_f32(LaunchCtx c, float* p, float v, long n);
 
+// ---- adaptor.cu ----------------------------------------------------------------------------------
+// feature adaptor layout kernels (model:193-199): enc_map [B,X,k] fp32 -> rows [B*k,X], mean [B,X]; and the backward
+//   d map[b,x,j] = d rows[b*k+j, x] + d mean[b,x] / k.   X % 8 == 0, k <= 64.  Return 0 / -1.
+template <typename T> int map_to_rows(LaunchCtx c, const float* map, int B, int X, int k, T* rows, T* mean);
+template <typename T> int rows_to_map(LaunchCtx c, const T* drows, const float* dmean, int B, int X, int k, float* dmap);
+template <typename T> void convert_to_f32(LaunchCtx c, const T* src, float* dst, long n);   // n % 8 == 0
+// PaddlePaddle 1.8 Adam over one flat fp32 buffer (see adaptor.cu); clip > 0: GradientClipByValue(clip) on the gradient
+int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+              float eps, float beta1_pow, float beta2_pow, float clip);
+
 // ---- attention.cu ------------------------------------------------------------------------------
 struct AttnShape {
   int H, k;             // hidden size, number of image positions (k+1 attention positions)

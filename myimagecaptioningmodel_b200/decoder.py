@@ -17,7 +17,8 @@ from typing import Dict, Optional
 import torch
 
 from . import _capi
-from ._capi import CapdecConfig, CapdecGrads, CapdecParams, PARAM_NAMES, check, ptr, stream_ptr
+from ._capi import (ADAPTOR_NAMES, CapdecAdaptorGrads, CapdecAdaptorParams, CapdecConfig, CapdecGrads, CapdecParams,
+                    PARAM_NAMES, check, ptr, stream_ptr)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -135,6 +136,62 @@ class ParameterStore:
         return {n: self.params[n].detach().cpu().clone() for n in PARAM_NAMES}
 
 
+class AdaptorStore:
+    """Parameters and gradients of the feature adaptor `_img2feature` (model:197, 199) as views into two flat fp32
+    buffers of their own (the decoder's ParameterStore layout stays what capdec_set_grad_ready_events describes)."""
+
+    def __init__(self, cfg: DecoderConfig, encoder_channel: int, device):
+        X, H = int(encoder_channel), cfg.hidden_dim
+        if X <= 0 or X % 8:
+            raise ValueError("encoder_channel must be a positive multiple of 8, got {}".format(X))
+        self.encoder_channel = X
+        self.device = torch.device(device)
+        self.shapes = {"fc_img_w": (X, H), "fc_img_b": (H,), "fc_glob_w": (X, H), "fc_glob_b": (H,)}
+        self.offsets, off = {}, 0
+        for n in ADAPTOR_NAMES:
+            self.offsets[n] = off
+            off += (math.prod(self.shapes[n]) + 63) // 64 * 64
+        self.numel_padded = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=self.device)
+        view = lambda flat, n: flat[self.offsets[n]:self.offsets[n] + math.prod(self.shapes[n])].view(self.shapes[n])
+        self.params = {n: view(self.flat, n) for n in ADAPTOR_NAMES}
+        self.grads = {n: view(self.flat_grad, n) for n in ADAPTOR_NAMES}
+        self.c_params = CapdecAdaptorParams(*[C.c_void_p(self.params[n].data_ptr()) for n in ADAPTOR_NAMES])
+        self.c_grads = CapdecAdaptorGrads(*[C.c_void_p(self.grads[n].data_ptr()) for n in ADAPTOR_NAMES])
+
+    @property
+    def num_parameters(self) -> int:
+        return sum(math.prod(s) for s in self.shapes.values())
+
+    def init_reference(self, seed: int = 0, bias_scale: float = 0.0):
+        """Paddle fc defaults: Xavier-uniform weights, zero biases (bias_scale > 0: U(-s, s), used by tests)."""
+        gen = torch.Generator().manual_seed(seed + 104729)
+        with torch.no_grad():
+            for n in ADAPTOR_NAMES:
+                shape = self.shapes[n]
+                if n.endswith("_w"):
+                    t = (torch.rand(shape, generator=gen) * 2 - 1) * math.sqrt(6.0 / (shape[0] + shape[1]))
+                else:
+                    t = (torch.rand(shape, generator=gen) * 2 - 1) * bias_scale
+                self.params[n].copy_(t)
+        return self
+
+    def load(self, state: Dict[str, "torch.Tensor"]):
+        for n in ADAPTOR_NAMES:
+            if n not in state:
+                raise KeyError("missing parameter {}".format(n))
+            t = torch.as_tensor(state[n]).to(torch.float32)
+            if tuple(t.shape) != tuple(self.shapes[n]):
+                raise ValueError("parameter {} has shape {}, expected {}".format(n, tuple(t.shape), self.shapes[n]))
+            with torch.no_grad():
+                self.params[n].copy_(t)
+        return self
+
+    def state_dict(self):
+        return {n: self.params[n].detach().cpu().clone() for n in ADAPTOR_NAMES}
+
+
 class CaptionDecoderEngine:
     """One handle per (process, GPU): owns the C handle and the ParameterStore; thin, sync-free wrappers of the
     C-ABI entry points.  This is what bench.py and the reference-shaped classes below drive."""
@@ -208,9 +265,92 @@ class CaptionDecoderEngine:
                                         C.byref(self.store.c_grads), stream_ptr()), "capdec_train_bwd")
         return dg, dP
 
+    # ---- feature adaptor: _img2feature from the encoder map on (model:193-199) -----------------------------------
+    def attach_adaptor(self, encoder_channel: int = 1280, seed: Optional[int] = 0, bias_scale: float = 0.0):
+        """Create the adaptor parameters (config.py:52 encoder_channel) next to the decoder's; returns the store."""
+        self.adaptor = AdaptorStore(self.cfg, encoder_channel, self.device)
+        if seed is not None:
+            self.adaptor.init_reference(seed, bias_scale)
+        self._adaptor_bound = False
+        return self.adaptor
+
+    def bind_adaptor(self):
+        if getattr(self, "adaptor", None) is None:
+            raise _capi.CapdecError("no adaptor attached: call attach_adaptor(encoder_channel) first")
+        check(self.lib.capdec_bind_adaptor(self.handle, self.adaptor.encoder_channel, C.byref(self.adaptor.c_params),
+                                           stream_ptr()), "capdec_bind_adaptor")
+        self._adaptor_bound = True
+
+    def _check_map(self, enc_map):
+        ad = getattr(self, "adaptor", None)
+        if ad is None:
+            raise _capi.CapdecError("no adaptor attached: call attach_adaptor(encoder_channel) first")
+        B = enc_map.shape[0]
+        if enc_map.dim() == 4:                                     # [B,1280,7,7] as the encoder returns it (model:193)
+            enc_map = enc_map.reshape(B, enc_map.shape[1], -1)     # layers.reshape(img, [0, 0, -1]), model:195
+        if tuple(enc_map.shape) != (B, ad.encoder_channel, self.cfg.num_positions):
+            raise ValueError("expected an encoder map [B,{},{}], got {}".format(ad.encoder_channel,
+                                                                                self.cfg.num_positions,
+                                                                                tuple(enc_map.shape)))
+        if enc_map.dtype != torch.float32 or not enc_map.is_cuda or not enc_map.is_contiguous():
+            raise ValueError("the encoder map must be a contiguous float32 CUDA tensor")
+        return enc_map, B
+
+    def img2feature(self, enc_map, want_outputs: bool = False):
+        """capdec_img2feature: stages (p_img_feat, global_img_feat) in the handle; returns fp32 copies if asked."""
+        enc_map, B = self._check_map(enc_map)
+        if not self._adaptor_bound:
+            self.bind_adaptor()
+        P = g = None
+        if want_outputs:
+            P = torch.empty(B, self.cfg.num_positions, self.cfg.hidden_dim, dtype=torch.float32, device=self.device)
+            g = torch.empty(B, self.cfg.hidden_dim, dtype=torch.float32, device=self.device)
+        check(self.lib.capdec_img2feature(self.handle, ptr(enc_map), B, ptr(P), ptr(g), stream_ptr()),
+              "capdec_img2feature")
+        self._staged = (enc_map, B)
+        return P, g
+
+    def train_forward_map(self, enc_map, caption, want_logits: bool = False):
+        """_img2feature + teacher-forced forward from the encoder map (model:177-183 after the encoder)."""
+        self.img2feature(enc_map)
+        enc_map, B = self._staged
+        cfg = self.cfg
+        if tuple(caption.shape) != (B, cfg.sentence_length) or caption.dtype != torch.int64 or not caption.is_cuda \
+                or not caption.is_contiguous():
+            raise ValueError("caption must be a contiguous int64 CUDA tensor [B,{}]".format(cfg.sentence_length))
+        if not self._bound:
+            self.bind_params()
+        logits = None
+        if want_logits:
+            logits = torch.empty(B, cfg.train_steps, cfg.vocab_size, dtype=torch.float32, device=self.device)
+        self._caption_keepalive = (None, None, caption)
+        check(self.lib.capdec_train_fwd(self.handle, None, None, ptr(caption), B, ptr(logits), ptr(self._loss_buf),
+                                        stream_ptr()), "capdec_train_fwd")
+        return self._loss_buf, logits
+
+    def train_backward_map(self, loss_scale: float = 1.0, inv_ntok: Optional[torch.Tensor] = None,
+                           want_dmap: bool = True):
+        """capdec_train_bwd + capdec_img2feature_bwd.  Fills store.flat_grad and adaptor.flat_grad; returns the
+        gradient w.r.t. the encoder map [B,X,k] (or None)."""
+        enc_map, _ = self._staged
+        check(self.lib.capdec_train_bwd(self.handle, C.c_float(loss_scale), ptr(inv_ntok), None, None,
+                                        C.byref(self.store.c_grads), stream_ptr()), "capdec_train_bwd")
+        dmap = torch.empty_like(enc_map) if want_dmap else None
+        check(self.lib.capdec_img2feature_bwd(self.handle, ptr(dmap), C.byref(self.adaptor.c_grads), stream_ptr()),
+              "capdec_img2feature_bwd")
+        return dmap
+
+    def decode_map(self, enc_map, beam: int = 1, finish_on_stop: bool = False, want_f32: bool = True):
+        """eval_network after the encoder (model:185-189): _img2feature + beam / greedy decode."""
+        self.img2feature(enc_map)
+        return self._decode(None, None, self._staged[1], beam, finish_on_stop, want_f32)
+
     def decode(self, g, P, beam: int = 1, finish_on_stop: bool = False, want_f32: bool = True):
         """capdec_decode.  Returns (ids int32 [B,beam,T], scores f32 [B,beam], ids_f32 [B,T] or None)."""
         B = self._check_inputs(g, P)
+        return self._decode(g, P, B, beam, finish_on_stop, want_f32)
+
+    def _decode(self, g, P, B, beam, finish_on_stop, want_f32):
         if not self._bound:
             self.bind_params()
         T = self.cfg.infer_max_length
@@ -349,9 +489,29 @@ class _TrainingLoss(torch.autograd.Function):
         return None, dg, dP, None, eng.store.flat_grad.clone()
 
 
+class _TrainingLossFromMap(torch.autograd.Function):
+    """loss = training_network(...) from the encoder output on (adaptor + decoder + masked CE); the backward hands the
+    gradient of the encoder map back to autograd (config.py:50 encoder_trainable)."""
+
+    @staticmethod
+    def forward(ctx, engine, enc_map, caption, flat_params, flat_adaptor):
+        loss_buf, _ = engine.train_forward_map(enc_map, caption)
+        ctx.engine = engine
+        ctx.shape = enc_map.shape
+        return loss_buf[2].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.engine
+        scale = (eng._loss_buf[3] * grad_out.to(torch.float32)).reshape(1).contiguous()   # no host sync
+        dmap = eng.train_backward_map(1.0, inv_ntok=scale, want_dmap=True)
+        return None, dmap.view(ctx.shape), None, eng.store.flat_grad.clone(), eng.adaptor.flat_grad.clone()
+
+
 class ImageCaptionModel:
-    """The decoder-side half of model_adaAttention_aic.ImageCaptionModel (model:138-212): everything after
-    `_img2feature` (the MobileNetV2 encoder and the feature adaptor are outside the hot path)."""
+    """model_adaAttention_aic.ImageCaptionModel (model:138-212) after the MobileNetV2 encoder: the feature adaptor
+    `_img2feature` (model:193-199, from the encoder output on), the decoder and the loss wiring.  The encoder itself is
+    library CNN work outside the hot path."""
 
     def __init__(self, engine: Optional[CaptionDecoderEngine] = None):
         self.engine = engine if engine is not None else default_engine()
@@ -372,6 +532,25 @@ class ImageCaptionModel:
     def eval_network(self, global_image_feat, image_embed):
         """model:185-189: greedy decode, float32 ids [B,35]."""
         return Decoder(self.engine.cfg.hidden_dim, mode="eval", engine=self.engine).call(global_image_feat, image_embed)
+
+    # ---- the same two networks from the encoder output on (what model:177 / model:186 hand to the decoder) ------
+    def _img2feature(self, encoder_map):
+        """model:193-199 after `self.encoder.net(img)`: encoder map [B,1280,7,7] or [B,1280,49] ->
+        (img_embed [B,49,H], img_global [B,H]) float32; the features also stay staged inside the engine."""
+        return self.engine.img2feature(encoder_map, want_outputs=True)
+
+    def training_network_from_map(self, encoder_map, caption):
+        """model:161-183 with `img` replaced by the encoder output: scalar loss, autograd-enabled w.r.t. the map."""
+        eng = self.engine
+        eng.bind_params()
+        eng.bind_adaptor()
+        if getattr(self, "_flat_adaptor", None) is None:
+            self._flat_adaptor = eng.adaptor.flat.requires_grad_(True)
+        return _TrainingLossFromMap.apply(eng, encoder_map, caption, self._flat, self._flat_adaptor)
+
+    def eval_network_from_map(self, encoder_map):
+        """model:185-189 with `img` replaced by the encoder output: float32 ids [B,35]."""
+        return self.engine.decode_map(encoder_map, beam=1, finish_on_stop=False)[2]
 
     @staticmethod
     def loss(ground_true, prediction):
