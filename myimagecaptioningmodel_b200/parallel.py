@@ -39,32 +39,53 @@ class DataParallelTrainer:
         """One data-parallel forward+backward on this rank's shard.  Returns the GLOBAL loss as a device tensor
         (no host sync).  After the call engine.store.flat_grad holds the all-reduced gradient."""
         eng = self.engine
-        loss_buf, _ = eng.train_forward(g, P, caption)
+        return self._run(lambda: eng.train_forward(g, P, caption)[0],
+                         lambda scale, inv: eng.train_backward(scale, inv, want_dg=want_input_grads,
+                                                               want_dP=want_input_grads),
+                         extra=(), overlap_ok=not want_input_grads)
+
+    def forward_backward_map(self, enc_map, caption, want_dmap: bool = False):
+        """The same from the encoder map (feature adaptor in front): additionally all-reduces
+        engine.adaptor.flat_grad.  Returns (global loss, d enc_map of this rank's shard or None); the map gradient of a
+        shard is already normalised by the global token count."""
+        eng = self.engine
+        out = {}
+
+        def bwd(scale, inv):
+            out["dmap"] = eng.train_backward_map(scale, inv, want_dmap=want_dmap)
+
+        loss = self._run(lambda: eng.train_forward_map(enc_map, caption)[0], bwd, extra=(eng.adaptor.flat_grad,),
+                         overlap_ok=not want_dmap)
+        return loss, out.get("dmap")
+
+    def _run(self, fwd, bwd, extra, overlap_ok):
+        eng = self.engine
+        loss_buf = fwd()
         if self.world == 1:
-            eng.train_backward(1.0, None, want_dg=want_input_grads, want_dP=want_input_grads)
+            bwd(1.0, None)
             return loss_buf[2]
         if self.pe_semantics:
             # ParallelExecutor default (CoeffNumDevice): mean over devices of per-device token means
-            eng.train_backward(1.0 / self.world, None, want_dg=want_input_grads, want_dP=want_input_grads)
+            bwd(1.0 / self.world, None)
             loss = loss_buf[2].clone()
             dist.all_reduce(loss, group=self.group)
             loss /= self.world
-            self._all_reduce_grads()
+            self._all_reduce_grads(extra)
             return loss
         if not getattr(self, "_overlap_ready", False):
             self._setup_overlap()
             self._overlap_ready = True
-        if self._overlap and not want_input_grads:
-            return self._forward_backward_overlapped(loss_buf)
+        if self._overlap and overlap_ok:
+            return self._forward_backward_overlapped(loss_buf, bwd, extra)
         tot = loss_buf[:2].clone()
         dist.all_reduce(tot, group=self.group)               # (sum ce*mask, sum mask) over all ranks
         inv = (1.0 / tot[1]).reshape(1)
-        eng.train_backward(1.0, inv, want_dg=want_input_grads, want_dP=want_input_grads)
+        bwd(1.0, inv)
         loss = tot[0] / tot[1]
-        self._all_reduce_grads()
+        self._all_reduce_grads(extra)
         return loss
 
-    def _forward_backward_overlapped(self, loss_buf):
+    def _forward_backward_overlapped(self, loss_buf, bwd, extra):
         """Global token normalisation without a synchronisation point between forward and backward: the backward pass
         runs with the LOCAL normaliser 1 / n_r straight away; the (sum ce*mask, sum mask) exchange runs beside it on the
         communication stream, and every gradient group is multiplied by n_r / n_global there before its all-reduce:
@@ -79,7 +100,7 @@ class DataParallelTrainer:
             dist.all_reduce(tot, group=self.group)
             weight = n_local / tot[1]
             loss = tot[0] / tot[1]
-        eng.train_backward(1.0, None, want_dg=False, want_dP=False)
+        bwd(1.0, None)
         if os.environ.get("CAPDEC_DP_DEBUG_SYNC") == "1":
             torch.cuda.synchronize()
         flat = eng.store.flat_grad
@@ -88,6 +109,11 @@ class DataParallelTrainer:
                 self._comm.wait_event(self._events[ev])
                 flat[lo:hi].mul_(weight)
                 dist.all_reduce(flat[lo:hi], group=self.group)
+            if extra:
+                self._comm.wait_stream(main)                 # the adaptor backward runs after capdec_train_bwd
+                for t in extra:
+                    t.mul_(weight)
+                    dist.all_reduce(t, group=self.group)
         main.wait_stream(self._comm)
         return loss
 
@@ -107,13 +133,15 @@ class DataParallelTrainer:
         self._fwd_done = torch.cuda.Event()
         self._overlap = True
 
-    def _all_reduce_grads(self):
+    def _all_reduce_grads(self, extra=()):
         eng = self.engine
         if not getattr(self, "_overlap_ready", False):
             self._setup_overlap()
             self._overlap_ready = True
         if not self._overlap:
             dist.all_reduce(eng.store.flat_grad, group=self.group)
+            for t in extra:
+                dist.all_reduce(t, group=self.group)
             return
         main = torch.cuda.current_stream()
         flat = eng.store.flat_grad
@@ -122,6 +150,10 @@ class DataParallelTrainer:
                 # every group waits for its own event, recorded by capdec_train_bwd in the middle of the backward pass
                 self._comm.wait_event(self._events[ev])
                 dist.all_reduce(flat[lo:hi], group=self.group)
+            if extra:
+                self._comm.wait_stream(main)
+                for t in extra:
+                    dist.all_reduce(t, group=self.group)
         main.wait_stream(self._comm)
 
 

@@ -34,6 +34,13 @@ def make_captions(cfg, B: int, seed: int = 20260, min_len: int = 5, max_len=None
     return cap
 
 
+def make_encoder_map(cfg, B: int, encoder_channel: int = 1280, seed: int = 20260, dtype=torch.float32):
+    """Synthetic MobileNetV2 output [B, X, k] (model:193-195): the encoder ends in ReLU6, so values lie in [0, 6]."""
+    gen = torch.Generator().manual_seed(seed + 31)
+    x = torch.randn(B, encoder_channel, cfg.num_positions, generator=gen, dtype=torch.float32)
+    return torch.clamp(x, 0.0, 6.0).to(dtype)
+
+
 def make_batch(cfg, B: int, seed: int = 20260, dtype=torch.float32):
     g, P = make_features(cfg, B, seed, dtype)
     return g, P, make_captions(cfg, B, seed)

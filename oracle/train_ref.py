@@ -42,11 +42,11 @@ def init_adaptor_params(cfg: R.DecoderConfig, encoder_channel: int = 1280, seed:
     return out
 
 
-def make_encoder_map(cfg: R.DecoderConfig, B: int, encoder_channel: int = 1280, seed: int = 20260, dtype=torch.float32):
-    """Synthetic MobileNetV2 output: the last op of the encoder is ReLU6, so values lie in [0, 6]."""
-    gen = torch.Generator().manual_seed(seed + 31)
-    x = torch.randn(B, encoder_channel, cfg.num_positions, generator=gen, dtype=torch.float32)
-    return torch.clamp(x, 0.0, 6.0).to(dtype)
+def make_encoder_map(cfg, B, encoder_channel=1280, seed=20260, dtype=torch.float32):
+    """Synthetic MobileNetV2 output (values in [0, 6]: the encoder ends in ReLU6); the generator lives in the product
+    package so that bench.py's own arm never imports oracle/."""
+    from myimagecaptioningmodel_b200.synth import make_encoder_map as _m
+    return _m(cfg, B, encoder_channel, seed, dtype)
 
 
 def img2feature(ap, enc_map: torch.Tensor):

@@ -17,6 +17,7 @@ ap.add_argument("--decode-images", type=int, default=512)
 ap.add_argument("--beam", type=int, default=3)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--axis", default="position")
+ap.add_argument("--from-map", action="store_true", help="widened step: feature adaptor in front, Adam behind (8f N1, N2)")
 args = ap.parse_args()
 
 cfg = M.DecoderConfig(dtype="bf16", softmax_axis=args.axis)
@@ -31,6 +32,21 @@ def step():
     eng.train_backward(want_dg=True, want_dP=True)
 
 
+if args.from_map:
+    eng.attach_adaptor(1280, seed=0)
+    opt, _ = M.get_optimizer(eng)
+    x = synth.make_encoder_map(cfg, args.batch, 1280, 4242).cuda()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def step():  # noqa: F811
+        eng.bind_params()
+        eng.bind_adaptor()
+        eng.train_forward_map(x, cap)
+        eng.train_backward_map(want_dmap=True)
+        ev[0].record()
+        opt.step()
+        ev[1].record()
+
 for _ in range(3):
     step()
 torch.cuda.synchronize()
@@ -43,6 +59,11 @@ print("train step B=%d: %.3f ms (sum of phases, avg of %d)" % (args.batch, total
 for k, v in rep.items():
     print("  %-24s %8.1f us  %5.1f%%" % (k, 1e3 * v / args.reps, 100 * v / total))
 out = {"train_us": {k: 1e3 * v / args.reps for k, v in rep.items()}}
+if args.from_map:
+    torch.cuda.synchronize()
+    a = ev[0].elapsed_time(ev[1])
+    print("  %-24s %8.1f us  (capdec_adam_step x2, last step; outside the handle's phase marks)" % ("adam", 1e3 * a))
+    out["adam_us"] = 1e3 * a
 if args.decode_images:
     gi, Pi, _ = synth.make_batch(cfg, args.decode_images, 777)
     gi, Pi = gi.cuda(), Pi.cuda()

@@ -16,6 +16,7 @@ ap.add_argument("--decode-images", type=int, default=0)
 ap.add_argument("--beam", type=int, default=3)
 ap.add_argument("--axis", default="position")
 ap.add_argument("--no-train", action="store_true")
+ap.add_argument("--from-map", action="store_true", help="widened step: feature adaptor in front, Adam behind")
 args = ap.parse_args()
 
 cfg = M.DecoderConfig(dtype="bf16", softmax_axis=args.axis)
@@ -29,6 +30,18 @@ def step():
     eng.train_forward(g, P, cap)
     eng.train_backward(want_dg=True, want_dP=True)
 
+
+if args.from_map:
+    eng.attach_adaptor(1280, seed=0)
+    opt, _ = M.get_optimizer(eng)
+    x = synth.make_encoder_map(cfg, args.batch, 1280, 4242).cuda()
+
+    def step():  # noqa: F811
+        eng.bind_params()
+        eng.bind_adaptor()
+        eng.train_forward_map(x, cap)
+        eng.train_backward_map(want_dmap=True)
+        opt.step()
 
 if not args.no_train:
     for _ in range(2):
