@@ -3,9 +3,10 @@ sm_100a CUDA behind a C-ABI (include/capdec.h), with the reference's Decoder / I
 from ._capi import CapdecError, PARAM_NAMES, library_path, load_library
 from .decoder import (AdaptorStore, CaptionDecoderEngine, Decoder, DecoderConfig, ImageCaptionModel, ParameterStore, default_engine,
                       filter_caption, param_shapes)
+from . import checkpoint, evaluation
 from .optim import Adam, LRSchedule, get_lr, get_optimizer
 from .parallel import DataParallelTrainer, shard_range, sharded_decode
 
-__all__ = ["AdaptorStore", "Adam", "LRSchedule", "get_lr", "get_optimizer", "CapdecError", "PARAM_NAMES", "library_path", "load_library", "CaptionDecoderEngine", "Decoder",
+__all__ = ["checkpoint", "evaluation", "AdaptorStore", "Adam", "LRSchedule", "get_lr", "get_optimizer", "CapdecError", "PARAM_NAMES", "library_path", "load_library", "CaptionDecoderEngine", "Decoder",
            "DecoderConfig", "ImageCaptionModel", "ParameterStore", "default_engine", "filter_caption", "param_shapes",
            "DataParallelTrainer", "shard_range", "sharded_decode"]

@@ -21,22 +21,43 @@ constexpr int kCh = 64;  // channels per CTA
 
 // CTA (x-tile, image): reads the contiguous [64 channels x k positions] fp32 block of one image, writes the k rows
 // (64 channels = one or two 128-byte lines each) and the 64 channel means.
-template <typename T>
+// K > 0: k is the compile-time constant K and the tile is full (64 channels) -- the index arithmetic becomes
+// multiply-shift and the loops unroll (all of a thread's loads are in flight together); the first version with run-time
+// divisions was issue-bound (ncu: SM 47 %, DRAM 21 %).  K = 0: any k <= 64, ragged channel tiles.
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
-map_to_rows_kernel(const float* __restrict__ map, int X, int k, T* __restrict__ rows, T* __restrict__ mean) {
+map_to_rows_kernel(const float* __restrict__ map, int X, int k_rt, T* __restrict__ rows, T* __restrict__ mean) {
   pdl_trigger();
   __shared__ float tile[64][kCh + 1];  // [position][channel]
+  const int k = K > 0 ? K : k_rt;
   const int b = blockIdx.y, x0 = blockIdx.x * kCh;
-  const int nx = min(kCh, X - x0);
+  const int nx = K > 0 ? kCh : min(kCh, X - x0);
   const float* src = map + ((long)b * X + x0) * k;
-  for (int i = threadIdx.x; i < nx * k; i += blockDim.x) tile[i % k][i / k] = src[i];
+  if (K > 0) {
+    constexpr int kN = kCh * (K > 0 ? K : 1);
+    constexpr int kIter = (kN + 255) / 256;
+    float v[kIter];
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int i = it * 256 + threadIdx.x;
+      v[it] = i < kN ? __ldcs(src + i) : 0.f;       // read once, never again
+    }
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int i = it * 256 + threadIdx.x;
+      if (i < kN) tile[i % (K > 0 ? K : 1)][i / (K > 0 ? K : 1)] = v[it];
+    }
+  } else {
+    for (int i = threadIdx.x; i < nx * k; i += blockDim.x) tile[i % k][i / k] = src[i];
+  }
   __syncthreads();
   if (threadIdx.x < nx) {
     float s = 0.f;
+#pragma unroll 7
     for (int j = 0; j < k; ++j) s += tile[j][threadIdx.x];
     mean[(long)b * X + x0 + threadIdx.x] = from_f<T>(s / (float)k);   // reduce_mean(dim=1), model:198
   }
-  const int groups = nx / 8;  // X % 8 == 0
+  const int groups = K > 0 ? kCh / 8 : nx / 8;  // X % 8 == 0
   for (int i = threadIdx.x; i < k * groups; i += blockDim.x) {
     const int j = i / groups, cg = i % groups;
     float v[8];
@@ -47,16 +68,17 @@ map_to_rows_kernel(const float* __restrict__ map, int X, int k, T* __restrict__ 
 }
 
 // backward of the above: d map[b, x, j] = d rows[b*k + j, x] + d mean[b, x] / k
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
-rows_to_map_kernel(const T* __restrict__ drows, const float* __restrict__ dmean, int X, int k, float* __restrict__ dmap) {
+rows_to_map_kernel(const T* __restrict__ drows, const float* __restrict__ dmean, int X, int k_rt, float* __restrict__ dmap) {
   pdl_trigger();
   __shared__ float tile[64][kCh + 1];
   __shared__ float dm[kCh];
+  const int k = K > 0 ? K : k_rt;
   const int b = blockIdx.y, x0 = blockIdx.x * kCh;
-  const int nx = min(kCh, X - x0);
+  const int nx = K > 0 ? kCh : min(kCh, X - x0);
   if (threadIdx.x < nx) dm[threadIdx.x] = dmean[(long)b * X + x0 + threadIdx.x] / (float)k;
-  const int groups = nx / 8;
+  const int groups = K > 0 ? kCh / 8 : nx / 8;
   for (int i = threadIdx.x; i < k * groups; i += blockDim.x) {
     const int j = i / groups, cg = i % groups;
     float v[8];
@@ -66,7 +88,16 @@ rows_to_map_kernel(const T* __restrict__ drows, const float* __restrict__ dmean,
   }
   __syncthreads();
   float* dst = dmap + ((long)b * X + x0) * k;
-  for (int i = threadIdx.x; i < nx * k; i += blockDim.x) dst[i] = tile[i % k][i / k] + dm[i / k];
+  if (K > 0) {
+    constexpr int kN = kCh * (K > 0 ? K : 1);
+#pragma unroll
+    for (int it = 0; it < (kN + 255) / 256; ++it) {
+      const int i = it * 256 + threadIdx.x;
+      if (i < kN) __stcs(dst + i, tile[i % (K > 0 ? K : 1)][i / (K > 0 ? K : 1)] + dm[i / (K > 0 ? K : 1)]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nx * k; i += blockDim.x) dst[i] = tile[i % k][i / k] + dm[i / k];
+  }
 }
 
 template <typename T> __global__ void to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long n8) {
@@ -126,14 +157,16 @@ __global__ void adam_scalar_kernel(float* p, const float* g, float* m, float* v,
 template <typename T> int map_to_rows(LaunchCtx c, const float* map, int B, int X, int k, T* rows, T* mean) {
   if (X % 8 || k < 1 || k > 64) { set_error("feature adaptor: need encoder_channel %% 8 == 0 and 1 <= k <= 64"); return -1; }
   dim3 grid((X + kCh - 1) / kCh, B);
-  map_to_rows_kernel<T><<<grid, 256, 0, c.stream>>>(map, X, k, rows, mean);
+  if (k == 49 && X % kCh == 0) map_to_rows_kernel<T, 49><<<grid, 256, 0, c.stream>>>(map, X, k, rows, mean);   // 7 x 7 encoder map
+  else map_to_rows_kernel<T, 0><<<grid, 256, 0, c.stream>>>(map, X, k, rows, mean);
   BUMP(c);
   return 0;
 }
 template <typename T> int rows_to_map(LaunchCtx c, const T* drows, const float* dmean, int B, int X, int k, float* dmap) {
   if (X % 8 || k < 1 || k > 64) { set_error("feature adaptor: need encoder_channel %% 8 == 0 and 1 <= k <= 64"); return -1; }
   dim3 grid((X + kCh - 1) / kCh, B);
-  rows_to_map_kernel<T><<<grid, 256, 0, c.stream>>>(drows, dmean, X, k, dmap);
+  if (k == 49 && X % kCh == 0) rows_to_map_kernel<T, 49><<<grid, 256, 0, c.stream>>>(drows, dmean, X, k, dmap);
+  else rows_to_map_kernel<T, 0><<<grid, 256, 0, c.stream>>>(drows, dmean, X, k, dmap);
   BUMP(c);
   return 0;
 }

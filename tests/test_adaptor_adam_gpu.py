@@ -33,7 +33,7 @@ def _setup(dims, X, dtype, axis="position", B=6, seed=5):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("dims,X,B", [(SMALL, 24, 3), (MID, 160, 6), (MID, 72, 1)])
+@pytest.mark.parametrize("dims,X,B", [(SMALL, 24, 3), (MID, 160, 6), (MID, 72, 1), (MID, 128, 5)])
 def test_img2feature_forward(dtype, dims, X, B):
     ocfg, params, ap, x, cap, eng = _setup(dims, X, dtype, B=B)
     P_ref, g_ref = TR.img2feature(ap, x)
@@ -49,7 +49,7 @@ def test_img2feature_forward(dtype, dims, X, B):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("dims,X,B", [(SMALL, 24, 4), (MID, 160, 6)])
+@pytest.mark.parametrize("dims,X,B", [(SMALL, 24, 4), (MID, 160, 6), (MID, 128, 6)])
 def test_train_from_encoder_map(dtype, dims, X, B):
     """adaptor + decoder + loss from the encoder map: loss, logits, every decoder / adaptor gradient and d(encoder map)"""
     ocfg, params, ap, x, cap, eng = _setup(dims, X, dtype, B=B)
