@@ -220,20 +220,13 @@ template <typename T> class Decoder : public DecoderBase {
         else permute_gate_cols(lc, jb.src, jb.lds, reinterpret_cast<bf16*>(jb.dst), H);
       }
     }
-    // out_fc_bias padded to Vp columns so the GEMM epilogue may read it in whole groups of 8
-    CUDA_OK(cudaMemsetAsync(b_vocab.p, 0, 4 * (size_t)Vp, s));
-    CUDA_OK(cudaMemcpyAsync(b_vocab.p, p->out_fc_bias, 4 * (size_t)V, cudaMemcpyDeviceToDevice, s));
-    // fused bias vectors: train [lstm_b | fc_xs_b]; decode [lstm_b | fc_xs_b + fc_hs_b]
-    CUDA_OK(cudaMemcpyAsync(b5.p, p->lstm_b, 4 * 4 * H, cudaMemcpyDeviceToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(b5.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(b5d.p, b5.p, 4 * 5 * H, cudaMemcpyDeviceToDevice, s));
-    add_f32(lc, b5d.as<float>() + 4 * H, p->fc_hs_b, H);
-    if (want_perm) {
-      ConvertTable bt;
-      bt.add(p->lstm_b, 4 * H, b5p.p, 4 * H, 1, 4 * H, 1, H);
-      if (multi_convert<float>(lc, bt) != 0) { set_error("capdec_bind_params: lstm_b must be 16-byte aligned"); return -1; }
-      CUDA_OK(cudaMemcpyAsync(b5p.as<float>() + 4 * H, p->fc_xs_b, 4 * H, cudaMemcpyDeviceToDevice, s));
-    }
+    // out_fc_bias padded to Vp columns so the GEMM epilogue may read it in whole groups of 8, and the fused bias vectors:
+    // train [lstm_b | fc_xs_b]; decode [lstm_b | fc_xs_b + fc_hs_b]; the unit-major copy for the persistent recurrence
+    BiasBind bb;
+    bb.out_fc_bias = p->out_fc_bias; bb.V = V; bb.Vp = Vp; bb.b_vocab = b_vocab.as<float>();
+    bb.lstm_b = p->lstm_b; bb.fc_xs_b = p->fc_xs_b; bb.fc_hs_b = p->fc_hs_b; bb.H = H;
+    bb.b5 = b5.as<float>(); bb.b5d = b5d.as<float>(); bb.b5p = want_perm ? b5p.as<float>() : nullptr;
+    bind_biases(lc, bb);
     CUDA_OK(cudaGetLastError());
     prof.mark("bind_params", s);
     bound = true;
@@ -632,7 +625,8 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E, gscale));
-    colsum_add<T>(lc, dproj.as<T>(), E, M, E, G.fc_e_b);
+    ColsumTable bias_sums;  // the bias gradients of the time-batched head: one launch, just before their group is marked
+    bias_sums.add(dproj.p, E, M, E, G.fc_e_b);
     OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, (int)M, G.fc_e_w, E));
     prof.mark("bwd.vocab_proj", s);
     // out = tanh(fc_o(ctx + p_hid))   (model:115)
@@ -642,7 +636,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.act = ACT_DTANH; c.epi.dact_y = outv.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
-    colsum_add<T>(lc, doutp.as<T>(), H, M, H, G.fc_o_b);
+    bias_sums.add(doutp.p, H, M, H, G.fc_o_b);
     OK(wgrad(gc, actx.p, H, H, doutp.p, H, H, (int)M, G.fc_o_w, H));
     {
       GemmCall c;  // d(ctx + p_hid)
@@ -658,9 +652,9 @@ template <typename T> class Decoder : public DecoderBase {
                         alpha.as<float>(), dactx.as<T>(), dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
                         dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(), dsemb.as<T>(), G.fc_a_w, G.fc_a_b));
     prof.mark("bwd.attention", s);
-    colsum_add<T>(lc, dhemb.as<T>(), H, M, H, G.fc_g_b);
+    bias_sums.add(dhemb.p, H, M, H, G.fc_g_b);
     OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, (int)M, G.fc_g_w, H));
-    colsum_add<T>(lc, dsemb.as<T>(), H, M, H, G.fc_s_b);
+    bias_sums.add(dsemb.p, H, M, H, G.fc_s_b);
     OK(wgrad(gc, sent.p, H, H, dsemb.p, H, H, (int)M, G.fc_s_w, H));
     {
       GemmCall c;  // d p_hid (pre-tanh) = (d actx + d hid_emb . fc_g^T) * (1 - p_hid^2)      (model:99, 102)
@@ -668,7 +662,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.addend = dactx.p; c.epi.ld_add = H; c.epi.act = ACT_DTANH; c.epi.dact_y = phid.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
-    colsum_add<T>(lc, dphp.as<T>(), H, M, H, G.fc_p_b);
+    bias_sums.add(dphp.p, H, M, H, G.fc_p_b);
     OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, (int)M, G.fc_p_w, H));
     {
       GemmCall c;  // d sentinel = alpha_k d ctx / (k+1) + d sentinel_emb . fc_s^T                (model:104, 111)
@@ -678,8 +672,7 @@ template <typename T> class Decoder : public DecoderBase {
     }
     // sentinel = sigmoid(p_word_emb + p_hidden) * tanh(c)     (model:89-92)
     sentinel_bwd<T>(lc, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
-    colsum_add<T>(lc, dG.as<T>() + 4 * H, 5 * H, M, H, G.fc_hs_b);
-    CUDA_OK(cudaMemcpyAsync(G.fc_xs_b, G.fc_hs_b, 4 * H, cudaMemcpyDeviceToDevice, s));  // same pre-activation
+    bias_sums.add(dG.as<T>() + 4 * H, 5 * H, M, H, G.fc_hs_b);
     OK(wgrad(gc, Hprev, H, H, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_hs_w, H));
     {
       GemmCall c;  // d h_t from p_hid
@@ -694,8 +687,8 @@ template <typename T> class Decoder : public DecoderBase {
     }
     prof.mark("bwd.head_fc", s);
     // once-per-image projections (model:52-53)
-    colsum_add<T>(lc, dkv.as<T>(), 2 * H, (long)B * k, H, G.fc_v_b);
-    colsum_add<T>(lc, dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
+    bias_sums.add(dkv.p, 2 * H, (long)B * k, H, G.fc_v_b);
+    bias_sums.add(dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
     OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
     OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
     if (dP) {
@@ -713,6 +706,8 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.act = ACT_DRELU; c.epi.dact_y = PT.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
+    colsum_multi<T>(lc, bias_sums);
+    CUDA_OK(cudaMemcpyAsync(G.fc_xs_b, G.fc_hs_b, 4 * H, cudaMemcpyDeviceToDevice, s));  // same pre-activation
     prof.mark("bwd.image_kv", s);
     // fc_hs .. fc_e (incl. fc_a) and fc_v, fc_k are final: their all-reduce overlaps the BPTT.  (The per-image
     // projections depend on the attention gradients only, so they run here rather than at the end of the pass, where

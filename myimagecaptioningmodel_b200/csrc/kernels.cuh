@@ -73,7 +73,27 @@ template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int 
 // out[n] += sum_m x[m, n]    (fp32 atomics)
 // out[n] += scale * sum_m x[m, n]   (fp32 atomics; scale read from a device scalar, or 1)
 template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out, const float* scale_dev = nullptr);
+// several out[n] += sum_m x[m, n] in one launch (falls back to one colsum_add per job for small / unaligned operands)
+struct ColsumJob {
+  const void* x; long ld; long M; int N; float* out; long rows_per_chunk;
+};
+constexpr int kMaxColsumJobs = 8;
+struct ColsumTable {
+  ColsumJob job[kMaxColsumJobs];
+  int first_block[kMaxColsumJobs + 1];
+  int n = 0;
+  void add(const void* x, long ld, long M, int N, float* out) { job[n++] = ColsumJob{x, ld, M, N, out, 0}; }
+};
+template <typename T> void colsum_multi(LaunchCtx c, ColsumTable& tab);
 void add_f32(LaunchCtx c, float* dst, const float* src, long n);
+// the fused bias vectors of capdec_bind_params: b_vocab [Vp] = out_fc_bias padded with zeros; b5 = [lstm_b | fc_xs_b];
+// b5d = [lstm_b | fc_xs_b + fc_hs_b]; b5p (optional) = b5 with unit-major gate columns
+struct BiasBind {
+  const float* out_fc_bias; int V, Vp; float* b_vocab;
+  const float* lstm_b; const float* fc_xs_b; const float* fc_hs_b; int H;
+  float* b5; float* b5d; float* b5p;
+};
+void bind_biases(LaunchCtx c, const BiasBind& a);
 // dEmb[id] += dX[(t*B+b)]  for id != pad        (lookup_table_v2_grad, padding_idx)
 template <typename T>
 void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,

@@ -320,15 +320,12 @@ colsum_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chu
 // 16 x 32 = 512 CTAs with every load of a thread in flight at once, while each output address still receives only
 // 32 atomics (see above).  Row groups meet through two shuffles and one shared-memory step.
 template <typename T>
-__global__ void __launch_bounds__(512)
-colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
-                     const float* __restrict__ scale_dev) {
-  pdl_trigger();
+__device__ __forceinline__ void colsum_narrow_body(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk,
+                                                   float* __restrict__ out, float sc, int bx, int by) {
   __shared__ float red[16][8][9];
-  const float sc = scale_dev ? __ldg(scale_dev) : 1.f;
   const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + ct) * 8;
-  const long m0 = (long)blockIdx.y * rows_per_chunk;
+  const int n0 = (bx * 8 + ct) * 8;
+  const long m0 = (long)by * rows_per_chunk;
   const long m1 = (m0 + rows_per_chunk < M) ? m0 + rows_per_chunk : M;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (n0 + 8 <= N) {
@@ -367,9 +364,27 @@ colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < 16; ++w) v += red[w][j][c];
-    const int n = (blockIdx.x * 8 + c) * 8 + j;
+    const int n = (bx * 8 + c) * 8 + j;
     if (n < N) atomicAdd(out + n, v * sc);
   }
+}
+template <typename T>
+__global__ void __launch_bounds__(512)
+colsum_narrow_kernel(const T* __restrict__ x, long ld, long M, int N, long rows_per_chunk, float* __restrict__ out,
+                     const float* __restrict__ scale_dev) {
+  pdl_trigger();
+  colsum_narrow_body<T>(x, ld, M, N, rows_per_chunk, out, scale_dev ? __ldg(scale_dev) : 1.f, blockIdx.x, blockIdx.y);
+}
+// several independent column sums (the bias gradients of the time-batched head) in one launch: blockIdx.x runs over the
+// 64-column blocks of all jobs.  Each of them alone is a 3 us kernel that costs 10 us as a launch of its own.
+template <typename T>
+__global__ void __launch_bounds__(512) colsum_multi_kernel(ColsumTable tab) {
+  pdl_trigger();
+  int j = 0;
+  while (j + 1 < tab.n && (int)blockIdx.x >= tab.first_block[j + 1]) ++j;
+  const ColsumJob& job = tab.job[j];
+  colsum_narrow_body<T>(reinterpret_cast<const T*>(job.x), job.ld, job.M, job.N, job.rows_per_chunk, job.out, 1.f,
+                        (int)blockIdx.x - tab.first_block[j], blockIdx.y);
 }
 
 template <typename T>
@@ -391,6 +406,23 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] += src[i];
+}
+
+// every fused bias vector of capdec_bind_params in one launch (was: 2 memsets / 5 copies / an add / a permute launch)
+__global__ void bind_bias_kernel(BiasBind a) {
+  pdl_trigger();
+  const int H = a.H, n5 = 5 * a.H;
+  const int n = a.Vp > n5 ? a.Vp : n5;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < a.Vp) a.b_vocab[i] = i < a.V ? a.out_fc_bias[i] : 0.f;   // padded so the GEMM epilogue reads whole groups of 8
+    if (i < n5) {
+      const bool gate_col = i < 4 * H;
+      const float v = gate_col ? a.lstm_b[i] : a.fc_xs_b[i - 4 * H];
+      a.b5[i] = v;                                                    // train:  [lstm_b | fc_xs_b]
+      a.b5d[i] = gate_col ? v : v + a.fc_hs_b[i - 4 * H];             // decode: [lstm_b | fc_xs_b + fc_hs_b]
+      if (a.b5p) a.b5p[gate_col ? 4 * (i % H) + i / H : i] = v;       // unit-major gate columns (col 4*unit + gate)
+    }
+  }
 }
 
 __global__ void fill_kernel(float* p, float v, long n) {
@@ -566,11 +598,40 @@ template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, 
   }
   BUMP(c);
 }
+template <typename T> void colsum_multi(LaunchCtx c, ColsumTable& tab) {
+  if (tab.n == 0) return;
+  const int chunks = 32;
+  bool batched = true;
+  for (int j = 0; j < tab.n; ++j) {
+    const ColsumJob& job = tab.job[j];
+    if (!(job.N <= 4096 && job.M >= 2048) || (job.ld % 8) || ((uintptr_t)job.x % (8 * sizeof(T)))) batched = false;
+  }
+  if (!batched) {  // small problems (tests): one launch each, colsum_add picks the kernel
+    for (int j = 0; j < tab.n; ++j)
+      colsum_add<T>(c, reinterpret_cast<const T*>(tab.job[j].x), tab.job[j].ld, tab.job[j].M, tab.job[j].N, tab.job[j].out,
+                    nullptr);
+    return;
+  }
+  int blocks = 0;
+  for (int j = 0; j < tab.n; ++j) {
+    tab.job[j].rows_per_chunk = (tab.job[j].M + chunks - 1) / chunks;
+    tab.first_block[j] = blocks;
+    blocks += (tab.job[j].N + 63) / 64;
+  }
+  tab.first_block[tab.n] = blocks;
+  colsum_multi_kernel<T><<<dim3(blocks, chunks), 512, 0, c.stream>>>(tab);
+  BUMP(c);
+}
 template <typename T>
 void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
                        int pad, float* dEmb) {
   embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, ids, ids_ld, B, steps, pad,
                                                                              dEmb);
+  BUMP(c);
+}
+void bind_biases(LaunchCtx c, const BiasBind& a) {
+  const int n = a.Vp > 5 * a.H ? a.Vp : 5 * a.H;
+  bind_bias_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(a);
   BUMP(c);
 }
 void add_f32(LaunchCtx c, float* dst, const float* src, long n) {
@@ -601,6 +662,7 @@ template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
                                  const T*, const float*, const float*, T*, long);                                      \
   template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long);                                 \
   template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*, const float*);                                           \
+  template void colsum_multi<T>(LaunchCtx, ColsumTable&);                                           \
   template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, const int64_t*, long, int, int, int, float*);
 
 INSTANTIATE(float)
