@@ -7,10 +7,13 @@ Contract (one JSON line on stdout from rank 0):
 
 A "step" of our arm = one teacher-forced decoder train step on one batch of synthetic features and captions at
 BASELINE.json configs[1]: B = 256 per GPU, T = 34, H = 1024, E = 256, V = 12295, k = 49, bf16 storage with fp32
-accumulation: capdec_bind_params (re-layout of the fp32 weights, as after an optimizer update) + capdec_train_fwd
-+ capdec_train_bwd (+ the data-parallel exchanges at N > 1).  Inputs are resident in HBM for `value`;
+accumulation: capdec_bind_params (re-layout of the fp32 weights after the previous update) + capdec_train_fwd
++ capdec_train_bwd (+ the data-parallel exchanges at N > 1) + capdec_adam_step over the flat decoder parameters
+(PaddlePaddle-1.8 rule, lr 5e-5: train.py:26-31, 44-45).  Inputs are resident in HBM for `value`;
 `e2e` goes through the same public calls with pinned HOST buffers (H2D of features and captions and a D2H read
-of the loss inside the timed region).  No optimizer is applied (outside the hot path).
+of the loss inside the timed region).  The reference arm does the same work on the host cores: the oracle's forward +
+autograd backward + Adam.  `extras.full_step_from_encoder_map` is the widened step: the feature adaptor
+in front of the decoder, Adam over decoder + adaptor parameters behind it.
 """
 from __future__ import annotations
 
@@ -42,7 +45,7 @@ SOFTMAX_AXIS = "position"     # the full attention arithmetic; th
 def workload_config(n_gpus):
     return {"workload": "teacher_forced_train_step_B256_per_gpu_T34_H1024_E256_V12295_k49", "global_batch": B_PER_GPU * n_gpus,
             "batch_per_gpu": B_PER_GPU, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
-            "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)",
+            "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)+adam(paddle-1.8 rule, lr 5e-5)",
             "e2e": "pinned host buffers, H2D of the next batch prefetched on a copy stream, loss D2H every step (read by the "
                    "host one step later)",
             "l2": "per-step working set ~1.5 GB >> 126 MB L2 (no flush needed)"}
@@ -143,9 +146,12 @@ def load_ncu_traffic():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port of the reference's Paddle graph, timed on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(params, cfg, g, P, cap):
+def cpu_reference_step(params, cfg, g, P, cap, adam_state):
+    """forward + autograd backward + the Adam update of every parameter (train.py:44-45), all on the host cores"""
     from oracle import decoder_ref as R
-    R.loss_and_grads(params, cfg, g, P, cap)
+    from oracle import train_ref as TR
+    _, _, _, grads = R.loss_and_grads(params, cfg, g, P, cap)
+    TR.adam_step_torch(params, grads, adam_state, lr=0.00005)
 
 
 def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
@@ -157,19 +163,20 @@ def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
     cfg = R.DecoderConfig(softmax_axis=SOFTMAX_AXIS)
     params = R.init_params(cfg, 0, torch.float32, bias_scale=0.0)
     g, P, cap = synth.make_batch(cfg, sample_B, 20260)
+    adam_state = {}
     for _ in range(max(1, warmup)):
-        cpu_reference_step(params, cfg, g, P, cap)
+        cpu_reference_step(params, cfg, g, P, cap, adam_state)
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        cpu_reference_step(params, cfg, g, P, cap)
+        cpu_reference_step(params, cfg, g, P, cap, adam_state)
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return {"value": sample_B * cfg.train_steps * done / dt, "unit": UNIT, "cores": torch.get_num_threads(),
             "kind": "port", "ms_per_step": 1e3 * dt / done, "steps": done,
-            "sample": "oracle/decoder_ref.py fwd+bwd, batch %d x 34 steps, fp32, %d thread(s), %d step(s)"
+            "sample": "oracle/decoder_ref.py fwd+bwd + oracle/train_ref.py Adam, batch %d x 34 steps, fp32, %d thread(s), %d step(s)"
                       % (sample_B, torch.get_num_threads(), done)}
 
 
@@ -235,9 +242,12 @@ def main_ours(args):
     g_d, P_d, cap_d = g_h.cuda(), P_h.cuda(), cap_h.cuda()
     ntok_nonpad = float((cap_h[:, 1:] != 0).sum())
 
+    opt_dec = M.Adam([(eng.store.flat, eng.store.flat_grad)], 0.00005)     # train.py:26-31 / config.py:32-33 defaults
+
     def step_resident(i):
         eng.bind_params()
         trainer.forward_backward(g_d, P_d, cap_d)
+        opt_dec.step()
 
     # ---- e2e: host buffers, double-buffered upload on a side stream, loss read back every step ----
     copy_stream = torch.cuda.Stream()
@@ -278,6 +288,7 @@ def main_ours(args):
         torch.cuda.current_stream().wait_event(ready[slot])
         eng.bind_params()
         loss = trainer.forward_backward(*bufs[slot])
+        opt_dec.step()
         consumed[slot].record()
         k = i & 1
         if k in pending:                                  # the buffer about to be reused (written two steps ago)
@@ -296,7 +307,7 @@ def main_ours(args):
         l0 = eng.launch_count
         with clocks.window():
             ms = timed_region(step_resident, args.steps, sync, barrier)
-        launches = eng.launch_count - l0
+        launches = eng.launch_count - l0 + args.steps * len(opt_dec.buffers)      # + one capdec_adam_step launch per step
         for i in range(max(2, args.warmup // 2)):
             step_e2e(i)
         sync()
@@ -307,6 +318,19 @@ def main_ours(args):
             ms_e2e = timed_region(step_e2e, args.steps, sync, barrier)
         drain(True)
     clk = clocks.summary()
+
+    # host link probe: the same pinned buffers copied alone (no compute beside them) -- what the e2e leg is bound by when
+    # the upload of one batch takes longer than the device needs for a step
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    with torch.cuda.stream(copy_stream):
+        pe0.record(copy_stream)
+        for _ in range(4):
+            for dst, src in zip(bufs[0], (g_h, P_h, cap_h)):
+                dst.copy_(src, non_blocking=True)
+        pe1.record(copy_stream)
+    sync()
+    ms_h2d = pe0.elapsed_time(pe1) / 4
 
     # ---- beam search (BASELINE.json configs[3], 512 images per GPU, beam 3, 35 steps): secondary number ----
     gi, Pi, _ = synth.make_batch(cfg, BEAM_IMAGES_PER_GPU, 777 + rank)
@@ -412,7 +436,8 @@ def main_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "h2d_alone_ms_per_step": ms_h2d,
+                        "h2d_alone_gbs": h2d / (ms_h2d * 1e-3) / 1e9},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "extras": {"nonpad_tokens_per_sec": world * ntok_nonpad * args.steps / (ms * 1e-3),
                            "step_gemm_tflops_algorithmic": step_tflops,

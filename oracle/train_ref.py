@@ -106,6 +106,24 @@ def adam_step_numpy(p, g, m, v, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, beta1_
     return f(beta1_pow * f(beta1)), f(beta2_pow * f(beta2))
 
 
+def adam_step_torch(params, grads, state, lr, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    """The same update on a dict of torch CPU tensors, in place, with torch's multi-threaded ops (the reference-arm timing
+    leg of bench.py applies it after every backward pass, like train.py:44-45).  `state` carries moments and beta powers."""
+    if not state:
+        state["m"] = {k: torch.zeros_like(v) for k, v in params.items()}
+        state["v"] = {k: torch.zeros_like(v) for k, v in params.items()}
+        state["b1p"], state["b2p"] = np.float32(beta1), np.float32(beta2)
+    lr_t = float(np.float32(lr) * np.sqrt(np.float32(1) - state["b2p"]) / (np.float32(1) - state["b1p"]))
+    with torch.no_grad():
+        for k, p in params.items():
+            g, m, v = grads[k], state["m"][k], state["v"][k]
+            m.mul_(beta1).add_(g, alpha=1 - beta1)
+            v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            p.addcdiv_(m, v.sqrt().add_(epsilon), value=-lr_t)
+    state["b1p"] = np.float32(state["b1p"] * np.float32(beta1))
+    state["b2p"] = np.float32(state["b2p"] * np.float32(beta2))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # learning-rate schedules: a run-by-run simulation of the graphs tools/util.py builds
 # ----------------------------------------------------------------------------------------------------------------

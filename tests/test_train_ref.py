@@ -96,6 +96,22 @@ def test_adam_paddle18_known_answers():
     assert np.abs(pn - pt.detach().numpy()).max() < 1e-5
 
 
+def test_adam_torch_form_equals_the_numpy_form():
+    torch.manual_seed(1)
+    params = {"a": torch.randn(7, 5), "b": torch.randn(11)}
+    pn = {k: v.numpy().copy() for k, v in params.items()}
+    st = {k: (np.zeros_like(v), np.zeros_like(v)) for k, v in pn.items()}
+    state, b1p, b2p = {}, None, None
+    for _ in range(4):
+        grads = {k: torch.randn_like(v) for k, v in params.items()}
+        TR.adam_step_torch(params, grads, state, lr=1e-2)
+        for k in pn:
+            nb = TR.adam_step_numpy(pn[k], grads[k].numpy(), st[k][0], st[k][1], 1e-2, beta1_pow=b1p, beta2_pow=b2p)
+        b1p, b2p = nb
+    for k in pn:
+        assert np.abs(params[k].numpy() - pn[k]).max() < 1e-6
+
+
 @pytest.mark.parametrize("strategy,kw", [
     (None, {}),
     ("cosine_decay", dict(decay_epoch=4)),
