@@ -246,8 +246,7 @@ def main_ours(args):
 
     def step_resident(i):
         eng.bind_params()
-        trainer.forward_backward(g_d, P_d, cap_d)
-        opt_dec.step()
+        trainer.forward_backward(g_d, P_d, cap_d, optimizer=opt_dec)     # Adam per gradient group, beside the backward pass
 
     # ---- e2e: host buffers, double-buffered upload on a side stream, loss read back every step ----
     copy_stream = torch.cuda.Stream()
@@ -287,8 +286,7 @@ def main_ours(args):
         upload(slot ^ 1)                                  # prefetch the next batch while this one computes
         torch.cuda.current_stream().wait_event(ready[slot])
         eng.bind_params()
-        loss = trainer.forward_backward(*bufs[slot])
-        opt_dec.step()
+        loss = trainer.forward_backward(*bufs[slot], optimizer=opt_dec)
         consumed[slot].record()
         k = i & 1
         if k in pending:                                  # the buffer about to be reused (written two steps ago)
@@ -307,7 +305,7 @@ def main_ours(args):
         l0 = eng.launch_count
         with clocks.window():
             ms = timed_region(step_resident, args.steps, sync, barrier)
-        launches = eng.launch_count - l0 + args.steps * len(opt_dec.buffers)      # + one capdec_adam_step launch per step
+        launches = eng.launch_count - l0 + args.steps * eng.N_GRAD_EVENTS     # + one capdec_adam_step launch per gradient group
         for i in range(max(2, args.warmup // 2)):
             step_e2e(i)
         sync()
@@ -367,15 +365,14 @@ def main_ours(args):
     def step_full(i):
         eng.bind_params()
         eng.bind_adaptor()
-        trainer.forward_backward_map(x_d, cap_d)
-        opt.step()
+        trainer.forward_backward_map(x_d, cap_d, optimizer=opt)
 
     for i in range(3):
         step_full(i)
     sync()
     l0 = eng.launch_count
     ms_full = timed_region(step_full, args.steps, sync, barrier)
-    launches_full = eng.launch_count - l0 + len(opt.buffers) * args.steps
+    launches_full = eng.launch_count - l0 + (eng.N_GRAD_EVENTS + 1) * args.steps
     adam_reps = 10
     ms_adam = timed_region(lambda i: opt.step(), adam_reps, sync, lambda: None) / adam_reps
     n_adam = sum(p.numel() for p, _ in opt.buffers)

@@ -128,16 +128,30 @@ class Adam:
     def current_lr(self) -> float:
         return float(self.lr(self.steps))
 
-    def step(self, stream=None) -> float:
-        """One update of every buffer from its gradient; returns the learning rate that was used."""
-        lr = self.current_lr()
-        for (p, g), m, v in zip(self.buffers, self.moment1, self.moment2):
-            check(self.lib.capdec_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, self.beta1, self.beta2,
-                                            self.epsilon, float(self.beta1_pow), float(self.beta2_pow),
-                                            self.gradient_clip, stream_ptr(stream)), "capdec_adam_step")
+    def step_range(self, buf: int, lo: int, hi: int, lr: Optional[float] = None, stream=None) -> None:
+        """Update elements [lo, hi) of flat buffer `buf` with the step's learning rate and bias corrections.  The update is
+        element-wise, so a step may be applied range by range (e.g. per gradient group, as soon as the group's all-reduce
+        has finished -- DataParallelTrainer); `advance()` closes the step."""
+        lr = self.current_lr() if lr is None else lr
+        (p, g), m, v = self.buffers[buf], self.moment1[buf], self.moment2[buf]
+        if hi <= lo:
+            return
+        check(self.lib.capdec_adam_step(ptr(p[lo:hi]), ptr(g[lo:hi]), ptr(m[lo:hi]), ptr(v[lo:hi]), hi - lo, lr, self.beta1,
+                                        self.beta2, self.epsilon, float(self.beta1_pow), float(self.beta2_pow),
+                                        self.gradient_clip, stream_ptr(stream)), "capdec_adam_step")
+
+    def advance(self) -> None:
+        """Paddle's Beta1Pow / Beta2Pow update and the step counter, once per optimizer step."""
         self.beta1_pow = np.float32(self.beta1_pow * np.float32(self.beta1))
         self.beta2_pow = np.float32(self.beta2_pow * np.float32(self.beta2))
         self.steps += 1
+
+    def step(self, stream=None) -> float:
+        """One update of every buffer from its gradient; returns the learning rate that was used."""
+        lr = self.current_lr()
+        for i, (p, _) in enumerate(self.buffers):
+            self.step_range(i, 0, p.numel(), lr, stream)
+        self.advance()
         return lr
 
     def state_dict(self):

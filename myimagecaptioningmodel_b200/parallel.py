@@ -36,15 +36,19 @@ class DataParallelTrainer:
         self.pe_semantics = pe_semantics
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
-    def forward_backward(self, g, P, caption, want_input_grads: bool = False):
+    def forward_backward(self, g, P, caption, want_input_grads: bool = False, optimizer=None):
         """One data-parallel forward+backward on this rank's shard.  Returns the GLOBAL loss as a device tensor
-        (no host sync).  After the call engine.store.flat_grad holds the all-reduced gradient."""
+        (no host sync).  After the call engine.store.flat_grad holds the all-reduced gradient.
+
+        optimizer (optim.Adam over [(store.flat, store.flat_grad), ...]): the parameter update is applied too, gradient
+        group by gradient group on the side stream, each as soon as the group is final (and all-reduced): the update of the
+        head parameters runs beside the BPTT kernel, only the last small group's update is exposed."""
         eng = self.engine
         return self._run(caption, lambda: eng.train_forward(g, P, caption)[0],
                          lambda scale, inv: eng.train_backward(scale, inv, want_dg=want_input_grads,
-                                                               want_dP=want_input_grads), extra=())
+                                                               want_dP=want_input_grads), extra=(), optimizer=optimizer)
 
-    def forward_backward_map(self, enc_map, caption, want_dmap: bool = False):
+    def forward_backward_map(self, enc_map, caption, want_dmap: bool = False, optimizer=None):
         """The same from the encoder map (feature adaptor in front): additionally all-reduces
         engine.adaptor.flat_grad.  Returns (global loss, d enc_map of this rank's shard or None); the map gradient of a
         shard is already normalised by the global token count."""
@@ -55,14 +59,21 @@ class DataParallelTrainer:
             out["dmap"] = eng.train_backward_map(scale, inv, want_dmap=want_dmap)
 
         loss = self._run(caption, lambda: eng.train_forward_map(enc_map, caption)[0], bwd,
-                         extra=(eng.adaptor.flat_grad,))
+                         extra=(eng.adaptor.flat_grad,), optimizer=optimizer)
         return loss, out.get("dmap")
 
-    def _run(self, caption, fwd, bwd, extra):
+    def _run(self, caption, fwd, bwd, extra, optimizer=None):
         eng = self.engine
+        if optimizer is not None:
+            want = 1 + len(extra)
+            if len(optimizer.buffers) != want or optimizer.buffers[0][1].data_ptr() != eng.store.flat_grad.data_ptr():
+                raise ValueError("the optimizer must be built over [(store.flat, store.flat_grad)%s]"
+                                 % (", (adaptor.flat, adaptor.flat_grad)" if extra else ""))
         if self.world == 1:
             loss_buf = fwd()
             bwd(1.0, None)
+            if optimizer is not None:
+                self._grouped_exchange(extra, optimizer, reduce=False)
             return loss_buf[2]
         if self.pe_semantics:
             # ParallelExecutor default (CoeffNumDevice): mean over devices of per-device token means
@@ -71,23 +82,26 @@ class DataParallelTrainer:
             loss = loss_buf[2].clone()
             dist.all_reduce(loss, group=self.group)
             loss /= self.world
-            self._all_reduce_grads(extra)
+            self._grouped_exchange(extra, optimizer, reduce=True)
             return loss
-        if not getattr(self, "_overlap_ready", False):
-            self._setup_overlap()
-            self._overlap_ready = True
+        self._ensure_overlap()
         if self._overlap and os.environ.get("CAPDEC_DP_EARLY_COUNT", "1") != "0":
-            return self._forward_backward_overlapped(caption, fwd, bwd, extra)
+            return self._forward_backward_overlapped(caption, fwd, bwd, extra, optimizer)
         loss_buf = fwd()
         tot = loss_buf[:2].clone()
         dist.all_reduce(tot, group=self.group)               # (sum ce*mask, sum mask) over all ranks
         inv = (1.0 / tot[1]).reshape(1)
         bwd(1.0, inv)
         loss = tot[0] / tot[1]
-        self._all_reduce_grads(extra)
+        self._grouped_exchange(extra, optimizer, reduce=True)
         return loss
 
-    def _forward_backward_overlapped(self, caption, fwd, bwd, extra):
+    def _ensure_overlap(self):
+        if not getattr(self, "_overlap_ready", False):
+            self._setup_overlap()
+            self._overlap_ready = True
+
+    def _forward_backward_overlapped(self, caption, fwd, bwd, extra, optimizer=None):
         """Global token normalisation without a synchronisation point between forward and backward.  The normaliser
         sum(mask) depends on the captions only (model:165-169), not on the forward pass: its all-reduce is issued on the
         communication stream BEFORE the forward pass and runs beside it, so the backward pass starts with the global
@@ -110,20 +124,12 @@ class DataParallelTrainer:
         self._fwd_done.record(main)
         main.wait_event(self._count_done)
         bwd(1.0, inv)
-        flat = eng.store.flat_grad
         with torch.cuda.stream(comm):
             comm.wait_event(self._fwd_done)
             tot = loss_buf[:1].clone()
             dist.all_reduce(tot, group=self.group)
             loss = (tot * inv).reshape(())
-            for ev, lo, hi in self._slices:
-                comm.wait_event(self._events[ev])
-                dist.all_reduce(flat[lo:hi], group=self.group)
-            if extra:
-                comm.wait_stream(main)                       # the adaptor backward runs after capdec_train_bwd
-                for t in extra:
-                    dist.all_reduce(t, group=self.group)
-        main.wait_stream(comm)
+        self._grouped_exchange(extra, optimizer, reduce=True)
         # tensors allocated on the communication stream and read on the main stream: keep them alive until the next step
         self._keep = (cnt, inv, tot, loss)
         return loss
@@ -133,7 +139,7 @@ class DataParallelTrainer:
         gradients is final (CaptionDecoderEngine.set_grad_ready_events) get three events and a communication stream."""
         eng = self.engine
         self._overlap = False
-        if self.world == 1 or not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
+        if not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
             return
         self._comm = torch.cuda.Stream()
         self._events = [torch.cuda.Event() for _ in range(getattr(eng, "N_GRAD_EVENTS", 5))]
@@ -146,28 +152,42 @@ class DataParallelTrainer:
         self._count_done = torch.cuda.Event()
         self._overlap = True
 
-    def _all_reduce_grads(self, extra=()):
+    def _grouped_exchange(self, extra=(), optimizer=None, reduce=True):
+        """Per gradient group, in the order capdec_train_bwd finalises them (its events): all-reduce the group (reduce) and
+        apply the optimizer to exactly that range (optimizer), on the side stream, beside the rest of the backward pass.
+        `extra`: further flat gradient buffers that are final when the main stream reaches this point (the adaptor's);
+        they are optimizer.buffers[1:]."""
         eng = self.engine
-        if not getattr(self, "_overlap_ready", False):
-            self._setup_overlap()
-            self._overlap_ready = True
-        if not self._overlap:
-            dist.all_reduce(eng.store.flat_grad, group=self.group)
-            for t in extra:
-                dist.all_reduce(t, group=self.group)
+        self._ensure_overlap()
+        flat = eng.store.flat_grad
+        if not self._overlap:                                # engines without gradient-ready events (CPU tests)
+            if reduce:
+                dist.all_reduce(flat, group=self.group)
+                for t in extra:
+                    dist.all_reduce(t, group=self.group)
+            if optimizer is not None:
+                optimizer.step()
             return
         main = torch.cuda.current_stream()
-        flat = eng.store.flat_grad
+        lr = optimizer.current_lr() if optimizer is not None else None
         with torch.cuda.stream(self._comm):
             for ev, lo, hi in self._slices:
                 # every group waits for its own event, recorded by capdec_train_bwd in the middle of the backward pass
                 self._comm.wait_event(self._events[ev])
-                dist.all_reduce(flat[lo:hi], group=self.group)
+                if reduce:
+                    dist.all_reduce(flat[lo:hi], group=self.group)
+                if optimizer is not None:
+                    optimizer.step_range(0, lo, hi, lr)
             if extra:
-                self._comm.wait_stream(main)
-                for t in extra:
-                    dist.all_reduce(t, group=self.group)
+                self._comm.wait_stream(main)                 # the adaptor backward runs after capdec_train_bwd
+                for i, t in enumerate(extra):
+                    if reduce:
+                        dist.all_reduce(t, group=self.group)
+                    if optimizer is not None:
+                        optimizer.step_range(1 + i, 0, t.numel(), lr)
         main.wait_stream(self._comm)
+        if optimizer is not None:
+            optimizer.advance()
 
 
 def sharded_decode(engine, g, P, beam: int, finish_on_stop: bool, rank: int, world: int):

@@ -184,3 +184,48 @@ def test_three_optimisation_steps_follow_the_oracle():
         want = pn[k] if k in pn else an[k]
         assert float((got - want).abs().mean()) < 1e-3, k
     assert opt.steps == 3 and abs(float(opt.beta1_pow) - 0.9 ** 4) < 1e-6
+
+
+def test_grouped_update_beside_the_backward_pass_equals_a_plain_step():
+    """DataParallelTrainer(optimizer=...) applies Adam gradient group by gradient group on the side stream as the groups
+    become final.  The update is element-wise, so replaying a plain whole-buffer Adam step from the parameters before the
+    call and the gradients the call left behind must give the same parameters and moments bit for bit -- which also shows
+    that no group was updated before its gradient was final."""
+    cfg = M.DecoderConfig(dtype="bf16", softmax_axis="position", **MID)
+    ocfg = R.DecoderConfig(softmax_axis="position", **MID)
+    x = TR.make_encoder_map(ocfg, 8, 128, 3).cuda()
+    g, P, cap = synth.make_batch(ocfg, 8, 3)
+    g, P, cap = g.cuda(), P.cuda(), cap.cuda()
+    eng = M.CaptionDecoderEngine(cfg, seed=4, bias_scale=0.1)
+    eng.attach_adaptor(128, seed=4, bias_scale=0.1)
+    opt = M.get_optimizer(eng, {"learning_rate": 1e-3, "gradient_clip": 0.5})[0]
+    tr = M.DataParallelTrainer(eng)
+    stores = (eng.store, eng.adaptor)
+    for step in range(3):
+        eng.bind_params()
+        eng.bind_adaptor()
+        before = [(st.flat.clone(), m.clone(), v.clone()) for st, m, v in zip(stores, opt.moment1, opt.moment2)]
+        b1p, b2p = float(opt.beta1_pow), float(opt.beta2_pow)
+        tr.forward_backward_map(x, cap, optimizer=opt)
+        torch.cuda.synchronize()
+        assert opt.steps == step + 1
+        for (p0, m0, v0), st, m, v in zip(before, stores, opt.moment1, opt.moment2):
+            replay = M.Adam([(p0, st.flat_grad)], 1e-3, gradient_clip=0.5)
+            replay.moment1[0].copy_(m0)
+            replay.moment2[0].copy_(v0)
+            replay.beta1_pow, replay.beta2_pow = np.float32(b1p), np.float32(b2p)
+            replay.step()
+            torch.cuda.synchronize()
+            assert float(st.flat_grad.abs().max()) > 0
+            assert torch.equal(p0, st.flat.detach()) and torch.equal(replay.moment1[0], m) and torch.equal(replay.moment2[0], v)
+    # decoder only, with a one-buffer optimizer
+    o0 = M.Adam([(eng.store.flat, eng.store.flat_grad)], 1e-3)
+    p0 = eng.store.flat.detach().clone()
+    eng.bind_params()
+    tr.forward_backward(g, P, cap, optimizer=o0)
+    replay = M.Adam([(p0, eng.store.flat_grad)], 1e-3)
+    replay.step()
+    torch.cuda.synchronize()
+    assert torch.equal(p0, eng.store.flat.detach()) and torch.equal(replay.moment2[0], o0.moment2[0]) and o0.steps == 1
+    with pytest.raises(ValueError):        # an optimizer over the wrong buffers
+        tr.forward_backward(g, P, cap, optimizer=opt)
