@@ -201,7 +201,9 @@ struct SeqFwdParams {
 //
 // CS = cluster size along the unit-slice dimension: the CS CTAs of a cluster work on the same batch tile, each loads
 // 128/CS rows of every h k-block and multicasts them.  Measured on B200: no gain over CS = 1 (474 / 468 / 469 us for
-// CS = 1 / 2 / 4) -- delivery into the SMs, not the L2 read, bounds the h stream -- so CS = 1 is the default.
+// CS = 1 / 2 / 4 on the first version, 336 / 336 / 334 us on the current one; the L2 already merges the unicast requests
+// of a few CTAs for the same line) -- delivery into the SMs, not the L2 read, bounds the h stream -- so CS = 1 is the
+// default.  CS = 8 cannot be launched: 16 clusters of 8 CTAs with 217 KB each are not co-schedulable on the GPCs.
 template <int CS>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
@@ -811,7 +813,7 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
   // cluster size: CAPDEC_REC_CLUSTER in {1, 2, 4} (tuning; see the kernel's comment)
   int cs = 1;
   if (const char* ev = getenv("CAPDEC_REC_CLUSTER")) cs = atoi(ev);
-  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;   // 8: 16 clusters of 8 x 217 KB cannot be co-scheduled ("too many blocks")
   while (cs > 1 && slices % cs) cs >>= 1;
   const void* kern = cs == 4   ? (const void*)lstm_seq_fwd_kernel<4>
                      : cs == 2 ? (const void*)lstm_seq_fwd_kernel<2>
