@@ -23,15 +23,11 @@ import numpy as np
 
 
 def filter(p, index_word, stop_tag: int = 3, padding_tag: int = 0):   # noqa: A001  (the reference's name, evaluate.py:15)
-    """evaluate.py:15-25: index list -> word list; stops at <stop>, skips <pad>."""
-    result = []
-    for idx in p:
-        if idx == stop_tag:
-            break
-        if idx == padding_tag:
-            continue
-        result.append(index_word[idx])
-    return result
+    """evaluate.py:15-25: ids -> words.  Everything from the first <stop> on is dropped, <pad> is skipped."""
+    ids = list(p)
+    if stop_tag in ids:
+        ids = ids[:ids.index(stop_tag)]
+    return [index_word[i] for i in ids if i != padding_tag]
 
 
 def words2sentence(words):
@@ -103,48 +99,47 @@ def sentence_bleu(references, hypothesis, weights=(0.25, 0.25, 0.25, 0.25), smoo
     return bp * math.exp(s)
 
 
-def calc_bleu(pred, real, index_word, weights=(0.25, 0.25, 0.25, 0.25), stop_tag: int = 3, padding_tag: int = 0,
-              method4_version: str = "3.5"):
-    """evaluate.py:28-40: mean over the batch of the smoothed sentence BLEU; captions of <= 1 word score 0 but still
-    count in the denominator.  `pred` may be the float32 id array the decoder returns (model:122)."""
+def _as_id_lists(pred):
+    """The decoder returns float32 ids (model:122): round to int like evaluate.py:30-32."""
     if isinstance(pred, np.ndarray):
         if pred.dtype == "float32":
             pred = np.rint(pred).astype("int32")
-        pred = pred.tolist()
-    total_score = 0
-    for p, r in zip(pred, real):
-        p = filter(p, index_word, stop_tag, padding_tag)
-        if len(p) <= 1:
-            continue
-        total_score += sentence_bleu(r, p, weights=weights, smoothing="method4", method4_version=method4_version)
-    return total_score / len(pred)
+        return pred.tolist()
+    return pred
+
+
+def calc_bleu(pred, real, index_word, weights=(0.25, 0.25, 0.25, 0.25), stop_tag: int = 3, padding_tag: int = 0,
+              method4_version: str = "3.5"):
+    """evaluate.py:28-40: mean over the batch of the smoothed sentence BLEU.  Captions of <= 1 word score 0 but still
+    count in the denominator (the guard that keeps NLTK 3.5's method4 away from ln(1) = 0)."""
+    pred = _as_id_lists(pred)
+    captions = [filter(p, index_word, stop_tag, padding_tag) for p in pred]
+    scores = [sentence_bleu(refs, words, weights=weights, smoothing="method4", method4_version=method4_version)
+              for words, refs in zip(captions, real) if len(words) > 1]
+    return sum(scores) / len(pred)
 
 
 def evaluate(decode_fn: Callable, batches: Iterable, index_word, sentence_statistics: bool = True, stop_tag: int = 3,
              padding_tag: int = 0):
     """evaluate.py:46-74 with the Paddle inference program replaced by `decode_fn(images) -> float32 ids [B,T]`
     (e.g. ``lambda x: engine.decode_map(x)[2].cpu().numpy()``).  `batches` yields lists of (image, references) like
-    DataReader.get_reader(batch_size, 'test') (reader.py:65-72).  Returns ([BLEU-1..4, mean], distinct sentences)."""
-    bleu_score = [0] * 5
-    bleu_vec = ([1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1])
-    sentence_said = set()
-    n_batches = 0
+    DataReader.get_reader(batch_size, 'test') (reader.py:65-72).  Returns ([BLEU-1, BLEU-2, BLEU-3, BLEU-4, their mean],
+    number of distinct sentences): per-order scores use one-hot weights and are averaged over BATCHES, not samples, exactly
+    like the reference (a short last batch weighs as much as a full one)."""
+    one_hot = np.eye(4).tolist()
+    per_batch = []                       # rows: [BLEU-1..4] of one batch
+    said = set()
     for data in batches:
-        img, real_cap = zip(*data)
-        cp = decode_fn(np.stack(img))
-        cp = np.asarray(cp)
-        for idx, vec in enumerate(bleu_vec):
-            bleu_score[idx] += calc_bleu(cp, real_cap, index_word, vec, stop_tag, padding_tag)
+        images = np.stack([d[0] for d in data])
+        refs = [d[1] for d in data]
+        ids = np.asarray(decode_fn(images))
+        per_batch.append([calc_bleu(ids, refs, index_word, w, stop_tag, padding_tag) for w in one_hot])
         if sentence_statistics:
-            for p in np.rint(cp).astype("int32").tolist():
-                sentence_said.add(words2sentence(filter(p, index_word, stop_tag, padding_tag)))
-        n_batches += 1
-    if n_batches == 0:
+            said.update(words2sentence(filter(p, index_word, stop_tag, padding_tag)) for p in _as_id_lists(ids))
+    if not per_batch:
         raise ValueError("no batches to evaluate")
-    for i in range(len(bleu_score)):
-        bleu_score[i] /= n_batches
-    bleu_score[4] = sum(bleu_score[:-1]) / 4
-    return bleu_score, len(sentence_said)
+    orders = np.mean(np.asarray(per_batch, dtype=np.float64), axis=0).tolist()
+    return orders + [sum(orders) / 4], len(said)
 
 
 class SyntheticReader:
