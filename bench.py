@@ -61,8 +61,9 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index = index
+        self.enabled = enabled
         self.samples = []      # (t, fields)
         self.windows = []      # [t0, t1]
         self.proc = None
@@ -78,6 +79,8 @@ class ClockSampler:
             pass
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
@@ -267,6 +270,11 @@ def main_ours(args):
     # enqueues the next step; the last value is read after the closing synchronisation of the timed region
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_evt = [torch.cuda.Event() for _ in range(2)]
+    # the 4-byte D2H copy runs on its own stream from a device-side staging scalar, so that the compute stream never waits
+    # for a copy-engine operation between two steps
+    d2h_stream = torch.cuda.Stream()
+    loss_stage = [torch.zeros(1, dtype=torch.float32, device="cuda") for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
     pending = []
 
     def drain(block, only=None):
@@ -291,14 +299,19 @@ def main_ours(args):
         k = i & 1
         if k in pending:                                  # the buffer about to be reused (written two steps ago)
             drain(True, only=k)
-        loss_host[k].copy_(loss.reshape(1), non_blocking=True)   # D2H read of the step's result
-        loss_evt[k].record()
+        loss_stage[k].copy_(loss.reshape(1))                # device-side copy on the compute stream
+        staged[k].record()
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(staged[k])
+            loss_host[k].copy_(loss_stage[k], non_blocking=True)   # D2H read of the step's result
+            loss_evt[k].record(d2h_stream)
         pending.append(k)
         drain(False)
 
     for c in consumed:
         c.record()
-    with ClockSampler(local_rank) as clocks:              # started before the warm-up: nvidia-smi needs a moment
+    # rank 0 prints the line and samples its own GPU; N polling nvidia-smi processes would only contend for the driver
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:   # started before the warm-up: nvidia-smi needs a moment
         for i in range(args.warmup):
             step_resident(i)
         sync()
