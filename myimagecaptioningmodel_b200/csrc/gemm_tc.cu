@@ -88,6 +88,30 @@ __device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// Shared-memory accesses of the epilogue by 32-bit shared-window address.  Going through generic pointers made ptxas
+// rebuild the generic address (S2UR SR_CgaCtaId + ULEA) and convert it back at every pass: 8 % of the stall samples of the
+// epilogue-bound vocabulary GEMM sat on that special-register read (ncu source page).
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_store_3d_s(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d_s(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -137,8 +161,8 @@ __device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, 
 // 128-byte row).  FULL = all 32 columns are < N: straight-line code the scheduler can interleave freely (the
 // epilogue has only two warps per scheduler, so exposed latencies are what it costs).
 template <bool OUT_F32, bool FULL>
-__device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float* bias_t, const bf16* add_p,
-                                                const bf16* y_p, int fact, float alpha, int left, uint8_t* dst_row,
+__device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, uint32_t bias_t, const bf16* add_p,
+                                                const bf16* y_p, int fact, float alpha, int left, uint32_t dst_row,
                                                 uint32_t swz, uint32_t chunk0, bool sm_grad = false, float lse_row = 0.f,
                                                 int tgt_rel = -1) {
   uint32_t r[32];
@@ -162,9 +186,9 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * alpha;
-      if (bias_t) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias_t + g * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias_t + g * 8 + 4);
+      if (bias_t) {  // shared-window address of this pass's 32 bias values (0: no bias)
+        const float4 b0 = lds_f4(bias_t + (uint32_t)(g * 32));
+        const float4 b1 = lds_f4(bias_t + (uint32_t)(g * 32 + 16));
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
@@ -200,14 +224,16 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, const float*
         }
       }
       if (OUT_F32) {
-        *reinterpret_cast<float4*>(dst_row + (((chunk0 + 2 * g) ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(dst_row + (((chunk0 + 2 * g + 1) ^ swz) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+        sts_v4(dst_row + (((chunk0 + 2 * g) ^ swz) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+               __float_as_uint(v[2]), __float_as_uint(v[3]));
+        sts_v4(dst_row + (((chunk0 + 2 * g + 1) ^ swz) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]),
+               __float_as_uint(v[6]), __float_as_uint(v[7]));
       } else {
         uint4 u;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        *reinterpret_cast<uint4*>(dst_row + (((chunk0 + g) ^ swz) << 4)) = u;
+        sts_v4(dst_row + (((chunk0 + g) ^ swz) << 4), u.x, u.y, u.z, u.w);
       }
     }
   }
@@ -251,7 +277,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + 256);  // [2][BN], 16-byte aligned
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + 256);  // [2][BN]
+  // the same two as shared-window addresses; the volatile move keeps ptxas from re-deriving the value (a special-register
+  // read and the alignment arithmetic) at every use instead of holding it in a register
+  uint32_t staging_sa;
+  asm volatile("mov.u32 %0, %1;" : "=r"(staging_sa) : "r"(smem_u32(staging)));
+  const uint32_t bias_sa = staging_sa + (uint32_t)Cfg::kStagingBytes + 256u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb_total = (sh.K + BK - 1) / BK;
@@ -372,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // stage this tile's bias slice (zero past the readable range) while the MMAs are still running
         const int n_read = (sh.N + 7) & ~7;
         for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
-          bias_s[(it & 1) * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
+          sts_f32(bias_sa + (uint32_t)(((it & 1) * BN + i) * 4), (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
       }
       mbar_wait(&tmem_full_bar[buf], acc_ph);
@@ -390,9 +421,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // Passes (128 bytes of output per row each) are dealt round-robin to the two warps of a lane quarter.  The
           // host guarantees (launch()) that bias / addend / dact_y may be read in whole groups of 8 columns up to the
           // next multiple of 8 past N; columns >= N are clipped by the TMA store, so there is no scalar edge path.
-          uint8_t* my_stage = staging + ew * 4096;
+          const uint32_t my_stage = staging_sa + (uint32_t)(ew * 4096);
           const uint32_t swz = (uint32_t)(lane & 7);
-          uint8_t* my_row = my_stage + lane * 128;
+          const uint32_t my_row = my_stage + (uint32_t)(lane * 128);
           const long add_row = epi.add_mod > 0 ? row % epi.add_mod : row;
           const bf16* add_p = (epi.addend && row_ok) ? reinterpret_cast<const bf16*>(epi.addend) + bt * epi.batch_add +
                                                            add_row * epi.ld_add + n0
@@ -424,7 +455,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int left = sh.N - (n0 + c0);  // valid columns from here on (warp-uniform)
             if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
             __syncwarp();
-            const float* bsp = has_bias ? bias_s + (it & 1) * BN + c0 : nullptr;
+            const float* bsp = has_bias ? bias_s + (it & 1) * BN + c0 : nullptr;          // ACT_ROWSTATS path only
+            const uint32_t bsa = has_bias ? bias_sa + (uint32_t)(((it & 1) * BN + c0) * 4) : 0u;
             const bf16* ap = add_p ? add_p + c0 : nullptr;
             const bf16* yp = y_p ? y_p + c0 : nullptr;
             if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
@@ -444,18 +476,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               continue;
             }
             if (f32_out) {
-              if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
-              else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+              if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsa, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+              else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsa, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
             } else {
 #pragma unroll 1
               for (int sub = 0; sub < 2; ++sub) {  // 2 x 32 columns = one 128-byte bf16 row
                 const int o = sub * 32;
                 if (left - o >= 32)
-                  epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                  epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                                yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
                                                (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
                 else
-                  epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+                  epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                                 yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
                                                (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
               }
@@ -470,8 +502,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
-              else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
+              if (epi.atomic) tma_reduce_add_3d_s(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
+              else tma_store_3d_s(&tmC, my_stage, n0 + c0, m0 + mh * BM + quarter * 32, bt);
               bulk_commit();
             }
           }
@@ -632,6 +664,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]  (used in the leader only)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + 256);  // [2][BN]
+  // the same two as shared-window addresses; the volatile move keeps ptxas from re-deriving the value (a special-register
+  // read and the alignment arithmetic) at every use instead of holding it in a register
+  uint32_t staging_sa;
+  asm volatile("mov.u32 %0, %1;" : "=r"(staging_sa) : "r"(smem_u32(staging)));
+  const uint32_t bias_sa = staging_sa + (uint32_t)Cfg::kStagingBytes + 256u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -670,6 +707,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===== TMA producer (both CTAs): my 128 rows of A, my 128 columns of B; bytes counted by the LEADER's barrier =====
       int s = 0;
       uint32_t ph = 0;
+      // the leader's full barriers in the cluster window: mapped once (mapa reads a special register: ncu showed 8 % of
+      // the stall samples of an epilogue-bound launch on that read when it sat inside the tile loops)
+      const uint32_t fb0 = map_to_rank(&full_bar[0], 0);
       for (int w = pair; w < total_work; w += n_pairs) {
         const int z = w / tb, bt = (w % tb) / tiles, tile = w % tiles;
         const int n0 = (tile % sh.tiles_n) * BN + (int)rank * (BN / 2);
@@ -679,7 +719,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_bd(&empty_bar[s], ph ^ 1);
           uint8_t* sA = smem + s * Cfg::kStageBytes;
           uint8_t* sB = sA + kABytes;
-          const uint32_t fb = map_to_rank(&full_bar[s], 0);
+          const uint32_t fb = fb0 + (uint32_t)s * 8u;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
           if (!A_MN) {
             tma_load_3d_pair(sA, &tmA, kb * BK, m0, bt, fb);
@@ -732,6 +772,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int half = ew >> 2;
     int it = 0;
+    const uint32_t empty_leader0 = map_to_rank(&tmem_empty_bar[0], 0);
     for (int w = pair; w < total_work; w += n_pairs, ++it) {
       const int bt = (w % tb) / tiles, tile = w % tiles;
       const int n0 = (tile % sh.tiles_n) * BN, m0 = (tile / sh.tiles_n) * (2 * BM) + (int)rank * BM;
@@ -743,7 +784,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (has_bias) {
         const int n_read = (sh.N + 7) & ~7;
         for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32)
-          bias_s[buf * BN + i] = (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f;
+          sts_f32(bias_sa + (uint32_t)((buf * BN + i) * 4), (n0 + i < n_read) ? epi.bias[n0 + i] : 0.f);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
       mbar_wait_bd(&tmem_full_bar[buf], acc_ph);
@@ -766,7 +807,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int pw = f32_out ? 32 : 64;
       const int n_pass = BN / pw;
       const int my_last = ((n_pass - 1 - half) & ~1) + half;
-      const uint32_t empty_leader = map_to_rank(&tmem_empty_bar[buf], 0);
+      const uint32_t empty_leader = empty_leader0 + (uint32_t)buf * 8u;
       const bool warp_empty = (m0 + quarter * 32) >= sh.M;  // none of this warp's rows exists: nothing to read or store
       if (warp_empty) {
         tc_fence_before();
@@ -777,11 +818,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
-        uint8_t* my_stage = staging + ew * 4096;
-        uint8_t* my_row = my_stage + lane * 128;
+        const uint32_t my_stage = staging_sa + (uint32_t)(ew * 4096);
+        const uint32_t my_row = my_stage + (uint32_t)(lane * 128);
         if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
         __syncwarp();
-        const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;
+        const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;                   // ACT_ROWSTATS path only
+        const uint32_t bsa = has_bias ? bias_sa + (uint32_t)((buf * BN + c0) * 4) : 0u;
         const bf16* ap = add_p ? add_p + c0 : nullptr;
         const bf16* yp = y_p ? y_p + c0 : nullptr;
         if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
@@ -801,18 +843,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           continue;
         }
         if (f32_out) {
-          if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
-          else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsp, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+          if (left >= 32) epilogue_cols32<true, true>(tmem_d + (uint32_t)c0, bsa, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
+          else epilogue_cols32<true, false>(tmem_d + (uint32_t)c0, bsa, ap, yp, do_tanh, alpha, left, my_row, swz, 0);
         } else {
 #pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             const int o = sub * 32;
             if (left - o >= 32)
-              epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+              epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
                                            sm_grad, lse_row, tgt_row - (n0 + c0 + o));
             else
-              epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsp ? bsp + o : nullptr, ap ? ap + o : nullptr,
+              epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                             yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
                                             sm_grad, lse_row, tgt_row - (n0 + c0 + o));
           }
@@ -827,8 +869,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (epi.atomic) tma_reduce_add_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
-          else tma_store_3d(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
+          if (epi.atomic) tma_reduce_add_3d_s(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
+          else tma_store_3d_s(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
           bulk_commit();
         }
       }
