@@ -577,17 +577,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   tmem_empty (leader)    : 2 x 8 epilogue warps arrive (the peer's through the cluster shared window)
 // ================================================================================================================
 constexpr int kPairBN = 256;
-struct PairCfg {
+// EPI2: the variant for short-K, epilogue-bound problems (K <= 512: the fp32 vocabulary logits, the x-part pre-activations):
+// four pipeline stages are enough for a 4..8 k-block mainloop, and the freed 64 KB give every epilogue warp a second
+// staging tile, so the tensor store of pass i drains while pass i+1 is converted (bulk_wait_read<1>).
+template <bool EPI2> struct PairCfgT {
   static constexpr int kBHalfBytes = (kPairBN / 2) * BK * 2;    // 16 KB
   static constexpr int kStageBytes = kABytes + kBHalfBytes;     // 32 KB per CTA and stage
-  static constexpr int kStages = 6;
+  static constexpr int kStages = EPI2 ? 4 : 6;
   static constexpr int kTmemCols = 2 * kPairBN;                 // two accumulator buffers
   static constexpr int kAlignSlack = 512;
   // one 32-row x 128-byte output tile per epilogue warp.  (Measured: two tiles per warp with 5 instead of 6 stages is
   // slower -- 3.01 vs 2.91 ms per train step -- the epilogue does not wait on its previous store.)
-  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kStagingBytes = kEpiWarps * 4096 * (EPI2 ? 2 : 1);
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAlignSlack + 256 + 2 * kPairBN * 4;
 };
+using PairCfg = PairCfgT<false>;
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -647,11 +651,11 @@ __device__ __forceinline__ void mbar_wait_bd(uint64_t* bar, uint32_t parity) {
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool EPI2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, TcShape sh, GemmEpi epi) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfgT<EPI2>;
   constexpr int BN = kPairBN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -772,6 +776,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int half = ew >> 2;
     int it = 0;
+    uint32_t stage_flip = 0;
     const uint32_t empty_leader0 = map_to_rank(&tmem_empty_bar[0], 0);
     for (int w = pair; w < total_work; w += n_pairs, ++it) {
       const int bt = (w % tb) / tiles, tile = w % tiles;
@@ -818,9 +823,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
-        const uint32_t my_stage = staging_sa + (uint32_t)(ew * 4096);
+        // EPI2: two staging tiles per warp, used alternately: only the store before the previous one must have drained
+        const uint32_t my_stage = staging_sa + (uint32_t)((EPI2 ? ew * 2 + (int)(stage_flip & 1u) : ew) * 4096);
         const uint32_t my_row = my_stage + (uint32_t)(lane * 128);
-        if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
+        if (lane == 0) bulk_wait_read<EPI2 ? 1 : 0>();  // the store that last used this staging tile has finished reading it
         __syncwarp();
         const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;                   // ACT_ROWSTATS path only
         const uint32_t bsa = has_bias ? bias_sa + (uint32_t)((buf * BN + c0) * 4) : 0u;
@@ -873,6 +879,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else tma_store_3d_s(&tmC, my_stage, n0 + c0, m0 + quarter * 32, bt);
           bulk_commit();
         }
+        ++stage_flip;  // the staging tiles alternate per ISSUED store (bulk_wait_read<1> counts stores, not passes)
       }
     }
   }
@@ -1043,12 +1050,12 @@ template <int BN, int MT> int launch_majors(GemmContext& ctx, const GemmCall& c,
   return c.b_mn ? launch<BN, false, true, MT>(ctx, c, splits, kbps) : launch<BN, false, false, MT>(ctx, c, splits, kbps);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool EPI2>
 int launch_pair(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfgT<EPI2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
@@ -1083,7 +1090,7 @@ int launch_pair(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN>, tmA, tmB, tmC, sh, c.epi);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN, EPI2>, tmA, tmB, tmC, sh, c.epi);
   ctx.launches++;
   if (err != cudaSuccess) { set_error("gemm_tc pair launch: %s", cudaGetErrorString(err)); return -1; }
   return 0;
@@ -1166,8 +1173,9 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (const char* ev = getenv("CAPDEC_GEMM_PAIR")) pair_env = atoi(ev);
   bool use_pair = false;
   int pair_sp = 1;
+  const long pair_tiles = (long)((c.M + 2 * BM - 1) / (2 * BM)) * ((c.N + kPairBN - 1) / kPairBN) * (c.batch > 0 ? c.batch : 1);
   if (pair_env != 0 && pair_eligible(c)) {
-    const long tiles = (long)((c.M + 2 * BM - 1) / (2 * BM)) * ((c.N + kPairBN - 1) / kPairBN) * (c.batch > 0 ? c.batch : 1);
+    const long tiles = pair_tiles;
     const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
     const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
     double pair_cost = 1e300;
@@ -1184,8 +1192,12 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (use_pair) {
     const int kbps2 = (nkb + pair_sp - 1) / pair_sp;
     const int splits2 = (nkb + kbps2 - 1) / kbps2;
-    if (c.a_mn) return c.b_mn ? launch_pair<true, true>(ctx, c, splits2, kbps2) : launch_pair<true, false>(ctx, c, splits2, kbps2);
-    return c.b_mn ? launch_pair<false, true>(ctx, c, splits2, kbps2) : launch_pair<false, false>(ctx, c, splits2, kbps2);
+    // short-K forward-form problems with many tiles per pair are epilogue-bound: the variant with two staging tiles per warp
+    static const int epi2_env = [] { const char* ev = getenv("CAPDEC_GEMM_EPI2"); return ev ? atoi(ev) : 1; }();
+    const bool epi2 = epi2_env != 0 && !c.a_mn && splits2 == 1 && kbps2 <= 8 && pair_tiles >= 3 * (kNumSMs / 2);
+    if (epi2) return c.b_mn ? launch_pair<false, true, true>(ctx, c, splits2, kbps2) : launch_pair<false, false, true>(ctx, c, splits2, kbps2);
+    if (c.a_mn) return c.b_mn ? launch_pair<true, true, false>(ctx, c, splits2, kbps2) : launch_pair<true, false, false>(ctx, c, splits2, kbps2);
+    return c.b_mn ? launch_pair<false, true, false>(ctx, c, splits2, kbps2) : launch_pair<false, false, false>(ctx, c, splits2, kbps2);
   }
   if (const char* ev = getenv("CAPDEC_GEMM_BN")) {  // tuning / profiling override
     const int v = atoi(ev);

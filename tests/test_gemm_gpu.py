@@ -180,3 +180,26 @@ def test_gemm_tile_heights(M, N, K, majors, mt, monkeypatch):
                    act=1)[:, :N]
         ref2 = torch.tanh(ref + bias[:N] + addend[:, :N].float())
         assert rel_err(out.float(), ref2) < BF16_TOL, rel_err(out.float(), ref2)
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(4096, 4000, 256, False), (4096, 4104, 448, True), (8704, 12295, 256, False)])
+def test_gemm_short_k_many_tiles(M, N, K, b_mn):
+    """short-K problems with several output tiles per CTA pair take the pair kernel's variant with two staging tiles per
+    epilogue warp (4 pipeline stages): fp32 and bf16 outputs, ragged right edge, relu / drelu epilogues"""
+    A = _rand((M, K), torch.bfloat16, 11)
+    B = _rand((K, N + (-N) % 8) if b_mn else (N, K), torch.bfloat16, 12)
+    Bm = B[:, :N].float() if b_mn else B.float().t()
+    ref = A.float() @ Bm
+    ldc = (N + 7) // 8 * 8
+    Cbuf = torch.zeros(M, ldc, dtype=torch.float32, device="cuda")
+    out = gemm(A, B, M, N, K, b_mn=b_mn, C_out=Cbuf, ldc=ldc, out_f32=True)[:, :N]
+    assert rel_err(out, ref) < F32_TOL, rel_err(out, ref)
+    if ldc > N:
+        assert float(Cbuf[:, N:].abs().max()) == 0.0
+    if M * N <= 2e7:
+        Cb = torch.zeros(M, ldc, dtype=torch.bfloat16, device="cuda")
+        outb = gemm(A, B, M, N, K, b_mn=b_mn, C_out=Cb, ldc=ldc, act=5)[:, :N]          # ACT_RELU
+        assert rel_err(outb.float(), torch.relu(ref)) < BF16_TOL
+        y = torch.relu(_rand((M, ldc), torch.float32, 13)).to(torch.bfloat16)
+        outd = gemm(A, B, M, N, K, b_mn=b_mn, C_out=Cb, ldc=ldc, dact_y=y, act=6)[:, :N]   # ACT_DRELU
+        assert rel_err(outd.float(), ref * (y[:, :N].float() > 0)) < BF16_TOL
