@@ -580,15 +580,19 @@ constexpr int kPairBN = 256;
 // EPI2: the variant for short-K, epilogue-bound problems (K <= 512: the fp32 vocabulary logits, the x-part pre-activations):
 // four pipeline stages are enough for a 4..8 k-block mainloop, and the freed 64 KB give every epilogue warp a second
 // staging tile, so the tensor store of pass i drains while pass i+1 is converted (bulk_wait_read<1>).
+#ifndef CAPDEC_EPI_DEPTH
+#define CAPDEC_EPI_DEPTH 2   // staging tiles per epilogue warp in the EPI2 variant (2: 4 pipeline stages, 3: 3 stages)
+#endif
+constexpr int kEpiDepth = CAPDEC_EPI_DEPTH;
 template <bool EPI2> struct PairCfgT {
   static constexpr int kBHalfBytes = (kPairBN / 2) * BK * 2;    // 16 KB
   static constexpr int kStageBytes = kABytes + kBHalfBytes;     // 32 KB per CTA and stage
-  static constexpr int kStages = EPI2 ? 4 : 6;
+  static constexpr int kStages = EPI2 ? (kEpiDepth == 3 ? 3 : 4) : 6;
   static constexpr int kTmemCols = 2 * kPairBN;                 // two accumulator buffers
   static constexpr int kAlignSlack = 512;
   // one 32-row x 128-byte output tile per epilogue warp.  (Measured: two tiles per warp with 5 instead of 6 stages is
   // slower -- 3.01 vs 2.91 ms per train step -- the epilogue does not wait on its previous store.)
-  static constexpr int kStagingBytes = kEpiWarps * 4096 * (EPI2 ? 2 : 1);
+  static constexpr int kStagingBytes = kEpiWarps * 4096 * (EPI2 ? kEpiDepth : 1);
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAlignSlack + 256 + 2 * kPairBN * 4;
 };
 using PairCfg = PairCfgT<false>;
@@ -824,9 +828,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
         // EPI2: two staging tiles per warp, used alternately: only the store before the previous one must have drained
-        const uint32_t my_stage = staging_sa + (uint32_t)((EPI2 ? ew * 2 + (int)(stage_flip & 1u) : ew) * 4096);
+        const uint32_t my_stage = staging_sa + (uint32_t)((EPI2 ? ew * kEpiDepth + (int)(stage_flip % kEpiDepth) : ew) * 4096);
         const uint32_t my_row = my_stage + (uint32_t)(lane * 128);
-        if (lane == 0) bulk_wait_read<EPI2 ? 1 : 0>();  // the store that last used this staging tile has finished reading it
+        if (lane == 0) bulk_wait_read<EPI2 ? kEpiDepth - 1 : 0>();  // the store that last used this staging tile has finished reading it
         __syncwarp();
         const float* bsp = has_bias ? bias_s + buf * BN + c0 : nullptr;                   // ACT_ROWSTATS path only
         const uint32_t bsa = has_bias ? bias_sa + (uint32_t)((buf * BN + c0) * 4) : 0u;
