@@ -1,0 +1,44 @@
+"""CPU: the bench.py contract that can be checked without a GPU -- the reference arm (`--impl reference`) prints ONE JSON
+line with the keys the driver reads, and rank != 0 exits without work; our arm refuses to run without a GPU (no fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None, timeout=600):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e,
+                          timeout=timeout, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "decoder_train_tokens_per_sec" and d["unit"] == "tokens/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["config"]["workload"].startswith("teacher_forced_train_step_B256")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "Adam" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1"], env={"RANK": "1", "WORLD_SIZE": "2"}, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_our_arm_needs_a_gpu():
+    r = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline"], timeout=300)
+    assert r.returncode != 0                                  # no CPU fallback: the product path fails loudly
+    assert "cuda" in (r.stderr + r.stdout).lower() or "gpu" in (r.stderr + r.stdout).lower()
