@@ -165,3 +165,32 @@ def test_adaptor_store_layout_cpu():
         st2.load({})
     full = M.AdaptorStore(M.DecoderConfig(), 1280, "cpu")
     assert full.num_parameters == 2623488                   # the `_img2feature` parameter count
+
+
+def test_golden_fixture_of_the_widened_rows(golden_dir):
+    """tests/golden/train_small.npz (make_golden_train.py): the oracle reproduces it, the product's LR schedules match it"""
+    import importlib.util
+    import os
+    z = np.load(os.path.join(golden_dir, "train_small.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden_train", os.path.join(golden_dir, "make_golden_train.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = R.DecoderConfig(softmax_axis="position", **mod.SMALL)
+    params = {k[6:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("param_") and k[6:] in R.param_shapes(cfg)}
+    ap = {k: torch.from_numpy(z["param_" + k]).double() for k in TR.ADAPTOR_NAMES}
+    x, cap = torch.from_numpy(z["enc_map"]).double(), torch.from_numpy(z["caption"])
+    loss, logits, grads, (P, g) = TR.loss_and_grads_from_map(params, ap, cfg, x, cap)
+    assert abs(float(loss) - float(z["loss"])) < 1e-12
+    assert np.abs(logits.numpy() - z["logits"]).max() < 1e-5 and np.abs(P.numpy() - z["P"]).max() < 1e-6
+    for k in TR.ADAPTOR_NAMES + ["enc_map", "lstm_w"]:
+        assert np.abs(grads[k].numpy() - z["grad_" + k]).max() < 1e-7 * max(1.0, float(np.abs(z["grad_" + k]).max())) + 1e-9, k
+    p = ap["fc_img_w"].float().numpy().copy()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    gr = torch.from_numpy(z["grad_fc_img_w"]).numpy()
+    b1p, b2p = TR.adam_step_numpy(p, gr, m, v, 1e-3, clip=0.01)
+    TR.adam_step_numpy(p, 0.5 * gr, m, v, 1e-3, beta1_pow=b1p, beta2_pow=b2p, clip=0.01)
+    assert np.abs(p - z["adam_p2"]).max() < 1e-7 and np.abs(v - z["adam_v2"]).max() < 1e-12
+    for name, kw in mod.LR_CASES:
+        sched = M.get_lr(name, 5e-5, 1000, 64, **kw)
+        table = z["lr_" + str(name)]
+        assert max(abs(sched(n) - table[n]) for n in range(len(table))) < 1e-15, name
