@@ -136,7 +136,7 @@ class DataParallelTrainer:
 
     def _setup_overlap(self):
         """Bucketed gradient exchange overlapped with the backward pass: engines that can signal when a group of
-        gradients is final (CaptionDecoderEngine.set_grad_ready_events) get three events and a communication stream."""
+        gradients is final (CaptionDecoderEngine.set_grad_ready_events) get one event per gradient range and a communication stream."""
         eng = self.engine
         self._overlap = False
         if not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
