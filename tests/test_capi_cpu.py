@@ -142,3 +142,35 @@ def test_shard_range():
 def test_filter_caption():
     assert M.filter_caption([5.0, 0.0, 7.0, 3.0, 9.0]) == [5, 7]     # evaluate.py:15-25
     assert M.filter_caption([3.0, 4.0]) == []
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/capdec.h is a C header (no C++ / torch types): a C99 program that uses every struct and takes the address of
+    every entry point compiles with gcc and links against libcapdec.so; without a GPU capdec_create fails with a message."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    syms = _declared_symbols()
+    src = ['#include "capdec.h"', "#include <stdio.h>", "typedef void (*fn_t)(void);", "int main(void) {",
+           "  capdec_config cfg = {1024, 256, 12295, 49, 35, 35, 0, 2, 3, CAPDEC_DTYPE_BF16, CAPDEC_SOFTMAX_POSITION, 0};",
+           "  capdec_params p = {0}; capdec_grads g = {0}; capdec_adaptor_params ap = {0}; capdec_adaptor_grads ag = {0};",
+           "  capdec_handle h = 0; (void)p; (void)g; (void)ap; (void)ag;",
+           "  fn_t fns[] = {" + ", ".join("(fn_t)%s" % s for s in syms) + "};",
+           "  int rc = capdec_create(&cfg, 0, &h);",
+           '  printf("%d %d %s\\n", (int)(sizeof(fns) / sizeof(fns[0])), rc, rc ? capdec_last_error() : "ok");',
+           "  if (!rc) capdec_destroy(h);", "  return 0;", "}"]
+    c_file = tmp_path / "use_capdec.c"
+    c_file.write_text("\n".join(src))
+    exe = str(tmp_path / "use_capdec")
+    lib_dir = os.path.dirname(_build.build())
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", exe,
+                        "-L", lib_dir, "-lcapdec", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    n, rc, msg = out.stdout.strip().split(" ", 2)
+    assert int(n) == len(syms)
+    if not torch.cuda.is_available():
+        assert int(rc) != 0 and ("CUDA" in msg or "no CPU fallback" in msg)
