@@ -183,6 +183,25 @@ def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
                       % (sample_B, torch.get_num_threads(), done)}
 
 
+def run_cpu_beam_reference(n_images=64, reps=2):
+    """The oracle's beam search (beam 3, 35 steps, finished-handling on) on all host threads, a bounded sample
+    of BASELINE.json configs[3]; images/s."""
+    from oracle import decoder_ref as R
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = R.DecoderConfig(softmax_axis=SOFTMAX_AXIS)
+    params = R.init_params(cfg, 0, torch.float32, bias_scale=0.0)
+    g, P, _ = synth.make_batch(cfg, n_images, 777)
+    R.beam_search(params, cfg, g[:8], P[:8], BEAM)          # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        R.beam_search(params, cfg, g, P, BEAM)
+    dt = time.perf_counter() - t0
+    return {"value": n_images * reps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle/decoder_ref.beam_search, %d images x beam %d x %d steps, fp32, %d thread(s), %d rep(s)"
+                      % (n_images, BEAM, cfg.infer_max_length, torch.get_num_threads(), reps)}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -194,6 +213,7 @@ def main_reference(args):
             "config": dict(workload_config(args.gpus), sample="batch 32 per step (bounded sample of the B=256 workload)"),
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extras": {"beam_search_cpu": run_cpu_beam_reference()},
             "note": "PaddlePaddle 1.8 cannot be installed (BASELINE.md section 2): the reference arm is the CPU "
                     "oracle port of model_adaAttention_aic.py on the box's host cores"}
     print(json.dumps(line), flush=True)
@@ -358,7 +378,7 @@ def main_ours(args):
         eng.decode(g1, P1, beam=1)
     sync()
     lat = []
-    for _ in range(20):
+    for _ in range(200):                                   # median / p99 over 200 runs
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         eng.decode(g1, P1, beam=1)
@@ -439,6 +459,7 @@ def main_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = run_cpu_reference(steps=1000, warmup=1, sample_B=32, budget_s=15.0)
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline["beam_search"] = run_cpu_beam_reference()      # the secondary metric's CPU figure (images/s)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -456,6 +477,7 @@ def main_ours(args):
                            "beam_config": "beam %d, %d steps, %d images per GPU, finish_on_stop" % (
                                BEAM, cfg.infer_max_length, BEAM_IMAGES_PER_GPU),
                            "batch1_greedy_latency_ms": {"median": lat[len(lat) // 2], "p95": lat[int(0.95 * (len(lat) - 1))],
+                                                        "p99": lat[int(0.99 * (len(lat) - 1))], "runs": len(lat),
                                                         "per_step_median": lat[len(lat) // 2] / cfg.infer_max_length,
                                                         "config": "1 image, beam 1, %d steps" % cfg.infer_max_length},
                            "full_step_from_encoder_map": {
