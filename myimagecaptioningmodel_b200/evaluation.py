@@ -142,6 +142,16 @@ def evaluate(decode_fn: Callable, batches: Iterable, index_word, sentence_statis
     return orders + [sum(orders) / 4], len(said)
 
 
+def caption_images(engine, encoder_map, index_word, beam: int = 1, finish_on_stop: bool = False):
+    """infer.py:26-38 from the encoder output on: decode and turn the ids into sentences.  beam = 1 without
+    finished-handling is the reference's greedy `eval_network` (model:185-189); a wider beam returns the best hypothesis.
+    Returns (float32 ids [B,T] as the reference prints them, list of sentences)."""
+    cfg = engine.cfg
+    ids_f32 = engine.decode_map(encoder_map, beam=beam, finish_on_stop=finish_on_stop)[2].cpu().numpy()
+    sentences = [words2sentence(filter(p, index_word, cfg.stop_idx, cfg.padding_idx)) for p in _as_id_lists(ids_f32)]
+    return ids_f32, sentences
+
+
 class SyntheticReader:
     """Stand-in for reader.DataReader (reader.py:31-94) on synthetic data: `get_reader(batch_size, mode)` returns a
     callable yielding batches (lists of (encoder_map [X,k] float32, caption)) where caption is an int64 id array in

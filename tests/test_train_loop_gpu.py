@@ -43,6 +43,11 @@ def test_train_eval_checkpoint_resume(tmp_path):
     a = eng.decode_map(xd, beam=3, finish_on_stop=True)[0]
     b = fresh.decode_map(xd, beam=3, finish_on_stop=True)[0]
     assert torch.equal(a, b)
+    # infer.py:26-38 from the encoder output on: ids -> sentence
+    reader = M.evaluation.SyntheticReader(cfg, 8, 64, 5)
+    ids, sentences = M.evaluation.caption_images(eng, xd, reader.index_word, beam=1)
+    assert ids.shape == (8, cfg.infer_max_length) and ids.dtype.name == "float32" and len(sentences) == 8
+    assert all(isinstance(t, str) and "<stop>" not in t and "<pad>" not in t for t in sentences)
     # resume: one more epoch continues from the stored optimizer state
     _, opt2, hist2 = train_synthetic.run(epochs=1, samples=32, batch=16, encoder_channel=64, dims=DIMS, lr=2e-3, ckpt=ck,
                                          resume=True, log=logs.append)
