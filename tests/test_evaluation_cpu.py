@@ -89,3 +89,17 @@ def test_evaluate_loop_and_synthetic_reader():
     assert distinct0 == 1 and bleu0[4] < 0.2
     with pytest.raises(ValueError):
         EV.evaluate(perfect_decoder, [], rd.index_word)
+
+
+def test_caption_images_with_a_stub_engine():
+    """infer.py:26-38 after the encoder: float32 ids in, sentences out (the engine is stubbed; the GPU version of this call is
+    exercised in tests/test_train_loop_gpu.py)"""
+    import torch
+    import types
+    cfg = M.DecoderConfig(hidden_dim=32, embedding_size=16, vocab_size=53, num_positions=7, sentence_length=9,
+                          infer_max_length=9)
+    rd = EV.SyntheticReader(cfg, n_samples=4, encoder_channel=16, seed=1, refs_per_image=1)
+    ids = torch.tensor([[5., 6., 7., 3., 9., 0., 0., 0., 0.], [3., 0., 0., 0., 0., 0., 0., 0., 0.]])
+    eng = types.SimpleNamespace(cfg=cfg, decode_map=lambda x, beam, finish_on_stop: (None, None, ids))
+    out_ids, sentences = EV.caption_images(eng, None, rd.index_word)
+    assert out_ids.dtype == np.float32 and sentences == ["w5 w6 w7", ""]
