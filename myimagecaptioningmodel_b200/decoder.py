@@ -4,7 +4,9 @@ Mirrors /root/reference/ImageCaptioning/model/model_adaAttention_aic.py:
   * ``Decoder(hidden_size, mode='train'|'eval', rnn_layer=1).call(global_img_feat, p_img_feat, embedding_fn, words)``
     (model:40-135): train -> logits [B,T,V] fp32 batch-major; eval -> float32 ids [B,infer_max_length];
     an unsupported mode raises ValueError exactly like model:43-44.
-  * ``ImageCaptionModel.training_network / eval_network / loss`` from the decoder boundary on (model:161-189, 205-212).
+  * ``ImageCaptionModel.training_network / eval_network / loss`` from the decoder boundary on (model:161-189, 205-212),
+    and ``_img2feature`` / ``training_network_from_map`` / ``eval_network_from_map`` from the encoder output on
+    (model:193-199: the feature adaptor in front of the decoder).
 PyTorch is used for tensor ownership, streams and torch.distributed only; all arithmetic is in libcapdec.so.
 """
 from __future__ import annotations
@@ -213,6 +215,9 @@ class CaptionDecoderEngine:
         self._loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._caption_keepalive = None
         self._bound = False
+        self.adaptor: Optional[AdaptorStore] = None      # attach_adaptor() creates the feature-adaptor parameters
+        self._adaptor_bound = False
+        self._staged = None
 
     def __del__(self):
         try:
