@@ -30,6 +30,16 @@ extern "C" {
 #define CAPDEC_SOFTMAX_FEATURE 0  /* model:107 as written: softmax over the size-1 axis, alpha == 1 */
 #define CAPDEC_SOFTMAX_POSITION 1 /* soft-max over the k+1 attention positions (Lu et al. 2017)                 */
 
+/* Validation schedule: run the recurrence of the teacher-forced step as one GEMM + one cell kernel per time step (the
+ * schedule every hidden size supports) instead of the two persistent kernels (hidden_dim % 128 == 0, <= 1024).  The
+ * parity tests compare the two; there is no environment switch anywhere in the library. */
+#define CAPDEC_FLAG_STEPWISE_RECURRENCE 1
+
+/* Bits of the asynchronous input-error report (capdec_status) */
+#define CAPDEC_ERR_SOURCE_ID 1 /* caption[:, :-1] holds an id outside [0, vocab_size)  (lookup_table_v2 enforces this) */
+#define CAPDEC_ERR_TARGET_ID 2 /* caption[:, 1:] holds an id outside [0, vocab_size)   (softmax_with_cross_entropy)    */
+#define CAPDEC_ERR_LENGTHS 4   /* lengths[b] cuts off non-padding tokens of caption[b]                                 */
+
 /* config.py:22-24 (ids) and config.py:51-60 (dims) */
 typedef struct capdec_config {
   int32_t hidden_dim;       /* config.py:59  (1024) multiple of 8          */
@@ -43,7 +53,7 @@ typedef struct capdec_config {
   int32_t stop_idx;         /* config.py:23  (3)                           */
   int32_t dtype;            /* CAPDEC_DTYPE_*                              */
   int32_t softmax_axis;     /* CAPDEC_SOFTMAX_*                            */
-  int32_t reserved;
+  int32_t flags;            /* CAPDEC_FLAG_*, normally 0                   */
 } capdec_config;
 
 /* The decoder's parameters, fp32, PaddlePaddle layouts (fc weight = [in, out]); names follow the construction
@@ -150,6 +160,17 @@ int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n
 int capdec_decode(capdec_handle h, const float* global_img_feat, const float* p_img_feat, int32_t B, int32_t beam,
                   int32_t finish_on_stop, int32_t* ids_out, float* scores_out, float* ids_f32_out, void* stream);
 
+/* Input checks that run on the device (token ids in range, lengths consistent with the captions) cannot fail the
+ * asynchronous call that launched them.  Offending entries are treated as padding (no out-of-bounds access ever happens)
+ * and the NEXT capdec_train_fwd / capdec_train_bwd on the handle fails with the report; capdec_status synchronises
+ * `stream` and returns it right away (< 0 and capdec_last_error(), the report is cleared by being returned). */
+int capdec_status(capdec_handle h, void* stream);
+
+/* The selections of the last capdec_decode on this handle, step by step: trace_out [T, B, beam, 2] int32 =
+ * (token, back-pointer into the previous step's beams) -- the beam lattice; ids_out is its back-traced form.  Parity
+ * tests compare it with the oracle's selections step by step (the near-tie protocol). */
+int capdec_decode_trace(capdec_handle h, int32_t* trace_out, void* stream);
+
 /* ---- the callers either side of the decoder ---------------------------------------------------- */
 
 /* Converts the adaptor's fp32 parameters into the handle's operand layout (call again after every optimizer update).
@@ -184,10 +205,11 @@ int capdec_adam_step(float* param, const float* grad, float* moment1, float* mom
  *   majors bit 0: A is stored [K,M] (MN-major) instead of [M,K];  bit 1: B is stored [K,N] instead of [N,K]
  *   (0 = data-grad form, 2 = forward fc with a PaddlePaddle [in,out] weight as B, 3 = weight-grad form)
  *   act: 0 none, 1 tanh, 2 multiply by (1 - y^2) with y = dact_y, 5 relu, 6 multiply by [y > 0];  atomic: fp32 atomicAdd into C (split-K)
- *   force_simt: route a bf16 GEMM through the SIMT kernel instead of tcgen05 (cross-check)                     */
+ *   variant (bf16 only): 0 = the library's own choice, 1 = SIMT kernel (cross-check), 2 = tcgen05 CTA-pair kernel
+ *   (cta_group::2) wherever the operands allow it, 3 = tcgen05 single-CTA kernel                              */
 int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,
-                const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t force_simt,
+                const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t variant,
                 void* stream);
 
 /* Fused additive attention, model:103-113 (+ "context + p_hid" of model:115 when p_hid != NULL).

@@ -20,17 +20,20 @@ EXPORTS = [
     "capdec_launch_count", "capdec_bind_params", "capdec_train_fwd", "capdec_train_bwd", "capdec_decode",
     "capdec_gemm", "capdec_attention_fwd", "capdec_attention_bwd", "capdec_lstm_cell_fwd", "capdec_beam_step",
     "capdec_profile", "capdec_profile_report", "capdec_set_grad_ready_events",
-    "capdec_bind_adaptor", "capdec_img2feature", "capdec_img2feature_bwd", "capdec_adam_step",
+    "capdec_bind_adaptor", "capdec_img2feature", "capdec_img2feature_bwd", "capdec_adam_step", "capdec_decode_trace",
+    "capdec_status",
 ]
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 SOFTMAX_FEATURE, SOFTMAX_POSITION = 0, 1
+FLAG_STEPWISE_RECURRENCE = 1
+GEMM_AUTO, GEMM_SIMT, GEMM_PAIR, GEMM_SINGLE = 0, 1, 2, 3
 
 
 class CapdecConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "hidden_dim", "embedding_size", "vocab_size", "num_positions", "sentence_length", "infer_max_length",
-        "padding_idx", "start_idx", "stop_idx", "dtype", "softmax_axis", "reserved")]
+        "padding_idx", "start_idx", "stop_idx", "dtype", "softmax_axis", "flags")]
 
 
 class CapdecParams(C.Structure):
@@ -88,6 +91,8 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_train_fwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     lib.capdec_train_bwd.argtypes = [vp, f32, vp, vp, vp, C.POINTER(CapdecGrads), vp]
     lib.capdec_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.capdec_decode_trace.argtypes = [vp, vp, vp]
+    lib.capdec_status.argtypes = [vp, vp]
     lib.capdec_bind_adaptor.argtypes = [vp, i32, C.POINTER(CapdecAdaptorParams), vp]
     lib.capdec_img2feature.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.capdec_img2feature_bwd.argtypes = [vp, vp, C.POINTER(CapdecAdaptorGrads), vp]
@@ -110,6 +115,22 @@ def check(rc: int, what: str = "capdec"):
     if rc != 0:
         msg = load_library().capdec_last_error()
         raise CapdecError("%s failed: %s" % (what, msg.decode("utf-8", "replace") if msg else "unknown error"))
+
+
+# Version counters of flat parameter buffers, keyed by device pointer.  Whoever writes parameters in place (optim.Adam,
+# ParameterStore.load / init_reference, checkpoint.load_params) bumps the buffer's version; the engine re-runs
+# capdec_bind_params / capdec_bind_adaptor whenever the version it bound last is stale (include/capdec.h: "call again
+# after every optimizer update" -- enforced here instead of being left to the caller).
+_param_versions = {}
+
+
+def bump_version(flat) -> None:
+    k = int(flat.data_ptr())
+    _param_versions[k] = _param_versions.get(k, 0) + 1
+
+
+def version_of(flat) -> int:
+    return _param_versions.get(int(flat.data_ptr()), 0)
 
 
 def ptr(t):

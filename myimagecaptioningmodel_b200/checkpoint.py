@@ -185,6 +185,9 @@ def load_params(dirname: str, engine, names: Optional[Dict[str, str]] = None, st
     engine._bound = False                # the operand copies inside the handle are stale
     if hasattr(engine, "_adaptor_bound"):
         engine._adaptor_bound = False
+    from . import _capi
+    for st in _stores(engine):
+        _capi.bump_version(st.flat)
     return missing
 
 
@@ -202,7 +205,16 @@ def save_persistables(dirname: str, engine, optimizer=None, names: Optional[Dict
             write_lod_tensor(os.path.join(dirname, base + "_moment2_0"), m2[o:o + cnt].view(st.shapes[n]).cpu().numpy())
             write_lod_tensor(os.path.join(dirname, base + "_beta1_pow_acc_0"), np.array([optimizer.beta1_pow], np.float32))
             write_lod_tensor(os.path.join(dirname, base + "_beta2_pow_acc_0"), np.array([optimizer.beta2_pow], np.float32))
-    write_lod_tensor(os.path.join(dirname, "@LR_DECAY_COUNTER@"), np.array([optimizer.steps], np.int64))
+    # The graph's step counter (util.py:48-52, layers.autoincreased_step_counter(begin)) starts at begin - 1 and is
+    # incremented BEFORE it is read: after n executor runs it holds n - 1 + begin.  begin is 1 for the two warm-up
+    # schedules and 0 for cosine_decay / cosine_decay_restart; with lr_decay_strategy None the variable does not exist.
+    sched = getattr(optimizer, "lr", None)
+    begin = getattr(sched, "counter_begin", None)
+    if begin is not None:
+        write_lod_tensor(os.path.join(dirname, "@LR_DECAY_COUNTER@"), np.array([optimizer.steps - 1 + begin], np.int64))
+        if sched.strategy == "cosine_decay_restart_warmup":            # the persistable of util.py:92-93
+            write_lod_tensor(os.path.join(dirname, "cur_epoch"),
+                             np.array([sched.cur_epoch_state(optimizer.steps)], np.float32))
 
 
 def load_persistables(dirname: str, engine, optimizer=None, names: Optional[Dict[str, str]] = None) -> None:
@@ -224,5 +236,11 @@ def load_persistables(dirname: str, engine, optimizer=None, names: Optional[Dict
                 optimizer.beta2_pow = np.float32(read_lod_tensor(base + "_beta2_pow_acc_0")[0])
                 first = False
     ctr = os.path.join(dirname, "@LR_DECAY_COUNTER@")
-    if os.path.isfile(ctr):
-        optimizer.steps = int(read_lod_tensor(ctr)[0])
+    sched = getattr(optimizer, "lr", None)
+    begin = getattr(sched, "counter_begin", None)
+    if begin is not None and os.path.isfile(ctr):
+        optimizer.steps = int(read_lod_tensor(ctr)[0]) + 1 - begin     # counter = steps - 1 + begin (see save_persistables)
+        ce = os.path.join(dirname, "cur_epoch")
+        if sched.strategy == "cosine_decay_restart_warmup" and os.path.isfile(ce):
+            sched._epoch_counter = float(read_lod_tensor(ce)[0])
+            sched._last_n = optimizer.steps - 1

@@ -744,9 +744,6 @@ void attention_fwd(LaunchCtx c, const AttnShape& s, const T* keys, const T* vals
 }
 
 bool attention_fwd_batched_supported(const AttnShape& s) {
-  if (const char* ev = getenv("CAPDEC_ATTN_BATCHED")) {
-    if (ev[0] == '0') return false;
-  }
   if (!s.position_softmax || s.q_per_img < 8 || s.k < 1 || s.k > 63) return false;
   if (s.H != 256 && s.H != 512 && s.H != 1024) return false;
   return scores_smem_bytes(s.H, s.k) <= 227 * 1024;
@@ -802,9 +799,6 @@ int attention_fwd_batched(GemmContext& gc, LaunchCtx c, const AttnShape& s, cons
 // context kernel.  Versus the fused single-CTA-per-image kernel (both tiles staged, 1 CTA per SM): the key tile alone
 // lets 2 CTAs share an SM and the tensor-core dot product frees the issue slots (70 -> ~30 us per step at 512 x 3 rows).
 bool attention_fwd_small_supported(const AttnShape& s) {
-  if (const char* ev = getenv("CAPDEC_ATTN_BATCHED")) {
-    if (ev[0] == '0') return false;
-  }
   if (!s.position_softmax || s.q_per_img < 1 || s.q_per_img > 8 || s.k < 1 || s.k > 63) return false;
   if (s.H != 256 && s.H != 512 && s.H != 1024) return false;
   return scores_smem_bytes(s.H, s.k) <= 227 * 1024;

@@ -115,12 +115,23 @@ class DecoderBase {
                         cudaStream_t s) = 0;
   virtual int decode(const float* g, const float* P, int B, int beam, int finish, int32_t* ids, float* scores,
                      float* ids_f32, cudaStream_t s) = 0;
+  virtual int decode_trace(int32_t* out, cudaStream_t s) = 0;
   virtual int bind_adaptor(int X, const capdec_adaptor_params* p, cudaStream_t s) = 0;
   virtual int img2feature(const float* enc_map, int B, float* P_out, float* g_out, cudaStream_t s) = 0;
   virtual int img2feature_bwd(float* d_enc_map, const capdec_adaptor_grads* gr, cudaStream_t s) = 0;
   size_t ws_bytes = 0;
   long launches = 0;
   int device = 0;
+  // Device-side input checks (token ids out of range, lengths that contradict the captions) cannot fail the asynchronous
+  // call that launched them: the kernels write a bit mask into this word of MAPPED host memory (only when something is
+  // wrong: no traffic otherwise), the next call on the handle and capdec_status report it.
+  int* err_flag = nullptr;
+  int take_async_error() {
+    if (!err_flag) return 0;
+    const int e = *reinterpret_cast<volatile int*>(err_flag);
+    if (e) *reinterpret_cast<volatile int*>(err_flag) = 0;
+    return e;
+  }
   // caller-owned events recorded by train_bwd when a group of gradients is final (capdec_set_grad_ready_events)
   cudaEvent_t grad_ready[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void mark_ready(int i, cudaStream_t s) {
@@ -134,8 +145,7 @@ template <typename T> class Decoder : public DecoderBase {
     H = c.hidden_dim; E = c.embedding_size; V = c.vocab_size; k = c.num_positions;
     S = c.sentence_length; Tt = S - 1; Ti = c.infer_max_length;
     Vp = ((V + 127) / 128) * 128;
-    const char* fs = getenv("CAPDEC_FORCE_SIMT");
-    force_simt = fs && fs[0] == '1';
+    stepwise = (c.flags & CAPDEC_FLAG_STEPWISE_RECURRENCE) != 0;
   }
   ~Decoder() override {
     dgraph.reset();
@@ -173,7 +183,7 @@ template <typename T> class Decoder : public DecoderBase {
     const float* lw_h = p->lstm_w + (size_t)X * 4 * H;   // hidden rows of lstm_w
     bool want_perm = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (!force_simt && lstm_seq_supported(1, H)) {  // unit-major copy for the persistent forward recurrence
+      if (!stepwise && lstm_seq_supported(1, H)) {  // unit-major copy for the persistent forward recurrence
         OK(w_hh_perm.ensure(e * H * 4 * H, &ws_bytes));
         OK(w_x_p.ensure(e * E * 5 * H, &ws_bytes));
         OK(w_g_p.ensure(e * H * 5 * H, &ws_bytes));
@@ -309,7 +319,7 @@ template <typename T> class Decoder : public DecoderBase {
   int img2feature(const float* enc_map, int B, float* P_out, float* g_out, cudaStream_t s) override {
     if (!adaptor_bound) { set_error("capdec_img2feature: adaptor parameters not bound"); return -1; }
     if (B <= 0) { set_error("capdec_img2feature: empty batch"); return -1; }
-    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    GemmContext gc; gc.stream = s;
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int X = Xc;
@@ -336,7 +346,7 @@ template <typename T> class Decoder : public DecoderBase {
       set_error("capdec_img2feature_bwd: needs capdec_img2feature -> capdec_train_fwd(NULL features) -> capdec_train_bwd first");
       return -1;
     }
-    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    GemmContext gc; gc.stream = s;
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int X = Xc, B = staged_B;
@@ -372,7 +382,7 @@ template <typename T> class Decoder : public DecoderBase {
                 cudaStream_t s) override {
     if (!bound) { set_error("capdec_train_fwd: parameters not bound"); return -1; }
     if (B <= 0) { set_error("capdec_train_fwd: empty batch"); return -1; }
-    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    GemmContext gc; gc.stream = s;
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const long M = (long)B * Tt;
@@ -403,9 +413,9 @@ template <typename T> class Decoder : public DecoderBase {
     OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
 
     // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
-    embed_gather<T>(lc, emb.as<T>(), E, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E);
+    embed_gather<T>(lc, emb.as<T>(), E, V, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E, err_flag);
     bool persistent = false;
-    if constexpr (std::is_same<T, bf16>::value) persistent = !force_simt && lstm_seq_supported(B, H) && w_hh_perm.p;
+    if constexpr (std::is_same<T, bf16>::value) persistent = !stepwise && lstm_seq_supported(B, H) && w_hh_perm.p;
     if (persistent) {
       // Persistent recurrence: ONE activation holds the complete x-part of the gate / sentinel pre-activations,
       //   xe[t*B+b] = emb(word).[lstm_w(word) | fc_xs(word)] + (g[b].[lstm_w(global) | fc_xs(global)] + biases),
@@ -458,7 +468,7 @@ template <typename T> class Decoder : public DecoderBase {
     AttnShape as = train_shape(B);
     bool attn_batched = false;
     if constexpr (std::is_same<T, bf16>::value) {
-      if (!force_simt && attention_fwd_batched_supported(as)) {
+      if (attention_fwd_batched_supported(as)) {
         // scores + soft-max on MUFU / mma.sync, context as one batched tcgen05 GEMM                  // model:103-115
         OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
         OK(sadd.ensure(e * M * H, &ws_bytes));
@@ -475,76 +485,24 @@ template <typename T> class Decoder : public DecoderBase {
     OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
     OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
-    bool ce_in_gemm = false;
-    if constexpr (std::is_same<T, bf16>::value) {
-      // Off by default: measured on B200 the two epilogue-bound K = 256 passes cost 289 + 202 us against 161 us (GEMM
-      // with fp32 logits) + 118 us (cross-entropy kernel) for the separate form; CAPDEC_CE_FUSED=1 selects it.
-      const char* ev = getenv("CAPDEC_CE_FUSED");
-      ce_in_gemm = ev && ev[0] == '1' && !force_simt && !logits_out && (E % 8) == 0;
-    }
-    if (ce_in_gemm) {
-      // The logits are never written: pass 1 of the tied projection (model:25) leaves only per-row soft-max statistics,
-      // ce_merge turns them into lse / loss (model:163-171, 180-183, 205-212), pass 2 recomputes the tile and writes the
-      // unscaled d logits = (softmax - onehot) * mask directly.  1.08 GB of HBM traffic (fp32 logits written + read,
-      // bf16 gradient written) becomes 0.23 GB at the price of a second K = 256 GEMM.
-      const int S = (V + 63) / 64;
-      const long sld = (S + 7) & ~7;
-      OK(ce_stats.ensure(2 * 4 * (size_t)M * sld, &ws_bytes));
-      OK(ce_rows.ensure(8 * (size_t)M, &ws_bytes));
-      float* st_m = ce_stats.as<float>();
-      float* st_s = st_m + (size_t)M * sld;
-      float* lse_eff = ce_rows.as<float>();
-      int* tgt = reinterpret_cast<int*>(lse_eff + M);
-      GemmCall c;
-      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = dlogits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
-      c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1;
-      c.epi.act = ACT_ROWSTATS; c.epi.stats_m = st_m; c.epi.stats_s = st_s; c.epi.stats_ld = sld;
+    OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
+    {
+      // Logits stay fp32 also on the bf16 path.  (Measured and dropped: bf16 logit storage -- 42 us faster, but soft-max
+      // probabilities from rounded logits carry a relative error of |x| * 2^-9 and d out_fc_bias = sum_rows(p - onehot)
+      // leaves the 2e-2 tolerance; and the cross entropy fused into two passes of this GEMM -- 289 + 202 us against
+      // 161 + 118 us for GEMM + kernel: the K = 256 GEMM is epilogue-bound, a second pass costs more than the round trip.)
+      GemmCall c;                                                                                     // model:25
+      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
+      c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
-      if constexpr (std::is_same<T, bf16>::value)
-        ce_merge(lc, M, S, st_m, st_s, sld, proj.as<bf16>(), E, emb.as<bf16>(), b_vocab.as<float>(), cap, S_len(), B,
-                 cfg.padding_idx, lse.as<float>(), lse_eff, tgt, acc.as<float>());
-      c.epi.act = ACT_SOFTMAX_GRAD; c.epi.stats_m = nullptr; c.epi.stats_s = nullptr; c.epi.row_lse = lse_eff;
-      c.epi.row_tgt = tgt;
-      OK(gemm<T>(gc, c));
-      prof.mark("fwd.out_proj_vocab", s);
-    } else {
-      // Logits stay fp32 also on the bf16 path.  CAPDEC_LOGITS_BF16=1 stores them in bf16 (216 MB instead of 432 MB
-      // written by the GEMM epilogue and read back by the cross-entropy kernel: 42 us faster per step), but soft-max
-      // probabilities from rounded logits carry a relative error of |x| * 2^-9 and the gradients that are differences
-      // of nearly cancelling sums (out_fc_bias = sum_rows(p - onehot)) leave the 2e-2 tolerance (4.2e-2 measured on
-      // the golden fixture), so it is an experiment switch, not the default.
-      logits_bf16 = false;
-      if constexpr (std::is_same<T, bf16>::value) {
-        const char* ev = getenv("CAPDEC_LOGITS_BF16");
-        logits_bf16 = ev && ev[0] == '1' && !force_simt;
-      }
-      OK(logits.ensure((logits_bf16 ? 2 : 4) * M * (size_t)Vp, &ws_bytes));
-      {
-        GemmCall c;                                                                                   // model:25
-        c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
-        c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = logits_bf16 ? 0 : 1;
-        OK(gemm<T>(gc, c));
-      }
-      prof.mark("fwd.out_proj_vocab", s);
-      // masked cross entropy (model:163-171, 180-183, 205-212)
-      // ... fused with the unscaled d logits = (softmax - onehot) * mask, so the logits leave HBM only once
-      if constexpr (std::is_same<T, bf16>::value) {
-        if (logits_bf16)
-          ce_fused<bf16, bf16>(lc, logits.as<bf16>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(),
-                               acc.as<float>(), dlogits.as<bf16>());
-        else
-          ce_fused<bf16, float>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(),
-                                acc.as<float>(), dlogits.as<bf16>());
-      } else {
-        ce_fused<float, float>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(),
-                               acc.as<float>(), dlogits.as<float>());
-      }
     }
+    prof.mark("fwd.out_proj_vocab", s);
+    // masked cross entropy (model:163-171, 180-183, 205-212) fused with the unscaled d logits = (softmax - onehot) * mask,
+    // so the logits leave HBM only once
+    ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
+                dlogits.as<T>(), err_flag);
     loss_finalize(lc, acc.as<float>());
-    if (logits_out) {                                                                                  // model:129-130
-      if (logits_bf16) logits_to_batch_major<bf16>(lc, logits.as<bf16>(), Vp, V, B, Tt, logits_out);
-      else logits_to_batch_major<float>(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);
-    }
+    if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);          // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
     prof.mark("fwd.cross_entropy", s);
     launches += gc.launches;
@@ -565,7 +523,7 @@ template <typename T> class Decoder : public DecoderBase {
   int train_bwd(float loss_scale, const float* inv_ntok, float* dg, float* dP, const capdec_grads* gr,
                 cudaStream_t s) override {
     if (!have_fwd) { set_error("capdec_train_bwd: no forward pass to differentiate"); return -1; }
-    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    GemmContext gc; gc.stream = s;
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int B = last_B, X = E + H;
@@ -749,7 +707,7 @@ template <typename T> class Decoder : public DecoderBase {
       c.K = 5 * H;
       OK(gemm<T>(gc, c));
     }
-    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
+    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
     mark_ready(1, s);  // word_embedding, out_fc_bias are final
     // weight gradients of the gate GEMM, batched over all steps
     OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
@@ -788,7 +746,7 @@ template <typename T> class Decoder : public DecoderBase {
     if (!bound) { set_error("capdec_decode: parameters not bound"); return -1; }
     if (B <= 0 || beam < 1 || beam > 8) { set_error("capdec_decode: need B > 0 and 1 <= beam <= 8"); return -1; }
     if (beam > V) { set_error("capdec_decode: beam wider than the vocabulary"); return -1; }
-    GemmContext gc; gc.stream = s; gc.force_simt = force_simt;
+    GemmContext gc; gc.stream = s;
     LaunchCtx lc{s, &launches};
     const size_t e = sizeof(T);
     const int R = B * beam, X = E + H;
@@ -813,6 +771,9 @@ template <typename T> class Decoder : public DecoderBase {
     OK(proj.ensure(e * (size_t)R * E, &ws_bytes));
     OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
     OK(d_state.ensure((size_t)R * (2 * 4 + 2 * 4 + 2 * 4 * Ti + 8) + 256, &ws_bytes));
+    OK(d_beam.ensure(beam_scratch_bytes(B, beam), &ws_bytes));
+    OK(d_trace.ensure(8 * (size_t)R * Ti, &ws_bytes));
+    trace_B = B; trace_beam = beam;
     // beam bookkeeping (double-buffered)
     float* score[2]; int* fin[2]; int* hist[2]; int *tok, *src;
     {
@@ -854,7 +815,7 @@ template <typename T> class Decoder : public DecoderBase {
         prof.mark("dec.head_fc", rs);
         bool attn_small = false;
         if constexpr (std::is_same<T, bf16>::value) {
-          if (!force_simt && attention_fwd_small_supported(as)) {
+          if (attention_fwd_small_supported(as)) {
             OK(attention_fwd_small(lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
                                    sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
                                    actx.as<bf16>()));
@@ -876,7 +837,8 @@ template <typename T> class Decoder : public DecoderBase {
         prof.mark("dec.out_proj_vocab", rs);
         // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
         beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
-                  score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src);
+                  score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
+                  d_trace.as<int>() + (size_t)step * R * 2);
         if (step + 1 < Ti)
           beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
                           xin.as<T>(), X, d_ccur.as<float>());
@@ -887,8 +849,7 @@ template <typename T> class Decoder : public DecoderBase {
     // Small batches are launch-latency bound (14 dependent launches per step, ~9 us each at one image): the step loop
     // is captured once into a CUDA graph per (images, beam, finish) and replayed.  The first call of a shape runs
     // eagerly (it allocates the workspace and warms the tensor-map cache), the second captures.
-    static const bool graph_ok = [] { const char* ev = getenv("CAPDEC_DECODE_GRAPH"); return !(ev && ev[0] == '0'); }();
-    const bool want_graph = graph_ok && R <= 96 && !prof.on;
+    const bool want_graph = R <= 96 && !prof.on;
     bool done = false;
     if (want_graph) {
       const unsigned long key_epoch = g_ws_epoch;
@@ -911,8 +872,6 @@ template <typename T> class Decoder : public DecoderBase {
           const int rc = run_steps();
           const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
           rs = s; gc.stream = s; lc.stream = s;
-          if (getenv("CAPDEC_DEBUG"))
-            fprintf(stderr, "[capdec] decode graph capture: rc=%d (%s) end=%s\n", rc, rc ? g_err : "", cudaGetErrorString(ce));
           if (rc == 0 && ce == cudaSuccess && graph &&
               cudaGraphInstantiate(&dgraph.exec, graph, 0) == cudaSuccess) {
             dgraph.B = B; dgraph.beam = beam; dgraph.finish = finish; dgraph.epoch = key_epoch; dgraph.stream = s;
@@ -944,6 +903,13 @@ template <typename T> class Decoder : public DecoderBase {
     return 0;
   }
 
+  // (token, back-pointer) of every selection of the last decode: [T, B, beam, 2] int32
+  int decode_trace(int32_t* out, cudaStream_t s) override {
+    if (trace_B <= 0 || !d_trace.p) { set_error("capdec_decode_trace: no decode has run on this handle"); return -1; }
+    CUDA_OK(cudaMemcpyAsync(out, d_trace.p, 8 * (size_t)trace_B * trace_beam * Ti, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+
   static void ids_to_f32(LaunchCtx lc, const int* hist, int B, int beam, int Ti, float* out);
 
  private:
@@ -951,8 +917,8 @@ template <typename T> class Decoder : public DecoderBase {
     return {&w_kv_n, &w_x_n, &w_g_n, &w_hh_n, &w_hs_n, &w_p_n, &w_g2_n, &w_s_n, &w_o_n, &w_e_n, &emb, &w_dec_n, &b5, &b5d, &b_vocab, &gT, &PT,
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
-            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &ce_stats, &ce_rows, &xin, &d_hnew, &d_cnew, &d_ccur,
-            &d_state, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
+            &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
+            &d_state, &d_beam, &d_trace, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
   // captured step loop of capdec_decode for small batches
@@ -974,7 +940,7 @@ template <typename T> class Decoder : public DecoderBase {
   capdec_config cfg;
   capdec_params prm{};
   int H, E, V, Vp, k, S, Tt, Ti;
-  bool bound = false, have_fwd = false, force_simt = false, fwd_persistent = false, logits_bf16 = false;
+  bool bound = false, have_fwd = false, stepwise = false, fwd_persistent = false;
   int last_B = 0;
   const int64_t* last_cap = nullptr;
   // operands
@@ -984,9 +950,10 @@ template <typename T> class Decoder : public DecoderBase {
       logits, lse, acc;
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
-      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd, ce_stats, ce_rows;
+      dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd;
   // decode state
-  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state;
+  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace;
+  int trace_B = 0, trace_beam = 0;
   // feature adaptor (capdec_img2feature)
   capdec_adaptor_params aprm{};
   int Xc = 0, staged_B = 0;
@@ -1025,6 +992,17 @@ static int check_device(capdec_handle h) {
   return 0;
 }
 
+// input errors found by kernels of an EARLIER call on this handle (see DecoderBase::err_flag)
+static int report_async_error(capdec_handle h) {
+  const int e = h->impl->take_async_error();
+  if (!e) return 0;
+  set_error("an earlier call on this handle was given bad input:%s%s%s (the offending entries were treated as padding)",
+            (e & CAPDEC_ERR_SOURCE_ID) ? " caption token id outside [0, vocab_size)" : "",
+            (e & CAPDEC_ERR_TARGET_ID) ? " target token id outside [0, vocab_size)" : "",
+            (e & CAPDEC_ERR_LENGTHS) ? " lengths[] shorter than the non-padding part of a caption" : "");
+  return -1;
+}
+
 namespace capdec { void set_gemm_trace(unsigned long long* buf); void set_rec_trace(unsigned long long* buf); }
 
 extern "C" {
@@ -1046,6 +1024,11 @@ int capdec_create(const capdec_config* c, int device, capdec_handle* out) {
   if (c->num_positions < 1 || c->num_positions > 63) { set_error("capdec_create: num_positions must be in [1,63]"); return -1; }
   if (c->vocab_size < 4 || c->sentence_length < 2 || c->infer_max_length < 1) {
     set_error("capdec_create: bad vocab_size / sentence_length / infer_max_length"); return -1;
+  }
+  if (c->vocab_size > beam_max_vocab()) {   // the reference caps its dictionary at 15000 words (ai_challenge_tokenizer.py:21-50)
+    set_error("capdec_create: vocab_size %d exceeds the %d tokens the top-k kernels hold in registers", c->vocab_size,
+              beam_max_vocab());
+    return -1;
   }
   if (c->padding_idx < 0 || c->padding_idx >= c->vocab_size || c->start_idx < 0 || c->start_idx >= c->vocab_size ||
       c->stop_idx < 0 || c->stop_idx >= c->vocab_size) {
@@ -1076,15 +1059,25 @@ int capdec_create(const capdec_config* c, int device, capdec_handle* out) {
   else { set_error("capdec_create: unsupported dtype %d", c->dtype); return -1; }
   if (!impl) { set_error("capdec_create: out of host memory"); return -1; }
   impl->device = device;
+  void* flag = nullptr;
+  e = cudaHostAlloc(&flag, 64, cudaHostAllocMapped);
+  if (e != cudaSuccess) { delete impl; set_error("capdec_create: cudaHostAlloc: %s", cudaGetErrorString(e)); return -1; }
+  memset(flag, 0, 64);
+  impl->err_flag = static_cast<int*>(flag);   // unified addressing: the same pointer is valid on the device
   capdec_handle h = new (std::nothrow) capdec_handle_s{impl};
-  if (!h) { delete impl; set_error("capdec_create: out of host memory"); return -1; }
+  if (!h) { cudaFreeHost(flag); delete impl; set_error("capdec_create: out of host memory"); return -1; }
   *out = h;
   return 0;
 }
 
 int capdec_destroy(capdec_handle h) {
   if (!h) return 0;
-  if (h->impl) { cudaSetDevice(h->impl->device); delete h->impl; }
+  if (h->impl) {
+    cudaSetDevice(h->impl->device);
+    int* flag = h->impl->err_flag;
+    delete h->impl;
+    if (flag) { cudaDeviceSynchronize(); cudaFreeHost(flag); }
+  }
   delete h;
   return 0;
 }
@@ -1124,14 +1117,14 @@ int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream) {
 
 int capdec_train_fwd(capdec_handle h, const float* g, const float* P, const int64_t* caption, int32_t B,
                      float* logits_out, float* loss_out, void* stream) {
-  if (check_device(h)) return -1;
+  if (check_device(h) || report_async_error(h)) return -1;
   if (!caption) { set_error("capdec_train_fwd: null caption"); return -1; }
   return h->impl->train_fwd(g, P, caption, B, logits_out, loss_out, (cudaStream_t)stream);
 }
 
 int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_dev, float* dg, float* dP,
                      const capdec_grads* gr, void* stream) {
-  if (check_device(h)) return -1;
+  if (check_device(h) || report_async_error(h)) return -1;
   if (!gr) { set_error("capdec_train_bwd: null grads"); return -1; }
   return h->impl->train_bwd(loss_scale, inv_ntok_dev, dg, dP, gr, (cudaStream_t)stream);
 }
@@ -1140,6 +1133,19 @@ int capdec_decode(capdec_handle h, const float* g, const float* P, int32_t B, in
                   int32_t* ids_out, float* scores_out, float* ids_f32_out, void* stream) {
   if (check_device(h)) return -1;
   return h->impl->decode(g, P, B, beam, finish_on_stop, ids_out, scores_out, ids_f32_out, (cudaStream_t)stream);
+}
+
+int capdec_status(capdec_handle h, void* stream) {
+  if (check_device(h)) return -1;
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("capdec_status: %s", cudaGetErrorString(e)); return -1; }
+  return report_async_error(h);
+}
+
+int capdec_decode_trace(capdec_handle h, int32_t* trace_out, void* stream) {
+  if (check_device(h)) return -1;
+  if (!trace_out) { set_error("capdec_decode_trace: null output"); return -1; }
+  return h->impl->decode_trace(trace_out, (cudaStream_t)stream);
 }
 
 int capdec_bind_adaptor(capdec_handle h, int32_t encoder_channel, const capdec_adaptor_params* p, void* stream) {
@@ -1178,9 +1184,10 @@ int capdec_adam_step(float* param, const float* grad, float* moment1, float* mom
 
 int capdec_gemm(int32_t dtype, int32_t majors, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_add,
-                const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t force_simt,
+                const void* dact_y, int64_t ld_y, int32_t act, int32_t out_f32, int32_t atomic, int32_t variant,
                 void* stream) {
-  GemmContext gc; gc.stream = (cudaStream_t)stream; gc.force_simt = force_simt != 0;
+  if (variant < GEMM_AUTO || variant > GEMM_SINGLE) { set_error("capdec_gemm: unknown kernel variant %d", variant); return -1; }
+  GemmContext gc; gc.stream = (cudaStream_t)stream; gc.variant = variant;
   GemmCall c;
   c.A = A; c.lda = lda; c.B = B; c.ldb = ldb; c.C = C; c.ldc = ldc; c.M = M; c.N = N; c.K = K;
   c.a_mn = (majors & 1) != 0; c.b_mn = (majors & 2) != 0;
@@ -1315,10 +1322,20 @@ int capdec_beam_step(const float* logits, int64_t ldl, int32_t V, int32_t n_img,
                      float* score_out, const int32_t* fin_in, int32_t* fin_out, const int32_t* hist_in,
                      int32_t* hist_out, int32_t* tok_out, int32_t* src_out, void* stream) {
   if (beam < 1 || beam > 8) { set_error("capdec_beam_step: 1 <= beam <= 8"); return -1; }
+  if (V < 1 || V > beam_max_vocab()) { set_error("capdec_beam_step: 1 <= V <= %d", beam_max_vocab()); return -1; }
+  if (n_img <= 0) return 0;
   LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  // the candidate scratch is owned by the decoder handle inside capdec_decode; the stand-alone entry point allocates it
+  void* scratch = nullptr;
+  if (cudaMalloc(&scratch, beam_scratch_bytes(n_img, beam)) != cudaSuccess) {
+    set_error("capdec_beam_step: out of device memory");
+    return -1;
+  }
   beam_step(lc, logits, ldl, V, n_img, beam, step, T_total, pad, stop, finish_on_stop, score_in, score_out, fin_in,
-            fin_out, hist_in, hist_out, tok_out, src_out);
+            fin_out, hist_in, hist_out, tok_out, src_out, scratch, nullptr);
   cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(scratch);
   if (e != cudaSuccess) { set_error("capdec_beam_step: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }

@@ -14,14 +14,13 @@
 
 namespace capdec {
 
-// ACT_ROWSTATS / ACT_SOFTMAX_GRAD (tensor-core kernels only): the two passes of a soft-max cross entropy fused into the
-// vocabulary GEMM, so the [M, V] logits are never written:
-//   ACT_ROWSTATS     no C output; per (row, 64-column group g) the partial max and sum exp(x - max) of x = acc + bias go to
-//                    stats_m / stats_s [M, stats_ld] at column g
-//   ACT_SOFTMAX_GRAD C = exp(x - row_lse[m]) - [n == row_tgt[m]]   (row_lse = +inf gives an all-zero row: masked position)
+//   ACT_ROWSTATS     (tensor-core kernels only) no C output; per (row, 64-column group g) the partial max and
+//                    sum exp(x - max) of x = acc + bias go to stats_m / stats_s [M, stats_ld] at column g
 //   ACT_RELU         max(x, 0)            (the feature adaptor, model:196-198)
 //   ACT_DRELU        x * [y > 0] with y = dact_y, the ReLU output
-enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_SOFTMAX_GRAD = 4, ACT_RELU = 5, ACT_DRELU = 6 };
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_RELU = 5, ACT_DRELU = 6 };
+// which kernel gemm<bf16> runs (GemmContext::variant; anything but AUTO is for the kernel-level parity tests)
+enum { GEMM_AUTO = 0, GEMM_SIMT = 1, GEMM_PAIR = 2, GEMM_SINGLE = 3 };
 
 struct GemmEpi {
   const float* bias = nullptr;   // [N] fp32, added to every row
@@ -39,8 +38,6 @@ struct GemmEpi {
   float* stats_m = nullptr;      // ACT_ROWSTATS outputs
   float* stats_s = nullptr;
   long stats_ld = 0;
-  const float* row_lse = nullptr;  // ACT_SOFTMAX_GRAD inputs
-  const int* row_tgt = nullptr;
 };
 
 struct GemmCall {
@@ -87,7 +84,7 @@ __device__ __forceinline__ void epi_store(float v, void* C, long ldc, int m, int
 
 struct GemmContext {
   cudaStream_t stream = nullptr;
-  bool force_simt = false;       // debugging: route bf16 GEMMs through the SIMT kernel
+  int variant = GEMM_AUTO;       // GEMM_*: AUTO = cost model; SIMT routes bf16 GEMMs through the SIMT kernel (cross-check)
   long launches = 0;             // number of kernels launched (bench accounting)
 };
 
@@ -98,7 +95,7 @@ template <typename T> int gemm_simt(GemmContext& ctx, const GemmCall& c);
 template <typename T> inline int gemm(GemmContext& ctx, const GemmCall& c);
 template <> inline int gemm<float>(GemmContext& ctx, const GemmCall& c) { return gemm_simt<float>(ctx, c); }
 template <> inline int gemm<bf16>(GemmContext& ctx, const GemmCall& c) {
-  return ctx.force_simt ? gemm_simt<bf16>(ctx, c) : gemm_bf16_tc(ctx, c);
+  return ctx.variant == GEMM_SIMT ? gemm_simt<bf16>(ctx, c) : gemm_bf16_tc(ctx, c);
 }
 
 void set_error(const char* fmt, ...);

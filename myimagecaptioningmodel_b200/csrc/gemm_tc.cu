@@ -163,8 +163,7 @@ __device__ __noinline__ void epi_store8_tail(const float* v, void* C, long ldc, 
 template <bool OUT_F32, bool FULL>
 __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, uint32_t bias_t, const bf16* add_p,
                                                 const bf16* y_p, int fact, float alpha, int left, uint32_t dst_row,
-                                                uint32_t swz, uint32_t chunk0, bool sm_grad = false, float lse_row = 0.f,
-                                                int tgt_rel = -1) {
+                                                uint32_t swz, uint32_t chunk0) {
   uint32_t r[32];
   uint4 aq[4], yq[4];
   __syncwarp();  // tcgen05.ld is .sync.aligned
@@ -206,10 +205,6 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, uint32_t bia
       } else if (fact & 2) {  // ACT_RELU
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (sm_grad) {  // soft-max cross-entropy gradient; tgt_rel = target column relative to this 32-column chunk
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __expf(v[i] - lse_row) - ((g * 8 + i) == tgt_rel ? 1.f : 0.f);
       }
       if (y_p) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yq[g]);
@@ -434,9 +429,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int do_tanh = (epi.act == ACT_TANH ? 1 : 0) | (epi.act == ACT_RELU ? 2 : 0) | (epi.act == ACT_DRELU ? 4 : 0);
           const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
           const bool f32_out = epi.out_f32 || epi.atomic;
-          const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;
-          const float lse_row = (sm_grad && row_ok) ? __ldg(epi.row_lse + row) : 0.f;
-          const int tgt_row = (sm_grad && row_ok) ? __ldg(epi.row_tgt + row) : -1;
           const int pw = f32_out ? 32 : 64;           // columns per pass
           const int n_pass = BN / pw;
           const int my_last = ((n_pass - 1 - half) & ~1) + half;  // last pass index owned by this warp (< 0: none)
@@ -485,11 +477,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (left - o >= 32)
                   epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                                yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                               (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
+                                               (uint32_t)(sub * 4));
                 else
                   epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
                                                 yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz,
-                                               (uint32_t)(sub * 4), sm_grad, lse_row, tgt_row - (n0 + c0 + o));
+                                               (uint32_t)(sub * 4));
               }
             }
             if (ps == my_last && last_block) {
@@ -810,9 +802,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int do_tanh = (epi.act == ACT_TANH ? 1 : 0) | (epi.act == ACT_RELU ? 2 : 0) | (epi.act == ACT_DRELU ? 4 : 0);
       const float alpha = epi.alpha_dev ? __ldg(epi.alpha_dev) : 1.f;
       const bool f32_out = epi.out_f32 || epi.atomic;
-      const bool sm_grad = epi.act == ACT_SOFTMAX_GRAD;
-      const float lse_row = (sm_grad && row_ok) ? __ldg(epi.row_lse + row) : 0.f;
-      const int tgt_row = (sm_grad && row_ok) ? __ldg(epi.row_tgt + row) : -1;
       const int pw = f32_out ? 32 : 64;
       const int n_pass = BN / pw;
       const int my_last = ((n_pass - 1 - half) & ~1) + half;
@@ -861,12 +850,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int o = sub * 32;
             if (left - o >= 32)
               epilogue_cols32<false, true>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
-                                           yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
-                                           sm_grad, lse_row, tgt_row - (n0 + c0 + o));
+                                           yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
             else
               epilogue_cols32<false, false>(tmem_d + (uint32_t)(c0 + o), bsa ? bsa + (uint32_t)(o * 4) : 0u, ap ? ap + o : nullptr,
-                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4),
-                                            sm_grad, lse_row, tgt_row - (n0 + c0 + o));
+                                            yp ? yp + o : nullptr, do_tanh, alpha, left - o, my_row, swz, (uint32_t)(sub * 4));
           }
         }
         if (ps == my_last) {
@@ -969,11 +956,8 @@ int get_map(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t
   return 0;
 }
 
-thread_local bool t_pdl_on = true;
-bool pdl_enabled() {  // CAPDEC_GEMM_PDL=0 switches programmatic dependent launch off (A/B measurements)
-  static const bool on = [] { const char* e = getenv("CAPDEC_GEMM_PDL"); return !(e && e[0] == '0'); }();
-  return on && t_pdl_on;
-}
+thread_local bool t_pdl_on = true;   // programmatic dependent launch; off while a CUDA graph is being captured
+bool pdl_enabled() { return t_pdl_on; }
 
 template <int BN, bool A_MN, bool B_MN, int MT>
 int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
@@ -1009,9 +993,7 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
                       (!e.addend || ((((uintptr_t)e.addend & 15) == 0) && (e.ld_add % 8) == 0)) &&
                       (!e.dact_y || ((((uintptr_t)e.dact_y & 15) == 0) && (e.ld_y % 8) == 0));
   // epilogue mode: 1 = swizzled smem tile + TMA tensor store / reduce-add, 0 = per-thread direct stores (unaligned C)
-  static int out_env = -1;
-  if (out_env < 0) { const char* ev = getenv("CAPDEC_GEMM_OUT"); out_env = ev ? atoi(ev) : 1; }
-  int out_mode = tma_out ? (out_env ? 1 : 0) : 0;
+  const int out_mode = tma_out ? 1 : 0;
   if (out_mode == 1) {
     if (get_map(c.C, c.N, c.M, c.ldc, out_elem == 2 ? 64 : 32, 32, &tmC, out_elem, c.batch, c.batch_c)) return -1;
   } else {
@@ -1024,11 +1006,7 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   sh.tiles_m = (c.M + BM * MT - 1) / (BM * MT); sh.tiles_n = (c.N + BN - 1) / BN;
   sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = vec_ok;
   sh.batch = c.batch > 0 ? c.batch : 1; sh.batch_c = c.batch_c;
-  {
-    static int rot_env = -1;
-    if (rot_env < 0) { const char* ev = getenv("CAPDEC_GEMM_ROT"); rot_env = ev ? atoi(ev) : 1; }
-    sh.rotate_k = rot_env;
-  }
+  sh.rotate_k = 1;
   const long total = (long)sh.tiles_m * sh.tiles_n * splits * sh.batch;
   const int grid = (int)std::min<long>(total, kNumSMs);
   cudaLaunchConfig_t cfg = {};
@@ -1125,13 +1103,12 @@ int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint3
 
 int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) return 0;
-  if (c.epi.act == ACT_ROWSTATS || c.epi.act == ACT_SOFTMAX_GRAD) {
+  if (c.epi.act == ACT_ROWSTATS) {
     const GemmEpi& e = c.epi;
     const bool ok = !e.out_f32 && !e.atomic && c.batch <= 1 && !e.addend && !e.dact_y && (!e.bias || e.aux_padded) &&
-                    (((uintptr_t)c.C & 15) == 0) && ((c.ldc * 2) % 16 == 0) &&
-                    (e.act == ACT_ROWSTATS ? (e.stats_m && e.stats_s && e.stats_ld >= (c.N + 63) / 64)
-                                           : (e.row_lse && e.row_tgt));
-    if (!ok) { set_error("gemm_tc: unsupported arguments for the fused soft-max epilogue"); return -1; }
+                    (((uintptr_t)c.C & 15) == 0) && ((c.ldc * 2) % 16 == 0) && e.stats_m && e.stats_s &&
+                    e.stats_ld >= (c.N + 63) / 64;
+    if (!ok) { set_error("gemm_tc: unsupported arguments for the row-statistics epilogue"); return -1; }
   }
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }
   if (c.batch > 1 && c.epi.atomic) { set_error("gemm_tc: batched GEMM with split-K is not supported"); return -1; }
@@ -1141,23 +1118,16 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
   //   per CTA: ceil(work / 148) items, each  kb_per_split * t_kblock + t_epilogue;
   //   t_kblock ~ operand bytes moved per k-block (the L2 -> smem stream bounds the mainloop), epilogue ~ tile area
   //   (x3 for reductions).
-  int best_bn = 64, best_sp = 1, best_mt = 1;
+  int best_bn = 64, best_sp = 1;
   double best_cost = 1e300;
   const int cands[3] = {256, 128, 64};
-  int mt_env = 0;  // CAPDEC_GEMM_MT = 1 / 2 forces the tile height (tests, tuning); read at every call
-  if (const char* ev = getenv("CAPDEC_GEMM_MT")) mt_env = atoi(ev);
-  for (int mtile = 1; mtile <= 2; ++mtile) {
-    // Measured on B200: the 256-row tile is NOT faster (head fc 25.8 vs 25.5 us, key/value projection 43.9 vs 32.1 us):
-    // the mainloop is bound by the shared-memory operand reads of the UMMAs (12 KB per 128x256x16), which a taller
-    // CTA tile does not reduce, and its single accumulator buffer exposes the epilogue.  It is kept selectable
-    // (CAPDEC_GEMM_MT=2) for the tests; auto-selection uses 128-row tiles.
-    if (mtile != (mt_env > 0 ? mt_env : 1)) continue;
-    if (mtile == 2 && c.M <= BM) continue;
-    const int mt = (c.M + BM * mtile - 1) / (BM * mtile);
+  // (A 256-row single-CTA tile was measured and dropped: head fc 25.8 vs 25.5 us, key/value projection 43.9 vs 32.1 us --
+  // the mainloop is bound by the shared-memory operand reads of the UMMAs, which a taller tile does not reduce.)
+  {
+    const int mt = (c.M + BM - 1) / BM;
     for (int i = 0; i < 3; ++i) {
       const int bn = cands[i];
       if (bn > 64 && c.N <= bn / 2) continue;
-      if (mtile == 2 && bn == 64) continue;  // not instantiated: a 256 x 64 tile has no use
       const long tiles = (long)mt * ((c.N + bn - 1) / bn) * (c.batch > 0 ? c.batch : 1);
       const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
       const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
@@ -1165,20 +1135,19 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
         const int kbps = (nkb + sp - 1) / sp;
         const int sp_eff = (nkb + kbps - 1) / kbps;
         const long per_cta = (tiles * sp_eff + kNumSMs - 1) / kNumSMs;
-        const double t_kb = (128.0 * mtile + bn) / 384.0;
-        const double t_epi = mtile * ((bn / 256.0) * (c.epi.atomic ? 6.0 : 2.0) + 1.0);
+        const double t_kb = (128.0 + bn) / 384.0;
+        const double t_epi = (bn / 256.0) * (c.epi.atomic ? 6.0 : 2.0) + 1.0;
         const double cost = per_cta * (kbps * t_kb + t_epi) + 4.0 /*fill*/;
-        if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; best_mt = mtile; }
+        if (cost < best_cost) { best_cost = cost; best_bn = bn; best_sp = sp_eff; }
       }
     }
   }
-  // CTA-pair 256 x 256 tiles (cta_group::2): 74 pairs, a k-block costs ~0.27 us instead of 0.37 us (see the kernel)
-  int pair_env = -1;  // CAPDEC_GEMM_PAIR = 0 / 1 forces the choice (tests, tuning); default: the cost model decides
-  if (const char* ev = getenv("CAPDEC_GEMM_PAIR")) pair_env = atoi(ev);
+  // CTA-pair 256 x 256 tiles (cta_group::2): 74 pairs, a k-block costs ~0.27 us instead of 0.37 us (see the kernel).
+  // ctx.variant (kernel-level tests through capdec_gemm): GEMM_PAIR / GEMM_SINGLE force the choice.
   bool use_pair = false;
   int pair_sp = 1;
   const long pair_tiles = (long)((c.M + 2 * BM - 1) / (2 * BM)) * ((c.N + kPairBN - 1) / kPairBN) * (c.batch > 0 ? c.batch : 1);
-  if (pair_env != 0 && pair_eligible(c)) {
+  if (ctx.variant != GEMM_SINGLE && pair_eligible(c)) {
     const long tiles = pair_tiles;
     const int sp_max = c.epi.atomic ? (c.splits > 0 ? c.splits : std::max(1, std::min(nkb / 4, 16))) : 1;
     const int sp_min = (c.epi.atomic && c.splits > 0) ? c.splits : 1;
@@ -1191,31 +1160,19 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
       const double cost = per_pair * (kbps * 0.75 + t_epi) + 5.0;
       if (cost < pair_cost) { pair_cost = cost; pair_sp = sp_eff; }
     }
-    use_pair = pair_env == 1 || pair_cost < best_cost;
+    use_pair = ctx.variant == GEMM_PAIR || pair_cost < best_cost;
   }
   if (use_pair) {
     const int kbps2 = (nkb + pair_sp - 1) / pair_sp;
     const int splits2 = (nkb + kbps2 - 1) / kbps2;
     // short-K forward-form problems with many tiles per pair are epilogue-bound: the variant with two staging tiles per warp
-    static const int epi2_env = [] { const char* ev = getenv("CAPDEC_GEMM_EPI2"); return ev ? atoi(ev) : 1; }();
-    const bool epi2 = epi2_env != 0 && !c.a_mn && splits2 == 1 && kbps2 <= 8 && pair_tiles >= 3 * (kNumSMs / 2);
+    const bool epi2 = !c.a_mn && splits2 == 1 && kbps2 <= 8 && pair_tiles >= 3 * (kNumSMs / 2);
     if (epi2) return c.b_mn ? launch_pair<false, true, true>(ctx, c, splits2, kbps2) : launch_pair<false, false, true>(ctx, c, splits2, kbps2);
     if (c.a_mn) return c.b_mn ? launch_pair<true, true, false>(ctx, c, splits2, kbps2) : launch_pair<true, false, false>(ctx, c, splits2, kbps2);
     return c.b_mn ? launch_pair<false, true, false>(ctx, c, splits2, kbps2) : launch_pair<false, false, false>(ctx, c, splits2, kbps2);
   }
-  if (const char* ev = getenv("CAPDEC_GEMM_BN")) {  // tuning / profiling override
-    const int v = atoi(ev);
-    if (v == 64 || v == 128 || v == 256) best_bn = v;
-    if (best_bn == 64) best_mt = 1;
-  }
   const int kbps = (nkb + best_sp - 1) / best_sp;
   const int splits = (nkb + kbps - 1) / kbps;
-  if (best_mt == 2) {
-    switch (best_bn) {
-      case 256: return launch_majors<256, 2>(ctx, c, splits, kbps);
-      default: return launch_majors<128, 2>(ctx, c, splits, kbps);
-    }
-  }
   switch (best_bn) {
     case 256: return launch_majors<256, 1>(ctx, c, splits, kbps);
     case 128: return launch_majors<128, 1>(ctx, c, splits, kbps);

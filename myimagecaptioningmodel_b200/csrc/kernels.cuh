@@ -41,14 +41,13 @@ struct ZeroTable {
 };
 void multi_zero(LaunchCtx c, ZeroTable& tab);
 template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* dst, long n);
-// dst[cc * ldd + r] = src[r * lds + cc]   (src fp32 [R, C])
-template <typename T> void transpose_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C);
 // dst[r * ldd + cc] = src[r * lds + cc]   (strided copy + convert)
 template <typename T> void copy2d_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C);
 // out[(t*B+b), :] = ids[b*ids_ld + t] == pad ? 0 : emb[id]      (model:28-32, 84)
+//   err: the handle's error word; an id outside [0, V) sets CAPDEC_ERR_SOURCE_ID there and reads as padding
 template <typename T>
-void embed_gather(LaunchCtx c, const T* emb, int E, const int64_t* ids, long ids_ld, int B, int steps, int pad, T* out,
-                  long ldo);
+void embed_gather(LaunchCtx c, const T* emb, int E, int V, const int64_t* ids, long ids_ld, int B, int steps, int pad,
+                  T* out, long ldo, int* err);
 // LSTM pointwise cell (Paddle lstm_unit op, gate order i,f,o,g; model:87-88).
 //   pre = gpre[r] (+ xe[r] if xe) (+ g5[(r % g5_mod) / g5_div] if g5);  c = sig(f) c_prev + sig(i) tanh(g); h = sig(o) tanh(c)
 template <typename T>
@@ -85,7 +84,6 @@ struct ColsumTable {
   void add(const void* x, long ld, long M, int N, float* out) { job[n++] = ColsumJob{x, ld, M, N, out, 0}; }
 };
 template <typename T> void colsum_multi(LaunchCtx c, ColsumTable& tab);
-void add_f32(LaunchCtx c, float* dst, const float* src, long n);
 // the fused bias vectors of capdec_bind_params: b_vocab [Vp] = out_fc_bias padded with zeros; b5 = [lstm_b | fc_xs_b];
 // b5d = [lstm_b | fc_xs_b + fc_hs_b]; b5p (optional) = b5 with unit-major gate columns
 struct BiasBind {
@@ -96,9 +94,8 @@ struct BiasBind {
 void bind_biases(LaunchCtx c, const BiasBind& a);
 // dEmb[id] += dX[(t*B+b)]  for id != pad        (lookup_table_v2_grad, padding_idx)
 template <typename T>
-void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
+void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, int V, const int64_t* ids, long ids_ld, int B, int steps,
                        int pad, float* dEmb);
-void fill_f32(LaunchCtx c, float* p, float v, long n);
 
 // ---- adaptor.cu ----------------------------------------------------------------------------------
 // feature adaptor layout kernels (model:193-199): enc_map [B,X,k] fp32 -> rows [B*k,X], mean [B,X]; and the backward
@@ -153,8 +150,8 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
 
 // ---- recurrent.cu (bf16 only) -------------------------------------------------------------------
 // The whole teacher-forced recurrence as one persistent cooperative kernel per direction (see recurrent.cu).
-//   *_supported: shape (and CAPDEC_RECURRENT != 0) allows the persistent kernel; otherwise the caller runs the
-//   per-step GEMM + cell schedule.  ctr: 64 unsigned arrival counters owned by the caller.
+//   *_supported: the shape allows the persistent kernels; otherwise (or with CAPDEC_FLAG_STEPWISE_RECURRENCE) the
+//   caller runs the per-step GEMM + cell schedule.  ctr: 64 unsigned arrival counters owned by the caller.
 bool lstm_seq_supported(int B, int H);
 // dst[k, 64*j + 4*u + gate] = src[k, gate*H + 16*j + u]: the forward kernel's unit-major weight copy
 void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H);
@@ -168,34 +165,26 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
 
 // ---- loss.cu -----------------------------------------------------------------------------------
 // masked soft-max cross entropy (model:163-171, 180-183, 205-212): target[t*B+b] = caption[b, t+1]
-//   lse[m];  acc[0] += sum(ce * mask), acc[1] += sum(mask)
-void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* caption, long cap_ld, int B, int steps,
-            int pad, float* lse, float* acc);
-// fused: the above plus the UNSCALED gradient  dlogits[m, n] = (softmax - onehot) * mask  (columns [V, Vp) zeroed);
-// the 1/sum(mask) * loss_scale factor is applied by the consumers (GemmEpi::alpha_dev, colsum_add scale)
-template <typename T, typename L>
-void ce_fused(LaunchCtx c, const L* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-              int steps, int pad, float* lse, float* acc, T* dlogits);
-// cross entropy fused into the vocabulary GEMM (gemm.cuh ACT_ROWSTATS / ACT_SOFTMAX_GRAD): merge of the row statistics,
-// target logit, loss sums and the per-row operands (lse_eff, tgt) of the gradient pass; E % 8 == 0
-void ce_merge(LaunchCtx c, long M, int S, const float* stats_m, const float* stats_s, long ld, const bf16* proj, int E,
-              const bf16* emb, const float* bias, const int64_t* caption, long cap_ld, int B, int pad, float* lse,
-              float* lse_eff, int* tgt, float* acc);
+//   lse[m];  acc[0] += sum(ce * mask), acc[1] += sum(mask);  and the UNSCALED gradient
+//   dlogits[m, n] = (softmax - onehot) * mask  (columns [V, Vp) zeroed); the 1/sum(mask) * loss_scale factor is applied
+//   by the consumers (GemmEpi::alpha_dev, colsum_add scale).  err: see embed_gather (CAPDEC_ERR_TARGET_ID)
+template <typename T>
+void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+              int steps, int pad, float* lse, float* acc, T* dlogits, int* err);
 // out[0] = in[0] * s
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out);
 // acc[2] = acc[0] / acc[1] (the loss), acc[3] = 1 / acc[1]
 void loss_finalize(LaunchCtx c, float* acc);
-// dlogits[m, n] = (exp(l - lse) - [n == target]) * mask * (*scale) * loss_scale; columns [V, Vp) are zeroed
-template <typename T>
-void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-            int steps, int pad, const float* lse, const float* scale, float loss_scale, T* dlogits);
 // out[b, t, :V] = logits[(t*B+b), :V]
-template <typename L>
-void logits_to_batch_major(LaunchCtx c, const L* logits, long ldl, int V, int B, int steps, float* out);
-// one beam-search step for every image; see loss.cu
+void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out);
+// one beam-search step for every image; see loss.cu.  V <= beam_max_vocab(), beam <= 8.
+//   scratch: beam_scratch_bytes(n_img, beam) bytes of device memory owned by the caller (the decoder handle)
+//   trace (optional): [n_img*beam, 2] = (token, back-pointer) of this step's selection
+size_t beam_scratch_bytes(int n_img, int beam);
+int beam_max_vocab();
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
-               const int* hist_in, int* hist_out, int* tok_out, int* src_out);
+               const int* hist_in, int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace);
 // initial beam state: score = 0 for prefix 0 of every image, -inf for the others; tok = start; src = r % beam
 void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src);
 // next-step operands: xin[r] = [emb[tok[r]] | h_new[src_row(r)]], c_next[r] = c_new[src_row(r)]

@@ -16,51 +16,23 @@ __device__ __forceinline__ int64_t target_of(const int64_t* caption, long cap_ld
   return caption[b * cap_ld + t + 1];
 }
 
-__global__ void __launch_bounds__(kCeThreads)
-ce_fwd_kernel(const float* __restrict__ logits, long ldl, int V, const int64_t* __restrict__ caption, long cap_ld, int B,
-              int pad, float* __restrict__ lse, float* __restrict__ acc) {
-  __shared__ float scratch[32];
-  const long m = blockIdx.x;
-  const float* row = logits + m * ldl;
-  const int V4 = V & ~3;
-  float mx = -INFINITY;
-  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
-    float4 v = *reinterpret_cast<const float4*>(row + n);
-    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-  }
-  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) mx = fmaxf(mx, row[n]);
-  mx = block_max(mx, scratch);
-  float sum = 0.f;
-  for (int n = threadIdx.x * 4; n < V4; n += kCeThreads * 4) {
-    float4 v = *reinterpret_cast<const float4*>(row + n);
-    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
-  }
-  for (int n = V4 + threadIdx.x; n < V; n += kCeThreads) sum += __expf(row[n] - mx);
-  sum = block_sum(sum, scratch);
-  if (threadIdx.x == 0) {
-    const float l = mx + logf(sum);
-    lse[m] = l;
-    const int64_t tgt = target_of(caption, cap_ld, B, m);
-    if (tgt != pad) {
-      atomicAdd(acc + 0, l - row[tgt]);
-      atomicAdd(acc + 1, 1.f);
-    }
-  }
-}
-
 // one pass for the online (max, sum), one L2-resident pass for the gradient: logits are read from HBM once.
-// L = storage type of the logits (fp32, or bf16 on the bf16 path: half the bytes of the [M, V] round trip; every
-// reduction is fp32)
-template <typename T, typename L>
+// A target id outside [0, V) is reported (CAPDEC_ERR_TARGET_ID) and treated as padding.
+template <typename T>
 __global__ void __launch_bounds__(kCeThreads)
-ce_fused_kernel(const L* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
-                long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits) {
+ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
+                long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits,
+                int* __restrict__ err) {
   pdl_trigger();
   __shared__ float scratch[32];
   const long m = blockIdx.x;
-  const L* row = logits + m * ldl;
+  const float* row = logits + m * ldl;
   T* out = dlogits + m * (long)Vp;
-  const int64_t tgt = target_of(caption, cap_ld, B, m);
+  int64_t tgt = target_of(caption, cap_ld, B, m);
+  if ((unsigned long)tgt >= (unsigned long)V) {
+    if (threadIdx.x == 0 && err) atomicOr(err, 2 /* CAPDEC_ERR_TARGET_ID */);
+    tgt = pad;
+  }
   const int V8 = V & ~7;
   float mx = -INFINITY, sum = 0.f;
   for (int n = threadIdx.x * 8; n < V8; n += kCeThreads * 8) {
@@ -109,63 +81,6 @@ ce_fused_kernel(const L* __restrict__ logits, long ldl, int V, int Vp, const int
   }
 }
 
-// Second half of the cross entropy that is fused into the vocabulary GEMM (gemm.cuh: ACT_ROWSTATS / ACT_SOFTMAX_GRAD):
-// merges the per-(row, 64-column group) partial (max, sum) pairs of the first GEMM pass into lse[row], computes the
-// target logit directly ( proj[row] . Emb[target] + bias[target], the same bf16 products the GEMM accumulates ) and
-// the masked loss sums, and writes the per-row operands of the second GEMM pass:
-//   lse_eff[row] = lse or +inf for a masked (padding) target -> exp(x - inf) = 0: an all-zero gradient row
-//   tgt[row]     = target id or -1
-// One warp per row.
-__global__ void __launch_bounds__(256)
-ce_merge_kernel(long M, int S, const float* __restrict__ sm, const float* __restrict__ ss, long ld,
-                const bf16* __restrict__ proj, int E, const bf16* __restrict__ emb, const float* __restrict__ bias,
-                const int64_t* __restrict__ caption, long cap_ld, int B, int pad, float* __restrict__ lse_out,
-                float* __restrict__ lse_eff, int* __restrict__ tgt_out, float* __restrict__ acc) {
-  pdl_trigger();
-  __shared__ float part[8][2];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * 8 + warp;
-  float loss = 0.f, cnt = 0.f;
-  if (row < M) {
-    float m = -INFINITY;
-    for (int g = lane; g < S; g += 32) m = fmaxf(m, sm[row * ld + g]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int g = lane; g < S; g += 32) sum += ss[row * ld + g] * __expf(sm[row * ld + g] - m);
-    sum = warp_sum(sum);
-    const float l = m + logf(sum);
-    const int64_t tgt = target_of(caption, cap_ld, B, row);
-    if (tgt != pad) {
-      float dot = 0.f;
-      for (int e0 = lane * 8; e0 < E; e0 += 256) {
-        float a[8], b[8];
-        load8(proj + row * E + e0, a);
-        load8(emb + tgt * E + e0, b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dot = fmaf(a[i], b[i], dot);
-      }
-      dot = warp_sum(dot) + bias[tgt];
-      loss = l - dot;
-      cnt = 1.f;
-    }
-    if (lane == 0) {
-      lse_out[row] = l;
-      lse_eff[row] = (tgt != pad) ? l : INFINITY;
-      tgt_out[row] = (tgt != pad) ? (int)tgt : -1;
-    }
-  }
-  if (lane == 0) { part[warp][0] = loss; part[warp][1] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < 8; ++w) { a += part[w][0]; b += part[w][1]; }
-    if (b > 0.f) {
-      atomicAdd(acc + 0, a);
-      atomicAdd(acc + 1, b);
-    }
-  }
-}
-
 __global__ void scale_scalar_kernel(const float* in, float s, float* out) { out[0] = in[0] * s; }
 
 __global__ void loss_finalize_kernel(float* acc) {
@@ -173,47 +88,13 @@ __global__ void loss_finalize_kernel(float* acc) {
   acc[3] = 1.f / acc[1];
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kCeThreads)
-ce_bwd_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
-              long cap_ld, int B, int pad, const float* __restrict__ lse, const float* __restrict__ scale,
-              float loss_scale, T* __restrict__ dlogits) {
-  const long m = blockIdx.x;
-  const float* row = logits + m * ldl;
-  T* out = dlogits + m * (long)Vp;
-  const int64_t tgt = target_of(caption, cap_ld, B, m);
-  if (tgt == pad) {  // masked position: zero gradient row
-    for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
-      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      store8(out + n, z);
-    }
-    return;
-  }
-  const float l = lse[m];
-  const float sc = scale[0] * loss_scale;
-  for (int n = threadIdx.x * 8; n < Vp; n += kCeThreads * 8) {
-    float v[8];
-    if (n + 8 <= V) {
-      load8(row + n, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (__expf(v[i] - l) - ((n + i) == tgt ? 1.f : 0.f)) * sc;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = (n + i < V) ? (__expf(row[n + i] - l) - ((n + i) == tgt ? 1.f : 0.f)) * sc : 0.f;
-    }
-    store8(out + n, v);
-  }
-}
-
-template <typename L>
-__global__ void logits_bm_kernel(const L* __restrict__ logits, long ldl, int V, int B, int steps,
+__global__ void logits_bm_kernel(const float* __restrict__ logits, long ldl, int V, int B, int steps,
                                  float* __restrict__ out) {
   const long m = blockIdx.x;  // time-major row
   const long t = m / B, b = m % B;
-  const L* src = logits + m * ldl;
+  const float* src = logits + m * ldl;
   float* dst = out + (b * steps + t) * (long)V;
-  for (int n = threadIdx.x; n < V; n += blockDim.x) dst[n] = to_f(src[n]);
+  for (int n = threadIdx.x; n < V; n += blockDim.x) dst[n] = src[n];
 }
 
 // ---- beam search step: one CTA per image --------------------------------------------------------------------
@@ -229,262 +110,15 @@ __device__ __forceinline__ Cand warp_best(Cand c) {
   return c;
 }
 
-constexpr int kBeamThreads = 512;
 constexpr int kMaxBeam = 8;
 
-// Single pass over the logits: for every live prefix each thread keeps (a) an online log-sum-exp (running max and
-// sum) and (b) its `beam` best (logit, token) pairs in registers; within one prefix the candidate score
-// score_p + (x - lse_p) is monotone in the raw logit x, so the per-prefix top-`beam` by x contains every global
-// winner.  Block merge: the per-thread lists go to shared memory and `beam` rounds of block arg-max pick the winners
-// (ties -> lower token), then beam*beam scored candidates are merged across prefixes (ties -> lower prefix, token).
-// A finished prefix offers exactly one candidate (itself, emitting pad, score unchanged).
-template <int BEAM>
-__global__ void __launch_bounds__(kBeamThreads)
-beam_step_generic_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int step, int T_total, int pad, int stop,
-                 int finish_on_stop, const float* __restrict__ score_in, float* __restrict__ score_out,
-                 const int* __restrict__ fin_in, int* __restrict__ fin_out, const int* __restrict__ hist_in,
-                 int* __restrict__ hist_out, int* __restrict__ tok_out, int* __restrict__ src_out) {
-  __shared__ float scratch[32];
-  __shared__ float s_v[32];
-  __shared__ int s_i[32];
-  __shared__ float cand_v[kBeamThreads * BEAM];
-  __shared__ int cand_i[kBeamThreads * BEAM];
-  __shared__ float win_v[kMaxBeam * kMaxBeam];   // scored candidates of all prefixes
-  __shared__ int win_i[kMaxBeam * kMaxBeam];     // flat index p*V + token
-  __shared__ int sel_idx[kMaxBeam];
-  __shared__ float sel_val[kMaxBeam];
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int INT_BIG = 0x7fffffff;
-  const bool greedy = (beam == 1 && !finish_on_stop);
-  int n_win = 0;  // number of scored candidates written so far (uniform across the block)
-  for (int p = 0; p < beam; ++p) {
-    const float sc = score_in[img * beam + p];
-    if (!(sc > -INFINITY)) continue;                       // dead prefix (uniform branch)
-    if (finish_on_stop && fin_in[img * beam + p]) {
-      if (tid == 0) { win_v[n_win] = sc; win_i[n_win] = p * V + pad; }
-      ++n_win;
-      continue;
-    }
-    const float* row = logits + ((long)img * beam + p) * ldl;
-    float bv[BEAM];
-    int bi[BEAM];
-#pragma unroll
-    for (int r = 0; r < BEAM; ++r) { bv[r] = -INFINITY; bi[r] = INT_BIG; }
-    float mx = -INFINITY, sum = 0.f;
-    for (int n = tid; n < V; n += kBeamThreads) {
-      const float x = row[n];
-      if (x > mx) { sum = sum * __expf(mx - x) + 1.f; mx = x; } else { sum += __expf(x - mx); }
-      if (better(x, n, bv[BEAM - 1], bi[BEAM - 1])) {      // sorted insertion (registers, unrolled)
-        bv[BEAM - 1] = x; bi[BEAM - 1] = n;
-#pragma unroll
-        for (int r = BEAM - 1; r > 0; --r) {
-          if (better(bv[r], bi[r], bv[r - 1], bi[r - 1])) {
-            const float tv = bv[r]; bv[r] = bv[r - 1]; bv[r - 1] = tv;
-            const int ti = bi[r]; bi[r] = bi[r - 1]; bi[r - 1] = ti;
-          }
-        }
-      }
-    }
-    // block log-sum-exp from the per-thread (max, sum) pairs
-    const float gmx = block_max(mx, scratch);
-    const float gsum = block_sum(mx > -INFINITY ? sum * __expf(mx - gmx) : 0.f, scratch);
-    const float lse = gmx + logf(gsum);
-#pragma unroll
-    for (int r = 0; r < BEAM; ++r) { cand_v[tid * BEAM + r] = bv[r]; cand_i[tid * BEAM + r] = bi[r]; }
-    __syncthreads();
-    // `beam` rounds of block arg-max over the kBeamThreads*BEAM per-thread winners
-    for (int r = 0; r < beam; ++r) {
-      Cand best{-INFINITY, INT_BIG};
-      for (int c = tid; c < kBeamThreads * BEAM; c += kBeamThreads) {
-        const float v = cand_v[c];
-        const int i = cand_i[c];
-        if (i != INT_BIG && better(v, i, best.v, best.idx)) { best.v = v; best.idx = i; }
-      }
-      best = warp_best(best);
-      if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
-      __syncthreads();
-      if (warp == 0) {
-        Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
-        c = warp_best(c);
-        if (lane == 0) {
-          // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
-          win_v[n_win + r] = (c.idx == INT_BIG) ? -INFINITY : (greedy ? c.v : sc + (c.v - lse));
-          win_i[n_win + r] = (c.idx == INT_BIG) ? INT_BIG : p * V + c.idx;
-          if (greedy) scratch[31] = sc + (c.v - lse);
-          s_i[0] = c.idx;
-        }
-      }
-      __syncthreads();
-      const int taken = s_i[0];
-      // remove the winner from the pool (token ids are unique within a prefix)
-      for (int c = tid; c < kBeamThreads * BEAM; c += kBeamThreads)
-        if (cand_i[c] == taken) cand_i[c] = INT_BIG;
-      __syncthreads();
-    }
-    n_win += beam;
-  }
-  __syncthreads();
-  // merge the scored candidates of all prefixes: `beam` winners, ties -> lower flat index
-  if (warp == 0) {
-    for (int r = 0; r < beam; ++r) {
-      Cand best{-INFINITY, INT_BIG};
-      for (int c = lane; c < n_win; c += 32) {
-        const int i = win_i[c];
-        if (i != INT_BIG && better(win_v[c], i, best.v, best.idx)) { best.v = win_v[c]; best.idx = i; }
-      }
-      best = warp_best(best);
-      if (lane == 0) { sel_idx[r] = best.idx; sel_val[r] = best.v; }
-      __syncwarp();
-      for (int c = lane; c < n_win; c += 32)
-        if (win_i[c] == best.idx) win_i[c] = INT_BIG;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  // write-out: token, back-pointer, score, finished flag, history (one warp per selected beam)
-  if (warp < beam) {
-    const int r = warp;
-    int idx = sel_idx[r];
-    float v = sel_val[r];
-    int src, tok;
-    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }  // fewer live candidates than beams (V < beam only)
-    else { src = idx / V; tok = idx % V; }
-    if (greedy && idx != INT_BIG) v = scratch[31];
-    const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
-    if (lane == 0) {
-      tok_out[img * beam + r] = tok;
-      src_out[img * beam + r] = src;
-      score_out[img * beam + r] = v;
-      fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
-    }
-    const int* hin = hist_in + ((long)img * beam + src) * T_total;
-    int* hout = hist_out + ((long)img * beam + r) * T_total;
-    for (int t = lane; t < T_total; t += 32) hout[t] = (t == step) ? tok : (t < step ? hin[t] : 0);
-  }
-}
-
-
-// Fast path for V <= kBeamThreads * EPT: every thread keeps its EPT logits of the row in registers (all loads in
-// flight at once), computes the block log-sum-exp from them, and each of the `beam` rounds is a block arg-max over the
-// per-thread maxima; only the winner's owner rescans its registers.  No divergent insertion, ~6x fewer instructions.
-template <int EPT>
-__global__ void __launch_bounds__(kBeamThreads)
-beam_step_kernel(const float* __restrict__ logits, long ldl, int V, int beam, int step, int T_total, int pad, int stop,
-                 int finish_on_stop, const float* __restrict__ score_in, float* __restrict__ score_out,
-                 const int* __restrict__ fin_in, int* __restrict__ fin_out, const int* __restrict__ hist_in,
-                 int* __restrict__ hist_out, int* __restrict__ tok_out, int* __restrict__ src_out) {
-  __shared__ float scratch[32];
-  __shared__ float s_v[32];
-  __shared__ int s_i[32];
-  __shared__ float win_v[kMaxBeam * kMaxBeam];   // scored candidates of all prefixes
-  __shared__ int win_i[kMaxBeam * kMaxBeam];     // flat index p*V + token
-  __shared__ int sel_idx[kMaxBeam];
-  __shared__ float sel_val[kMaxBeam];
-  __shared__ float greedy_score;
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int INT_BIG = 0x7fffffff;
-  const bool greedy = (beam == 1 && !finish_on_stop);
-  int n_win = 0;  // scored candidates written so far (uniform across the block)
-  for (int p = 0; p < beam; ++p) {
-    const float sc = score_in[img * beam + p];
-    if (!(sc > -INFINITY)) continue;                       // dead prefix (uniform branch)
-    if (finish_on_stop && fin_in[img * beam + p]) {        // finished: one candidate, itself + pad, score unchanged
-      if (tid == 0) { win_v[n_win] = sc; win_i[n_win] = p * V + pad; }
-      ++n_win;
-      continue;
-    }
-    const float* row = logits + ((long)img * beam + p) * ldl;
-    float x[EPT];
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      const int n = tid + i * kBeamThreads;
-      x[i] = (n < V) ? row[n] : -INFINITY;
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) mx = fmaxf(mx, x[i]);
-    const float gmx = block_max(mx, scratch);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) sum += __expf(x[i] - gmx);   // exp(-inf) = 0 for the padding slots
-    const float lse = gmx + logf(block_sum(sum, scratch));
-    for (int r = 0; r < beam; ++r) {
-      // local arg-max over the registers (ties -> lower token = lower i)
-      float lv = -INFINITY;
-      int li = INT_BIG;
-#pragma unroll
-      for (int i = 0; i < EPT; ++i)
-        if (x[i] > lv) { lv = x[i]; li = tid + i * kBeamThreads; }
-      Cand best = warp_best(Cand{lv, li});
-      if (lane == 0) { s_v[warp] = best.v; s_i[warp] = best.idx; }
-      __syncthreads();
-      if (warp == 0) {
-        Cand c{lane < kBeamThreads / 32 ? s_v[lane] : -INFINITY, lane < kBeamThreads / 32 ? s_i[lane] : INT_BIG};
-        c = warp_best(c);
-        if (lane == 0) {
-          // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
-          win_v[n_win + r] = (c.idx == INT_BIG) ? -INFINITY : (greedy ? c.v : sc + (c.v - lse));
-          win_i[n_win + r] = (c.idx == INT_BIG) ? INT_BIG : p * V + c.idx;
-          if (greedy) greedy_score = sc + (c.v - lse);
-          s_i[0] = c.idx;
-        }
-      }
-      __syncthreads();
-      const int taken = s_i[0];
-      __syncthreads();  // s_i[0] is rewritten by the next round
-      if (taken != INT_BIG && (taken % kBeamThreads) == tid) {
-        const int slot = taken / kBeamThreads;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i)
-          if (i == slot) x[i] = -INFINITY;                  // remove the winner from this thread's pool
-      }
-    }
-    n_win += beam;
-  }
-  __syncthreads();
-  // merge the scored candidates of all prefixes: `beam` winners, ties -> lower flat index
-  if (warp == 0) {
-    for (int r = 0; r < beam; ++r) {
-      Cand best{-INFINITY, INT_BIG};
-      for (int c = lane; c < n_win; c += 32) {
-        const int i = win_i[c];
-        if (i != INT_BIG && better(win_v[c], i, best.v, best.idx)) { best.v = win_v[c]; best.idx = i; }
-      }
-      best = warp_best(best);
-      if (lane == 0) { sel_idx[r] = best.idx; sel_val[r] = best.v; }
-      __syncwarp();
-      for (int c = lane; c < n_win; c += 32)
-        if (win_i[c] == best.idx) win_i[c] = INT_BIG;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (warp < beam) {
-    const int r = warp;
-    int idx = sel_idx[r];
-    float v = sel_val[r];
-    int src, tok;
-    if (idx == INT_BIG) { src = 0; tok = pad; v = -INFINITY; }
-    else { src = idx / V; tok = idx % V; }
-    if (greedy && idx != INT_BIG) v = greedy_score;
-    const int was_fin = finish_on_stop ? fin_in[img * beam + src] : 0;
-    if (lane == 0) {
-      tok_out[img * beam + r] = tok;
-      src_out[img * beam + r] = src;
-      score_out[img * beam + r] = v;
-      fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
-    }
-    const int* hin = hist_in + ((long)img * beam + src) * T_total;
-    int* hout = hist_out + ((long)img * beam + r) * T_total;
-    for (int t = lane; t < T_total; t += 32) hout[t] = (t == step) ? tok : (t < step ? hin[t] : 0);
-  }
-}
-
-// ---- beam search step, split form: one CTA per (image, prefix) ROW, then one warp per image -----------------------
-// beam_rows_kernel: the row's log-sum-exp and its `beam` best tokens, all logits of the row in registers (EPT per
-// thread, every load in flight at once), one block barrier per selection round (every warp re-reduces the 8 warp
-// winners from a double-buffered shared array).  3x the CTAs of the per-image kernel and a third of its serial chain:
-// 57 -> ~20 us per step at 512 images x beam 3 on B200.
+// ---- beam search step: one CTA per (image, prefix) ROW, then one warp per image -------------------------------------
+// Within one prefix the candidate score  score_p + (x - lse_p)  is monotone in the raw logit x, so the per-prefix
+// top-`beam` by x contains every global winner.
+// beam_rows_kernel: the row's log-sum-exp and its `beam` best tokens (ties -> lower token), all logits of the row in
+// registers (EPT per thread, every load in flight at once), one block barrier per selection round (every warp
+// re-reduces the 8 warp winners from a double-buffered shared array).  A finished prefix offers exactly one candidate
+// (itself, emitting pad, score unchanged).
 // beam_merge_kernel: merges the beam*beam scored candidates of an image (ties -> lower prefix, then lower token) and
 // writes tokens, back-pointers, scores, finished flags and histories.
 constexpr int kRowThreads = 256;
@@ -561,7 +195,7 @@ beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, in
                   const float* __restrict__ cand_v, const int* __restrict__ cand_i, const float* __restrict__ gscore,
                   float* __restrict__ score_out, const int* __restrict__ fin_in, int* __restrict__ fin_out,
                   const int* __restrict__ hist_in, int* __restrict__ hist_out, int* __restrict__ tok_out,
-                  int* __restrict__ src_out) {
+                  int* __restrict__ src_out, int* __restrict__ trace) {
   pdl_trigger();
   const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (img >= n_img) return;
@@ -600,6 +234,10 @@ beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, in
       src_out[img * beam + r] = src;
       score_out[img * beam + r] = v;
       fin_out[img * beam + r] = (was_fin || (finish_on_stop && tok == stop)) ? 1 : 0;
+      if (trace) {  // per-step record (token, back-pointer) of this selection
+        trace[2 * (img * beam + r)] = tok;
+        trace[2 * (img * beam + r) + 1] = src;
+      }
     }
     const int* hin = hist_in + ((long)img * beam + src) * T_total;
     int* hout = hist_out + ((long)img * beam + r) * T_total;
@@ -654,30 +292,17 @@ __global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad,
 
 }  // namespace
 
-void ce_fwd(LaunchCtx c, const float* logits, long ldl, int V, const int64_t* caption, long cap_ld, int B, int steps,
-            int pad, float* lse, float* acc) {
-  ce_fwd_kernel<<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, caption, cap_ld, B, pad, lse, acc);
+template <typename T>
+void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
+              int steps, int pad, float* lse, float* acc, T* dlogits, int* err) {
+  ce_fused_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits,
+                                                            err);
   if (c.launches) ++*c.launches;
 }
-template <typename T, typename L>
-void ce_fused(LaunchCtx c, const L* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-              int steps, int pad, float* lse, float* acc, T* dlogits) {
-  ce_fused_kernel<T, L><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits);
-  if (c.launches) ++*c.launches;
-}
-template void ce_fused<float, float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*,
-                                     float*, float*);
-template void ce_fused<bf16, float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*,
-                                    float*, bf16*);
-template void ce_fused<bf16, bf16>(LaunchCtx, const bf16*, long, int, int, const int64_t*, long, int, int, int, float*,
-                                   float*, bf16*);
-void ce_merge(LaunchCtx c, long M, int S, const float* stats_m, const float* stats_s, long ld, const bf16* proj, int E,
-              const bf16* emb, const float* bias, const int64_t* caption, long cap_ld, int B, int pad, float* lse,
-              float* lse_eff, int* tgt, float* acc) {
-  ce_merge_kernel<<<(unsigned)((M + 7) / 8), 256, 0, c.stream>>>(M, S, stats_m, stats_s, ld, proj, E, emb, bias, caption,
-                                                               cap_ld, B, pad, lse, lse_eff, tgt, acc);
-  if (c.launches) ++*c.launches;
-}
+template void ce_fused<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
+                              float*, int*);
+template void ce_fused<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
+                             bf16*, int*);
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out) {
   scale_scalar_kernel<<<1, 1, 0, c.stream>>>(in, s, out);
   if (c.launches) ++*c.launches;
@@ -686,75 +311,36 @@ void loss_finalize(LaunchCtx c, float* acc) {
   loss_finalize_kernel<<<1, 1, 0, c.stream>>>(acc);
   if (c.launches) ++*c.launches;
 }
-template <typename T>
-void ce_bwd(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-            int steps, int pad, const float* lse, const float* scale, float loss_scale, T* dlogits) {
-  ce_bwd_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, scale,
-                                                          loss_scale, dlogits);
+void logits_to_batch_major(LaunchCtx c, const float* logits, long ldl, int V, int B, int steps, float* out) {
+  logits_bm_kernel<<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
   if (c.launches) ++*c.launches;
 }
-template <typename L>
-void logits_to_batch_major(LaunchCtx c, const L* logits, long ldl, int V, int B, int steps, float* out) {
-  logits_bm_kernel<L><<<B * steps, 256, 0, c.stream>>>(logits, ldl, V, B, steps, out);
-  if (c.launches) ++*c.launches;
+size_t beam_scratch_bytes(int n_img, int beam) {
+  const size_t rows = (size_t)n_img * beam;
+  return rows * kMaxBeam * 8 + rows * 4;
 }
-template void logits_to_batch_major<float>(LaunchCtx, const float*, long, int, int, int, float*);
-template void logits_to_batch_major<bf16>(LaunchCtx, const bf16*, long, int, int, int, float*);
-namespace {
-// candidate scratch of the split beam step (per device, grown on demand, process lifetime)
-struct BeamScratch { void* p = nullptr; size_t cap = 0; };
-BeamScratch g_beam_scratch[64];
-void* beam_scratch(size_t bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  BeamScratch& b = g_beam_scratch[dev];
-  if (bytes > b.cap) {
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr; b.cap = 0;
-    if (cudaMalloc(&b.p, bytes) != cudaSuccess) { b.p = nullptr; return nullptr; }
-    b.cap = bytes;
-  }
-  return b.p;
-}
-}  // namespace
+int beam_max_vocab() { return kRowThreads * 64; }
 
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
-               const int* hist_in, int* hist_out, int* tok_out, int* src_out) {
-  static const bool split_ok = [] { const char* e = getenv("CAPDEC_BEAM_SPLIT"); return !(e && e[0] == '0'); }();
-  if (split_ok && V <= kRowThreads * 64 && n_img > 0) {
-    const long rows = (long)n_img * beam;
-    const size_t nb = (size_t)rows * kMaxBeam * 8 + (size_t)rows * 4;
-    char* sp = static_cast<char*>(beam_scratch(nb));
-    if (sp) {
-      float* cv = reinterpret_cast<float*>(sp);
-      int* ci = reinterpret_cast<int*>(sp + (size_t)rows * kMaxBeam * 4);
-      float* gs = reinterpret_cast<float*>(sp + (size_t)rows * kMaxBeam * 8);
+               const int* hist_in, int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace) {
+  if (n_img <= 0) return;
+  const long rows = (long)n_img * beam;
+  char* sp = static_cast<char*>(scratch);
+  float* cv = reinterpret_cast<float*>(sp);
+  int* ci = reinterpret_cast<int*>(sp + (size_t)rows * kMaxBeam * 4);
+  float* gs = reinterpret_cast<float*>(sp + (size_t)rows * kMaxBeam * 8);
 #define LAUNCH_ROWS(EPTV)                                                                                           \
   beam_rows_kernel<EPTV><<<(unsigned)rows, kRowThreads, 0, c.stream>>>(logits, ldl, V, beam, pad, finish_on_stop,   \
                                                                        score_in, fin_in, cv, ci, gs)
-      if (V <= kRowThreads * 8) LAUNCH_ROWS(8);
-      else if (V <= kRowThreads * 49) LAUNCH_ROWS(49);
-      else LAUNCH_ROWS(64);
+  if (V <= kRowThreads * 8) LAUNCH_ROWS(8);
+  else if (V <= kRowThreads * 49) LAUNCH_ROWS(49);      // config.py:55 (12295)
+  else LAUNCH_ROWS(64);                                  // up to beam_max_vocab()
 #undef LAUNCH_ROWS
-      beam_merge_kernel<<<(n_img + 3) / 4, 128, 0, c.stream>>>(n_img, V, beam, step, T_total, pad, stop, finish_on_stop, cv,
-                                                              ci, gs, score_out, fin_in, fin_out, hist_in, hist_out,
-                                                              tok_out, src_out);
-      if (c.launches) *c.launches += 2;
-      return;
-    }
-  }
-#define LAUNCH_BEAM(KERNEL)                                                                                          \
-  KERNEL<<<n_img, kBeamThreads, 0, c.stream>>>(logits, ldl, V, beam, step, T_total, pad, stop, finish_on_stop, score_in, \
-                                               score_out, fin_in, fin_out, hist_in, hist_out, tok_out, src_out)
-  if (V <= kBeamThreads * 8) LAUNCH_BEAM(beam_step_kernel<8>);
-  else if (V <= kBeamThreads * 32) LAUNCH_BEAM(beam_step_kernel<32>);
-  else if (beam <= 1) LAUNCH_BEAM(beam_step_generic_kernel<1>);
-  else if (beam <= 2) LAUNCH_BEAM(beam_step_generic_kernel<2>);
-  else if (beam <= 4) LAUNCH_BEAM(beam_step_generic_kernel<4>);
-  else LAUNCH_BEAM(beam_step_generic_kernel<8>);
-#undef LAUNCH_BEAM
-  if (c.launches) ++*c.launches;
+  beam_merge_kernel<<<(n_img + 3) / 4, 128, 0, c.stream>>>(n_img, V, beam, step, T_total, pad, stop, finish_on_stop, cv, ci,
+                                                          gs, score_out, fin_in, fin_out, hist_in, hist_out, tok_out,
+                                                          src_out, trace);
+  if (c.launches) *c.launches += 2;
 }
 void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src) {
   beam_init_kernel<<<(R + 255) / 256, 256, 0, c.stream>>>(R, beam, start, score, tok, src);
@@ -772,10 +358,6 @@ void beam_reorder(LaunchCtx c, int n_img, int beam, int E, int H, int pad, const
   if (c.launches) ++*c.launches;
 }
 
-template void ce_bwd<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, const float*,
-                            const float*, float, float*);
-template void ce_bwd<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, const float*,
-                           const float*, float, bf16*);
 template void beam_reorder<float>(LaunchCtx, int, int, int, int, int, const float*, const int*, const int*,
                                   const float*, const float*, float*, long, float*);
 template void beam_reorder<bf16>(LaunchCtx, int, int, int, int, int, const bf16*, const int*, const int*, const bf16*,

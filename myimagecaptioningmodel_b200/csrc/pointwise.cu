@@ -25,21 +25,6 @@ template <typename T> __global__ void convert_kernel(const float* __restrict__ s
 }
 
 template <typename T>
-__global__ void transpose_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, int R, int C) {
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int r = r0 + i, cc = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && cc < C) ? src[(long)r * lds + cc] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int cc = c0 + i, r = r0 + threadIdx.x;
-    if (cc < C && r < R) dst[(long)cc * ldd + r] = from_f<T>(tile[threadIdx.x][i]);
-  }
-}
-
-template <typename T>
 __global__ void copy2d_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, int R, int C) {
   pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,9 +35,11 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long lds, T* __rest
   }
 }
 
+// An id outside [0, V) (a vocabulary that does not match the checkpoint) reads as padding and raises the handle's
+// error word (include/capdec.h, capdec_status); PaddlePaddle's lookup_table_v2 enforces the same range.
 template <typename T>
-__global__ void embed_gather_kernel(const T* __restrict__ emb, int E, const int64_t* __restrict__ ids, long ids_ld,
-                                    int B, int steps, int pad, T* __restrict__ out, long ldo) {
+__global__ void embed_gather_kernel(const T* __restrict__ emb, int E, int V, const int64_t* __restrict__ ids, long ids_ld,
+                                    int B, int steps, int pad, T* __restrict__ out, long ldo, int* __restrict__ err) {
   pdl_trigger();
   const int vec_per_row = E / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,8 +49,10 @@ __global__ void embed_gather_kernel(const T* __restrict__ emb, int E, const int6
     const int v = (int)(i % vec_per_row);
     const int t = (int)(m / B), b = (int)(m % B);
     const long id = ids[(long)b * ids_ld + t];
+    const bool in_range = (unsigned long)id < (unsigned long)V;
+    if (!in_range && v == 0 && err) atomicOr(err, 1 /* CAPDEC_ERR_SOURCE_ID */);
     float x[8];
-    if (id == pad) {
+    if (id == pad || !in_range) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = 0.f;
     } else {
@@ -388,7 +377,7 @@ __global__ void __launch_bounds__(512) colsum_multi_kernel(ColsumTable tab) {
 }
 
 template <typename T>
-__global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, const int64_t* __restrict__ ids,
+__global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, int V, const int64_t* __restrict__ ids,
                                      long ids_ld, int B, int steps, int pad, float* __restrict__ dEmb) {
   pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,14 +387,9 @@ __global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, c
     const int e = (int)(i % E);
     const int t = (int)(m / B), b = (int)(m % B);
     const long id = ids[(long)b * ids_ld + t];
-    if (id != pad) atomicAdd(dEmb + id * E + e, to_f(dX[m * ld + e]));
+    // ids outside [0, V) were reported by the forward gather and read as padding there: no gradient either
+    if (id != pad && (unsigned long)id < (unsigned long)V) atomicAdd(dEmb + id * E + e, to_f(dX[m * ld + e]));
   }
-}
-
-__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] += src[i];
 }
 
 // every fused bias vector of capdec_bind_params in one launch (was: 2 memsets / 5 copies / an add / a permute launch)
@@ -423,12 +407,6 @@ __global__ void bind_bias_kernel(BiasBind a) {
       if (a.b5p) a.b5p[gate_col ? 4 * (i % H) + i / H : i] = v;       // unit-major gate columns (col 4*unit + gate)
     }
   }
-}
-
-__global__ void fill_kernel(float* p, float v, long n) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = v;
 }
 
 // ---- multi-tensor kernels: one launch for the whole parameter re-layout / gradient clearing ----
@@ -528,20 +506,15 @@ template <typename T> void convert_from_f32(LaunchCtx c, const float* src, T* ds
   convert_kernel<T><<<grid_for(n), 256, 0, c.stream>>>(src, dst, n);
   BUMP(c);
 }
-template <typename T> void transpose_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C) {
-  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-  transpose_kernel<T><<<grid, block, 0, c.stream>>>(src, lds, dst, ldd, R, C);
-  BUMP(c);
-}
 template <typename T> void copy2d_from_f32(LaunchCtx c, const float* src, long lds, T* dst, long ldd, int R, int C) {
   copy2d_kernel<T><<<grid_for((long)R * C), 256, 0, c.stream>>>(src, lds, dst, ldd, R, C);
   BUMP(c);
 }
 template <typename T>
-void embed_gather(LaunchCtx c, const T* emb, int E, const int64_t* ids, long ids_ld, int B, int steps, int pad, T* out,
-                  long ldo) {
-  embed_gather_kernel<T><<<grid_for((long)B * steps * (E / 8)), 256, 0, c.stream>>>(emb, E, ids, ids_ld, B, steps, pad,
-                                                                                 out, ldo);
+void embed_gather(LaunchCtx c, const T* emb, int E, int V, const int64_t* ids, long ids_ld, int B, int steps, int pad,
+                  T* out, long ldo, int* err) {
+  embed_gather_kernel<T><<<grid_for((long)B * steps * (E / 8)), 256, 0, c.stream>>>(emb, E, V, ids, ids_ld, B, steps, pad,
+                                                                                 out, ldo, err);
   BUMP(c);
 }
 template <typename T>
@@ -623,9 +596,9 @@ template <typename T> void colsum_multi(LaunchCtx c, ColsumTable& tab) {
   BUMP(c);
 }
 template <typename T>
-void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, const int64_t* ids, long ids_ld, int B, int steps,
+void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, int V, const int64_t* ids, long ids_ld, int B, int steps,
                        int pad, float* dEmb) {
-  embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, ids, ids_ld, B, steps, pad,
+  embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, V, ids, ids_ld, B, steps, pad,
                                                                              dEmb);
   BUMP(c);
 }
@@ -634,25 +607,13 @@ void bind_biases(LaunchCtx c, const BiasBind& a) {
   bind_bias_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(a);
   BUMP(c);
 }
-void add_f32(LaunchCtx c, float* dst, const float* src, long n) {
-  if (n <= 0) return;
-  add_f32_kernel<<<grid_for(n), 256, 0, c.stream>>>(dst, src, n);
-  BUMP(c);
-}
-void fill_f32(LaunchCtx c, float* p, float v, long n) {
-  if (n <= 0) return;
-  fill_kernel<<<grid_for(n), 256, 0, c.stream>>>(p, v, n);
-  BUMP(c);
-}
-
 template int multi_convert<float>(LaunchCtx, ConvertTable&);
 template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
 
 #define INSTANTIATE(T)                                                                                                 \
   template void convert_from_f32<T>(LaunchCtx, const float*, T*, long);                                                \
-  template void transpose_from_f32<T>(LaunchCtx, const float*, long, T*, long, int, int);                              \
   template void copy2d_from_f32<T>(LaunchCtx, const float*, long, T*, long, int, int);                                 \
-  template void embed_gather<T>(LaunchCtx, const T*, int, const int64_t*, long, int, int, int, T*, long);              \
+  template void embed_gather<T>(LaunchCtx, const T*, int, int, const int64_t*, long, int, int, int, T*, long, int*);   \
   template void lstm_cell_fwd<T>(LaunchCtx, int, int, const float*, long, const T*, long, const float*, long, int,    \
                                  int, const float*, T*, long, float*, T*);                                             \
   template void sentinel_fwd<T>(LaunchCtx, long, int, const T*, long, const T*, long, const float*, long, int, int,    \
@@ -663,7 +624,7 @@ template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
   template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long);                                 \
   template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*, const float*);                                           \
   template void colsum_multi<T>(LaunchCtx, ColsumTable&);                                           \
-  template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, const int64_t*, long, int, int, int, float*);
+  template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, int, const int64_t*, long, int, int, int, float*);
 
 INSTANTIATE(float)
 INSTANTIATE(bf16)

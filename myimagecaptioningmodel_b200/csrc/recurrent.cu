@@ -70,30 +70,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// cluster helpers: the CTAs of a cluster load disjoint row blocks of the same h tile and multicast them to each other
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-// the mbarrier at the same shared-memory offset in every CTA of `mask` receives one arrival once the MMAs retire
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
@@ -153,10 +129,10 @@ template <int kStages> __device__ __forceinline__ Bars carve_bars(uint8_t* p) {
   return b;
 }
 template <int kStages>
-__device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals, uint32_t consumers = 1) {
+__device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals) {
   for (int s = 0; s < kStages; ++s) {
     mbar_init(&b.full[s], 1);
-    mbar_init(&b.empty[s], consumers);  // one MMA commit per CTA that reads the stage (cluster multicast: all of them)
+    mbar_init(&b.empty[s], 1);
   }
   for (int i = 0; i < 2; ++i) {
     mbar_init(&b.tmem_full[i], 1);
@@ -189,7 +165,6 @@ struct SeqFwdParams {
   const float* cs;              // [(T+1)*B, H]  cs[0] = c_0 (zeros); written through the tensor map
   unsigned* ctr;                // [gridDim.y]   arrival counters (zeroed by the host)
   unsigned long long* trace;    // debug timeline or nullptr
-  int stagger_ns;               // start offset between batch groups (0 = none)
 };
 
 // Everything except h_t moves through the TMA engine in whole 128-byte lines: the per-step x-part pre-activations
@@ -199,12 +174,9 @@ struct SeqFwdParams {
 // ~400 K sector requests per step, which either delayed the producer's polls of the arrival counter (~3 us per step)
 // or, when issued after the barrier, slowed the h tile stream by 70 %.
 //
-// CS = cluster size along the unit-slice dimension: the CS CTAs of a cluster work on the same batch tile, each loads
-// 128/CS rows of every h k-block and multicasts them.  Measured on B200: no gain over CS = 1 (474 / 468 / 469 us for
-// CS = 1 / 2 / 4 on the first version, 336 / 336 / 334 us on the current one; the L2 already merges the unicast requests
-// of a few CTAs for the same line) -- delivery into the SMs, not the L2 read, bounds the h stream -- so CS = 1 is the
-// default.  CS = 8 cannot be launched: 16 clusters of 8 CTAs with 217 KB each are not co-schedulable on the GPCs.
-template <int CS>
+// (Measured and dropped: clusters of 2 / 4 CTAs sharing a batch tile, each loading 128/CS rows of every h k-block and
+// multicasting them -- 336 / 336 / 334 us for CS = 1 / 2 / 4: the L2 already merges the unicast requests of a few CTAs for
+// the same line; clusters of 8 with 217 KB per CTA are not co-schedulable.  Staggering the two batch groups: no effect.)
 __global__ void __launch_bounds__(kFwdThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmCs,
@@ -230,16 +202,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmCs);
     tma_prefetch_desc(&tmGa);
-    init_bars<kFwdStages>(bar, kFwdEpiWarps, CS);
+    init_bars<kFwdStages>(bar, kFwdEpiWarps);
   }
   if (warp == 1) tmem_alloc<2 * kFwdN>(bar.tmem_ptr);
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // every CTA's barriers are initialised before a peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *bar.tmem_ptr;
-  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -248,16 +217,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       for (int kb = 0; kb < nkb; ++kb) tma_load_3d(wsm + (size_t)kb * kFwdWTile, &tmW, slice * kFwdN, kb * BK, 0, bar.w_bar);
       int s = 0;
       uint32_t ph = 0;
-      if (p.stagger_ns > 0 && y > 0) {
-        // The batch groups are independent chains that all stream through the same L2 at the same moment; starting group
-        // y half a step late lets each group's h stream run while the others are in their epilogue / barrier phase.
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-          __nanosleep(200);
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (t1 - t0 < (unsigned long long)p.stagger_ns * (unsigned)y / (unsigned)MG);
-      }
       for (int t = 0; t < p.T; ++t) {
         if (t > 0) {
           spin_until(p.ctr + y, (unsigned)t * (unsigned)G);  // every CTA of this batch group has written its h_t slice
@@ -268,11 +227,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait_b(&bar.empty[s], ph ^ 1);
             mbar_expect_tx(&bar.full[s], kATile);
-            if (CS == 1)
-              tma_load_3d(stages + s * kATile, &tmH, kb * BK, mt * 128, t, &bar.full[s]);
-            else
-              tma_load_3d_mc(stages + s * kATile + crank * (kATile / CS), &tmH, kb * BK, mt * 128 + crank * (128 / CS), t,
-                             &bar.full[s], cmask);
+            tma_load_3d(stages + s * kATile, &tmH, kb * BK, mt * 128, t, &bar.full[s]);
             if (++s == kFwdStages) { s = 0; ph ^= 1; }
           }
         }
@@ -302,8 +257,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16(tmem_d, desc_kmajor(a_addr, k), desc_mnmajor(b_addr, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (CS == 1) umma_commit(&bar.empty[s]);
-            else umma_commit_mc(&bar.empty[s], cmask);
+            umma_commit(&bar.empty[s]);
             if (++s == kFwdStages) { s = 0; ph ^= 1; }
           }
           umma_commit(&bar.tmem_full[buf]);
@@ -428,7 +382,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // no peer still multicasts into, or signals barriers of, an exited CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<2 * kFwdN>(tmem_base);
@@ -771,13 +724,7 @@ __global__ void permute_gate_cols_kernel(const float* __restrict__ src, long lds
   }
 }
 
-// CAPDEC_RECURRENT=0 selects the per-step schedule (read at every call so tests can compare the two paths)
 unsigned long long* g_rec_trace = nullptr;
-
-bool env_enabled() {
-  const char* e = getenv("CAPDEC_RECURRENT");
-  return !(e && e[0] == '0');
-}
 
 }  // namespace
 
@@ -796,7 +743,7 @@ void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H
 //   forward : W_hh slice [H x 64] bf16 resident  -> H <= 1024;  H / 16 CTAs per batch group
 //   backward: (H / 128)^2 CTAs per batch group   -> H % 128 == 0
 bool lstm_seq_supported(int B, int H) {
-  if (!env_enabled() || B <= 0 || H % 128 || H > 1024) return false;
+  if (B <= 0 || H % 128 || H > 1024) return false;
   return H / kFwdUnits <= kNumSMs && (H / 128) * (H / 128) <= kNumSMs;
 }
 
@@ -810,22 +757,14 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
   const int mg = std::max(1, std::min(n_mtiles, kNumSMs / slices));
   const int nkb = H / BK;
   const size_t smem = (size_t)nkb * kFwdWTile + kFwdStages * kATile + kFwdXStage + kFwdCStage + 256 + 1024;
-  // cluster size: CAPDEC_REC_CLUSTER in {1, 2, 4} (tuning; see the kernel's comment)
-  int cs = 1;
-  if (const char* ev = getenv("CAPDEC_REC_CLUSTER")) cs = atoi(ev);
-  if (cs != 1 && cs != 2 && cs != 4) cs = 1;   // 8: 16 clusters of 8 x 217 KB cannot be co-scheduled ("too many blocks")
-  while (cs > 1 && slices % cs) cs >>= 1;
-  const void* kern = cs == 4   ? (const void*)lstm_seq_fwd_kernel<4>
-                     : cs == 2 ? (const void*)lstm_seq_fwd_kernel<2>
-                               : (const void*)lstm_seq_fwd_kernel<1>;
-  static bool attr_set[5] = {};
-  if (!attr_set[cs]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("lstm_seq_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set[cs] = true;
+    attr_set = true;
   }
   CUtensorMap tmH, tmW, tmX, tmCs, tmGa;
-  if (tma_map_3d(hs, H, B, H, BK, 128 / cs, &tmH, 2, T + 1, (uint64_t)B * H)) return -1;
+  if (tma_map_3d(hs, H, B, H, BK, 128, &tmH, 2, T + 1, (uint64_t)B * H)) return -1;
   if (tma_map_3d(w_perm, 4 * H, H, 4 * H, kFwdN, BK, &tmW, 2, 1, 0)) return -1;
   if (tma_map_3d(xe, 4 * H, B, ld_xe, kFwdN, 128, &tmX, 2, T, (uint64_t)B * ld_xe)) return -1;
   if (tma_map_3d(cs_buf, H, B, H, kFwdUnits, 128, &tmCs, 4, T + 1, (uint64_t)B * H, false)) return -1;
@@ -834,27 +773,12 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
   p.B = B; p.H = H; p.T = T; p.n_mtiles = n_mtiles;
   p.hs = hs; p.cs = cs_buf; p.ctr = ctr;
   p.trace = g_rec_trace;
-  p.stagger_ns = 0;
-  if (const char* ev = getenv("CAPDEC_REC_STAGGER_NS")) p.stagger_ns = atoi(ev);
   cudaError_t e = cudaMemsetAsync(ctr, 0, 64 * sizeof(unsigned), c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_fwd: memset: %s", cudaGetErrorString(e)); return -1; }
   void* args[] = {&tmH, &tmW, &tmX, &tmCs, &tmGa, &p};
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(slices, mg);
-  cfg.blockDim = dim3(kFwdThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = c.stream;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = cs;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = cs > 1 ? 2 : 1;
-  e = cudaLaunchKernelExC(&cfg, kern, args);
-  if (e != cudaSuccess) { set_error("lstm_seq_fwd: cooperative launch (cluster %d): %s", cs, cudaGetErrorString(e)); return -1; }
+  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_fwd_kernel, dim3(slices, mg), dim3(kFwdThreads), args, smem,
+                                  c.stream);
+  if (e != cudaSuccess) { set_error("lstm_seq_fwd: cooperative launch: %s", cudaGetErrorString(e)); return -1; }
   if (c.launches) ++*c.launches;
   return 0;
 }

@@ -37,6 +37,7 @@ class DecoderConfig:
     stop_idx: int = 3
     dtype: str = "bf16"             # 'bf16' (tcgen05 path) | 'fp32' (validation precision)
     softmax_axis: str = "feature"   # 'feature' = reference as written (alpha == 1) | 'position' = intended
+    stepwise_recurrence: bool = False   # validation: one GEMM + cell launch per step instead of the persistent kernels
 
     @property
     def train_steps(self) -> int:
@@ -50,7 +51,8 @@ class DecoderConfig:
         return CapdecConfig(self.hidden_dim, self.embedding_size, self.vocab_size, self.num_positions,
                             self.sentence_length, self.infer_max_length, self.padding_idx, self.start_idx,
                             self.stop_idx, _capi.DTYPE_BF16 if self.dtype == "bf16" else _capi.DTYPE_F32,
-                            _capi.SOFTMAX_POSITION if self.softmax_axis == "position" else _capi.SOFTMAX_FEATURE, 0)
+                            _capi.SOFTMAX_POSITION if self.softmax_axis == "position" else _capi.SOFTMAX_FEATURE,
+                            _capi.FLAG_STEPWISE_RECURRENCE if self.stepwise_recurrence else 0)
 
 
 def param_shapes(cfg: DecoderConfig) -> Dict[str, tuple]:
@@ -120,6 +122,7 @@ class ParameterStore:
                 else:
                     t = (torch.rand(shape, generator=gen) * 2 - 1) * bias_scale
                 self.params[n].copy_(t)
+        _capi.bump_version(self.flat)
         return self
 
     def load(self, state: Dict[str, "torch.Tensor"]):
@@ -132,6 +135,7 @@ class ParameterStore:
                 raise ValueError("parameter {} has shape {}, expected {}".format(n, tuple(t.shape), self.shapes[n]))
             with torch.no_grad():
                 self.params[n].copy_(t)
+        _capi.bump_version(self.flat)
         return self
 
     def state_dict(self):
@@ -177,6 +181,7 @@ class AdaptorStore:
                 else:
                     t = (torch.rand(shape, generator=gen) * 2 - 1) * bias_scale
                 self.params[n].copy_(t)
+        _capi.bump_version(self.flat)
         return self
 
     def load(self, state: Dict[str, "torch.Tensor"]):
@@ -188,6 +193,7 @@ class AdaptorStore:
                 raise ValueError("parameter {} has shape {}, expected {}".format(n, tuple(t.shape), self.shapes[n]))
             with torch.no_grad():
                 self.params[n].copy_(t)
+        _capi.bump_version(self.flat)
         return self
 
     def state_dict(self):
@@ -215,6 +221,8 @@ class CaptionDecoderEngine:
         self._loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._caption_keepalive = None
         self._bound = False
+        self._bound_version = -1
+        self._adaptor_version = -1
         self.adaptor: Optional[AdaptorStore] = None      # attach_adaptor() creates the feature-adaptor parameters
         self._adaptor_bound = False
         self._staged = None
@@ -229,8 +237,21 @@ class CaptionDecoderEngine:
 
     # ---- C-ABI wrappers --------------------------------------------------------------------------------------
     def bind_params(self):
+        """capdec_bind_params: re-layout of the fp32 parameters into the handle's operand copies."""
         check(self.lib.capdec_bind_params(self.handle, C.byref(self.store.c_params), stream_ptr()), "capdec_bind_params")
         self._bound = True
+        self._bound_version = _capi.version_of(self.store.flat)
+
+    def _ensure_bound(self):
+        """(Re-)bind when the parameters were written since the last bind: optim.Adam, ParameterStore.load /
+        init_reference and checkpoint.load_params bump the buffer's version (_capi.bump_version).  A caller that writes
+        store.flat by other means calls bind_params() itself (include/capdec.h)."""
+        if not self._bound or self._bound_version != _capi.version_of(self.store.flat):
+            self.bind_params()
+
+    def _ensure_adaptor_bound(self):
+        if not self._adaptor_bound or self._adaptor_version != _capi.version_of(self.adaptor.flat):
+            self.bind_adaptor()
 
     def _check_inputs(self, g, P, caption=None):
         cfg = self.cfg
@@ -250,8 +271,7 @@ class CaptionDecoderEngine:
     def train_forward(self, g, P, caption, want_logits: bool = False):
         """capdec_train_fwd.  Returns (loss_buf[4] device tensor, logits or None)."""
         B = self._check_inputs(g, P, caption)
-        if not self._bound:
-            self.bind_params()
+        self._ensure_bound()
         logits = None
         if want_logits:
             logits = torch.empty(B, self.cfg.train_steps, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
@@ -285,6 +305,7 @@ class CaptionDecoderEngine:
         check(self.lib.capdec_bind_adaptor(self.handle, self.adaptor.encoder_channel, C.byref(self.adaptor.c_params),
                                            stream_ptr()), "capdec_bind_adaptor")
         self._adaptor_bound = True
+        self._adaptor_version = _capi.version_of(self.adaptor.flat)
 
     def _check_map(self, enc_map):
         ad = getattr(self, "adaptor", None)
@@ -304,8 +325,7 @@ class CaptionDecoderEngine:
     def img2feature(self, enc_map, want_outputs: bool = False):
         """capdec_img2feature: stages (p_img_feat, global_img_feat) in the handle; returns fp32 copies if asked."""
         enc_map, B = self._check_map(enc_map)
-        if not self._adaptor_bound:
-            self.bind_adaptor()
+        self._ensure_adaptor_bound()
         P = g = None
         if want_outputs:
             P = torch.empty(B, self.cfg.num_positions, self.cfg.hidden_dim, dtype=torch.float32, device=self.device)
@@ -323,8 +343,7 @@ class CaptionDecoderEngine:
         if tuple(caption.shape) != (B, cfg.sentence_length) or caption.dtype != torch.int64 or not caption.is_cuda \
                 or not caption.is_contiguous():
             raise ValueError("caption must be a contiguous int64 CUDA tensor [B,{}]".format(cfg.sentence_length))
-        if not self._bound:
-            self.bind_params()
+        self._ensure_bound()
         logits = None
         if want_logits:
             logits = torch.empty(B, cfg.train_steps, cfg.vocab_size, dtype=torch.float32, device=self.device)
@@ -356,8 +375,7 @@ class CaptionDecoderEngine:
         return self._decode(g, P, B, beam, finish_on_stop, want_f32)
 
     def _decode(self, g, P, B, beam, finish_on_stop, want_f32):
-        if not self._bound:
-            self.bind_params()
+        self._ensure_bound()
         T = self.cfg.infer_max_length
         ids = torch.empty(B, beam, T, dtype=torch.int32, device=self.device)
         scores = torch.empty(B, beam, dtype=torch.float32, device=self.device)
@@ -365,6 +383,17 @@ class CaptionDecoderEngine:
         check(self.lib.capdec_decode(self.handle, ptr(g), ptr(P), B, beam, 1 if finish_on_stop else 0, ptr(ids),
                                      ptr(scores), ptr(ids_f32), stream_ptr()), "capdec_decode")
         return ids, scores, ids_f32
+
+    def check_status(self):
+        """capdec_status: synchronise the current stream and raise CapdecError if a kernel of an earlier call found bad
+        input (token ids outside the vocabulary, lengths that cut off non-padding tokens)."""
+        check(self.lib.capdec_status(self.handle, stream_ptr()), "capdec_status")
+
+    def decode_trace(self, B: int, beam: int):
+        """capdec_decode_trace: (token, back-pointer) of every selection of the last decode, int32 [T,B,beam,2]."""
+        out = torch.empty(self.cfg.infer_max_length, B, beam, 2, dtype=torch.int32, device=self.device)
+        check(self.lib.capdec_decode_trace(self.handle, ptr(out), stream_ptr()), "capdec_decode_trace")
+        return out
 
     @property
     def workspace_bytes(self) -> int:

@@ -57,6 +57,19 @@ class LRSchedule:
         self._epoch_counter = 0.0          # the persistable `cur_epoch` variable of util.py:92-93
         self._last_n = -1
 
+    @property
+    def counter_begin(self):
+        """`begin` of the graph's @LR_DECAY_COUNTER@ variable (util.py:48-52): the variable starts at begin - 1 and is
+        incremented before it is read, so after n executor runs it holds n - 1 + begin.  None: the graph has no counter
+        (strategy None, util.py:44-45)."""
+        if self.strategy is None:
+            return None
+        return 1 if self.strategy in ("cosine_decay_warmup", "cosine_decay_restart_warmup") else 0
+
+    def cur_epoch_state(self, n: int) -> float:
+        """value of the persistable `cur_epoch` variable (util.py:92-99) after n executor runs"""
+        return float(sum(1 for t in range(1, n + 1) if t % self.step_each_epoch == 0))
+
     def __call__(self, n: int) -> float:
         s = self.strategy
         if s is None:
@@ -145,6 +158,8 @@ class Adam:
         self.beta1_pow = np.float32(self.beta1_pow * np.float32(self.beta1))
         self.beta2_pow = np.float32(self.beta2_pow * np.float32(self.beta2))
         self.steps += 1
+        for p, _ in self.buffers:           # the handle's operand copies of these parameters are stale now
+            _capi.bump_version(p)
 
     def step(self, stream=None) -> float:
         """One update of every buffer from its gradient; returns the learning rate that was used."""

@@ -13,7 +13,6 @@ host logic is testable on CPU with the gloo backend (tests/test_parallel_cpu.py 
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -74,7 +73,7 @@ class DataParallelTrainer:
             bwd(1.0, None)
             if optimizer is not None:
                 self._grouped_exchange(extra, optimizer, reduce=False)
-            return loss_buf[2]
+            return loss_buf[2].clone()      # not a view of the engine's live buffer: the next forward pass overwrites it
         if self.pe_semantics:
             # ParallelExecutor default (CoeffNumDevice): mean over devices of per-device token means
             loss_buf = fwd()
@@ -85,7 +84,7 @@ class DataParallelTrainer:
             self._grouped_exchange(extra, optimizer, reduce=True)
             return loss
         self._ensure_overlap()
-        if self._overlap and os.environ.get("CAPDEC_DP_EARLY_COUNT", "1") != "0":
+        if self._overlap:
             return self._forward_backward_overlapped(caption, fwd, bwd, extra, optimizer)
         loss_buf = fwd()
         tot = loss_buf[:2].clone()

@@ -252,15 +252,54 @@ def first_argmax(x: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
+def beam_select(cfg: DecoderConfig, score, logp, finished, beam: int, finish_on_stop: bool = True):
+    """One selection step of the beam spec for every image.
+
+    score [B,beam] prefix scores (-inf = dead prefix), logp [B,beam,V] log-probabilities of the next token,
+    finished [B,beam] bool.  A finished prefix offers exactly one candidate (itself, score unchanged, emitting
+    padding_idx); the top-`beam` of the <= beam*V candidates win, ties -> lower flat index = (lower prefix, lower
+    token) -- a stable descending sort.  Returns (top_val [B,beam], src [B,beam], tok [B,beam], new_finished,
+    margin [B] = gap between the last winner and the first loser, adjacent [B] = smallest gap between neighbours
+    among the best beam+1 candidates: below it the ORDER of the winners may change too)."""
+    B, _, V = logp.shape
+    NEG = -float("inf")
+    cand = score.unsqueeze(-1) + logp                   # [B,beam,V]
+    if finish_on_stop:
+        fin = finished.unsqueeze(-1)
+        only_pad = torch.full_like(cand, NEG)
+        only_pad[:, :, cfg.padding_idx] = score         # the single "stay finished" candidate
+        cand = torch.where(fin, only_pad, cand)
+    flat = cand.reshape(B, beam * V)
+    # stable top-k: ties -> lower flat index = (lower prefix, lower token)
+    order = torch.sort(flat, dim=-1, descending=True, stable=True)
+    top_val, top_idx = order.values[:, :beam], order.indices[:, :beam]
+    if flat.shape[1] > beam:
+        margin = order.values[:, beam - 1] - order.values[:, beam]
+        gaps = order.values[:, :beam] - order.values[:, 1:beam + 1]
+        gaps = torch.where(torch.isnan(gaps), torch.full_like(gaps, float("inf")), gaps)   # -inf - -inf
+        adjacent = gaps.min(dim=1).values
+    else:
+        margin = torch.full((B,), float("inf"), dtype=score.dtype)
+        adjacent = margin.clone()
+    src = top_idx // V                                   # backpointer [B,beam]
+    tok = top_idx % V
+    was_fin = torch.gather(finished, 1, src)
+    new_fin = was_fin | ((tok == cfg.stop_idx) if finish_on_stop else torch.zeros_like(was_fin))
+    return top_val, src, tok, new_fin, margin, adjacent
+
+
+@torch.no_grad()
 def beam_search(params, cfg: DecoderConfig, global_img_feat, p_img_feat, beam: int,
-                finish_on_stop: bool = True, return_margin: bool = False):
+                finish_on_stop: bool = True, return_margin: bool = False, return_trace: bool = False):
     """Beam search as specified in SURVEY.md 8c row C5 (the reference has none, F1).
 
     rows = image x beam; score = sum of log-probs, no length normalisation; a prefix that ended in
     stop_idx contributes exactly one candidate (itself, score unchanged) and emits padding_idx
     afterwards; per image the top-`beam` candidates are taken with ties broken by (lower prefix
     index, lower token id); at step 0 only prefix 0 is live; exactly infer_max_length steps.
-    Returns ids int64 [B,beam,T] sorted by final score (desc, stable) and scores [B,beam].
+    Returns ids int64 [B,beam,T] sorted by final score (desc, stable) and scores [B,beam]
+    (+ margin [B,T] with return_margin; + a dict of per-step records with return_trace: tok, src [T,B,beam],
+    adjacent [B,T] -- see beam_select).
     With beam=1 and finish_on_stop=False this is bit-identical to greedy_decode."""
     B = global_img_feat.shape[0]
     dt = global_img_feat.dtype
@@ -276,38 +315,28 @@ def beam_search(params, cfg: DecoderConfig, global_img_feat, p_img_feat, beam: i
     score[:, 1:] = NEG                                      # only prefix 0 live at step 0
     finished = torch.zeros(B, beam, dtype=torch.bool)
     hist = torch.zeros(B, beam, T, dtype=torch.int64)
-    margins = []
+    margins, adjacents, toks, srcs = [], [], [], []
     for t in range(T):
         logits, h_new, c_new, _, _ = decoder_step(params, cfg, word, g_r, v_r, k_r, hid, cell)
         logp = torch.log_softmax(logits, dim=-1).reshape(B, beam, V)
-        cand = score.unsqueeze(-1) + logp                   # [B,beam,V]
-        if finish_on_stop:
-            fin = finished.unsqueeze(-1)
-            only_pad = torch.full_like(cand, NEG)
-            only_pad[:, :, cfg.padding_idx] = score         # the single "stay finished" candidate
-            cand = torch.where(fin, only_pad, cand)
-        flat = cand.reshape(B, beam * V)
-        # stable top-k: ties -> lower flat index = (lower prefix, lower token)
-        order = torch.sort(flat, dim=-1, descending=True, stable=True)
-        top_val, top_idx = order.values[:, :beam], order.indices[:, :beam]
-        if return_margin:
-            margins.append(order.values[:, beam - 1] - order.values[:, beam]
-                           if flat.shape[1] > beam else torch.full((B,), float("inf"), dtype=dt))
-        src = top_idx // V                                   # backpointer [B,beam]
-        tok = top_idx % V
+        score, src, tok, finished, margin, adjacent = beam_select(cfg, score, logp, finished, beam, finish_on_stop)
+        margins.append(margin)
+        adjacents.append(adjacent)
+        toks.append(tok)
+        srcs.append(src)
         base = (torch.arange(B) * beam).unsqueeze(-1)
         rows = (base + src).reshape(-1)
         hid, cell = h_new[rows], c_new[rows]
         hist = torch.gather(hist, 1, src.unsqueeze(-1).expand(B, beam, T)).clone()
         hist[:, :, t] = tok
-        was_fin = torch.gather(finished, 1, src)
-        finished = was_fin | ((tok == cfg.stop_idx) if finish_on_stop else torch.zeros_like(was_fin))
-        score = top_val
         word = tok.reshape(-1)
     # beams are already in descending score order (stable sort each step)
+    out = (hist, score)
     if return_margin:
-        return hist, score, torch.stack(margins, 1)
-    return hist, score
+        out = out + (torch.stack(margins, 1),)
+    if return_trace:
+        out = out + ({"tok": torch.stack(toks, 0), "src": torch.stack(srcs, 0), "adjacent": torch.stack(adjacents, 1)},)
+    return out
 
 
 def filter_caption(ids, cfg: DecoderConfig):

@@ -48,22 +48,20 @@ def run(epochs=1, samples=64, batch=16, encoder_channel=1280, dims=None, lr=0.00
         t0 = time.time()
         epoch_loss, steps = 0.0, 0
         for step, data in enumerate(reader.get_reader(batch * world, "train")()):
-            lo, hi = M.shard_range(len(data), rank, world)
-            if hi <= lo:
+            if len(data) < world:
+                # a ragged last global batch with fewer samples than ranks: EVERY rank drops it (len(data) is the same
+                # on all ranks), so that no rank skips collectives the others enter
                 continue
+            lo, hi = M.shard_range(len(data), rank, world)
             img, cap = zip(*data[lo:hi])
             x = torch.from_numpy(np.stack(img)).cuda()
             c = torch.from_numpy(np.stack(cap)).cuda()
-            eng.bind_params()
-            eng.bind_adaptor()
-            loss, _ = trainer.forward_backward_map(x, c, optimizer=opt)
+            loss, _ = trainer.forward_backward_map(x, c, optimizer=opt)   # (re-)binds after the previous update
             step_loss = float(loss)                                                          # fetch_list=[loss, lrate], train.py:139
             if np.isnan(step_loss):
                 raise AssertionError("Epoch:{} Step:{} Loss为Nan".format(epoch, step + 1))    # train.py:140-141
             epoch_loss += step_loss
             steps += 1
-        eng.bind_params()
-        eng.bind_adaptor()
         bleu, n_sentences = evaluation.evaluate(                                             # train.py:151-166
             lambda im: eng.decode_map(torch.from_numpy(im).cuda(), beam=1)[2].cpu().numpy(),
             reader.get_reader(batch, "dev")(), reader.index_word, stop_tag=cfg.stop_idx, padding_tag=cfg.padding_idx)

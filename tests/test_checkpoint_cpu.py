@@ -59,7 +59,8 @@ def test_save_load_roundtrip_with_optimizer_state(tmp_path):
     opt = types.SimpleNamespace(
         moment1=[torch.randn_like(eng.store.flat), torch.randn_like(eng.adaptor.flat)],
         moment2=[torch.rand_like(eng.store.flat), torch.rand_like(eng.adaptor.flat)],
-        beta1_pow=np.float32(0.9 ** 5), beta2_pow=np.float32(0.999 ** 5), steps=4)
+        beta1_pow=np.float32(0.9 ** 5), beta2_pow=np.float32(0.999 ** 5), steps=4,
+        lr=M.get_lr("cosine_decay_warmup", 1e-3, 64, 16))
     d = str(tmp_path / "checkpoint")
     CK.save_persistables(d, eng, opt)
     files = set(os.listdir(d))
@@ -71,7 +72,8 @@ def test_save_load_roundtrip_with_optimizer_state(tmp_path):
     eng2.adaptor.flat.zero_()
     opt2 = types.SimpleNamespace(moment1=[torch.zeros_like(eng.store.flat), torch.zeros_like(eng.adaptor.flat)],
                                  moment2=[torch.zeros_like(eng.store.flat), torch.zeros_like(eng.adaptor.flat)],
-                                 beta1_pow=np.float32(0.9), beta2_pow=np.float32(0.999), steps=0)
+                                 beta1_pow=np.float32(0.9), beta2_pow=np.float32(0.999), steps=0,
+                                 lr=M.get_lr("cosine_decay_warmup", 1e-3, 64, 16))
     CK.load_persistables(d, eng2, opt2)
     for n in M.PARAM_NAMES:
         assert torch.equal(eng2.store.params[n], eng.store.params[n]), n
@@ -90,3 +92,44 @@ def test_save_load_roundtrip_with_optimizer_state(tmp_path):
     CK.write_lod_tensor(os.path.join(d, "fc_7.w_0"), np.zeros((3, 3), np.float32))
     with pytest.raises(ValueError):
         CK.load_params(d, eng2)
+
+
+@pytest.mark.parametrize("strategy,begin", [(None, None), ("cosine_decay", 0), ("cosine_decay_restart", 0),
+                                            ("cosine_decay_warmup", 1), ("cosine_decay_restart_warmup", 1)])
+def test_lr_decay_counter_follows_the_graphs_begin(tmp_path, strategy, begin):
+    """@LR_DECAY_COUNTER@ (util.py:48-52, autoincreased_step_counter(begin)): the variable starts at begin - 1 and is
+    incremented before it is read, so after n executor runs it holds n - 1 + begin: n for the two warm-up schedules
+    (begin = 1), n - 1 for cosine_decay / cosine_decay_restart (begin = 0); with strategy None it does not exist.  The
+    restart-warm-up schedule also carries the persistable `cur_epoch` (util.py:92-99)."""
+    eng = _engine()
+    n = 9
+    sched = M.get_lr(strategy, 1e-3, 64, 16, decay_epoch=2)          # 4 steps per epoch
+    mk = lambda steps, s: types.SimpleNamespace(
+        moment1=[torch.zeros_like(eng.store.flat), torch.zeros_like(eng.adaptor.flat)],
+        moment2=[torch.zeros_like(eng.store.flat), torch.zeros_like(eng.adaptor.flat)],
+        beta1_pow=np.float32(0.9), beta2_pow=np.float32(0.999), steps=steps, lr=s)
+    d = str(tmp_path / "ck")
+    CK.save_persistables(d, eng, mk(n, sched))
+    ctr = os.path.join(d, "@LR_DECAY_COUNTER@")
+    if begin is None:
+        assert not os.path.exists(ctr)
+        return
+    assert int(CK.read_lod_tensor(ctr)[0]) == n - 1 + begin
+    # the graph itself: simulate n runs of the counter op and compare
+    var = begin - 1
+    for _ in range(n):
+        var += 1
+    assert var == int(CK.read_lod_tensor(ctr)[0])
+    sched2 = M.get_lr(strategy, 1e-3, 64, 16, decay_epoch=2)
+    opt2 = mk(0, sched2)
+    CK.load_persistables(d, eng, opt2)
+    assert opt2.steps == n
+    if strategy == "cosine_decay_restart_warmup":
+        ce = float(CK.read_lod_tensor(os.path.join(d, "cur_epoch"))[0])
+        assert ce == 2.0                                              # global_step 4 and 8 hit `cur_part <= 0`
+        # resumed and uninterrupted schedules give the same learning rates from here on
+        full = M.get_lr(strategy, 1e-3, 64, 16, decay_epoch=2)
+        want = [full(i) for i in range(n + 6)][n:]
+        assert [sched2(i) for i in range(n, n + 6)] == want
+    else:
+        assert not os.path.exists(os.path.join(d, "cur_epoch"))

@@ -116,19 +116,21 @@ def test_train_step_reference_config_batch8(dtype):
 
 
 @pytest.mark.parametrize("dims,B", [(MID, 9), (MID, 130), (MID, 300), ({}, 131), ({}, 300)])
-def test_persistent_recurrence_matches_per_step_schedule(dims, B, monkeypatch):
+def test_persistent_recurrence_matches_per_step_schedule(dims, B):
     """The persistent cooperative recurrence kernels (recurrent.cu: W_hh resident in shared memory, one launch per
-    direction) against the per-step GEMM + cell schedule they replace, on ragged batch tiles (B % 128 != 0, more
-    batch tiles than CTA groups), and against the oracle at the small sizes."""
+    direction) against the per-step GEMM + cell schedule they replace (CAPDEC_FLAG_STEPWISE_RECURRENCE), on ragged batch
+    tiles (B % 128 != 0, more batch tiles than CTA groups), and against the oracle at the small sizes."""
     ocfg = R.DecoderConfig(softmax_axis="position", **dims)
     params = R.init_params(ocfg, 11, torch.float32, bias_scale=0.1)
     g, P, cap = synth.make_batch(ocfg, B, 99)
-    eng = _engine(dims, "position", "bf16", params)
     gd, Pd, capd = g.cuda(), P.cuda(), cap.cuda()
     out = {}
+    engines = {}
     for mode in ("1", "0"):
-        monkeypatch.setenv("CAPDEC_RECURRENT", mode)
-        eng.bind_params()
+        eng = M.CaptionDecoderEngine(M.DecoderConfig(dtype="bf16", softmax_axis="position",
+                                                     stepwise_recurrence=(mode == "0"), **dims), seed=None)
+        eng.store.load(params)
+        engines[mode] = eng
         n0 = eng.launch_count
         loss_buf, logits = eng.train_forward(gd, Pd, capd, want_logits=True)
         dg, dP = eng.train_backward()
@@ -147,38 +149,7 @@ def test_persistent_recurrence_matches_per_step_schedule(dims, B, monkeypatch):
         assert rel_err(a["grads"][name], b["grads"][name]) < 1e-2, name
     if B <= 130 and dims:
         p64 = {k: v.double() for k, v in params.items()}
-        monkeypatch.setenv("CAPDEC_RECURRENT", "1")
-        _check_train(eng, ocfg, p64, g.double(), P.double(), cap, TOL["bf16"])
-
-
-@pytest.mark.parametrize("dims,B", [(MID, 9), (MID, 140), ({}, 8)])
-def test_cross_entropy_fused_into_vocab_gemm(dims, B, monkeypatch):
-    """Loss-only forward with CAPDEC_CE_FUSED=1: the soft-max cross entropy runs inside the two passes of the vocabulary
-    GEMM (row statistics, then the gradient tile) and the [M, V] logits are never written.  Loss and every gradient
-    against the oracle, with padded targets and ragged tiles (V = 1000 / 12295, M % 128 != 0).  (The default schedule
-    keeps the separate cross-entropy kernel: it is faster on B200, see decoder.cu.)"""
-    monkeypatch.setenv("CAPDEC_CE_FUSED", "1")
-    ocfg = R.DecoderConfig(softmax_axis="position", **dims)
-    params = R.init_params(ocfg, 13, torch.float32, bias_scale=0.1)
-    g, P, cap = synth.make_batch(ocfg, B, 57)
-    cap[1, 2:] = 0
-    cap[1, 2] = 3
-    eng = _engine(dims, "position", "bf16", params)
-    p64 = {k: v.double() for k, v in params.items()} if dims else params
-    gg, PP = (g.double(), P.double()) if dims else (g, P)
-    _check_train(eng, ocfg, p64, gg, PP, cap, TOL["bf16"], want_logits=False)
-    # and the same step with the logits requested (separate cross-entropy kernel): the two paths agree closely
-    la, _ = eng.train_forward(g.cuda(), P.cuda(), cap.cuda(), want_logits=False)
-    eng.train_backward()
-    torch.cuda.synchronize()
-    loss_a = float(la[2])          # the loss buffer is reused by the next call
-    ga = {k: v.clone() for k, v in eng.store.grads.items()}
-    lb, _ = eng.train_forward(g.cuda(), P.cuda(), cap.cuda(), want_logits=True)
-    eng.train_backward()
-    torch.cuda.synchronize()
-    assert abs(loss_a - float(lb[2])) < 1e-4 * abs(float(lb[2]))
-    for name in ("word_embedding", "out_fc_bias", "fc_e_w", "lstm_w"):
-        assert rel_err(ga[name], eng.store.grads[name]) < 5e-3, name
+        _check_train(engines["1"], ocfg, p64, g.double(), P.double(), cap, TOL["bf16"])
 
 
 @pytest.mark.parametrize("B,beam,finish", [(1, 1, False), (4, 3, True), (20, 2, True)])

@@ -148,17 +148,14 @@ def test_gemm_linearity_at_full_size():
     assert torch.equal(c1, A1.float() @ B.float().t())
 
 
-@pytest.mark.parametrize("mt", ["1", "2", "pair"])
+@pytest.mark.parametrize("mt", ["single", "pair"])
 @pytest.mark.parametrize("majors", [0, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(304, 520, 192), (264, 136, 64), (8704, 1024, 1024), (1024, 1024, 8704), (136, 72, 40),
                                    (640, 12295, 256)])
-def test_gemm_tile_heights(M, N, K, majors, mt, monkeypatch):
-    """Both CTA tile heights (128 rows, and 256 rows = two UMMA row blocks sharing every B k-block) on ragged and
-    full-size shapes, every operand-major form, bf16 output with the fused epilogue and fp32 split-K reduction."""
-    if mt == "pair":   # CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) wherever eligible
-        monkeypatch.setenv("CAPDEC_GEMM_PAIR", "1")
-    else:
-        monkeypatch.setenv("CAPDEC_GEMM_MT", mt)
+def test_gemm_both_tensor_core_kernels(M, N, K, majors, mt):
+    """The single-CTA kernel (cta_group::1, 128-row tiles) and the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles,
+    wherever eligible) forced through capdec_gemm's `variant`, on ragged and full-size shapes, every operand-major form,
+    bf16 output with the fused epilogue and fp32 split-K reduction."""
     a_mn, b_mn = bool(majors & 1), bool(majors & 2)
     if b_mn and N % 8:
         pytest.skip("an MN-major operand needs a 16-byte row pitch")
@@ -170,14 +167,14 @@ def test_gemm_tile_heights(M, N, K, majors, mt, monkeypatch):
     ldc = (N + 7) // 8 * 8
     if majors == 3:   # weight-gradient form: fp32 accumulation into C (split-K, TMA reduce-add)
         Cbuf = torch.ones(M, ldc, dtype=torch.float32, device="cuda")
-        out = gemm(A, B, M, N, K, a_mn=True, b_mn=True, C_out=Cbuf, ldc=ldc, atomic=True)[:, :N]
+        out = gemm(A, B, M, N, K, a_mn=True, b_mn=True, C_out=Cbuf, ldc=ldc, atomic=True, variant=mt)[:, :N]
         assert rel_err(out - 1.0, ref) < 5e-5, rel_err(out - 1.0, ref)
     else:
         bias = _rand((ldc,), torch.float32, 13)
         addend = _rand((M, ldc), torch.bfloat16, 14)
         Cbuf = torch.zeros(M, ldc, dtype=torch.bfloat16, device="cuda")
         out = gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, C_out=Cbuf, ldc=ldc, bias=bias, addend=addend,
-                   act=1)[:, :N]
+                   act=1, variant=mt)[:, :N]
         ref2 = torch.tanh(ref + bias[:N] + addend[:, :N].float())
         assert rel_err(out.float(), ref2) < BF16_TOL, rel_err(out.float(), ref2)
 

@@ -1,0 +1,301 @@
+"""-m gpu: oracle parity ON THE HEADLINE CONFIGURATIONS of BASELINE.json (VERDICT r01 "next" #1).
+
+  * configs[1]: the teacher-forced train step at config.py dimensions, batch 256 (two batch tiles, two CTA groups of the
+    persistent recurrence), bf16 and fp32 storage: loss, logits, all 24 parameter gradients, d global_img_feat and
+    d p_img_feat against oracle/decoder_ref.loss_and_grads (model_adaAttention_aic.py:50-130, 161-183, 205-212);
+  * configs[3]: beam search, beam 3, finished-prefix handling, at the real vocabulary (V = 12295 -> the
+    beam_rows_kernel<49> specialisation) and at V > 12544 (<64>): the device's per-step selections (capdec_decode_trace)
+    against the oracle's, step by step, with the near-tie protocol of SURVEY.md section 7 H5;
+  * capdec_beam_step alone, with constructed EXACT ties across tokens and across prefixes, against the oracle's stable
+    sort (oracle/decoder_ref.beam_select); capdec_lstm_cell_fwd against the Paddle lstm_unit formulas.
+
+Tolerances (north_star): fp32 storage rel 1e-3 (2e-3 at full size: the fp32 oracle itself carries ~1e-6 per op over
+34 steps of a 1024-wide recurrence), bf16 storage rel 2e-2, Frobenius-relative per tensor; additionally the largest
+element error relative to the largest reference element (`max_err`) is bounded so that one bad row cannot hide in a
+norm.  Token ids: bit-exact wherever the oracle's decision gap exceeds the stated numerical noise."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import myimagecaptioningmodel_b200 as M
+from gpu_util import max_err, rel_err, vp
+from myimagecaptioningmodel_b200 import _capi
+from oracle import decoder_ref as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-3, "bf16": 2e-2}
+MAX_TOL = {"fp32": 5e-3, "bf16": 6e-2}
+
+
+def _engine(dims, axis, dtype, params):
+    eng = M.CaptionDecoderEngine(M.DecoderConfig(dtype=dtype, softmax_axis=axis, **dims), seed=None)
+    eng.store.load(params)
+    return eng
+
+
+def oracle_loss_and_grads_chunked(params, cfg, g, P, cap, chunk=64):
+    """oracle/decoder_ref.loss_and_grads at a batch that would need ~12 GB of autograd state in one piece: samples are
+    independent and the loss is sum(ce * mask) / sum(mask), so the batch is run in chunks on the un-normalised loss sum
+    and the gradients are added up and divided by the global token count."""
+    ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    gg = g.detach().clone().requires_grad_(True)
+    PP = P.detach().clone().requires_grad_(True)
+    ntok = (cap[:, 1:] != cfg.padding_idx).sum().to(g.dtype)
+    total, logits = 0.0, []
+    for lo in range(0, g.shape[0], chunk):
+        hi = min(g.shape[0], lo + chunk)
+        lg, _ = R.decoder_train(ps, cfg, gg[lo:hi], PP[lo:hi], cap[lo:hi, :-1])
+        _, loss_sum, _ = R.masked_loss(cfg, lg, cap[lo:hi])
+        (loss_sum / ntok).backward()
+        total += float(loss_sum)
+        logits.append(lg.detach())
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
+    grads["global_img_feat"], grads["p_img_feat"] = gg.grad, PP.grad
+    return total / float(ntok), torch.cat(logits, 0), grads
+
+
+@pytest.fixture(scope="module")
+def full_b256():
+    """config.py dimensions, B = 256 (BASELINE.json configs[1]), position soft-max; the oracle in fp32 on the host."""
+    cfg = R.DecoderConfig(softmax_axis="position")
+    params = R.init_params(cfg, 3, torch.float32, bias_scale=0.1)
+    g, P, cap = synth.make_batch(cfg, 256, 20260)
+    loss, logits, grads = oracle_loss_and_grads_chunked(params, cfg, g, P, cap)
+    return dict(cfg=cfg, params=params, g=g, P=P, cap=cap, loss=loss, logits=logits, grads=grads)
+
+
+def check_train_against(eng, ref, dtype, want_logits=True, lengths=None):
+    g, P, cap = ref["g"], ref["P"], ref["cap"]
+    gd, Pd, capd = g.cuda(), P.cuda(), cap.cuda()
+    kw = {} if lengths is None else {"lengths": lengths}
+    loss_buf, logits = eng.train_forward(gd, Pd, capd, want_logits=want_logits, **kw)
+    dg, dP = eng.train_backward()
+    torch.cuda.synchronize()
+    tol, mtol = TOL[dtype], MAX_TOL[dtype]
+    lb = loss_buf.cpu()
+    assert lb[1].item() == float((cap[:, 1:] != 0).sum())
+    assert abs(lb[2].item() - ref["loss"]) < tol * abs(ref["loss"]), (lb[2].item(), ref["loss"])
+    table = {}
+    if want_logits:
+        table["logits"] = (rel_err(logits, ref["logits"]), max_err(logits, ref["logits"]))
+    for name in M.PARAM_NAMES:
+        r, got = ref["grads"][name], eng.store.grads[name]
+        if name == "fc_a_b":   # d loss / d b_alpha == 0 for a soft-max (shift invariance): absolute, against its sibling
+            assert float((got.cpu().double() - r.double()).abs().max()) < tol * float(ref["grads"]["fc_a_w"].abs().max())
+            continue
+        table[name] = (rel_err(got, r), max_err(got, r))
+    table["d_global"] = (rel_err(dg, ref["grads"]["global_img_feat"]), max_err(dg, ref["grads"]["global_img_feat"]))
+    table["d_p_img"] = (rel_err(dP, ref["grads"]["p_img_feat"]), max_err(dP, ref["grads"]["p_img_feat"]))
+    print("\n%s storage, B=%d: rel (Frobenius) / max-abs over max-ref" % (dtype, g.shape[0]))
+    for k, (a, b) in table.items():
+        print("  %-16s %.2e  %.2e" % (k, a, b))
+    bad = {k: v for k, v in table.items() if not (v[0] < tol and v[1] < mtol)}
+    assert not bad, bad
+    return table
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_train_step_full_size_batch256_vs_oracle(full_b256, dtype):
+    eng = _engine({}, "position", dtype, full_b256["params"])
+    check_train_against(eng, full_b256, dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# beam search at the real vocabulary: per-step selections against the oracle (H5 near-tie protocol)
+# ---------------------------------------------------------------------------------------------------------------------
+def first_divergence(trace_gpu, tok_ref, src_ref):
+    """per image: the first step whose (token, back-pointer) selection differs from the oracle's, or -1"""
+    T, B, beam, _ = trace_gpu.shape
+    out = np.full(B, -1, np.int64)
+    for b in range(B):
+        for t in range(T):
+            if (trace_gpu[t, b, :, 0] != tok_ref[t, b]).any() or (trace_gpu[t, b, :, 1] != src_ref[t, b]).any():
+                out[b] = t
+                break
+    return out
+
+
+def check_decode_against_oracle(dims, dtype, n_img, beam, finish, noise, seed=33, min_exact=0.0, stop_bias=0.0):
+    ocfg = R.DecoderConfig(softmax_axis="position", **dims)
+    params = R.init_params(ocfg, 5, torch.float32, bias_scale=0.1)
+    if stop_bias:
+        params["out_fc_bias"][ocfg.stop_idx] += stop_bias      # make <stop> likely: finished-prefix handling is exercised
+    g, P, _ = synth.make_batch(ocfg, n_img, seed)
+    p64 = {k: v.double() for k, v in params.items()}
+    ref_ids, ref_sc, ref_tr = R.beam_search(p64, ocfg, g.double(), P.double(), beam, finish_on_stop=finish,
+                                            return_trace=True)
+    eng = _engine(dims, "position", dtype, params)
+    ids, sc, ids_f32 = eng.decode(g.cuda(), P.cuda(), beam=beam, finish_on_stop=finish)
+    trace = eng.decode_trace(n_img, beam)
+    torch.cuda.synchronize()
+    ids, sc, trace = ids.cpu().long(), sc.cpu(), trace.cpu().numpy()
+    div = first_divergence(trace, ref_tr["tok"].numpy(), ref_tr["src"].numpy())
+    adj = ref_tr["adjacent"].numpy()
+    unexplained = [(b, int(t), float(adj[b, t])) for b, t in enumerate(div) if t >= 0 and not adj[b, t] < noise]
+    same = div < 0
+    print("\n%s V=%d beam=%d: %d/%d images select exactly like the oracle at every step; first-divergence gaps: %s" % (
+        dtype, ocfg.vocab_size, beam, int(same.sum()), n_img,
+        np.array2string(np.sort([adj[b, t] for b, t in enumerate(div) if t >= 0]), precision=4)))
+    assert not unexplained, unexplained         # every first divergence sits on a decision gap below the numerical noise
+    assert same.mean() >= min_exact
+    # images without a divergence: the back-traced ids are the oracle's, bit for bit, and so are the float32 ids
+    assert torch.equal(ids[same], ref_ids[torch.from_numpy(same)])
+    assert torch.equal(ids_f32.cpu().long()[same], ref_ids[torch.from_numpy(same), 0])
+    if same.any():
+        stol = 1e-3 if dtype == "fp32" else 0.5
+        assert float((sc[same] - ref_sc[torch.from_numpy(same)].float()).abs().max()) < stol
+    assert (sc[:, :-1] >= sc[:, 1:]).all()
+    # the lattice back-traces to ids_out: the trace and the history kernels agree with each other
+    T = ocfg.infer_max_length
+    for b in range(min(n_img, 8)):
+        for r in range(beam):
+            seq, cur = [], r
+            for t in range(T - 1, -1, -1):
+                seq.append(int(trace[t, b, cur, 0]))
+                cur = int(trace[t, b, cur, 1])
+            assert seq[::-1] == ids[b, r].tolist()
+    return same.mean()
+
+
+@pytest.mark.parametrize("dtype,noise,min_exact", [("fp32", 1e-3, 0.8), ("bf16", 0.25, 0.1)])
+def test_beam3_full_size_vocab12295_vs_oracle(dtype, noise, min_exact):
+    """BASELINE.json configs[3] shape: H = 1024, V = 12295 (beam_rows_kernel<49>), beam 3, finish_on_stop, 64 images."""
+    check_decode_against_oracle({}, dtype, 64, 3, True, noise, min_exact=min_exact)
+
+
+def test_greedy_full_size_vocab12295_vs_oracle():
+    """the reference's own decode (model:119-123): beam 1, never stops, fp32 storage, V = 12295"""
+    check_decode_against_oracle({}, "fp32", 16, 1, False, 1e-3, seed=34, min_exact=0.8)
+
+
+@pytest.mark.parametrize("dtype,noise", [("fp32", 1e-3), ("bf16", 0.25)])
+def test_beam_vocab_above_12544_uses_the_64_per_thread_kernel(dtype, noise):
+    """V = 13001 > 256 * 49: beam_rows_kernel<64>; small hidden size keeps the oracle fast; <stop> made likely"""
+    dims = dict(hidden_dim=256, embedding_size=64, vocab_size=13001, num_positions=49, sentence_length=12,
+                infer_max_length=12)
+    check_decode_against_oracle(dims, dtype, 12, 3, True, noise, stop_bias=6.0)
+    check_decode_against_oracle(dims, dtype, 5, 8, True, noise, seed=35, stop_bias=6.0)
+
+
+def test_vocab_beyond_the_register_top_k_is_rejected():
+    with pytest.raises(_capi.CapdecError):
+        M.CaptionDecoderEngine(M.DecoderConfig(vocab_size=16385), seed=None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# capdec_beam_step alone: exact ties
+# ---------------------------------------------------------------------------------------------------------------------
+def _beam_step_gpu(logits, score, fin, hist, beam, step, T, pad, stop, finish):
+    lib = _capi.load_library()
+    n_rows, V = logits.shape
+    n_img = n_rows // beam
+    ld = (V + 7) // 8 * 8
+    lg = torch.full((n_rows, ld), float("nan"), dtype=torch.float32, device="cuda")
+    lg[:, :V] = logits.cuda()
+    sc_in, fin_in, hist_in = score.float().reshape(-1).cuda(), fin.int().reshape(-1).cuda(), hist.int().reshape(n_rows, T).cuda()
+    sc_out = torch.empty(n_rows, dtype=torch.float32, device="cuda")
+    fin_out = torch.empty(n_rows, dtype=torch.int32, device="cuda")
+    hist_out = torch.empty(n_rows, T, dtype=torch.int32, device="cuda")
+    tok = torch.empty(n_rows, dtype=torch.int32, device="cuda")
+    src = torch.empty(n_rows, dtype=torch.int32, device="cuda")
+    _capi.check(lib.capdec_beam_step(vp(lg), ld, V, n_img, beam, step, T, pad, stop, 1 if finish else 0, vp(sc_in),
+                                     vp(sc_out), vp(fin_in), vp(fin_out), vp(hist_in), vp(hist_out), vp(tok), vp(src),
+                                     _capi.stream_ptr()), "capdec_beam_step")
+    torch.cuda.synchronize()
+    sh = (n_img, beam)
+    return sc_out.cpu().reshape(sh), fin_out.cpu().reshape(sh), hist_out.cpu().reshape(n_img, beam, T), \
+        tok.cpu().reshape(sh).long(), src.cpu().reshape(sh).long()
+
+
+@pytest.mark.parametrize("V", [1000, 12295, 13001])        # beam_rows_kernel<8>, <49>, <64>
+@pytest.mark.parametrize("beam", [1, 3, 8])
+def test_beam_step_exact_ties_match_the_oracles_stable_sort(V, beam):
+    """Logits quantised to multiples of 1/4 (many exact ties between tokens), the rows of an image copies of each other
+    with equal prefix scores (exact ties between prefixes), dead prefixes (-inf) and finished prefixes mixed in: the
+    winners and their ORDER must be the oracle's stable descending sort -- lower prefix, then lower token."""
+    cfg = R.DecoderConfig(vocab_size=V)
+    gen = torch.Generator().manual_seed(1000 * beam + V)
+    n_img, T, step = 24, 7, 3
+    base = torch.randint(0, 9, (n_img, 1, V), generator=gen).float() / 4.0
+    logits = base.expand(n_img, beam, V).clone()
+    score = torch.zeros(n_img, beam)
+    fin = torch.zeros(n_img, beam, dtype=torch.bool)
+    hist = torch.randint(4, V, (n_img, beam, T), generator=gen)
+    hist[:, :, step:] = 0
+    for b in range(n_img):
+        kind = b % 6
+        if kind == 1 and beam > 1:                   # distinct rows and scores: no cross-prefix ties
+            logits[b] = torch.randint(0, 9, (beam, V), generator=gen).float() / 4.0
+            score[b] = -torch.arange(beam).float() * 0.5
+        elif kind == 2 and beam > 1:                 # the last prefix is dead
+            score[b, -1] = -float("inf")
+        elif kind == 3 and beam > 1:                 # one finished prefix competing with live ones at an equal score
+            fin[b, beam // 2] = True
+        elif kind == 4:                              # only prefix 0 live (the state of step 0)
+            score[b, 1:] = -float("inf")
+        elif kind == 5 and beam > 1:                 # every prefix finished
+            fin[b] = True
+            score[b] = -torch.arange(beam).float()
+    logits32 = logits.reshape(n_img * beam, V)
+    logp = torch.log_softmax(logits32.double(), dim=-1).reshape(n_img, beam, V)
+    top_val, src_r, tok_r, fin_r, margin, adjacent = R.beam_select(cfg, score.double(), logp, fin, beam, True)
+    sc, fo, ho, tok, src = _beam_step_gpu(logits32, score, fin, hist, beam, step, T, cfg.padding_idx, cfg.stop_idx, True)
+    # an exact tie has gap 0 and must be resolved like the oracle; a positive gap below fp32 noise (different rows, never
+    # constructed here on purpose) would be a coin flip: skip such images
+    ok = ~((adjacent > 0) & (adjacent < 1e-4))
+    assert ok.float().mean() > 0.9
+    live = torch.isfinite(top_val)
+    assert torch.equal(tok[ok][live[ok]], tok_r[ok][live[ok]])
+    assert torch.equal(src[ok][live[ok]], src_r[ok][live[ok]])
+    assert torch.equal(fo[ok].bool()[live[ok]], fin_r[ok][live[ok]])
+    assert float((sc[ok][live[ok]] - top_val[ok][live[ok]].float()).abs().max()) < 1e-4
+    assert (sc[~live] == -float("inf")).all()
+    exp_hist = torch.gather(hist, 1, src.unsqueeze(-1).expand(n_img, beam, T)).clone()
+    exp_hist[:, :, step] = tok
+    exp_hist[:, :, step + 1:] = 0
+    assert torch.equal(ho.long(), exp_hist)
+    assert int((adjacent == 0).sum()) > 0            # the case really contains exact ties
+
+
+def test_greedy_argmax_tie_takes_the_lowest_index():
+    """layers.argmax (model:120): first maximal index; beam 1 without finished handling ranks the raw logits"""
+    V, n_img = 12295, 6
+    logits = torch.zeros(n_img, V)
+    for b in range(n_img):
+        logits[b, [7 + b, 300 + b, 12000 + b]] = 5.0          # three-way tie per row
+    sc, fo, ho, tok, src = _beam_step_gpu(logits, torch.zeros(n_img, 1), torch.zeros(n_img, 1, dtype=torch.bool),
+                                          torch.zeros(n_img, 1, 4, dtype=torch.long), 1, 0, 4, 0, 3, False)
+    assert tok.reshape(-1).tolist() == [7 + b for b in range(n_img)]
+    assert torch.equal(tok.reshape(-1), R.first_argmax(logits))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# capdec_lstm_cell_fwd alone
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("R_,H", [(1, 8), (5, 64), (300, 1024)])
+def test_lstm_cell_fwd_matches_paddle_lstm_unit(dtype, R_, H):
+    """Paddle lstm_unit (model:87-88; gate column blocks i, f, o, g; forget_bias 0):
+    c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c')"""
+    lib = _capi.load_library()
+    gen = torch.Generator().manual_seed(R_ * 131 + H)
+    pre = torch.randn(R_, 4 * H, generator=gen) * 2.0
+    c_prev = torch.randn(R_, H, generator=gen)
+    i, f, o, g = (pre[:, j * H:(j + 1) * H].double() for j in range(4))
+    c_ref = torch.sigmoid(f) * c_prev.double() + torch.sigmoid(i) * torch.tanh(g)
+    h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    h_out = torch.empty(R_, H, dtype=td, device="cuda")
+    c_out = torch.empty(R_, H, dtype=torch.float32, device="cuda")
+    _capi.check(lib.capdec_lstm_cell_fwd(_capi.DTYPE_F32 if dtype == "fp32" else _capi.DTYPE_BF16, R_, H, vp(pre.cuda()),
+                                         vp(c_prev.cuda()), vp(h_out), vp(c_out), _capi.stream_ptr()),
+                "capdec_lstm_cell_fwd")
+    torch.cuda.synchronize()
+    # fp32 storage: libm tanh / exp; bf16 storage: MUFU tanh.approx (abs err ~5e-4) and a bf16 h
+    atol = 2e-6 if dtype == "fp32" else 4e-3
+    assert float((c_out.cpu().double() - c_ref).abs().max()) < (2e-6 if dtype == "fp32" else 3e-3)
+    assert float((h_out.float().cpu().double() - h_ref).abs().max()) < atol
