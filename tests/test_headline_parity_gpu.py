@@ -51,7 +51,7 @@ def oracle_loss_and_grads_chunked(params, cfg, g, P, cap, chunk=64):
         lg, _ = R.decoder_train(ps, cfg, gg[lo:hi], PP[lo:hi], cap[lo:hi, :-1])
         _, loss_sum, _ = R.masked_loss(cfg, lg, cap[lo:hi])
         (loss_sum / ntok).backward()
-        total += float(loss_sum)
+        total += float(loss_sum.detach())
         logits.append(lg.detach())
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
     grads["global_img_feat"], grads["p_img_feat"] = gg.grad, PP.grad
@@ -146,8 +146,11 @@ def check_decode_against_oracle(dims, dtype, n_img, beam, finish, noise, seed=33
     assert torch.equal(ids[same], ref_ids[torch.from_numpy(same)])
     assert torch.equal(ids_f32.cpu().long()[same], ref_ids[torch.from_numpy(same), 0])
     if same.any():
-        stol = 1e-3 if dtype == "fp32" else 0.5
-        assert float((sc[same] - ref_sc[torch.from_numpy(same)].float()).abs().max()) < stol
+        # scores are sums of up to 35 log-probabilities (~ -100 at the full vocabulary): relative bound, the storage
+        # type's tolerance class (fp32 1e-3 -> measured 1e-6; bf16 2e-2 -> measured 5e-3)
+        ref_same = ref_sc[torch.from_numpy(same)].float()
+        stol = 1e-5 if dtype == "fp32" else 1e-2
+        assert float(((sc[same] - ref_same).abs() / ref_same.abs().clamp_min(1.0)).max()) < stol
     assert (sc[:, :-1] >= sc[:, 1:]).all()
     # the lattice back-traces to ids_out: the trace and the history kernels agree with each other
     T = ocfg.infer_max_length
@@ -161,7 +164,9 @@ def check_decode_against_oracle(dims, dtype, n_img, beam, finish, noise, seed=33
     return same.mean()
 
 
-@pytest.mark.parametrize("dtype,noise,min_exact", [("fp32", 1e-3, 0.8), ("bf16", 0.25, 0.1)])
+# bf16 noise: the first-divergence gaps measured on B200 are all below 0.04 (random-init weights give flat
+# distributions: 54 of 64 images hit such a gap somewhere in 35 steps x 3 beams); bound = 2x that
+@pytest.mark.parametrize("dtype,noise,min_exact", [("fp32", 1e-3, 0.8), ("bf16", 0.08, 0.1)])
 def test_beam3_full_size_vocab12295_vs_oracle(dtype, noise, min_exact):
     """BASELINE.json configs[3] shape: H = 1024, V = 12295 (beam_rows_kernel<49>), beam 3, finish_on_stop, 64 images."""
     check_decode_against_oracle({}, dtype, 64, 3, True, noise, min_exact=min_exact)
@@ -172,7 +177,7 @@ def test_greedy_full_size_vocab12295_vs_oracle():
     check_decode_against_oracle({}, "fp32", 16, 1, False, 1e-3, seed=34, min_exact=0.8)
 
 
-@pytest.mark.parametrize("dtype,noise", [("fp32", 1e-3), ("bf16", 0.25)])
+@pytest.mark.parametrize("dtype,noise", [("fp32", 1e-3), ("bf16", 0.08)])
 def test_beam_vocab_above_12544_uses_the_64_per_thread_kernel(dtype, noise):
     """V = 13001 > 256 * 49: beam_rows_kernel<64>; small hidden size keeps the oracle fast; <stop> made likely"""
     dims = dict(hidden_dim=256, embedding_size=64, vocab_size=13001, num_positions=49, sentence_length=12,
