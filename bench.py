@@ -45,6 +45,8 @@ SOFTMAX_AXIS = "position"     # the full attention arithmetic; th
 def workload_config(n_gpus):
     return {"workload": "teacher_forced_train_step_B256_per_gpu_T34_H1024_E256_V12295_k49", "global_batch": B_PER_GPU * n_gpus,
             "batch_per_gpu": B_PER_GPU, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
+            "lengths": "host token counts passed (captions L ~ U{5..33} words: 57 % of the B x 34 rows carry a target; the "
+                       "head skips the others, loss and gradients unchanged); tokens/s counts all B x 34 positions",
             "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)+adam(paddle-1.8 rule, lr 5e-5)",
             "e2e": "pinned host buffers, H2D of the next batch prefetched on a copy stream, loss D2H every step (read by the "
                    "host one step later)",
@@ -264,12 +266,19 @@ def main_ours(args):
     g_h, P_h, cap_h = g_h.pin_memory(), P_h.pin_memory(), cap_h.pin_memory()
     g_d, P_d, cap_d = g_h.cuda(), P_h.cuda(), cap_h.cuda()
     ntok_nonpad = float((cap_h[:, 1:] != 0).sum())
+    # host-side token counts of the batch (what a data loader knows before the upload): with them the time-batched head
+    # runs on the rows that carry a target only (capdec_train_fwd `lengths`) -- same loss and gradients
+    lengths_h = M.caption_lengths(cap_h)
 
     opt_dec = M.Adam([(eng.store.flat, eng.store.flat_grad)], 0.00005)     # train.py:26-31 / config.py:32-33 defaults
 
     def step_resident(i):
         eng.bind_params()
-        trainer.forward_backward(g_d, P_d, cap_d, optimizer=opt_dec)     # Adam per gradient group, beside the backward pass
+        trainer.forward_backward(g_d, P_d, cap_d, optimizer=opt_dec, lengths=lengths_h)   # Adam per gradient group, beside the backward pass
+
+    def step_resident_all_rows(i):        # the same step without `lengths`: all B x 34 rows through the head
+        eng.bind_params()
+        trainer.forward_backward(g_d, P_d, cap_d, optimizer=opt_dec)
 
     # ---- e2e: host buffers, double-buffered upload on a side stream, loss read back every step ----
     copy_stream = torch.cuda.Stream()
@@ -314,7 +323,7 @@ def main_ours(args):
         upload(slot ^ 1)                                  # prefetch the next batch while this one computes
         torch.cuda.current_stream().wait_event(ready[slot])
         eng.bind_params()
-        loss = trainer.forward_backward(*bufs[slot], optimizer=opt_dec)
+        loss = trainer.forward_backward(*bufs[slot], optimizer=opt_dec, lengths=M.caption_lengths(cap_h))
         consumed[slot].record()
         k = i & 1
         if k in pending:                                  # the buffer about to be reused (written two steps ago)
@@ -339,6 +348,10 @@ def main_ours(args):
         with clocks.window():
             ms = timed_region(step_resident, args.steps, sync, barrier)
         launches = eng.launch_count - l0 + args.steps * eng.N_GRAD_EVENTS     # + one capdec_adam_step launch per gradient group
+        for i in range(3):
+            step_resident_all_rows(i)
+        sync()
+        ms_all_rows = timed_region(step_resident_all_rows, args.steps, sync, barrier)
         for i in range(max(2, args.warmup // 2)):
             step_e2e(i)
         sync()
@@ -398,7 +411,7 @@ def main_ours(args):
     def step_full(i):
         eng.bind_params()
         eng.bind_adaptor()
-        trainer.forward_backward_map(x_d, cap_d, optimizer=opt)
+        trainer.forward_backward_map(x_d, cap_d, optimizer=opt, lengths=lengths_h)
 
     for i in range(3):
         step_full(i)
@@ -446,10 +459,10 @@ def main_ours(args):
     step_tflops = step_flops / (ms / args.steps * 1e-3) / 1e12
 
     # max over ranks of the device times
-    t = torch.tensor([ms, ms_e2e, ms_beam, ms_full], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_beam, ms_full, ms_all_rows], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_beam, ms_full = (float(x) for x in t.cpu())
+    ms, ms_e2e, ms_beam, ms_full, ms_all_rows = (float(x) for x in t.cpu())
     tokens_per_step = world * B * cfg.train_steps
     value = tokens_per_step * args.steps / (ms * 1e-3)
     e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
@@ -471,6 +484,10 @@ def main_ours(args):
                         "h2d_alone_gbs": h2d / (ms_h2d * 1e-3) / 1e9},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "extras": {"nonpad_tokens_per_sec": world * ntok_nonpad * args.steps / (ms * 1e-3),
+                           "live_rows_per_gpu": int(ntok_nonpad), "rows_per_gpu": B * cfg.train_steps,
+                           "without_lengths": {"ms_per_step": ms_all_rows / args.steps,
+                                               "tokens_per_sec": tokens_per_step * args.steps / (ms_all_rows * 1e-3),
+                                               "note": "the same step with lengths=NULL: all B x 34 rows through the head"},
                            "step_gemm_tflops_algorithmic": step_tflops,
                            "step_gemm_frac_of_sustained_peak": step_tflops / peaks["bf16_sustained"],
                            "beam_search_images_per_sec": world * BEAM_IMAGES_PER_GPU * beam_reps / (ms_beam * 1e-3),

@@ -38,7 +38,7 @@ extern "C" {
 /* Bits of the asynchronous input-error report (capdec_status) */
 #define CAPDEC_ERR_SOURCE_ID 1 /* caption[:, :-1] holds an id outside [0, vocab_size)  (lookup_table_v2 enforces this) */
 #define CAPDEC_ERR_TARGET_ID 2 /* caption[:, 1:] holds an id outside [0, vocab_size)   (softmax_with_cross_entropy)    */
-#define CAPDEC_ERR_LENGTHS 4   /* lengths[b] cuts off non-padding tokens of caption[b]                                 */
+#define CAPDEC_ERR_LENGTHS 4   /* lengths[] does not describe the captions (see capdec_train_fwd)                      */
 
 /* config.py:22-24 (ids) and config.py:51-60 (dims) */
 typedef struct capdec_config {
@@ -129,10 +129,18 @@ int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream);
 /* Teacher-forced forward: Decoder(mode='train').call + training_network loss wiring (model:50-130, 161-183).
  *   global_img_feat [B,H] f32, p_img_feat [B,k,H] f32, caption [B,sentence_length] int64
  *   (both feature pointers NULL: use the features staged in the handle by capdec_img2feature for the same B)
+ *   lengths         HOST array [B] (the only host-side operand of the library) or NULL: the number of leading
+ *                   non-padding tokens of caption[b] = [start, w_1 .. w_L, stop, pad ..] (ai_challenge_tokenizer.py:81-86),
+ *                   i.e. L + 2.  The reference has no such input (every sample runs all 34 steps, the mask
+ *                   is target != pad, model:163-171); rows past the last target contribute exactly nothing to the loss or
+ *                   to any gradient, so with `lengths` (and logits_out == NULL) everything downstream of the recurrence runs
+ *                   on the sum_b (lengths[b] - 1) live rows only.  Results equal the call without `lengths`.  The array is
+ *                   read before the call returns and only sizes the work; the device takes the live steps from the captions
+ *                   themselves and reports a total that differs (CAPDEC_ERR_LENGTHS, capdec_status).
  *   logits_out      [B,T,V] f32 batch-major (model:129-130) or NULL when only the loss is wanted
  *   loss_out        4 floats on the device: {sum(ce*mask), sum(mask), loss = ratio, 1/sum(mask)}            */
 int capdec_train_fwd(capdec_handle h, const float* global_img_feat, const float* p_img_feat, const int64_t* caption,
-                     int32_t B, float* logits_out, float* loss_out, void* stream);
+                     const int32_t* lengths, int32_t B, float* logits_out, float* loss_out, void* stream);
 
 /* Backward of the last capdec_train_fwd (Paddle's appended *_grad / while_grad ops).
  *   d(loss)/d(logits) = (softmax - onehot) * mask * inv_ntok * loss_scale, where inv_ntok is read from

@@ -2,11 +2,11 @@
 sm_100a CUDA behind a C-ABI (include/capdec.h), with the reference's Decoder / ImageCaptionModel interface on top."""
 from ._capi import CapdecError, PARAM_NAMES, library_path, load_library
 from .decoder import (AdaptorStore, CaptionDecoderEngine, Decoder, DecoderConfig, ImageCaptionModel, ParameterStore, default_engine,
-                      filter_caption, param_shapes)
+                      caption_lengths, filter_caption, param_shapes)
 from . import checkpoint, evaluation
 from .optim import Adam, LRSchedule, get_lr, get_optimizer
 from .parallel import DataParallelTrainer, shard_range, sharded_decode
 
 __all__ = ["checkpoint", "evaluation", "AdaptorStore", "Adam", "LRSchedule", "get_lr", "get_optimizer", "CapdecError", "PARAM_NAMES", "library_path", "load_library", "CaptionDecoderEngine", "Decoder",
-           "DecoderConfig", "ImageCaptionModel", "ParameterStore", "default_engine", "filter_caption", "param_shapes",
+           "DecoderConfig", "ImageCaptionModel", "ParameterStore", "default_engine", "caption_lengths", "filter_caption", "param_shapes",
            "DataParallelTrainer", "shard_range", "sharded_decode"]

@@ -88,7 +88,7 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.capdec_bind_params.argtypes = [vp, C.POINTER(CapdecParams), vp]
-    lib.capdec_train_fwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.capdec_train_fwd.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.capdec_train_bwd.argtypes = [vp, f32, vp, vp, vp, C.POINTER(CapdecGrads), vp]
     lib.capdec_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.capdec_decode_trace.argtypes = [vp, vp, vp]

@@ -43,6 +43,20 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Row addressing of query q of image img.  Padded row (alpha, alpha_T, de, ...): img * row0_stride + q * q_stride; the row
+// of the per-query [rows, H] operands: the same, or with packed rows (AttnShape::prow) prow[padded row].
+__device__ __forceinline__ long padded_row(const AttnShape& s, int img, int q) {
+  return (long)img * s.row0_stride + (long)q * s.q_stride;
+}
+__device__ __forceinline__ long operand_row(const AttnShape& s, long prow_idx) {
+  if (!s.prow) return prow_idx;
+  const int r = s.prow[prow_idx];
+  return r < 0 ? 0 : r;   // -1 only when `lengths` was wrong (reported, CAPDEC_ERR_LENGTHS): stay inside the buffers
+}
+__device__ __forceinline__ int live_queries(const AttnShape& s, int img) {
+  return s.nq ? min(s.nq[img], s.q_per_img) : s.q_per_img;
+}
+
 // shared-memory carve-up shared by the forward and the backward-score kernels
 struct SmemLayout {
   int off_e, off_alpha, off_bar, off_q, off_tile0, off_tile1, total;
@@ -143,7 +157,8 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   T* qring = reinterpret_cast<T*>(smem + L.off_q);  // [3][4][H]: hid_emb, sent_emb, sentinel, p_hid
   const int img = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  const int q0 = chunk * q_per_chunk, q1 = min(s.q_per_img, q0 + q_per_chunk);
+  const int q0 = chunk * q_per_chunk, q1 = min(live_queries(s, img), q0 + q_per_chunk);
+  if (q0 >= q1) return;   // no live query in this chunk (packed rows)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const T* Kt = keys + (long)img * k * H;
   const T* Vt = vals + (long)img * k * H;
@@ -161,7 +176,7 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   }
   const int vec_per_row = H / 8;  // 16-byte chunks of T=bf16 (or half-chunks of fp32) per H-vector
   auto prefetch = [&](int q) {
-    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const long row = operand_row(s, padded_row(s, img, q));
     T* dst = qring + (size_t)(q % 3) * 4 * H;
     const T* src[4] = {hid_emb + row * H, sent_emb + row * H, sentinel + row * H, p_hid ? p_hid + row * H : sentinel + row * H};
     constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte cp.async
@@ -186,7 +201,8 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
   __syncthreads();  // barrier init + first query vectors visible
   if (STAGE) mbar_wait(bar, 0);
   for (int q = q0; q < q1; ++q) {
-    const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+    const long row = padded_row(s, img, q);         // alpha
+    const long orow = operand_row(s, row);          // actx / ctx_out (per-query [rows, H] operands)
     const T* qv = qring + (size_t)(q % 3) * 4 * H;
     const T* he_s = qv;
     const T* se_s = qv + H;
@@ -277,13 +293,13 @@ attn_fwd_kernel(AttnShape s, int chunks, int q_per_chunk, const T* __restrict__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[i] = fmaf(a, v[i], acc[i]);
         }
-        if (ctx_out) store4(ctx_out + row * H + h0, acc);
+        if (ctx_out) store4(ctx_out + orow * H + h0, acc);
         if (actx) {
           float ph[4];
           load4(ph_s + h0, ph);
 #pragma unroll
           for (int i = 0; i < 4; ++i) ph[i] += acc[i];
-          store4(actx + row * H + h0, ph);
+          store4(actx + orow * H + h0, ph);
         }
       }
     }
@@ -354,13 +370,14 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
   constexpr int cpr = H / 8;  // 16-byte chunks per row
   auto prefetch = [&](int q) {
     if (tid < 2 * cpr) {
-      const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+      const long row = operand_row(s, padded_row(s, img, q));
       const int a = tid / cpr, c = tid % cpr;
       cp_async16(ring + (size_t)((q & 1) * 2 + a) * pitch + c * 16, (a == 0 ? hid_emb : sent_emb) + row * H + c * 8);
     }
     cp_async_commit();
   };
-  prefetch(0);
+  const int nq = live_queries(s, img);
+  if (nq > 0) prefetch(0);
   // B fragments: w in column 0 (fragment lanes 0..3), zero elsewhere
   const int col0 = warp * kWarpCols + 8 * lc;  // first column of this lane's chunk in block 0
   uint32_t wq[NB][4];
@@ -379,7 +396,6 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
   cp_async_wait_all();
   __syncthreads();
   mbar_wait(bar, 0);
-  const int nq = s.q_per_img;
   for (int q = 0; q < nq; ++q) {
     if (q + 1 < nq) prefetch(q + 1);  // slot (q+1)&1 was last read in query q-1: everyone is past its barrier
     const uint8_t* he_row = ring + (size_t)((q & 1) * 2) * pitch;
@@ -422,7 +438,7 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
     __syncthreads();
     if (warp == (q & 7)) {
       // ---- soft-max over the k+1 positions (P <= 64: two values per lane) ----
-      const long row = (long)img * s.row0_stride + (long)q * s.q_stride;
+      const long row = padded_row(s, img, q);
       const float* eb = e_part + (q & 1) * 8 * Ppad;
       float e0 = -INFINITY, e1 = -INFINITY;
       if (lane < P) {
@@ -452,9 +468,11 @@ attn_scores_kernel(AttnShape s, const bf16* __restrict__ keys, const bf16* __res
 
 // sadd[row, :] = p_hid[row, :] + alpha[row, k] / (k+1) * sentinel[row, :]: the two per-query terms the context GEMM
 // adds in its epilogue (p_hid may be NULL)
+// pm (packed rows): operand row r is padded row pm[r] of alpha / sadd; dead rows of sadd are not written (the context rows
+// they feed are never read)
 __global__ void __launch_bounds__(256)
-attn_sadd_kernel(long rows, int H, int P, const float* __restrict__ alpha, const bf16* __restrict__ sentinel,
-                 const bf16* __restrict__ p_hid, bf16* __restrict__ sadd) {
+attn_sadd_kernel(long rows, int H, int P, const int* __restrict__ pm, const float* __restrict__ alpha,
+                 const bf16* __restrict__ sentinel, const bf16* __restrict__ p_hid, bf16* __restrict__ sadd) {
   pdl_trigger();
   const int vec_per_row = H / 8;
   const float inv_p = 1.f / (float)P;
@@ -462,7 +480,8 @@ attn_sadd_kernel(long rows, int H, int P, const float* __restrict__ alpha, const
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / vec_per_row;
     const int h0 = (int)(i % vec_per_row) * 8;
-    const float a = alpha[r * P + (P - 1)] * inv_p;
+    const long m = pm ? pm[r] : r;
+    const float a = alpha[m * P + (P - 1)] * inv_p;
     float v[8], ph[8];
     load8(sentinel + r * H + h0, v);
     if (p_hid) {
@@ -473,7 +492,7 @@ attn_sadd_kernel(long rows, int H, int P, const float* __restrict__ alpha, const
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= a;
     }
-    store8(sadd + r * H + h0, v);
+    store8(sadd + m * H + h0, v);
   }
 }
 
@@ -536,19 +555,21 @@ attn_ctx_small_kernel(AttnShape s, const bf16* __restrict__ vals, const bf16* __
 //   here: d alpha_k = dctx . sentinel,  de = alpha * (d alpha - sum alpha d alpha) / (k+1)  (soft-max backward),
 //   db_alpha += sum de,  dS_ctx = alpha_k / (k+1) * dctx,  and the storage-type copy alpha_T = alpha / (k+1)
 //   that the second batched GEMM (d values) uses as its A operand.
+//   pm (packed rows): the loop runs over the live rows; `orow` indexes sentinel / dS, row = pm[orow] everything else.
 template <typename T>
 __global__ void __launch_bounds__(256)
-attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const T* __restrict__ sentinel,
-                     const float* __restrict__ alpha, const T* __restrict__ dactx, const float* __restrict__ dal,
-                     int ld_dal, float* __restrict__ de, T* __restrict__ alpha_T, int ld_at, T* __restrict__ dS,
-                     float* __restrict__ db_alpha) {
+attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const int* __restrict__ pm,
+                     const T* __restrict__ sentinel, const float* __restrict__ alpha, const T* __restrict__ dactx,
+                     const float* __restrict__ dal, int ld_dal, float* __restrict__ de, T* __restrict__ alpha_T, int ld_at,
+                     T* __restrict__ dS, float* __restrict__ db_alpha) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int P = k + 1;
   const float inv_p = 1.f / (float)P;
   float db_acc = 0.f;
-  for (long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
-       row += (long)gridDim.x * (blockDim.x >> 5)) {
+  for (long orow = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); orow < rows;
+       orow += (long)gridDim.x * (blockDim.x >> 5)) {
+    const long row = pm ? pm[orow] : orow;
     const T* dc = dactx + row * H;
     const float a0 = (lane < P) ? alpha[row * P + lane] : 0.f;
     const float a1 = (lane + 32 < P) ? alpha[row * P + lane + 32] : 0.f;
@@ -560,14 +581,14 @@ attn_bwd_rows_kernel(long rows, int H, int k, int position_softmax, const T* __r
       float d[8], sv[8];
       load8(dc + h0, d);
       if (position_softmax) {
-        load8(sentinel + row * H + h0, sv);
+        load8(sentinel + orow * H + h0, sv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dot_s = fmaf(d[i], sv[i], dot_s);
       }
       const float sc = ak * inv_p;
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] *= sc;
-      store8(dS + row * H + h0, d);
+      store8(dS + orow * H + h0, d);
     }
     if (position_softmax) {
       dot_s = warp_sum(dot_s);
@@ -610,8 +631,12 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
   constexpr bool F = fast_math<T>::value;
   constexpr int KHP = (KH + 3) & ~3;  // each half of a query's de row starts 16-byte aligned
   extern __shared__ __align__(16) float de_s[];  // [q_per_img][2 halves][KHP], zero past the valid positions
-  const int H = s.H, k = s.k, P = s.k + 1, nq = s.q_per_img;
+  const int H = s.H, k = s.k, P = s.k + 1;
   const int img = blockIdx.x;
+  const int nq = live_queries(s, img);
+  // operand rows of this image's queries (packed rows: irregular), behind the de tile
+  int* rows_s = reinterpret_cast<int*>(de_s + (size_t)s.q_per_img * 2 * (((KH + 3) & ~3)));
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) rows_s[q] = (int)operand_row(s, padded_row(s, img, q));
   const int h = blockIdx.y * (blockDim.x >> 1) + (threadIdx.x >> 1);
   const int half = threadIdx.x & 1;
   // positions of this thread: the upper half owns the LAST KH positions, so the sentinel (position k) always sits in
@@ -621,7 +646,7 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
   for (int i = threadIdx.x; i < nq * 2 * KHP; i += blockDim.x) {
     const int q = i / (2 * KHP), r = i % (2 * KHP);
     const int hf = r / KHP, ii = r % KHP, j = (hf ? P - KH : 0) + ii;
-    de_s[i] = (ii < (hf ? KH : P - KH)) ? de[((long)img * s.row0_stride + (long)q * s.q_stride) * P + j] : 0.f;
+    de_s[i] = (ii < (hf ? KH : P - KH)) ? de[padded_row(s, img, q) * P + j] : 0.f;
   }
   __syncthreads();
   const bool active = h < H;
@@ -634,24 +659,25 @@ attn_bwd_dk_kernel(AttnShape s, const T* __restrict__ keys, const T* __restrict_
   }
   const float wh = w_alpha[hc];
   float dw = 0.f;
-  long row = (long)img * s.row0_stride;
   if (nq > 1) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(hid_emb + (row + s.q_stride) * H + hc));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(sent_emb + (row + s.q_stride) * H + hc));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(hid_emb + (long)rows_s[1] * H + hc));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(sent_emb + (long)rows_s[1] * H + hc));
   }
   // The per-query operands are loaded one iteration ahead, and the line of the query after that is prefetched into L1:
   // under the 80-register cap ptxas sinks the look-ahead loads to ~30 instructions before their first use (26 % of
   // all stall samples sat there), the prefetch costs no register and turns that wait into an L1 hit.
-  T he_raw = hid_emb[row * H + hc], se_raw = sent_emb[row * H + hc];
-  for (int q = 0; q < nq; ++q, row += s.q_stride) {
+  T he_raw = from_f<T>(0.f), se_raw = from_f<T>(0.f);
+  if (nq > 0) { he_raw = hid_emb[(long)rows_s[0] * H + hc]; se_raw = sent_emb[(long)rows_s[0] * H + hc]; }
+  for (int q = 0; q < nq; ++q) {
+    const long row = rows_s[q];
     const float he = to_f(he_raw), se = to_f(se_raw);
     if (q + 2 < nq) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(hid_emb + (row + 2 * s.q_stride) * H + hc));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(sent_emb + (row + 2 * s.q_stride) * H + hc));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(hid_emb + (long)rows_s[q + 2] * H + hc));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(sent_emb + (long)rows_s[q + 2] * H + hc));
     }
     if (q + 1 < nq) {
-      he_raw = hid_emb[(row + s.q_stride) * H + hc];
-      se_raw = sent_emb[(row + s.q_stride) * H + hc];
+      he_raw = hid_emb[(long)rows_s[q + 1] * H + hc];
+      se_raw = sent_emb[(long)rows_s[q + 1] * H + hc];
     }
     const float4* dq4 = reinterpret_cast<const float4*>(de_s + (q * 2 + half) * KHP);
     float dhe = 0.f, g_s = 0.f;
@@ -778,9 +804,10 @@ int attention_fwd_batched(GemmContext& gc, LaunchCtx c, const AttnShape& s, cons
 #undef LAUNCH_SC
   if (c.launches) ++*c.launches;
   {
-    long blocks = (rows * (H / 8) + 255) / 256;
+    const long live = s.pm ? s.packed_rows : rows;
+    long blocks = (live * (H / 8) + 255) / 256;
     if (blocks > 8L * kNumSMs) blocks = 8L * kNumSMs;
-    attn_sadd_kernel<<<(int)blocks, 256, 0, c.stream>>>(rows, H, P, alpha, sentinel, p_hid, sadd);
+    if (blocks > 0) attn_sadd_kernel<<<(int)blocks, 256, 0, c.stream>>>(live, H, P, s.pm, alpha, sentinel, p_hid, sadd);
     if (c.launches) ++*c.launches;
   }
   GemmCall g;
@@ -857,10 +884,13 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
     cudaMemset2DAsync(dKV + H, (size_t)2 * H * sizeof(T), 0, (size_t)H * sizeof(T), (size_t)s.n_img * k, c.stream);
   }
   {
-    long blocks = (rows + 7) / 8;
+    const long live = s.pm ? s.packed_rows : rows;
+    long blocks = (live + 7) / 8;
     if (blocks > 16L * kNumSMs) blocks = 16L * kNumSMs;
-    attn_bwd_rows_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(rows, H, k, s.position_softmax, sentinel, alpha, dactx, dal,
-                                                              kDalLd, de, alpha_T, kAlphaTLd, dS_ctx, db_alpha);
+    if (blocks > 0)
+      attn_bwd_rows_kernel<T><<<(int)blocks, 256, 0, c.stream>>>(live, H, k, s.position_softmax, s.pm, sentinel, alpha,
+                                                                dactx, dal, kDalLd, de, alpha_T, kAlphaTLd, dS_ctx,
+                                                                db_alpha);
     if (c.launches) ++*c.launches;
   }
   {
@@ -881,7 +911,7 @@ int attention_bwd(GemmContext& gc, LaunchCtx c, const AttnShape& s, const T* key
 #define DISPATCH_KC(KERNEL, ...)                                                                                     \
   do {                                                                                                               \
     const int kh = P <= 8 ? 4 : P <= 16 ? 8 : P <= 32 ? 16 : P <= 50 ? 25 : 32;                                      \
-    const size_t a_bytes = (size_t)s.q_per_img * 2 * ((kh + 3) & ~3) * sizeof(float);                                \
+    const size_t a_bytes = (size_t)s.q_per_img * (2 * ((kh + 3) & ~3) * sizeof(float) + sizeof(int));                \
     if (kh == 25) KERNEL<T, 25><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                                 \
     else if (kh == 4) KERNEL<T, 4><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                              \
     else if (kh == 8) KERNEL<T, 8><<<grid_cols, 256, a_bytes, c.stream>>>(__VA_ARGS__);                              \

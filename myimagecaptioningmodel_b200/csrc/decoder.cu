@@ -109,8 +109,8 @@ class DecoderBase {
   virtual ~DecoderBase() {}
   PhaseTimer prof;
   virtual int bind(const capdec_params* p, cudaStream_t s) = 0;
-  virtual int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
-                        cudaStream_t s) = 0;
+  virtual int train_fwd(const float* g, const float* P, const int64_t* cap, const int32_t* lengths, int B,
+                        float* logits_out, float* loss_out, cudaStream_t s) = 0;
   virtual int train_bwd(float loss_scale, const float* inv_ntok, float* dg, float* dP, const capdec_grads* gr,
                         cudaStream_t s) = 0;
   virtual int decode(const float* g, const float* P, int B, int beam, int finish, int32_t* ids, float* scores,
@@ -378,8 +378,8 @@ template <typename T> class Decoder : public DecoderBase {
     return 0;
   }
 
-  int train_fwd(const float* g, const float* P, const int64_t* cap, int B, float* logits_out, float* loss_out,
-                cudaStream_t s) override {
+  int train_fwd(const float* g, const float* P, const int64_t* cap, const int32_t* lengths, int B, float* logits_out,
+                float* loss_out, cudaStream_t s) override {
     if (!bound) { set_error("capdec_train_fwd: parameters not bound"); return -1; }
     if (B <= 0) { set_error("capdec_train_fwd: empty batch"); return -1; }
     GemmContext gc; gc.stream = s;
@@ -387,7 +387,19 @@ template <typename T> class Decoder : public DecoderBase {
     const size_t e = sizeof(T);
     const long M = (long)B * Tt;
     last_B = B; last_cap = cap;
-    fwd_staged = (g == nullptr); have_dz = false;
+    fwd_staged = (g == nullptr); have_dz = false; have_fwd = false;
+    // Packed rows: with `lengths` the time-batched head runs only on the rows (t, b) that carry a target,
+    // t < lengths[b] - 1 (captions are [start, w.., stop, pad..]): Mp of the M = B*T rows.  The per-step logits of the dead
+    // rows would be needed for logits_out, so the full schedule runs when they are requested; it also runs when there is
+    // (almost) nothing to drop.
+    long Mp = M;
+    if (lengths && !logits_out) {
+      Mp = 0;
+      for (int b = 0; b < B; ++b) Mp += std::min<long>(std::max<long>((long)lengths[b] - 1, 0), Tt);
+    }
+    packed = lengths && !logits_out && Mp > 0 && Mp * 20 <= M * 19;
+    if (!packed) Mp = M;
+    head_rows = Mp;
     prof.mark("^fwd", s);
     OK(image_projections(gc, lc, g, P, B));
     prof.mark("fwd.image_kv", s);
@@ -411,6 +423,23 @@ template <typename T> class Decoder : public DecoderBase {
     OK(lse.ensure(4 * M, &ws_bytes));
     OK(acc.ensure(64, &ws_bytes));
     OK(dlogits.ensure(e * M * (size_t)Vp, &ws_bytes));
+    const int* d_prow = nullptr;
+    const int* d_pm = nullptr;
+    const int* d_steps = nullptr;
+    if (packed) {
+      OK(row_steps.ensure(4 * (size_t)B, &ws_bytes));
+      OK(row_prow.ensure(4 * (size_t)M, &ws_bytes));
+      OK(row_pm.ensure(4 * (size_t)M, &ws_bytes));
+      OK(hprev_c.ensure(e * M * H, &ws_bytes));
+      OK(hcur_c.ensure(e * M * H, &ws_bytes));
+      OK(actx_p.ensure(e * M * H, &ws_bytes));
+      // the live steps of every sample come from the captions themselves (last non-padding target); `lengths` only sizes
+      // the launches, a different total is reported (CAPDEC_ERR_LENGTHS) and can never index out of bounds
+      CUDA_OK(cudaMemsetAsync(row_pm.p, 0, 4 * (size_t)Mp, s));
+      OK(build_row_map(lc, cap, S, B, Tt, cfg.padding_idx, Mp, row_steps.as<int>(), row_prow.as<int>(), row_pm.as<int>(),
+                       err_flag));
+      d_prow = row_prow.as<int>(); d_pm = row_pm.as<int>(); d_steps = row_steps.as<int>();
+    }
 
     // word embeddings of the source tokens caption[:, :-1] (model:84, 164), time-major
     embed_gather<T>(lc, emb.as<T>(), E, V, cap, S, B, Tt, cfg.padding_idx, embx.as<T>(), E, err_flag);
@@ -454,27 +483,38 @@ template <typename T> class Decoder : public DecoderBase {
                        cs.as<float>() + (size_t)(t + 1) * B * H, gact.as<T>() + (size_t)t * B * 4 * H);
     }
     prof.mark("fwd.recurrence", s);
+    // h_{t-1}, h_t of the head's rows: views of hs, or (packed rows) gathered copies of the live rows
     const T* Hprev = hs.as<T>();
     const T* Hcur = hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
-    // time-batched head
-    OK(fc(gc, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, (int)M, H, H, ACT_NONE));                       // model:90
-    sentinel_fwd<T>(lc, M, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, persistent ? nullptr : g5.as<float>() + 4 * H,
-                    5 * H, B, 1, Ccur, sgate.as<T>(), sent.as<T>());                                  // model:91-92
-    OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, (int)M, H, H, ACT_TANH));                        // model:99
-    OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, (int)M, H, H, ACT_NONE));                     // model:102
-    OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, (int)M, H, H, ACT_NONE));                      // model:104
+    if (packed) {
+      gather_rows<T>(lc, Hprev, Hcur, H, d_pm, Mp, H, hprev_c.as<T>(), hcur_c.as<T>(), H);
+      Hprev = hprev_c.as<T>(); Hcur = hcur_c.as<T>();
+    }
+    const int Mh = (int)Mp;   // rows of the time-batched head
+    OK(fc(gc, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, Mh, H, H, ACT_NONE));                           // model:90
+    sentinel_fwd<T>(lc, Mp, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, persistent ? nullptr : g5.as<float>() + 4 * H,
+                    5 * H, B, 1, Ccur, sgate.as<T>(), sent.as<T>(), d_pm);                            // model:91-92
+    OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, Mh, H, H, ACT_TANH));                            // model:99
+    OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, Mh, H, H, ACT_NONE));                         // model:102
+    OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, Mh, H, H, ACT_NONE));                          // model:104
     prof.mark("fwd.head_fc", s);
     AttnShape as = train_shape(B);
+    as.prow = d_prow; as.pm = d_pm; as.nq = d_steps; as.packed_rows = packed ? Mp : 0;
+    // packed rows: the batched GEMMs of the attention (context forward, d alpha / d values backward) keep the padded row
+    // index (rows of one image are B apart); the dead rows of their operand alpha_T stay zero from here to the backward pass
+    OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
+    if (packed) CUDA_OK(cudaMemsetAsync(alpha_t.p, 0, e * M * kAlphaTLd, s));
     bool attn_batched = false;
     if constexpr (std::is_same<T, bf16>::value) {
       if (attention_fwd_batched_supported(as)) {
-        // scores + soft-max on MUFU / mma.sync, context as one batched tcgen05 GEMM                  // model:103-115
-        OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
+        // scores + soft-max on MUFU / mma.sync, context as one batched tcgen05 GEMM (its output gathered into the packed
+        // actx with packed rows)                                                                     // model:103-115
         OK(sadd.ensure(e * M * H, &ws_bytes));
         OK(attention_fwd_batched(gc, lc, as, keys.as<bf16>(), vals.as<bf16>(), hemb.as<bf16>(), semb.as<bf16>(),
                                  sent.as<bf16>(), phid.as<bf16>(), prm.fc_a_w, prm.fc_a_b, alpha.as<float>(),
-                                 alpha_t.as<bf16>(), sadd.as<bf16>(), actx.as<bf16>()));
+                                 alpha_t.as<bf16>(), sadd.as<bf16>(), packed ? actx_p.as<bf16>() : actx.as<bf16>()));
+        if (packed) gather_rows<T>(lc, actx_p.as<T>(), nullptr, H, d_pm, Mp, H, actx.as<T>(), nullptr, H);
         attn_batched = true;
       }
     }
@@ -482,8 +522,8 @@ template <typename T> class Decoder : public DecoderBase {
       attention_fwd<T>(lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), phid.as<T>(),
                        prm.fc_a_w, prm.fc_a_b, alpha.as<float>(), actx.as<T>(), nullptr);             // model:103-115
     prof.mark("fwd.attention", s);
-    OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, (int)M, H, H, ACT_TANH));                      // model:115
-    OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, (int)M, E, H, ACT_NONE));                      // model:24
+    OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, Mh, H, H, ACT_TANH));                          // model:115
+    OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, Mh, E, H, ACT_NONE));                          // model:24
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
     OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
     {
@@ -492,7 +532,7 @@ template <typename T> class Decoder : public DecoderBase {
       // leaves the 2e-2 tolerance; and the cross entropy fused into two passes of this GEMM -- 289 + 202 us against
       // 161 + 118 us for GEMM + kernel: the K = 256 GEMM is epilogue-bound, a second pass costs more than the round trip.)
       GemmCall c;                                                                                     // model:25
-      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = (int)M; c.N = V; c.K = E;
+      c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = Mh; c.N = V; c.K = E;
       c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
       OK(gemm<T>(gc, c));
     }
@@ -500,7 +540,7 @@ template <typename T> class Decoder : public DecoderBase {
     // masked cross entropy (model:163-171, 180-183, 205-212) fused with the unscaled d logits = (softmax - onehot) * mask,
     // so the logits leave HBM only once
     ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
-                dlogits.as<T>(), err_flag);
+                dlogits.as<T>(), err_flag, Mp, d_pm);
     loss_finalize(lc, acc.as<float>());
     if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);          // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
@@ -528,6 +568,8 @@ template <typename T> class Decoder : public DecoderBase {
     const size_t e = sizeof(T);
     const int B = last_B, X = E + H;
     const long M = (long)B * Tt;
+    const long Mp = head_rows;         // rows of the time-batched head: M, or the live rows (packed, see train_fwd)
+    const int Mh = (int)Mp;
     const int64_t* cap = last_cap;
     const capdec_grads& G = *gr;
     OK(dproj.ensure(e * M * E, &ws_bytes));
@@ -548,6 +590,15 @@ template <typename T> class Decoder : public DecoderBase {
     OK(dcrec.ensure(4 * (size_t)B * H, &ws_bytes));
     OK(dGsum.ensure(e * (size_t)B * 5 * H, &ws_bytes));
     OK(dembx.ensure(e * M * E, &ws_bytes));
+    if (packed) {
+      OK(dactx_p.ensure(e * M * H, &ws_bytes));
+      OK(dsg_c.ensure(e * M * H, &ws_bytes));
+      OK(dHhead_c.ensure(e * M * H, &ws_bytes));
+      OK(dHprev_c.ensure(e * M * H, &ws_bytes));
+    }
+    const int* d_prow = packed ? row_prow.as<int>() : nullptr;
+    const int* d_pm = packed ? row_pm.as<int>() : nullptr;
+    const int* d_steps = packed ? row_steps.as<int>() : nullptr;
 
     prof.mark("^bwd", s);
     // gradients are overwritten: start from zero, every contribution below is an fp32 atomic add
@@ -566,83 +617,104 @@ template <typename T> class Decoder : public DecoderBase {
     }
     multi_zero(lc, zt);
     prof.mark("bwd.zero_grads", s);
-    const T* Hprev = hs.as<T>();
-    const T* Hcur = hs.as<T>() + (size_t)B * H;
+    // h_{t-1}, h_t, c_t of the head's rows (see train_fwd)
+    const T* Hprev = packed ? hprev_c.as<T>() : hs.as<T>();
+    const T* Hcur = packed ? hcur_c.as<T>() : hs.as<T>() + (size_t)B * H;
     const float* Ccur = cs.as<float>() + (size_t)B * H;
 
     // d logits = (softmax - onehot) * mask was written by the forward pass; the factor 1/sum(mask) * loss_scale
     // (softmax_with_cross_entropy_grad + the mask/scale ops) is applied by its three consumers
     float* gscale = acc.as<float>() + 4;
     scale_scalar(lc, inv_ntok ? inv_ntok : acc.as<float>() + 3, loss_scale, gscale);
-    colsum_add<T>(lc, dlogits.as<T>(), Vp, M, V, G.out_fc_bias, gscale);
+    colsum_add<T>(lc, dlogits.as<T>(), Vp, Mp, V, G.out_fc_bias, gscale);
     // tied output projection (model:24-25): d proj, d Emb (output side), d fc_e
     {
       GemmCall c;
-      c.A = dlogits.p; c.lda = Vp; c.B = emb.p; c.ldb = E; c.b_mn = true; c.C = dproj.p; c.ldc = E; c.M = (int)M; c.N = E;
+      c.A = dlogits.p; c.lda = Vp; c.B = emb.p; c.ldb = E; c.b_mn = true; c.C = dproj.p; c.ldc = E; c.M = Mh; c.N = E;
       c.K = V; c.epi.alpha_dev = gscale;
       OK(gemm<T>(gc, c));
     }
-    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, (int)M, G.word_embedding, E, gscale));
+    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, Mh, G.word_embedding, E, gscale));
     ColsumTable bias_sums;  // the bias gradients of the time-batched head: one launch, just before their group is marked
-    bias_sums.add(dproj.p, E, M, E, G.fc_e_b);
-    OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, (int)M, G.fc_e_w, E));
+    bias_sums.add(dproj.p, E, Mp, E, G.fc_e_b);
+    OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, Mh, G.fc_e_w, E));
     prof.mark("bwd.vocab_proj", s);
     // out = tanh(fc_o(ctx + p_hid))   (model:115)
     {
       GemmCall c;
-      c.A = dproj.p; c.lda = E; c.B = w_e_n.p; c.ldb = E; c.C = doutp.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = E;
+      c.A = dproj.p; c.lda = E; c.B = w_e_n.p; c.ldb = E; c.C = doutp.p; c.ldc = H; c.M = Mh; c.N = H; c.K = E;
       c.epi.act = ACT_DTANH; c.epi.dact_y = outv.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
-    bias_sums.add(doutp.p, H, M, H, G.fc_o_b);
-    OK(wgrad(gc, actx.p, H, H, doutp.p, H, H, (int)M, G.fc_o_w, H));
+    bias_sums.add(doutp.p, H, Mp, H, G.fc_o_b);
+    OK(wgrad(gc, actx.p, H, H, doutp.p, H, H, Mh, G.fc_o_w, H));
     {
       GemmCall c;  // d(ctx + p_hid)
-      c.A = doutp.p; c.lda = H; c.B = w_o_n.p; c.ldb = H; c.C = dactx.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.A = doutp.p; c.lda = H; c.B = w_o_n.p; c.ldb = H; c.C = dactx.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
       OK(gemm<T>(gc, c));
     }
     prof.mark("bwd.out_fc", s);
     // attention (model:103-113)
     AttnShape as = train_shape(B);
+    as.prow = d_prow; as.pm = d_pm; as.nq = d_steps; as.packed_rows = packed ? Mp : 0;
     OK(dal.ensure(4 * M * kDalLd, &ws_bytes));
     OK(alpha_t.ensure(e * M * kAlphaTLd, &ws_bytes));
+    // packed rows: the two batched GEMMs of the attention gradient index rows by (image, step); they read d context in
+    // the padded layout with zeros in the dead rows (alpha_T is zero there since the forward pass)
+    const T* dctx_att = dactx.as<T>();
+    if (packed) {
+      scatter_rows_zero<T>(lc, dactx.as<T>(), nullptr, d_prow, M, H, dactx_p.as<T>(), nullptr);
+      dctx_att = dactx_p.as<T>();
+    }
     OK(attention_bwd<T>(gc, lc, as, keys.as<T>(), vals.as<T>(), hemb.as<T>(), semb.as<T>(), sent.as<T>(), prm.fc_a_w,
-                        alpha.as<float>(), dactx.as<T>(), dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
+                        alpha.as<float>(), dctx_att, dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
                         dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(), dsemb.as<T>(), G.fc_a_w, G.fc_a_b));
     prof.mark("bwd.attention", s);
-    bias_sums.add(dhemb.p, H, M, H, G.fc_g_b);
-    OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, (int)M, G.fc_g_w, H));
-    bias_sums.add(dsemb.p, H, M, H, G.fc_s_b);
-    OK(wgrad(gc, sent.p, H, H, dsemb.p, H, H, (int)M, G.fc_s_w, H));
+    bias_sums.add(dhemb.p, H, Mp, H, G.fc_g_b);
+    OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, Mh, G.fc_g_w, H));
+    bias_sums.add(dsemb.p, H, Mp, H, G.fc_s_b);
+    OK(wgrad(gc, sent.p, H, H, dsemb.p, H, H, Mh, G.fc_s_w, H));
     {
       GemmCall c;  // d p_hid (pre-tanh) = (d actx + d hid_emb . fc_g^T) * (1 - p_hid^2)      (model:99, 102)
-      c.A = dhemb.p; c.lda = H; c.B = w_g2_n.p; c.ldb = H; c.C = dphp.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.A = dhemb.p; c.lda = H; c.B = w_g2_n.p; c.ldb = H; c.C = dphp.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
       c.epi.addend = dactx.p; c.epi.ld_add = H; c.epi.act = ACT_DTANH; c.epi.dact_y = phid.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
-    bias_sums.add(dphp.p, H, M, H, G.fc_p_b);
-    OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, (int)M, G.fc_p_w, H));
+    bias_sums.add(dphp.p, H, Mp, H, G.fc_p_b);
+    OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, Mh, G.fc_p_w, H));
     {
       GemmCall c;  // d sentinel = alpha_k d ctx / (k+1) + d sentinel_emb . fc_s^T                (model:104, 111)
-      c.A = dsemb.p; c.lda = H; c.B = w_s_n.p; c.ldb = H; c.C = dS.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.A = dsemb.p; c.lda = H; c.B = w_s_n.p; c.ldb = H; c.C = dS.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
       c.epi.addend = dsctx.p; c.epi.ld_add = H;
       OK(gemm<T>(gc, c));
     }
-    // sentinel = sigmoid(p_word_emb + p_hidden) * tanh(c)     (model:89-92)
-    sentinel_bwd<T>(lc, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
-    bias_sums.add(dG.as<T>() + 4 * H, 5 * H, M, H, G.fc_hs_b);
-    OK(wgrad(gc, Hprev, H, H, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_hs_w, H));
+    // sentinel = sigmoid(p_word_emb + p_hidden) * tanh(c)     (model:89-92); d(gate pre-activation) is one column block
+    // of dG [M, 5H] (padded rows: the BPTT kernel and the x-side weight gradients read it), d c goes to dChead
+    const T* dsg = dG.as<T>() + 4 * H;   // d(sentinel gate pre-activation) of the head's rows, and its pitch
+    long ld_dsg = 5 * H;
+    if (packed) {
+      sentinel_bwd_packed<T>(lc, M, H, d_prow, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H,
+                             dChead.as<float>(), dsg_c.as<T>());
+      dsg = dsg_c.as<T>(); ld_dsg = H;
+    } else {
+      sentinel_bwd<T>(lc, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
+    }
+    bias_sums.add(dsg, ld_dsg, Mp, H, G.fc_hs_b);
+    OK(wgrad(gc, Hprev, H, H, dsg, ld_dsg, H, Mh, G.fc_hs_w, H));
     {
       GemmCall c;  // d h_t from p_hid
-      c.A = dphp.p; c.lda = H; c.B = w_p_n.p; c.ldb = H; c.C = dHhead.p; c.ldc = H; c.M = (int)M; c.N = H; c.K = H;
+      c.A = dphp.p; c.lda = H; c.B = w_p_n.p; c.ldb = H; c.C = packed ? dHhead_c.p : dHhead.p; c.ldc = H; c.M = Mh;
+      c.N = H; c.K = H;
       OK(gemm<T>(gc, c));
     }
     {
       GemmCall c;  // d h_{t-1} from p_hidden
-      c.A = dG.as<T>() + 4 * H; c.lda = 5 * H; c.B = w_hs_n.p; c.ldb = H; c.C = dHprev.p; c.ldc = H; c.M = (int)M;
+      c.A = dsg; c.lda = ld_dsg; c.B = w_hs_n.p; c.ldb = H; c.C = packed ? dHprev_c.p : dHprev.p; c.ldc = H; c.M = Mh;
       c.N = H; c.K = H;
       OK(gemm<T>(gc, c));
     }
+    if (packed)   // the BPTT kernel reads both by (step, sample): back to padded rows, zeros where no target exists
+      scatter_rows_zero<T>(lc, dHhead_c.as<T>(), dHprev_c.as<T>(), d_prow, M, H, dHhead.as<T>(), dHprev.as<T>());
     prof.mark("bwd.head_fc", s);
     // once-per-image projections (model:52-53)
     bias_sums.add(dkv.p, 2 * H, (long)B * k, H, G.fc_v_b);
@@ -701,6 +773,7 @@ template <typename T> class Decoder : public DecoderBase {
     prof.mark("bwd.recurrence", s);
     // After the BPTT everything left is independent; it is ordered so that the gradients become final in large groups
     // early and a small one last (capdec_set_grad_ready_events): each group's all-reduce runs behind the remaining work.
+    const T* HprevFull = hs.as<T>();   // h_{t-1} of ALL rows: the recurrence ran on every (step, sample)
     {
       GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
       c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
@@ -710,7 +783,7 @@ template <typename T> class Decoder : public DecoderBase {
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
     mark_ready(1, s);  // word_embedding, out_fc_bias are final
     // weight gradients of the gate GEMM, batched over all steps
-    OK(wgrad(gc, Hprev, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
+    OK(wgrad(gc, HprevFull, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
     mark_ready(2, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
     sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
     OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
@@ -918,7 +991,8 @@ template <typename T> class Decoder : public DecoderBase {
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
-            &d_state, &d_beam, &d_trace, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
+            &d_state, &d_beam, &d_trace, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
+            &dHhead_c, &dHprev_c, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
   // captured step loop of capdec_decode for small batches
@@ -951,6 +1025,10 @@ template <typename T> class Decoder : public DecoderBase {
   // backward scratch
   DevBuf dlogits, dproj, doutp, dactx, de, dsctx, dkv, dhemb, dsemb, dphp, dS, dG, dChead, dHhead, dHprev, dhrec, dcrec,
       dGsum, dembx, dal, alpha_t, w_hh_perm, rec_ctr, w_x_p, w_g_p, b5p, g5b, sadd;
+  // packed rows of the time-batched head (train_fwd with lengths)
+  bool packed = false;
+  long head_rows = 0;
+  DevBuf row_steps, row_prow, row_pm, hprev_c, hcur_c, actx_p, dactx_p, dsg_c, dHhead_c, dHprev_c;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace;
   int trace_B = 0, trace_beam = 0;
@@ -996,10 +1074,12 @@ static int check_device(capdec_handle h) {
 static int report_async_error(capdec_handle h) {
   const int e = h->impl->take_async_error();
   if (!e) return 0;
-  set_error("an earlier call on this handle was given bad input:%s%s%s (the offending entries were treated as padding)",
+  set_error("an earlier call on this handle was given bad input:%s%s%s (offending token ids were treated as padding; with"
+            " wrong lengths the step's results are undefined)",
             (e & CAPDEC_ERR_SOURCE_ID) ? " caption token id outside [0, vocab_size)" : "",
             (e & CAPDEC_ERR_TARGET_ID) ? " target token id outside [0, vocab_size)" : "",
-            (e & CAPDEC_ERR_LENGTHS) ? " lengths[] shorter than the non-padding part of a caption" : "");
+            (e & CAPDEC_ERR_LENGTHS) ? " lengths[] does not describe the captions (sum of lengths[b] - 1 differs from the"
+                                       " number of decode steps up to the last non-padding target)" : "");
   return -1;
 }
 
@@ -1115,11 +1195,11 @@ int capdec_bind_params(capdec_handle h, const capdec_params* p, void* stream) {
   return h->impl->bind(p, (cudaStream_t)stream);
 }
 
-int capdec_train_fwd(capdec_handle h, const float* g, const float* P, const int64_t* caption, int32_t B,
-                     float* logits_out, float* loss_out, void* stream) {
+int capdec_train_fwd(capdec_handle h, const float* g, const float* P, const int64_t* caption, const int32_t* lengths,
+                     int32_t B, float* logits_out, float* loss_out, void* stream) {
   if (check_device(h) || report_async_error(h)) return -1;
   if (!caption) { set_error("capdec_train_fwd: null caption"); return -1; }
-  return h->impl->train_fwd(g, P, caption, B, logits_out, loss_out, (cudaStream_t)stream);
+  return h->impl->train_fwd(g, P, caption, lengths, B, logits_out, loss_out, (cudaStream_t)stream);
 }
 
 int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_dev, float* dg, float* dP,

@@ -55,9 +55,26 @@ void lstm_cell_fwd(LaunchCtx c, int R, int H, const float* gpre, long ld_gpre, c
                    long ld_g5, int g5_mod, int g5_div, const float* c_prev, T* h_out, long ld_h, float* c_out,
                    T* gates_act);
 // sentinel (model:89-92): sg = sig(ph + xe + g5);  s = sg * tanh(c)
+//   rowmap (optional, packed rows): row r of ph / sgate / s_out is row rowmap[r] of xe / g5 / cc
 template <typename T>
 void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* xe, long ld_xe, const float* g5,
-                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out);
+                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out, const int* rowmap = nullptr);
+// ---- packed rows of the time-batched head (see pointwise.cu) ----
+//   out: steps [B] live steps per sample (from the captions); prow [T*B] padded -> packed row or -1; pm [Mp] packed ->
+//   padded row (zero it first: entries the captions do not fill must stay valid rows).  Mp = the host's row count.
+int build_row_map(LaunchCtx c, const int64_t* caption, long cap_ld, int B, int T, int pad, long Mp, int* steps, int* prow,
+                  int* pm, int* err);
+// dst{0,1}[r, :] = src{0,1}[pm[r], :]   (src1 / dst1 optional);  N % 8 == 0
+template <typename T>
+void gather_rows(LaunchCtx c, const T* src0, const T* src1, long ld_src, const int* pm, long Mp, int N, T* dst0, T* dst1,
+                 long ld_dst);
+// dst{0,1}[m, :] = prow[m] >= 0 ? src{0,1}[prow[m], :] : 0   (all pitches N)
+template <typename T>
+void scatter_rows_zero(LaunchCtx c, const T* src0, const T* src1, const int* prow, long M, int N, T* dst0, T* dst1);
+// sentinel_bwd over the M padded rows with packed operands dS, sgate [*, H]; also writes the packed copy dsg_packed
+template <typename T>
+void sentinel_bwd_packed(LaunchCtx c, long M, int H, const int* prow, const T* dS, const T* sgate, const float* cc,
+                         T* dsg_pre, long ld_dsg, float* dC_head, T* dsg_packed);
 // dsg_pre = dS * tanh(c) * sg (1 - sg)  -> dG[:, 4H:5H];   dC_head = dS * sg * (1 - tanh(c)^2)
 template <typename T>
 void sentinel_bwd(LaunchCtx c, long R, int H, const T* dS, const T* sgate, const float* cc, T* dsg_pre, long ld_dsg,
@@ -115,6 +132,14 @@ struct AttnShape {
   long row0_stride;     // row of query 0 of image i = i * row0_stride
   long q_stride;        // row of query q = row0 + q * q_stride      (train: 1 / B; decode: beam / 1)
   int position_softmax; // 1 = softmax over the k+1 positions; 0 = reference as written (alpha == 1)
+  // Packed rows (training with lengths): only queries q < nq[img] of an image are live, and the per-query [rows, H]
+  // operands (hid_emb, sent_emb, sentinel, p_hid and their gradients) hold the live rows only, row prow[padded row];
+  // alpha, alpha_T, de, dal, sadd and the operands of the batched GEMMs (the context output, d context) keep the padded
+  // row index.  pm = inverse map, packed_rows = number of live rows.  All nullptr / 0: every row is live.
+  const int* prow = nullptr;
+  const int* pm = nullptr;
+  const int* nq = nullptr;
+  long packed_rows = 0;
 };
 // fused additive attention forward (model:103-113 + the "context + p_hid" of model:115)
 //   alpha [rows, k+1] fp32;  actx [rows, H] = mean_j(alpha_j v_j) + p_hid;  ctx_out (optional) without p_hid
@@ -168,9 +193,11 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
 //   lse[m];  acc[0] += sum(ce * mask), acc[1] += sum(mask);  and the UNSCALED gradient
 //   dlogits[m, n] = (softmax - onehot) * mask  (columns [V, Vp) zeroed); the 1/sum(mask) * loss_scale factor is applied
 //   by the consumers (GemmEpi::alpha_dev, colsum_add scale).  err: see embed_gather (CAPDEC_ERR_TARGET_ID)
+//   rows / rowmap: the number of logit rows and (packed rows) the padded row t*B+b of each of them; nullptr: rows = B*steps
 template <typename T>
 void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-              int steps, int pad, float* lse, float* acc, T* dlogits, int* err);
+              int steps, int pad, float* lse, float* acc, T* dlogits, int* err, long rows = -1,
+              const int* rowmap = nullptr);
 // out[0] = in[0] * s
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out);
 // acc[2] = acc[0] / acc[1] (the loss), acc[3] = 1 / acc[1]

@@ -22,13 +22,13 @@ template <typename T>
 __global__ void __launch_bounds__(kCeThreads)
 ce_fused_kernel(const float* __restrict__ logits, long ldl, int V, int Vp, const int64_t* __restrict__ caption,
                 long cap_ld, int B, int pad, float* __restrict__ lse, float* __restrict__ acc, T* __restrict__ dlogits,
-                int* __restrict__ err) {
+                int* __restrict__ err, const int* __restrict__ rowmap) {
   pdl_trigger();
   __shared__ float scratch[32];
-  const long m = blockIdx.x;
+  const long m = blockIdx.x;   // row of logits / lse / dlogits; with packed rows its (t, b) is rowmap[m] = t*B + b
   const float* row = logits + m * ldl;
   T* out = dlogits + m * (long)Vp;
-  int64_t tgt = target_of(caption, cap_ld, B, m);
+  int64_t tgt = target_of(caption, cap_ld, B, rowmap ? rowmap[m] : m);
   if ((unsigned long)tgt >= (unsigned long)V) {
     if (threadIdx.x == 0 && err) atomicOr(err, 2 /* CAPDEC_ERR_TARGET_ID */);
     tgt = pad;
@@ -294,15 +294,17 @@ __global__ void beam_reorder_kernel(int n_rows, int beam, int E, int H, int pad,
 
 template <typename T>
 void ce_fused(LaunchCtx c, const float* logits, long ldl, int V, int Vp, const int64_t* caption, long cap_ld, int B,
-              int steps, int pad, float* lse, float* acc, T* dlogits, int* err) {
-  ce_fused_kernel<T><<<B * steps, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc, dlogits,
-                                                            err);
+              int steps, int pad, float* lse, float* acc, T* dlogits, int* err, long rows, const int* rowmap) {
+  if (rows < 0) rows = (long)B * steps;
+  if (rows == 0) return;
+  ce_fused_kernel<T><<<(unsigned)rows, kCeThreads, 0, c.stream>>>(logits, ldl, V, Vp, caption, cap_ld, B, pad, lse, acc,
+                                                                 dlogits, err, rowmap);
   if (c.launches) ++*c.launches;
 }
 template void ce_fused<float>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
-                              float*, int*);
+                              float*, int*, long, const int*);
 template void ce_fused<bf16>(LaunchCtx, const float*, long, int, int, const int64_t*, long, int, int, int, float*, float*,
-                             bf16*, int*);
+                             bf16*, int*, long, const int*);
 void scale_scalar(LaunchCtx c, const float* in, float s, float* out) {
   scale_scalar_kernel<<<1, 1, 0, c.stream>>>(in, s, out);
   if (c.launches) ++*c.launches;

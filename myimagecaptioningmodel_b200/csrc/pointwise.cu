@@ -115,10 +115,12 @@ __global__ void lstm_cell_fwd_kernel(int R, int H, const float* __restrict__ gpr
   }
 }
 
+// rowmap (packed rows, see row_map_kernel): row r of ph / sgate / s_out is row rowmap[r] of xe / g5 / cc
 template <typename T>
 __global__ void sentinel_fwd_kernel(long R, int H, const T* __restrict__ ph, long ld_ph, const T* __restrict__ xe,
                                     long ld_xe, const float* __restrict__ g5, long ld_g5, int g5_mod, int g5_div,
-                                    const float* __restrict__ cc, T* __restrict__ sgate, T* __restrict__ s_out) {
+                                    const float* __restrict__ cc, T* __restrict__ sgate, T* __restrict__ s_out,
+                                    const int* __restrict__ rowmap) {
   pdl_trigger();
   constexpr bool F = fast_math<T>::value;
   const int vec_per_row = H / 8;
@@ -127,19 +129,20 @@ __global__ void sentinel_fwd_kernel(long R, int H, const T* __restrict__ ph, lon
   for (; i < n; i += stride) {
     const long r = i / vec_per_row;
     const int h0 = (int)(i % vec_per_row) * 8;
+    const long m = rowmap ? rowmap[r] : r;
     float a[8], x[8], c8[8], sg[8], s[8];
     load8(ph + r * ld_ph + h0, a);
     if (xe) {
-      load8(xe + r * ld_xe + h0, x);
+      load8(xe + m * ld_xe + h0, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += x[j];
     }
     if (g5) {
-      load8(g5 + ((r % g5_mod) / g5_div) * ld_g5 + h0, x);
+      load8(g5 + ((m % g5_mod) / g5_div) * ld_g5 + h0, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += x[j];
     }
-    load8(cc + r * H + h0, c8);
+    load8(cc + m * H + h0, c8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sg[j] = sigmoid_t<F>(a[j]);
@@ -174,6 +177,173 @@ __global__ void sentinel_bwd_kernel(long R, int H, const T* __restrict__ dS, con
     }
     store8(dsg_pre + r * ld_dsg + h0, o1);
     store8(dC_head + r * H + h0, o2);
+  }
+}
+
+// The same over PADDED rows when the head ran on packed rows: padded row m is packed row prow[m] (-1: a row past the
+// caption's last target, no gradient).  d(sentinel gate pre-activation) goes to dG[:, 4H:5H] and d c to dC_head in the
+// padded layout the BPTT kernel reads (zeros in dead rows), and to dsg_packed for the packed weight / data gradients.
+template <typename T>
+__global__ void sentinel_bwd_packed_kernel(long M, int H, const int* __restrict__ prow, const T* __restrict__ dS,
+                                           const T* __restrict__ sgate, const float* __restrict__ cc,
+                                           T* __restrict__ dsg_pre, long ld_dsg, float* __restrict__ dC_head,
+                                           T* __restrict__ dsg_packed) {
+  pdl_trigger();
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = M * vec_per_row;
+  for (; i < n; i += stride) {
+    const long m = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    const long r = prow[m];
+    float o1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (r >= 0) {
+      float d[8], sg[8], c8[8];
+      load8(dS + r * H + h0, d);
+      load8(sgate + r * H + h0, sg);
+      load8(cc + m * H + h0, c8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float tc = tanh_t<F>(c8[j]);
+        o1[j] = d[j] * tc * sg[j] * (1.f - sg[j]);
+        o2[j] = d[j] * sg[j] * (1.f - tc * tc);
+      }
+      store8(dsg_packed + r * H + h0, o1);
+    }
+    store8(dsg_pre + m * ld_dsg + h0, o1);
+    store8(dC_head + m * H + h0, o2);
+  }
+}
+
+// ---- packed rows of the time-batched head (capdec_train_fwd with lengths) -----------------------------
+// Captions are [start, w.., stop, pad..] (ai_challenge_tokenizer.py:81-86), the loss mask is target != pad
+// (model:163-171): a row (t, b) past the last non-padding target of caption b has d logits == 0 exactly, and nothing
+// downstream of (h_t, c_t) feeds back into the recurrence, so the head only has to run on the rows
+// t < steps[b], steps[b] = 1 + the last t with caption[b, t+1] != pad (rows in a hole of the mask stay: they are masked by
+// the cross entropy as always).  Packed order = padded (time-major) order with the dead rows removed:
+//   prow[t*B + b] = packed row of (t, b), or -1;   pm[r] = padded row of packed row r.
+// The host sized every launch for Mp = sum_b (lengths[b] - 1) rows; the device works from the captions themselves, a
+// different total raises CAPDEC_ERR_LENGTHS and surplus rows are dropped, so a wrong `lengths` cannot index out of bounds.
+constexpr int kMapThreads = 1024;
+__global__ void __launch_bounds__(kMapThreads)
+caption_steps_kernel(const int64_t* __restrict__ caption, long cap_ld, int B, int T, int pad, long Mp,
+                     int* __restrict__ steps, int* __restrict__ err) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int part = 0;
+  for (int b = tid; b < B; b += kMapThreads) {
+    int n = 0;
+    for (int t = 0; t < T; ++t)
+      if (caption[(long)b * cap_ld + t + 1] != pad) n = t + 1;
+    steps[b] = n;
+    part += n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) wsum[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    long total = 0;
+    for (int w = 0; w < kMapThreads / 32; ++w) total += wsum[w];
+    if (total != Mp && err) atomicOr(err, 4 /* CAPDEC_ERR_LENGTHS */);
+  }
+}
+// one CTA per step t: its first packed row is sum_b min(steps[b], t), the rank of b inside the step a block scan
+__global__ void __launch_bounds__(kMapThreads)
+row_map_kernel(const int* __restrict__ steps, int B, int T, long Mp, int* __restrict__ prow, int* __restrict__ pm) {
+  __shared__ int wsum[32];
+  __shared__ int s_total;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int part = 0;
+  for (int b = tid; b < B; b += kMapThreads) part += min(steps[b], t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) wsum[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int w = 0; w < kMapThreads / 32; ++w) a += wsum[w];
+    s_total = a;
+  }
+  __syncthreads();
+  int base = s_total;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += kMapThreads) {
+    const int b = b0 + tid;
+    const int live = (b < B && steps[b] > t) ? 1 : 0;
+    int incl = live;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kMapThreads / 32; ++w) {
+      const int v = wsum[w];
+      if (w < warp) before += v;
+      total += v;
+    }
+    if (b < B) {
+      const long m = (long)t * B + b;
+      const long r = (long)base + before + incl - 1;
+      if (live && r < Mp) {
+        prow[m] = (int)r;
+        pm[r] = (int)m;
+      } else {
+        prow[m] = -1;
+      }
+    }
+    base += total;
+    __syncthreads();
+  }
+}
+
+// dst[r, :] = src[pm[r], :] for up to two tensors of the same shape (h_{t-1} and h_t rows of the packed head)
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src0, const T* __restrict__ src1, long ld_src,
+                                   const int* __restrict__ pm, long Mp, int N, T* __restrict__ dst0,
+                                   T* __restrict__ dst1, long ld_dst) {
+  pdl_trigger();
+  const int vec_per_row = N / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = Mp * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int n0 = (int)(i % vec_per_row) * 8;
+    const long m = pm[r];
+    float v[8];
+    load8(src0 + m * ld_src + n0, v);
+    store8(dst0 + r * ld_dst + n0, v);
+    if (src1) {
+      load8(src1 + m * ld_src + n0, v);
+      store8(dst1 + r * ld_dst + n0, v);
+    }
+  }
+}
+// dst[m, :] = prow[m] >= 0 ? src[prow[m], :] : 0 for up to two tensors [M, N] (pitch N)
+template <typename T>
+__global__ void scatter_rows_zero_kernel(const T* __restrict__ src0, const T* __restrict__ src1,
+                                         const int* __restrict__ prow, long M, int N, T* __restrict__ dst0,
+                                         T* __restrict__ dst1) {
+  pdl_trigger();
+  const int vec_per_row = N / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = M * vec_per_row;
+  for (; i < n; i += stride) {
+    const long m = i / vec_per_row;
+    const int n0 = (int)(i % vec_per_row) * 8;
+    const long r = prow[m];
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (r >= 0) load8(src0 + r * N + n0, v);
+    store8(dst0 + m * N + n0, v);
+    if (src1) {
+      float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (r >= 0) load8(src1 + r * N + n0, w);
+      store8(dst1 + m * N + n0, w);
+    }
   }
 }
 
@@ -527,9 +697,39 @@ void lstm_cell_fwd(LaunchCtx c, int R, int H, const float* gpre, long ld_gpre, c
 }
 template <typename T>
 void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* xe, long ld_xe, const float* g5,
-                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out) {
+                  long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out, const int* rowmap) {
+  if (R <= 0) return;
   sentinel_fwd_kernel<T><<<grid_for(R * (H / 8)), 256, 0, c.stream>>>(R, H, ph, ld_ph, xe, ld_xe, g5, ld_g5, g5_mod,
-                                                                    g5_div, cc, sgate, s_out);
+                                                                    g5_div, cc, sgate, s_out, rowmap);
+  BUMP(c);
+}
+template <typename T>
+void sentinel_bwd_packed(LaunchCtx c, long M, int H, const int* prow, const T* dS, const T* sgate, const float* cc,
+                         T* dsg_pre, long ld_dsg, float* dC_head, T* dsg_packed) {
+  if (M <= 0) return;
+  sentinel_bwd_packed_kernel<T><<<grid_for(M * (H / 8)), 256, 0, c.stream>>>(M, H, prow, dS, sgate, cc, dsg_pre, ld_dsg,
+                                                                           dC_head, dsg_packed);
+  BUMP(c);
+}
+int build_row_map(LaunchCtx c, const int64_t* caption, long cap_ld, int B, int T, int pad, long Mp, int* steps, int* prow,
+                  int* pm, int* err) {
+  if (B <= 0 || T <= 0) return 0;
+  caption_steps_kernel<<<1, kMapThreads, 0, c.stream>>>(caption, cap_ld, B, T, pad, Mp, steps, err);
+  row_map_kernel<<<T, kMapThreads, 0, c.stream>>>(steps, B, T, Mp, prow, pm);
+  if (c.launches) *c.launches += 2;
+  return 0;
+}
+template <typename T>
+void gather_rows(LaunchCtx c, const T* src0, const T* src1, long ld_src, const int* pm, long Mp, int N, T* dst0, T* dst1,
+                 long ld_dst) {
+  if (Mp <= 0) return;
+  gather_rows_kernel<T><<<grid_for(Mp * (N / 8)), 256, 0, c.stream>>>(src0, src1, ld_src, pm, Mp, N, dst0, dst1, ld_dst);
+  BUMP(c);
+}
+template <typename T>
+void scatter_rows_zero(LaunchCtx c, const T* src0, const T* src1, const int* prow, long M, int N, T* dst0, T* dst1) {
+  if (M <= 0) return;
+  scatter_rows_zero_kernel<T><<<grid_for(M * (N / 8)), 256, 0, c.stream>>>(src0, src1, prow, M, N, dst0, dst1);
   BUMP(c);
 }
 template <typename T>
@@ -617,7 +817,11 @@ template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
   template void lstm_cell_fwd<T>(LaunchCtx, int, int, const float*, long, const T*, long, const float*, long, int,    \
                                  int, const float*, T*, long, float*, T*);                                             \
   template void sentinel_fwd<T>(LaunchCtx, long, int, const T*, long, const T*, long, const float*, long, int, int,    \
-                                const float*, T*, T*);                                                                 \
+                                const float*, T*, T*, const int*);                                                     \
+  template void sentinel_bwd_packed<T>(LaunchCtx, long, int, const int*, const T*, const T*, const float*, T*, long,   \
+                                       float*, T*);                                                                    \
+  template void gather_rows<T>(LaunchCtx, const T*, const T*, long, const int*, long, int, T*, T*, long);              \
+  template void scatter_rows_zero<T>(LaunchCtx, const T*, const T*, const int*, long, int, T*, T*);                    \
   template void sentinel_bwd<T>(LaunchCtx, long, int, const T*, const T*, const float*, T*, long, float*);             \
   template void lstm_cell_bwd<T>(LaunchCtx, int, int, const T*, const T*, const float*, const float*, float*,          \
                                  const T*, const float*, const float*, T*, long);                                      \

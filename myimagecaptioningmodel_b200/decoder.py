@@ -268,16 +268,34 @@ class CaptionDecoderEngine:
                 raise ValueError("caption must be a contiguous int64 CUDA tensor [B,{}]".format(cfg.sentence_length))
         return B
 
-    def train_forward(self, g, P, caption, want_logits: bool = False):
-        """capdec_train_fwd.  Returns (loss_buf[4] device tensor, logits or None)."""
+    def _host_lengths(self, lengths, B):
+        """`lengths` (HOST: list, numpy array or CPU tensor of B token counts, see caption_lengths) as the int32 array
+        capdec_train_fwd reads before it returns; None stays None (no packing)."""
+        if lengths is None:
+            return None, None
+        if isinstance(lengths, torch.Tensor):
+            if lengths.is_cuda:
+                raise ValueError("lengths must live on the host (it sizes the launches); pass caption_lengths(caption_cpu)")
+            lengths = lengths.numpy()
+        import numpy as np
+        arr = np.ascontiguousarray(lengths, dtype=np.int32)
+        if arr.shape != (B,):
+            raise ValueError("lengths must have shape [{}], got {}".format(B, arr.shape))
+        return arr, arr.ctypes.data_as(C.c_void_p)
+
+    def train_forward(self, g, P, caption, want_logits: bool = False, lengths=None):
+        """capdec_train_fwd.  Returns (loss_buf[4] device tensor, logits or None).
+        lengths: optional HOST array [B] of non-padding token counts per caption (caption_lengths): the time-batched
+        head then runs on the rows that carry a target only -- same results, less work."""
         B = self._check_inputs(g, P, caption)
         self._ensure_bound()
         logits = None
         if want_logits:
             logits = torch.empty(B, self.cfg.train_steps, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
         self._caption_keepalive = (g, P, caption)
-        check(self.lib.capdec_train_fwd(self.handle, ptr(g), ptr(P), ptr(caption), B, ptr(logits), ptr(self._loss_buf),
-                                        stream_ptr()), "capdec_train_fwd")
+        arr, lp = self._host_lengths(lengths, B)
+        check(self.lib.capdec_train_fwd(self.handle, ptr(g), ptr(P), ptr(caption), lp, B, ptr(logits),
+                                        ptr(self._loss_buf), stream_ptr()), "capdec_train_fwd")
         return self._loss_buf, logits
 
     def train_backward(self, loss_scale: float = 1.0, inv_ntok: Optional[torch.Tensor] = None, want_dg: bool = True,
@@ -335,7 +353,7 @@ class CaptionDecoderEngine:
         self._staged = (enc_map, B)
         return P, g
 
-    def train_forward_map(self, enc_map, caption, want_logits: bool = False):
+    def train_forward_map(self, enc_map, caption, want_logits: bool = False, lengths=None):
         """_img2feature + teacher-forced forward from the encoder map (model:177-183 after the encoder)."""
         self.img2feature(enc_map)
         enc_map, B = self._staged
@@ -348,7 +366,8 @@ class CaptionDecoderEngine:
         if want_logits:
             logits = torch.empty(B, cfg.train_steps, cfg.vocab_size, dtype=torch.float32, device=self.device)
         self._caption_keepalive = (None, None, caption)
-        check(self.lib.capdec_train_fwd(self.handle, None, None, ptr(caption), B, ptr(logits), ptr(self._loss_buf),
+        arr, lp = self._host_lengths(lengths, B)
+        check(self.lib.capdec_train_fwd(self.handle, None, None, ptr(caption), lp, B, ptr(logits), ptr(self._loss_buf),
                                         stream_ptr()), "capdec_train_fwd")
         return self._loss_buf, logits
 
@@ -592,6 +611,19 @@ class ImageCaptionModel:
         loss used for training lives inside capdec_train_fwd)."""
         lp = torch.log_softmax(prediction, dim=-1)
         return -torch.gather(lp, -1, ground_true.unsqueeze(-1))
+
+
+def caption_lengths(caption, padding_idx: int = 0):
+    """Number of leading non-padding tokens of every caption [B,S] = [start, w.., stop, pad..]
+    (preprocess/ai_challenge_tokenizer.py:81-86), as the HOST int32 array `lengths` of capdec_train_fwd.  `caption` is the
+    host copy of the batch (CPU tensor or numpy array) -- the data loader has it before the upload."""
+    import numpy as np
+    c = caption.numpy() if isinstance(caption, torch.Tensor) else np.asarray(caption)
+    nz = c != padding_idx
+    # position after the last non-padding token (holes inside a caption are kept)
+    S = c.shape[1]
+    last = S - np.argmax(nz[:, ::-1], axis=1)
+    return np.where(nz.any(axis=1), last, 0).astype(np.int32)
 
 
 def filter_caption(ids, stop_idx=3, padding_idx=0):

@@ -35,7 +35,7 @@ class DataParallelTrainer:
         self.pe_semantics = pe_semantics
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
-    def forward_backward(self, g, P, caption, want_input_grads: bool = False, optimizer=None):
+    def forward_backward(self, g, P, caption, want_input_grads: bool = False, optimizer=None, lengths=None):
         """One data-parallel forward+backward on this rank's shard.  Returns the GLOBAL loss as a device tensor
         (no host sync).  After the call engine.store.flat_grad holds the all-reduced gradient.
 
@@ -43,11 +43,12 @@ class DataParallelTrainer:
         group by gradient group on the side stream, each as soon as the group is final (and all-reduced): the update of the
         head parameters runs beside the BPTT kernel, only the last small group's update is exposed."""
         eng = self.engine
-        return self._run(caption, lambda: eng.train_forward(g, P, caption)[0],
+        kw = {} if lengths is None else {"lengths": lengths}     # host token counts: the head runs on the live rows only
+        return self._run(caption, lambda: eng.train_forward(g, P, caption, **kw)[0],
                          lambda scale, inv: eng.train_backward(scale, inv, want_dg=want_input_grads,
                                                                want_dP=want_input_grads), extra=(), optimizer=optimizer)
 
-    def forward_backward_map(self, enc_map, caption, want_dmap: bool = False, optimizer=None):
+    def forward_backward_map(self, enc_map, caption, want_dmap: bool = False, optimizer=None, lengths=None):
         """The same from the encoder map (feature adaptor in front): additionally all-reduces
         engine.adaptor.flat_grad.  Returns (global loss, d enc_map of this rank's shard or None); the map gradient of a
         shard is already normalised by the global token count."""
@@ -57,7 +58,8 @@ class DataParallelTrainer:
         def bwd(scale, inv):
             out["dmap"] = eng.train_backward_map(scale, inv, want_dmap=want_dmap)
 
-        loss = self._run(caption, lambda: eng.train_forward_map(enc_map, caption)[0], bwd,
+        kw = {} if lengths is None else {"lengths": lengths}
+        loss = self._run(caption, lambda: eng.train_forward_map(enc_map, caption, **kw)[0], bwd,
                          extra=(eng.adaptor.flat_grad,), optimizer=optimizer)
         return loss, out.get("dmap")
 
