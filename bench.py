@@ -138,30 +138,45 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def load_ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu --set full
-    capture (profiles/r01_head_gemm_ncu.json, written by scripts/ncu_traffic.py); None if no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r01_head_gemm_ncu.json")
+def load_ncu_traffic_table():
+    """{phase: dram__bytes_read.sum + dram__bytes_write.sum per launch} of the kernels in the roofline table, from the
+    committed ncu --set full capture (profiles/r02_kernel_traffic.json, written by scripts/ncu_traffic.py); {} if none."""
+    path = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
     try:
-        return float(json.load(open(path))["dram_bytes_per_launch"])
+        return {k: float(v) for k, v in json.load(open(path)).items()}
     except Exception:
-        return None
+        return {}
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port of the reference's Paddle graph, timed on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(params, cfg, g, P, cap, adam_state):
-    """forward + autograd backward + the Adam update of every parameter (train.py:44-45), all on the host cores"""
+def cpu_reference_step(params, cfg, g, P, cap, adam_state, chunk=64):
+    """forward + autograd backward + the Adam update of every parameter (train.py:44-45), all on the host cores.
+    The batch goes through the oracle in chunks of `chunk` samples (samples are independent; the loss is
+    sum(ce * mask) / sum(mask) over the WHOLE batch, so every chunk back-propagates its loss sum over the global token
+    count and the gradients add up): the same arithmetic as one pass, with the autograd state of 64 instead of 256
+    samples alive at a time (2.6 GB instead of ~10 GB)."""
     from oracle import decoder_ref as R
     from oracle import train_ref as TR
-    _, _, _, grads = R.loss_and_grads(params, cfg, g, P, cap)
+    B = g.shape[0]
+    if B <= chunk:
+        _, _, _, grads = R.loss_and_grads(params, cfg, g, P, cap)
+    else:
+        ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        ntok = (cap[:, 1:] != cfg.padding_idx).sum().to(g.dtype)
+        for lo in range(0, B, chunk):
+            lg, _ = R.decoder_train(ps, cfg, g[lo:lo + chunk], P[lo:lo + chunk], cap[lo:lo + chunk, :-1])
+            _, loss_sum, _ = R.masked_loss(cfg, lg, cap[lo:lo + chunk])
+            (loss_sum / ntok).backward()
+        grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
     TR.adam_step_torch(params, grads, adam_state, lr=0.00005)
 
 
-def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
+def run_cpu_reference(steps, warmup, sample_B=B_PER_GPU, budget_s=None):
     """Times the oracle (PyTorch-CPU fp32, op-for-op the reference graph incl. the materialised [B,50,H] tensors,
-    Python loop over 34 steps, autograd backward) on all host threads.  Returns tokens/s and a description."""
+    Python loop over 34 steps for every sample -- the reference has no length input, SURVEY.md F5 -- autograd backward)
+    on all host threads, at the bench's own batch.  Returns tokens/s and a description."""
     from oracle import decoder_ref as R
     from oracle import synth
     torch.set_num_threads(os.cpu_count() or 1)
@@ -181,8 +196,8 @@ def run_cpu_reference(steps, warmup, sample_B=8, budget_s=None):
     dt = time.perf_counter() - t0
     return {"value": sample_B * cfg.train_steps * done / dt, "unit": UNIT, "cores": torch.get_num_threads(),
             "kind": "port", "ms_per_step": 1e3 * dt / done, "steps": done,
-            "sample": "oracle/decoder_ref.py fwd+bwd + oracle/train_ref.py Adam, batch %d x 34 steps, fp32, %d thread(s), %d step(s)"
-                      % (sample_B, torch.get_num_threads(), done)}
+            "sample": "oracle/decoder_ref.py fwd+bwd + oracle/train_ref.py Adam, batch %d x 34 steps (autograd in chunks of 64 "
+                      "samples), fp32, %d thread(s), %d step(s)" % (sample_B, torch.get_num_threads(), done)}
 
 
 def run_cpu_beam_reference(n_images=64, reps=2):
@@ -208,11 +223,12 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res = run_cpu_reference(args.steps, args.warmup, sample_B=32)
+    res = run_cpu_reference(args.steps, args.warmup, sample_B=args.reference_batch)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.gpus), sample="batch 32 per step (bounded sample of the B=256 workload)"),
+            "config": workload_config(args.gpus) if args.reference_batch == B_PER_GPU else
+            dict(workload_config(args.gpus), sample="batch %d per step (--reference-batch)" % args.reference_batch),
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "extras": {"beam_search_cpu": run_cpu_beam_reference()},
@@ -448,21 +464,122 @@ def main_ours(args):
     peaks = load_peaks()
     flops = 2.0 * Mh * Nh * Kh
     achieved = flops / (ms_gemm * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_tc_pair_kernel<A K-major,B MN-major> (tcgen05 cta_group::2, 256x256 tile per CTA pair) "
-                          "head fc M=%d N=%d K=%d bias+tanh" % (Mh, Nh, Kh),
-                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_burst"], "traffic": load_ncu_traffic(),
-                "peak_source": peaks["source"] + ", burst", "ms_per_launch": ms_gemm,
-                "algorithmic_flops_per_launch": flops, "l2": "8 rotating A/C buffer pairs, 285 MB > L2"}
+    head_isolated = {"kernel": "gemm_tc_pair_kernel<A K-major,B MN-major> (tcgen05 cta_group::2, 256x256 tile per CTA pair) "
+                               "head fc M=%d N=%d K=%d bias+tanh, timed alone back to back" % (Mh, Nh, Kh),
+                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_burst"], "us": 1e3 * ms_gemm, "algorithmic_flops": flops,
+                     "peak_source": peaks["source"] + ", burst", "l2": "8 rotating A/C buffer pairs, 285 MB > L2"}
+
+    # ---- per-kernel roofline table, timed LIVE inside the step: the library's phase timeline records CUDA events on the
+    # launching stream around these kernels while the bench's own step runs (stream order, warm caches, sustained clocks)
+    def phase_profile(fn, reps=5):
+        for i in range(2):
+            fn(i)
+        sync()
+        eng.profile(True)
+        for i in range(reps):
+            fn(i)
+        rep_ms = eng.profile_report()
+        eng.profile(False)
+        return {k: 1e3 * v / reps for k, v in rep_ms.items()}      # us per step
+
+    ph = phase_profile(step_resident)
+    ph_dec = phase_profile(lambda i: eng.decode(gi, Pi, beam=BEAM, finish_on_stop=True), reps=2)
+    Hh, Ee, Vv, kk, Tt = cfg.hidden_dim, cfg.embedding_size, cfg.vocab_size, cfg.num_positions, cfg.train_steps
+    Vp = (Vv + 127) // 128 * 128
+    Mrows, Mlive = B * Tt, int(ntok_nonpad)                          # all rows / rows that carry a target (the head's rows)
+    traffic_db = load_ncu_traffic_table()
+
+    def entry(key, kernel, bound, work, us, unit_scale, peak, unit, what):
+        ach = work / (us * 1e-6) / unit_scale if us and us > 0 else None
+        return {"phase": key, "kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                "frac": (ach / peak) if ach else None, "us": us, "algorithmic_work": work, "work_is": what,
+                "traffic": traffic_db.get(key)}
+
+    TF, GB = 1e12, 1e9
+    sus, hbm = peaks["bf16_sustained"], peaks["hbm_gbs"]
+    mufu_peak = 16.0 * 148 * 1.965e9 / 1e9                           # MUFU ops / ns: 16 per clock per SM at 1965 MHz
+    kernels = [
+        entry("bwd.recurrence", "lstm_seq_bwd_kernel (persistent, all 34 BPTT steps: d h = d gates . W_hh^T + cell backward)",
+              "tensor", 2.0 * B * Hh * 4 * Hh * (Tt - 1), ph.get("bwd.recurrence"), TF, sus, "TFLOP/s",
+              "2*B*H*4H flops x 33 steps"),
+        entry("fwd.recurrence", "lstm_seq_fwd_kernel (persistent, all 34 steps: gates = h . W_hh, cell in the MMA epilogue)",
+              "tensor", 2.0 * B * Hh * 4 * Hh * Tt, ph.get("fwd.recurrence"), TF, sus, "TFLOP/s", "2*B*H*4H flops x 34 steps"),
+        entry("fwd.xe_gemm", "gemm_tc_pair_kernel short-K variant: x-part pre-activations M=%d N=5H K=E" % Mrows, "tensor",
+              2.0 * Mrows * Ee * 5 * Hh, ph.get("fwd.xe_gemm"), TF, sus, "TFLOP/s", "2*M*E*5H flops"),
+        entry("fwd.out_proj_vocab", "gemm_tc_pair_kernel short-K variant: fp32 logits M=%d N=V K=E (output-write bound: 128 "
+              "flop per byte written < the 212 flop/B ridge)" % Mlive, "hbm", 4.0 * Mlive * Vp + 2.0 * (Mlive + Vv) * Ee,
+              ph.get("fwd.out_proj_vocab"), GB, hbm, "GB/s", "fp32 logits written + bf16 operands read"),
+        entry("fwd.cross_entropy", "ce_fused_kernel (online log-sum-exp + d logits)", "hbm",
+              4.0 * Mlive * Vv + 2.0 * Mlive * Vp, ph.get("fwd.cross_entropy"), GB, hbm, "GB/s",
+              "fp32 logits read + bf16 d logits written"),
+        entry("fwd.attention", "attn_scores_kernel + attn_sadd + batched context GEMM + gather (phase)", "mufu",
+              1.0 * Mlive * (kk + 1) * Hh, ph.get("fwd.attention"), 1e9, mufu_peak, "Gtanh/s",
+              "one MUFU.TANH per (row, position, column)"),
+        entry("dec.beam_topk", "beam_rows_kernel<49> + beam_merge_kernel, 35 steps of %d rows" % (BEAM_IMAGES_PER_GPU * BEAM),
+              "hbm", 4.0 * BEAM_IMAGES_PER_GPU * BEAM * Vv * cfg.infer_max_length, ph_dec.get("dec.beam_topk"), GB, hbm,
+              "GB/s", "fp32 logits of every row read once per step"),
+        entry("dec.attention", "attn_scores_kernel + attn_ctx_small_kernel, 35 steps", "hbm",
+              2.0 * 2 * BEAM_IMAGES_PER_GPU * kk * Hh * cfg.infer_max_length, ph_dec.get("dec.attention"), GB, hbm, "GB/s",
+              "bf16 keys + values of every image read once per step"),
+    ]
+    # the `roofline` object of the line = the longest single kernel of the train step (hbm / tensor bound), with the table
+    main = max((e for e in kernels if e["bound"] in ("hbm", "tensor") and e["phase"].split(".")[0] in ("fwd", "bwd")
+                and e["us"]), key=lambda e: e["us"])
+    roofline = {"kernel": main["kernel"], "bound": main["bound"], "achieved": main["achieved"], "peak": main["peak"],
+                "unit": main["unit"], "frac": main["frac"], "traffic": main["traffic"],
+                "peak_source": peaks["source"] + (", sustained (timed inside the step)" if main["bound"] == "tensor" else ""),
+                "ms_per_launch": main["us"] * 1e-3, "algorithmic_work_per_launch": main["algorithmic_work"],
+                "work_is": main["work_is"], "timed": "CUDA events on the launching stream around the kernel, inside the "
+                "bench step (capdec_profile), average of 5 steps", "kernels": kernels, "head_fc_isolated": head_isolated}
     # whole-step view: algorithmic GEMM flops of one train step over the measured step time
     step_flops = 116.7e6 * B * cfg.train_steps + 616.6e6 * B
     step_tflops = step_flops / (ms / args.steps * 1e-3) / 1e12
 
+    # ---- sustained: >= 5 s of back-to-back steps (the timed region above lasts tens of milliseconds: a burst), with the
+    # clocks sampled inside it ----
+    n_sus = int(5500.0 / (ms / args.steps)) + 1
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks_s:
+        for i in range(3):
+            step_resident(i)
+        with clocks_s.window():
+            ms_sus = timed_region(step_resident, n_sus, sync, barrier)
+    clk_sus = clocks_s.summary()
+
+    # ---- data-parallel parity (N > 1): the all-reduced shard gradients against ONE full-batch step on the same weights,
+    # computed locally on rank 0 from the gathered shards (train.py:119-127 is what the
+    # data-parallel wrapper replaces) ----
+    dp_parity = None
+    if world > 1:
+        eng.store.init_reference(0)
+        eng.bind_params()
+        loss_dp = trainer.forward_backward(g_d, P_d, cap_d, lengths=lengths_h)
+        sync()
+        grad_dp = eng.store.flat_grad.clone()
+        gathered = []
+        for x in (g_d, P_d, cap_d):
+            parts = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(parts, x)
+            gathered.append(torch.cat(parts, 0))
+        if rank == 0:
+            lb, _ = eng.train_forward(gathered[0], gathered[1], gathered[2], lengths=M.caption_lengths(gathered[2].cpu()))
+            eng.train_backward(want_dg=False, want_dP=False)
+            sync()
+            ref = eng.store.flat_grad.double()
+            dp_parity = {"flat_grad_rel_err": float((grad_dp.double() - ref).norm() / ref.norm()),
+                         "flat_grad_max_err_over_max": float((grad_dp.double() - ref).abs().max() / ref.abs().max()),
+                         "loss_rel_diff": abs(float(loss_dp) - float(lb[2])) / abs(float(lb[2])),
+                         "global_batch": int(gathered[0].shape[0]),
+                         "what": "all-reduced gradient of %d shards vs one local step at the global batch, bf16 storage "
+                                 "(the split changes the fp32 summation order and the bf16 rounding points)" % world}
+        del gathered
+        barrier()
+
     # max over ranks of the device times
-    t = torch.tensor([ms, ms_e2e, ms_beam, ms_full, ms_all_rows], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_beam, ms_full, ms_all_rows, ms_sus], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_beam, ms_full, ms_all_rows = (float(x) for x in t.cpu())
+    ms, ms_e2e, ms_beam, ms_full, ms_all_rows, ms_sus = (float(x) for x in t.cpu())
     tokens_per_step = world * B * cfg.train_steps
     value = tokens_per_step * args.steps / (ms * 1e-3)
     e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
@@ -470,7 +587,7 @@ def main_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = run_cpu_reference(steps=1000, warmup=1, sample_B=32, budget_s=15.0)
+        res = run_cpu_reference(steps=1000, warmup=1, sample_B=B, budget_s=15.0)
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu_baseline["beam_search"] = run_cpu_beam_reference()      # the secondary metric's CPU figure (images/s)
 
@@ -485,6 +602,9 @@ def main_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "extras": {"nonpad_tokens_per_sec": world * ntok_nonpad * args.steps / (ms * 1e-3),
                            "live_rows_per_gpu": int(ntok_nonpad), "rows_per_gpu": B * cfg.train_steps,
+                           "sustained": {"seconds": ms_sus * 1e-3, "steps": n_sus, "ms_per_step": ms_sus / n_sus,
+                                         "tokens_per_sec": tokens_per_step * n_sus / (ms_sus * 1e-3), "clocks": clk_sus},
+                           "dp_parity": dp_parity,
                            "without_lengths": {"ms_per_step": ms_all_rows / args.steps,
                                                "tokens_per_sec": tokens_per_step * args.steps / (ms_all_rows * 1e-3),
                                                "note": "the same step with lengths=NULL: all B x 34 rows through the head"},
@@ -519,6 +639,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-batch", type=int, default=B_PER_GPU,
+                    help="batch of the --impl reference arm (default: the bench's own 256; the CPU contract test uses a smaller one)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

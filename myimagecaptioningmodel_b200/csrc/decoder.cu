@@ -452,6 +452,7 @@ template <typename T> class Decoder : public DecoderBase {
       // per-image term is added by the GEMM epilogue (row-broadcast addend, row m -> m % B).
       OK(g5b.ensure(e * (size_t)B * 5 * H, &ws_bytes));
       OK(fc(gc, gT.p, H, w_g_p.as<T>(), 5 * H, b5p.as<float>(), g5b.p, 5 * H, B, 5 * H, H, ACT_NONE));
+      prof.mark("fwd.embed_g5", s);
       GemmCall c;
       c.A = embx.p; c.lda = E; c.B = w_x_p.p; c.ldb = 5 * H; c.b_mn = true; c.C = xe.p; c.ldc = 5 * H; c.M = (int)M;
       c.N = 5 * H; c.K = E; c.epi.addend = g5b.p; c.epi.ld_add = 5 * H; c.epi.add_mod = B;
@@ -462,10 +463,10 @@ template <typename T> class Decoder : public DecoderBase {
       // ... and the global-image columns (+ biases) once per image
       OK(fc(gc, gT.p, H, w_g_n.as<T>(), 5 * H, b5.as<float>(), g5.p, 5 * H, B, 5 * H, H, ACT_NONE, true));
     }
-    prof.mark("fwd.embed_xe_g5", s);
     // recurrent core (model:63, 87-88, 94-95)
     CUDA_OK(cudaMemsetAsync(hs.p, 0, e * (size_t)B * H, s));
     CUDA_OK(cudaMemsetAsync(cs.p, 0, 4 * (size_t)B * H, s));
+    prof.mark("fwd.xe_gemm", s);
     if constexpr (std::is_same<T, bf16>::value) {
       if (persistent) {
         // all T steps in one persistent kernel: W_hh resident in shared memory, cell fused into the MMA epilogue
@@ -525,6 +526,7 @@ template <typename T> class Decoder : public DecoderBase {
     OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, Mh, H, H, ACT_TANH));                          // model:115
     OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, Mh, E, H, ACT_NONE));                          // model:24
     CUDA_OK(cudaMemsetAsync(acc.p, 0, 64, s));
+    prof.mark("fwd.out_fc", s);
     OK(logits.ensure(4 * M * (size_t)Vp, &ws_bytes));
     {
       // Logits stay fp32 also on the bf16 path.  (Measured and dropped: bf16 logit storage -- 42 us faster, but soft-max
@@ -541,10 +543,11 @@ template <typename T> class Decoder : public DecoderBase {
     // so the logits leave HBM only once
     ce_fused<T>(lc, logits.as<float>(), Vp, V, Vp, cap, S, B, Tt, cfg.padding_idx, lse.as<float>(), acc.as<float>(),
                 dlogits.as<T>(), err_flag, Mp, d_pm);
+    prof.mark("fwd.cross_entropy", s);
     loss_finalize(lc, acc.as<float>());
     if (logits_out) logits_to_batch_major(lc, logits.as<float>(), Vp, V, B, Tt, logits_out);          // model:129-130
     if (loss_out) CUDA_OK(cudaMemcpyAsync(loss_out, acc.p, 16, cudaMemcpyDeviceToDevice, s));
-    prof.mark("fwd.cross_entropy", s);
+    prof.mark("fwd.loss_out", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     have_fwd = true;
@@ -912,10 +915,11 @@ template <typename T> class Decoder : public DecoderBase {
         beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
                   score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
                   d_trace.as<int>() + (size_t)step * R * 2);
+        prof.mark("dec.beam_topk", rs);
         if (step + 1 < Ti)
           beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
                           xin.as<T>(), X, d_ccur.as<float>());
-        prof.mark("dec.beam_step_reorder", rs);
+        prof.mark("dec.reorder", rs);
       }
       return 0;
     };

@@ -19,7 +19,7 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--reference-batch", "96"])   # > one autograd chunk
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -29,6 +29,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("teacher_forced_train_step_B256")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "Adam" in cb["sample"]
+    assert "batch 96" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
