@@ -146,7 +146,10 @@ __device__ __forceinline__ void init_bars(const Bars& b, uint32_t epi_arrivals) 
 // ================================================================================================================
 // forward
 // ================================================================================================================
-constexpr int kFwdStages = 4;
+#ifndef CAPDEC_FWD_STAGES
+#define CAPDEC_FWD_STAGES 4   // h-tile ring depth (build-time: profiling experiments vary it)
+#endif
+constexpr int kFwdStages = CAPDEC_FWD_STAGES;
 constexpr int kFwdEpiWarps = 8;   // two per TMEM lane quarter: 8 of the CTA's 16 hidden units each
 constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
 constexpr int kFwdThreads = 64 + kFwdEpiThreads;
@@ -391,7 +394,10 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
 // ================================================================================================================
 // backward
 // ================================================================================================================
-constexpr int kBwdStages = 4;
+#ifndef CAPDEC_BWD_STAGES
+#define CAPDEC_BWD_STAGES 4
+#endif
+constexpr int kBwdStages = CAPDEC_BWD_STAGES;
 constexpr int kBwdN = 128;                  // output hidden units per CTA
 constexpr int kBwdKb = 8;                   // k-blocks per CTA (512 of the 4H gate columns)
 constexpr int kBwdWTile = kBwdN * BK * 2;   // 16 KB
