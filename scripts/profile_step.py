@@ -17,17 +17,19 @@ ap.add_argument("--beam", type=int, default=3)
 ap.add_argument("--axis", default="position")
 ap.add_argument("--no-train", action="store_true")
 ap.add_argument("--from-map", action="store_true", help="widened step: feature adaptor in front, Adam behind")
+ap.add_argument("--no-lengths", action="store_true", help="all B x 34 rows through the head (no packed rows)")
 args = ap.parse_args()
 
 cfg = M.DecoderConfig(dtype="bf16", softmax_axis=args.axis)
 eng = M.CaptionDecoderEngine(cfg, seed=0)
 g, P, cap = synth.make_batch(cfg, args.batch, 20260)
+lengths = None if args.no_lengths else M.caption_lengths(cap)
 g, P, cap = g.cuda(), P.cuda(), cap.cuda()
 
 
 def step():
     eng.bind_params()
-    eng.train_forward(g, P, cap)
+    eng.train_forward(g, P, cap, lengths=lengths)
     eng.train_backward(want_dg=True, want_dP=True)
 
 
@@ -39,7 +41,7 @@ if args.from_map:
     def step():  # noqa: F811
         eng.bind_params()
         eng.bind_adaptor()
-        eng.train_forward_map(x, cap)
+        eng.train_forward_map(x, cap, lengths=lengths)
         eng.train_backward_map(want_dmap=True)
         opt.step()
 

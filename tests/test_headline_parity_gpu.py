@@ -296,8 +296,9 @@ def test_lstm_cell_fwd_matches_paddle_lstm_unit(dtype, R_, H):
     td = torch.float32 if dtype == "fp32" else torch.bfloat16
     h_out = torch.empty(R_, H, dtype=td, device="cuda")
     c_out = torch.empty(R_, H, dtype=torch.float32, device="cuda")
-    _capi.check(lib.capdec_lstm_cell_fwd(_capi.DTYPE_F32 if dtype == "fp32" else _capi.DTYPE_BF16, R_, H, vp(pre.cuda()),
-                                         vp(c_prev.cuda()), vp(h_out), vp(c_out), _capi.stream_ptr()),
+    pre_d, c_prev_d = pre.cuda(), c_prev.cuda()          # named: the device copies must outlive the launch
+    _capi.check(lib.capdec_lstm_cell_fwd(_capi.DTYPE_F32 if dtype == "fp32" else _capi.DTYPE_BF16, R_, H, vp(pre_d),
+                                         vp(c_prev_d), vp(h_out), vp(c_out), _capi.stream_ptr()),
                 "capdec_lstm_cell_fwd")
     torch.cuda.synchronize()
     # fp32 storage: libm tanh / exp; bf16 storage: MUFU tanh.approx (abs err ~5e-4) and a bf16 h
