@@ -244,3 +244,8 @@ def load_persistables(dirname: str, engine, optimizer=None, names: Optional[Dict
         if sched.strategy == "cosine_decay_restart_warmup" and os.path.isfile(ce):
             sched._epoch_counter = float(read_lod_tensor(ce)[0])
             sched._last_n = optimizer.steps - 1
+    elif begin is None and float(optimizer.beta1_pow) > 0.0 and hasattr(optimizer, "beta1"):
+        # constant learning rate (util.py:44-45): the graph has no step counter; the number of updates taken is what the
+        # Beta1Pow accumulator encodes (beta1^(n+1) after n updates) -- only our own bookkeeping needs it
+        import math
+        optimizer.steps = max(0, int(round(math.log(float(optimizer.beta1_pow)) / math.log(optimizer.beta1))) - 1)

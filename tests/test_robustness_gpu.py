@@ -31,7 +31,7 @@ def test_optimizer_updates_rebind_the_handle(from_map):
     old weights silently."""
     cfg = M.DecoderConfig(dtype="bf16", softmax_axis="position", **MID)
     g, P, cap = synth.make_batch(cfg, 12, 5)
-    x = synth.make_encoder_map(cfg, 12, 64, 6).cuda()
+    x = M.synth.make_encoder_map(cfg, 12, 64, 6).cuda()
     gd, Pd, capd = g.cuda(), P.cuda(), cap.cuda()
     losses = {}
     for manual in (False, True):
@@ -87,10 +87,11 @@ def test_token_ids_outside_the_vocabulary_are_reported_not_dereferenced(dtype):
     bad[1, 2] = ocfg.vocab_size          # read as source token at step 2 and as target at step 1
     bad[4, 3] = -5
     eng.train_forward(gd, Pd, bad.cuda())
-    eng.train_backward()
     with pytest.raises(_capi.CapdecError) as ei:
-        eng.check_status()
+        eng.check_status()                # synchronises; without it the NEXT call on the handle reports (below)
     assert "vocab_size" in str(ei.value) and "target" in str(ei.value)
+    eng.train_backward()
+    eng.check_status()
     assert torch.isfinite(eng.store.flat_grad).all()
     # the offending entries were treated as padding: same result as the caption with those entries zeroed
     asp = cap.clone()
@@ -98,11 +99,12 @@ def test_token_ids_outside_the_vocabulary_are_reported_not_dereferenced(dtype):
     asp[4, 3] = 0
     eng.check_status()                    # the report was cleared by being returned
     lb = eng.train_forward(gd, Pd, bad.cuda())[0].clone()
-    eng.train_backward()
+    torch.cuda.synchronize()
+    with pytest.raises(_capi.CapdecError):        # ... and the NEXT call on the handle reports it without a status call
+        eng.train_backward()
+    eng.train_backward()                          # reported once; the step itself is intact
     torch.cuda.synchronize()
     gb = eng.store.flat_grad.clone()
-    with pytest.raises(_capi.CapdecError):        # ... and the NEXT call on the handle reports it without a status call
-        eng.train_forward(gd, Pd, asp.cuda())
     la = eng.train_forward(gd, Pd, asp.cuda())[0].clone()
     eng.train_backward()
     eng.check_status()
