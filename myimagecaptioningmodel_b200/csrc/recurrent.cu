@@ -15,10 +15,9 @@
 //             accumulator in TMEM, and the epilogue warps apply the cell (i,f,o,g; c,h) straight from TMEM and write
 //             h_t (bf16), c_t (fp32) and the gate activations.  One barrier per step.
 //   backward: d h_{t-1} = d gates_t . W_hh^T contracts over 4H, so a column partition would stream 1 MB per CTA and
-//             step; instead CTA (n, ks) owns a [64 units x 512 k] slice of W_hh (K-major B, 64 KB resident), adds its
+//             step; instead CTA (n, ks) owns a [128 units x 512 k] slice of W_hh (K-major B, 128 KB resident), adds its
 //             partial product into a ping-pong fp32 d h buffer by TMA reduce-add, and the cell backward runs as a
-//             second phase spread over all CTAs.  Two arrival counters per step AND batch tile: the tiles are
-//             independent recurrences and every CTA works on all of them, so the waits of one hide behind the other.
+//             second phase spread over all CTAs.  Two barriers per step.
 #include <cuda.h>
 
 #include <algorithm>
@@ -85,9 +84,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_3() { asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); }
 
 // UMMA shared-memory descriptors, SWIZZLE_128B (same encoding as gemm_tc.cu)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -170,7 +166,7 @@ struct SeqFwdParams {
   int n_mtiles;
   bf16* hs;                     // [(T+1)*B, H]  hs[0] = h_0 (zeros)
   const float* cs;              // [(T+1)*B, H]  cs[0] = c_0 (zeros); written through the tensor map
-  unsigned* ctr;                // [n_mtiles]    arrival counters, one per batch tile (zeroed by the host)
+  unsigned* ctr;                // [gridDim.y]   arrival counters (zeroed by the host)
   unsigned long long* trace;    // debug timeline or nullptr
 };
 
@@ -196,8 +192,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint8_t* wsm = smem;                                  // nkb x 8 KB   resident weight slice
   uint8_t* stages = wsm + (size_t)nkb * kFwdWTile;      // kFwdStages x 16 KB   h tiles
   uint8_t* x_stage = stages + kFwdStages * kATile;      // 16 KB (1024-aligned)
-  uint8_t* c_stage = x_stage + kFwdXStage;              // 2 x 8 KB: c_t of the (up to two) batch tiles kept on chip
-  const Bars bar = carve_bars<kFwdStages>(c_stage + 2 * kFwdCStage);
+  uint8_t* c_stage = x_stage + kFwdXStage;              // 8 KB
+  const Bars bar = carve_bars<kFwdStages>(c_stage + kFwdCStage);
   uint64_t* x_full = bar.go;                            // the x tile of the next batch tile has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,14 +221,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < p.T; ++t) {
+        if (t > 0) {
+          spin_until(p.ctr + y, (unsigned)t * (unsigned)G);  // every CTA of this batch group has written its h_t slice
+          fence_proxy_async_all();                            // generic-proxy writes -> async-proxy (TMA) reads
+        }
+        rec_trace(p.trace, p.T, t, 0);
         for (int mt = y; mt < p.n_mtiles; mt += MG) {
-          if (t > 0) {
-            // every slice CTA has written its part of h_t of THIS batch tile.  The tiles of a CTA are independent
-            // recurrences: while one waits here (and in its epilogue), the MMAs of the other run
-            spin_until(p.ctr + mt, (unsigned)t * (unsigned)G);
-            fence_proxy_async_all();                          // generic-proxy writes -> async-proxy (TMA) reads
-          }
-          if (mt == y) rec_trace(p.trace, p.T, t, 0);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait_b(&bar.empty[s], ph ^ 1);
             mbar_expect_tx(&bar.full[s], kATile);
@@ -284,11 +278,11 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     const long BH = (long)p.B * p.H;
     const int trow = quarter * 32 + lane;  // row of the 128-row tile = TMEM lane
     uint8_t* x_row = x_stage + trow * 128;
+    uint8_t* c_row = c_stage + trow * 64 + hh * 32;
     const uint32_t swz = (uint32_t)(lane & 7);
-    // c_{t-1} of this thread's row: with at most two batch tiles per CTA it is still in the tile's c staging slot from the
-    // previous step; otherwise it is read back from global memory once the tensor stores that wrote it have completed
-    const int tiles_here = (p.n_mtiles - y + MG - 1) / MG;
-    const bool single_tile = (tiles_here <= 2);
+    // c_{t-1} of this thread's row: with one batch tile per CTA it is still in the c staging tile of the previous
+    // step; otherwise it is read back from global memory once the tensor stores that wrote it have completed
+    const bool single_tile = (MG >= p.n_mtiles);
     if (et == 0) {  // x tile of the first (step, batch tile)
       mbar_expect_tx(x_full, kFwdXStage);
       tma_load_3d(x_stage, &tmX, 4 * u0, y * 128, 0, x_full);
@@ -306,8 +300,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         const int buf = it & 1;
         const int row = mt * 128 + trow;
         const bool row_ok = row < p.B;
-        uint8_t* c_tile = c_stage + (single_tile ? ((mt - y) / MG) * kFwdCStage : 0);
-        uint8_t* c_row = c_tile + trow * 64 + hh * 32;
         float cp[8];
         if (t > 0 && single_tile) {
           load8(reinterpret_cast<const float*>(c_row), cp);
@@ -359,20 +351,21 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
-        const bool release = (t + 1 < p.T);
+        const bool last_tile = (mt + MG >= p.n_mtiles);
+        const bool release = (t + 1 < p.T) && last_tile;
         if (t + 1 < p.T) __threadfence();  // this thread's h_t stores are performed at GPU scope
         fence_proxy_async_all();            // staging writes -> async proxy
         if (et == 0) rec_trace(p.trace, p.T, t, 5);
         fwd_bar_sync();
         if (et == 0) {
           if (release) {
-            // release this CTA's slice of h_t of batch tile mt to the other slice CTAs
+            // release h_t of this CTA's slice to the other CTAs of the batch group
             rec_trace(p.trace, p.T, t, 6);
             __threadfence();
-            atomicAdd(p.ctr + mt, 1u);
+            atomicAdd(p.ctr + y, 1u);
             rec_trace(p.trace, p.T, t, 7);
           }
-          tma_store_3d(&tmCs, c_tile, u0, mt * 128, t + 1);
+          tma_store_3d(&tmCs, c_stage, u0, mt * 128, t + 1);
           tma_store_3d(&tmGa, x_stage, 4 * u0, mt * 128, t);
           bulk_commit();
           // next (step, batch tile) of this CTA: its x tile goes into the same buffer once the store has read it
@@ -405,10 +398,10 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
 #define CAPDEC_BWD_STAGES 4
 #endif
 constexpr int kBwdStages = CAPDEC_BWD_STAGES;
-constexpr int kBwdN = 64;                   // output hidden units per CTA
+constexpr int kBwdN = 128;                  // output hidden units per CTA
 constexpr int kBwdKb = 8;                   // k-blocks per CTA (512 of the 4H gate columns)
-constexpr int kBwdWTile = kBwdN * BK * 2;   // 8 KB
-constexpr int kBwdEpiWarps = 8;             // two per TMEM lane quarter: one 32-column half of the accumulator each
+constexpr int kBwdWTile = kBwdN * BK * 2;   // 16 KB
+constexpr int kBwdEpiWarps = 8;             // two per TMEM lane quarter: half of the accumulator columns each
 constexpr int kBwdEpiThreads = kBwdEpiWarps * 32;
 constexpr int kBwdThreads = 64 + kBwdEpiThreads;
 __device__ __forceinline__ void bwd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpiThreads) : "memory"); }
@@ -424,8 +417,8 @@ struct SeqBwdParams {
   bf16* dG; long ld_dg;  // [T*B, ld_dg] cols gate*H + unit
   float* dhrec;          // [2, B, H] ping-pong d h through the gates (zeroed by the host)
   float* dcrec;          // [B, H]    running d c (zeroed by the host)
-  unsigned* ctr_c;       // [n_mtiles] cell phases completed, per batch tile
-  unsigned* ctr_g;       // [n_mtiles] GEMM phases completed, per batch tile
+  unsigned* ctr_c;       // [gridDim.y] cell phases completed
+  unsigned* ctr_g;       // [gridDim.y] GEMM phases completed
   unsigned long long* trace;
 };
 
@@ -546,11 +539,6 @@ __device__ __forceinline__ void cell_store_state(const SeqBwdParams& p, int t, b
   }
 }
 
-// Every CTA works on ALL batch tiles, and every tile has its own pair of arrival counters: the tiles are independent
-// recurrences, so while the slice CTAs wait for each other on tile 0 (cell phase complete -> GEMM may start; all partial
-// products reduced -> next cell phase may start) the same CTAs compute on tile 1.  Per step and tile a CTA runs, in program
-// order:  C(t, 0), C(t, 1), ..  then the GEMM epilogues  G(t, 0), G(t, 1), ..; the producer / MMA warps run ahead as far as
-// the counters allow.  (First version: one CTA group per tile, two grid-wide barriers per step exposed: 12.4 us per step.)
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, SeqBwdParams p) {
@@ -558,15 +546,15 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + misalign;
-  uint8_t* wsm = smem;                                   // 8 x 8 KB   resident W_hh slice [64 units x 512 k]
+  uint8_t* wsm = smem;                                   // 8 x 16 KB   resident W_hh slice [128 units x 512 k]
   uint8_t* stages = wsm + kBwdKb * kBwdWTile;            // kBwdStages x 16 KB   d gates tiles
-  uint8_t* staging = stages + kBwdStages * kATile;       // 8 warps x 2 x 4 KB  epilogue tiles (32 rows x 128 B)
-  const Bars bar = carve_bars<kBwdStages>(staging + kBwdEpiWarps * 2 * 4096);
+  uint8_t* staging = stages + kBwdStages * kATile;       // 8 warps x 4 KB  epilogue tiles (32 rows x 128 B)
+  const Bars bar = carve_bars<kBwdStages>(staging + kBwdEpiWarps * 4096);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KS = p.H / 128;  // = 4H / 512 k-slices
-  const int cta = blockIdx.x, G = gridDim.x;
-  const int ns = cta / KS, ks = cta % KS;   // unit slice [64 ns, +64), gate-column slice [512 ks, +512)
+  const int KS = p.H / 128;  // = 4H / 512 k-slices, and H / 128 unit slices
+  const int cta = blockIdx.x, y = blockIdx.y, G = gridDim.x, MG = gridDim.y;
+  const int ns = cta / KS, ks = cta % KS;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -589,30 +577,30 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int t = p.T - 1, i = 0; t > 0; --t, ++i) {
-        for (int mt = 0; mt < p.n_mtiles; ++mt) {
-          spin_until(p.ctr_c + mt, (unsigned)(i + 1) * (unsigned)G);  // d gates_t of this batch tile is complete
-          fence_proxy_async_all();
-          if (mt == 0) rec_trace(p.trace, p.T, t, 3);
+        spin_until(p.ctr_c + y, (unsigned)(i + 1) * (unsigned)G);  // d gates_t of this batch group is complete
+        fence_proxy_async_all();
+        rec_trace(p.trace, p.T, t, 3);
+        for (int mt = y; mt < p.n_mtiles; mt += MG) {
           for (int kb = 0; kb < kBwdKb; ++kb) {
             mbar_wait_b(&bar.empty[s], ph ^ 1);
             mbar_expect_tx(&bar.full[s], kATile);
             tma_load_3d(stages + s * kATile, &tmA, ks * (kBwdKb * BK) + kb * BK, mt * 128, t, &bar.full[s]);
             if (++s == kBwdStages) { s = 0; ph ^= 1; }
           }
-          if (mt == 0) rec_trace(p.trace, p.T, t, 4);
         }
+        rec_trace(p.trace, p.T, t, 4);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====  D[128 x 64 units] += dgates_tile[128 x 64k] . W_slice[64 units x 64k]^T
+      // ===== MMA issuer =====  D[128 x 128 units] += dgates_tile[128 x 64k] . W_slice[128 units x 64k]^T
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBwdN >> 3) << 17) |
                                  ((uint32_t)(128 >> 4) << 24);
       mbar_wait_b(bar.w_bar, 0);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = p.T - 1; t > 0; --t) {
-        for (int mt = 0; mt < p.n_mtiles; ++mt, ++it) {
+        for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
           const int buf = it & 1;
           mbar_wait_b(&bar.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -635,96 +623,90 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ===== cell backward (phase C) and GEMM epilogue (phase G) =====
     const int quarter = warp & 3;          // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;      // which 32-column half of the accumulator
+    const int half = (warp - 2) >> 2;      // which half of the accumulator columns
     const int et = threadIdx.x - 64;       // 0..255
+    uint8_t* my_stage = staging + (warp - 2) * 4096;
+    uint8_t* st_row = my_stage + lane * 128;
     const uint32_t swz = (uint32_t)(lane & 7);
-    const int items = 128 * (p.H / 8);
     int it = 0;
     for (int t = p.T - 1, i = 0; t >= 0; --t, ++i) {
-      const bool last = (t == p.T - 1);
-      // ---- phase C: d gates_t, d c_{t-1}, tile after tile ----
-      for (int mt = 0; mt < p.n_mtiles; ++mt) {
-        if (i > 0) {
-          if (et == 0) {
-            spin_until(p.ctr_g + mt, (unsigned)i * (unsigned)G);  // every partial product of d h_t of this tile has been added
-            __threadfence();
-          }
-          bwd_bar_sync();
+      // ---- phase C: d gates_t, d c_{t-1} ----
+      if (i > 0) {
+        if (et == 0) {
+          spin_until(p.ctr_g + y, (unsigned)i * (unsigned)G);  // every partial product of d h_t has been added
+          __threadfence();
         }
-        if (et == 0 && mt == 0) rec_trace(p.trace, p.T, t, 0);
-        // the items of consecutive tiles go to different halves of the grid (a tile has items for half of the threads)
-        const int cta_rot = (cta + mt * ((G + 1) / 2)) % G;
-        CellItem ia;
-        for (int i0 = cta_rot * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) {
+        bwd_bar_sync();
+      }
+      if (et == 0) rec_trace(p.trace, p.T, t, 0);
+      const bool last = (t == p.T - 1);
+      const int items = 128 * (p.H / 8);
+      CellItem ia;
+      for (int mt = y; mt < p.n_mtiles; mt += MG) {
+        for (int i0 = cta * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) {
           cell_load(p, t, mt, i0, last, ia);
           cell_compute_store_dg(p, last, ia);
           cell_store_state(p, t, last, ia);
         }
-        if (t > 0) {
-          __threadfence();  // every thread: its d gates (and d h zeroing) stores are performed at GPU scope
-          if (et == 0 && mt == 0) rec_trace(p.trace, p.T, t, 1);
-          bwd_bar_sync();
-          if (et == 0) {
-            __threadfence();
-            atomicAdd(p.ctr_c + mt, 1u);
-            if (mt == 0) rec_trace(p.trace, p.T, t, 2);
-          }
+      }
+      if (t > 0) {
+        __threadfence();  // every thread: its d gates (and d h zeroing) stores are performed at GPU scope
+        if (et == 0) rec_trace(p.trace, p.T, t, 1);
+        bwd_bar_sync();
+        if (et == 0) {
+          __threadfence();
+          atomicAdd(p.ctr_c + y, 1u);
+          rec_trace(p.trace, p.T, t, 2);
         }
       }
       if (t == 0) break;
       // next step's cell operands on their way from HBM to L2 while the GEMM phase runs
-      for (int mt = 0; mt < p.n_mtiles; ++mt) {
-        const int cta_rot = (cta + mt * ((G + 1) / 2)) % G;
-        for (int i0 = cta_rot * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) cell_prefetch(p, t - 1, mt, i0);
-      }
-      // ---- phase G epilogue: partial d h_{t-1} -> fp32 reduce-add into dhrec[(t-1) & 1], tile after tile ----
-      for (int mt = 0; mt < p.n_mtiles; ++mt, ++it) {
+      for (int mt = y; mt < p.n_mtiles; mt += MG)
+        for (int i0 = cta * kBwdEpiThreads + et; i0 < items; i0 += G * kBwdEpiThreads) cell_prefetch(p, t - 1, mt, i0);
+      // ---- phase G epilogue: partial d h_{t-1} -> fp32 reduce-add into dhrec[(t-1) & 1] ----
+      for (int mt = y; mt < p.n_mtiles; mt += MG, ++it) {
         const int buf = it & 1;
-        uint8_t* my_stage = staging + ((warp - 2) * 2 + (it & 1)) * 4096;
-        uint8_t* st_row = my_stage + lane * 128;
         mbar_wait_b(&bar.tmem_full[buf], (it >> 1) & 1);
-        if (et == 0 && mt == 0) rec_trace(p.trace, p.T, t, 5);
+        if (et == 0) rec_trace(p.trace, p.T, t, 5);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kBwdN + half * 32) + ((uint32_t)(quarter * 32) << 16);
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_d, r);
-        if (lane == 0) bulk_wait_read_1();  // the reduce that last used THIS staging tile (two tiles ago) has read it
-        tmem_ld_wait();
-        __syncwarp();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kBwdN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp) {
+          const int ps = half * 2 + pp;  // 32-column pass of the 128-column accumulator
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tmem_d + (uint32_t)(ps * 32), r);
+          if (lane == 0) bulk_wait_read_all();  // the previous reduce has finished reading this warp's staging tile
+          tmem_ld_wait();
+          __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(st_row + (((uint32_t)g ^ swz) << 4)) =
-              make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                          __uint_as_float(r[4 * g + 3]));
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
-        fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_3d(&tmC, my_stage, ns * kBwdN + half * 32, mt * 128 + quarter * 32, (t - 1) & 1);
-          bulk_commit();
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(st_row + (((uint32_t)g ^ swz) << 4)) =
+                make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                            __uint_as_float(r[4 * g + 3]));
+          if (pp == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar.tmem_empty[buf]);
+          }
+          fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&tmC, my_stage, ns * kBwdN + ps * 32, mt * 128 + quarter * 32, (t - 1) & 1);
+            bulk_commit();
+          }
         }
       }
       if (et == 0) rec_trace(p.trace, p.T, t, 6);
-      // completion, tile after tile: this warp's reduce-add of tile mt has been PERFORMED once at most
-      // (n_mtiles - 1 - mt) younger groups are pending
-      for (int mt = 0; mt < p.n_mtiles; ++mt) {
-        if (lane == 0) {
-          const int younger = p.n_mtiles - 1 - mt;
-          if (younger == 1) bulk_wait_1();
-          else if (younger == 2) bulk_wait_2();
-          else if (younger == 3) bulk_wait_3();
-          else bulk_wait_all();
-          fence_proxy_async_all();
-        }
-        bwd_bar_sync();
-        if (et == 0) {
-          __threadfence();
-          atomicAdd(p.ctr_g + mt, 1u);
-          if (mt == 0) rec_trace(p.trace, p.T, t, 7);
-        }
+      if (lane == 0) {
+        bulk_wait_all();  // this warp's reduce-adds have been performed
+        fence_proxy_async_all();
+      }
+      bwd_bar_sync();
+      if (et == 0) {
+        __threadfence();
+        atomicAdd(p.ctr_g + y, 1u);
+        rec_trace(p.trace, p.T, t, 7);
       }
     }
   }
@@ -765,10 +747,10 @@ void permute_gate_cols(LaunchCtx c, const float* src, long lds, bf16* dst, int H
 // One condition for both directions: the persistent kernels keep the gate activations unit-major (col 4*unit + gate),
 // the per-step kernels gate-major, so a step must run entirely on one schedule.
 //   forward : W_hh slice [H x 64] bf16 resident  -> H <= 1024;  H / 16 CTAs per batch group
-//   backward: (H / 64) * (H / 128) CTAs            -> H % 128 == 0
+//   backward: (H / 128)^2 CTAs per batch group   -> H % 128 == 0
 bool lstm_seq_supported(int B, int H) {
-  if (B <= 0 || B > 4096 || H % 128 || H > 1024) return false;
-  return H / kFwdUnits <= kNumSMs && (H / kBwdN) * (H / 128) <= kNumSMs;
+  if (B <= 0 || H % 128 || H > 1024) return false;
+  return H / kFwdUnits <= kNumSMs && (H / 128) * (H / 128) <= kNumSMs;
 }
 
 // ctr: >= 2 * 64 zero-initialised-by-us unsigned counters owned by the caller
@@ -778,14 +760,9 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
                  float* cs_buf, bf16* gact, unsigned* ctr) {
   const int slices = H / kFwdUnits;
   const int n_mtiles = (B + 127) / 128;
-  if (n_mtiles > 32) { set_error("lstm_seq_fwd: more than 32 batch tiles (B > 4096)"); return -1; }
-  // CTA groups along the batch: a CTA should own at least two batch tiles when there are that many -- the tiles are
-  // independent recurrences, and the barrier / epilogue latency of one hides behind the MMAs of the other
-  // (9.4 -> ~7.5 us per step at B = 256, where the 64 slice CTAs now take both tiles)
-  const int mg_max = std::max(1, kNumSMs / slices);
-  const int mg = std::max(1, std::min(mg_max, n_mtiles / 2));
+  const int mg = std::max(1, std::min(n_mtiles, kNumSMs / slices));
   const int nkb = H / BK;
-  const size_t smem = (size_t)nkb * kFwdWTile + kFwdStages * kATile + kFwdXStage + 2 * kFwdCStage + 256 + 1024;
+  const size_t smem = (size_t)nkb * kFwdWTile + kFwdStages * kATile + kFwdXStage + kFwdCStage + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -815,10 +792,10 @@ int lstm_seq_fwd(LaunchCtx c, int B, int H, int T, const bf16* w_perm, const bf1
 int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16* dHhead, const bf16* dHprev,
                  const float* dChead, const bf16* gact, const float* cs, bf16* dG, long ld_dg, float* dhrec2,
                  float* dcrec, unsigned* ctr) {
-  const int g = (H / kBwdN) * (H / 128);   // unit slices x gate-column slices: 128 CTAs at H = 1024
+  const int g = (H / 128) * (H / 128);
   const int n_mtiles = (B + 127) / 128;
-  if (n_mtiles > 32) { set_error("lstm_seq_bwd: more than 32 batch tiles (B > 4096)"); return -1; }
-  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + kBwdEpiWarps * 2 * 4096 + 256 + 1024;
+  const int mg = std::max(1, std::min(n_mtiles, kNumSMs / g));
+  const size_t smem = (size_t)kBwdKb * kBwdWTile + kBwdStages * kATile + kBwdEpiWarps * 4096 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -839,7 +816,7 @@ int lstm_seq_bwd(LaunchCtx c, int B, int H, int T, const bf16* w_hh, const bf16*
   if (e == cudaSuccess) e = cudaMemsetAsync(dcrec, 0, sizeof(float) * (size_t)B * H, c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_bwd: memset: %s", cudaGetErrorString(e)); return -1; }
   void* args[] = {&tmA, &tmW, &tmC, &p};
-  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_bwd_kernel, dim3(g, 1), dim3(kBwdThreads), args, smem, c.stream);
+  e = cudaLaunchCooperativeKernel((const void*)lstm_seq_bwd_kernel, dim3(g, mg), dim3(kBwdThreads), args, smem, c.stream);
   if (e != cudaSuccess) { set_error("lstm_seq_bwd: cooperative launch: %s", cudaGetErrorString(e)); return -1; }
   if (c.launches) ++*c.launches;
   return 0;

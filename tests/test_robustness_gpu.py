@@ -38,7 +38,7 @@ def test_optimizer_updates_rebind_the_handle(from_map):
         eng = M.CaptionDecoderEngine(cfg, seed=4)
         if from_map:
             eng.attach_adaptor(64, seed=4)
-        opt, _ = M.get_optimizer(eng, {"learning_rate": 1e-3})
+        opt, _ = M.get_optimizer(eng, {"learning_rate": 5e-3})
         tr = M.DataParallelTrainer(eng)
         out = []
         for _ in range(3):
@@ -53,12 +53,12 @@ def test_optimizer_updates_rebind_the_handle(from_map):
         losses[manual] = [float(v) for v in out]
         assert opt.steps == 3
     a, b = losses[False], losses[True]
-    assert a[0] > a[1] > a[2], a                  # the parameters the forward pass sees really change (and it learns)
+    assert a[0] > a[1] > a[2], a                  # the parameters the forward pass sees really change
     # ... and as with a bind before every step (fp32 atomics make the sums order-dependent in the last bits)
     assert all(abs(x - y) < 1e-4 * abs(y) for x, y in zip(a, b)), (a, b)
     # Adam driven directly (no trainer) invalidates the binding too
     eng = M.CaptionDecoderEngine(cfg, seed=4)
-    opt = M.Adam([(eng.store.flat, eng.store.flat_grad)], 1e-3)
+    opt = M.Adam([(eng.store.flat, eng.store.flat_grad)], 5e-3)
     l0 = float(eng.train_forward(gd, Pd, capd)[0][2])
     eng.train_backward()
     opt.step()
