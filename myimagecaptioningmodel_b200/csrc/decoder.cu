@@ -832,8 +832,7 @@ template <typename T> class Decoder : public DecoderBase {
     prof.mark("dec.image_kv", s);
     OK(g5.ensure(4 * (size_t)B * 5 * H, &ws_bytes));
     OK(xin.ensure(e * (size_t)R * X, &ws_bytes));
-    OK(gpre.ensure(4 * (size_t)R * 4 * H, &ws_bytes));
-    OK(ph.ensure(e * (size_t)R * H, &ws_bytes));
+    OK(gpre.ensure(4 * (size_t)R * 5 * H, &ws_bytes));
     OK(d_hnew.ensure(e * (size_t)R * H, &ws_bytes));
     OK(d_cnew.ensure(4 * (size_t)R * H, &ws_bytes));
     OK(d_ccur.ensure(4 * (size_t)R * H, &ws_bytes));
@@ -845,7 +844,18 @@ template <typename T> class Decoder : public DecoderBase {
     OK(actx.ensure(e * (size_t)R * H, &ws_bytes));
     OK(outv.ensure(e * (size_t)R * H, &ws_bytes));
     OK(proj.ensure(e * (size_t)R * E, &ws_bytes));
-    OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
+    // bf16 storage: the vocabulary GEMM's epilogue leaves per-group soft-max statistics and top-k candidates (ACT_ROWSTATS +
+    // topk_k) and the logits are never written; fp32 storage (SIMT GEMM): logits + the full-row top-k kernel
+    constexpr bool kFusedTopk = std::is_same<T, bf16>::value;
+    const int n_groups = (V + 63) / 64;
+    const long sld = (n_groups + 7) & ~7;
+    const int KB = beam <= 4 ? 4 : 8;
+    if (kFusedTopk) {
+      OK(dec_stats.ensure(2 * 4 * (size_t)R * sld + 256, &ws_bytes));
+      OK(dec_topk.ensure(2 * 4 * (size_t)R * sld * KB + 256, &ws_bytes));
+    } else {
+      OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
+    }
     OK(d_state.ensure((size_t)R * (2 * 4 + 2 * 4 + 2 * 4 * Ti + 8) + 256, &ws_bytes));
     OK(d_beam.ensure(beam_scratch_bytes(B, beam), &ws_bytes));
     OK(d_trace.ensure(8 * (size_t)R * Ti, &ws_bytes));
@@ -877,13 +887,11 @@ template <typename T> class Decoder : public DecoderBase {
       prof.mark("dec.setup", rs);
       for (int step = 0; step < Ti; ++step) {
         const int cur = step & 1, nxt = cur ^ 1;
-        // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid)]  and  . [fc_xs(word) ; fc_hs]      (model:86-90)
-        OK(fc(gc, xin.p, X, w_dec_n.as<T>(), 5 * H, nullptr, gpre.p, 4 * H, R, 4 * H, X, ACT_NONE, true));
-        OK(fc(gc, xin.p, X, w_dec_n.as<T>() + 4 * H, 5 * H, nullptr, ph.p, H, R, H, X, ACT_NONE));
-        lstm_cell_fwd<T>(lc, R, H, gpre.as<float>(), 4 * H, (const T*)nullptr, 0, g5.as<float>(), 5 * H, INT_MAX, beam,
-                         d_ccur.as<float>(), d_hnew.as<T>(), H, d_cnew.as<float>(), (T*)nullptr);
-        sentinel_fwd<T>(lc, R, H, ph.as<T>(), H, (const T*)nullptr, 0, g5.as<float>() + 4 * H, 5 * H, INT_MAX, beam,
-                        d_cnew.as<float>(), (T*)nullptr, sent.as<T>());
+        // [word_emb | h_{t-1}] . [lstm_w(word) ; lstm_w(hid) | fc_xs(word) ; fc_hs]: gate and sentinel-gate pre-activations
+        // in one fp32 product, then cell + sentinel in one kernel                                        (model:86-92)
+        OK(fc(gc, xin.p, X, w_dec_n.as<T>(), 5 * H, nullptr, gpre.p, 5 * H, R, 5 * H, X, ACT_NONE, true));
+        lstm_cell_sentinel_fwd<T>(lc, R, H, gpre.as<float>(), g5.as<float>(), beam, d_ccur.as<float>(), d_hnew.as<T>(),
+                                  d_cnew.as<float>(), sent.as<T>());
         prof.mark("dec.gates_cell", rs);
         OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
         OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
@@ -904,17 +912,33 @@ template <typename T> class Decoder : public DecoderBase {
         prof.mark("dec.attention", rs);
         OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
         OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
+        float* st_m = dec_stats.as<float>();
+        float* st_s = st_m + (size_t)R * sld;
+        float* tk_v = dec_topk.as<float>();
+        int* tk_i = reinterpret_cast<int*>(tk_v + (size_t)R * sld * KB);
         {
-          GemmCall c;
-          c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
-          c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
+          GemmCall c;                                                                                 // model:25
+          c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
+          c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1;
+          if (kFusedTopk) {
+            c.C = dec_stats.p;   // never written: the epilogue only leaves the group records
+            c.epi.act = ACT_ROWSTATS; c.epi.stats_m = st_m; c.epi.stats_s = st_s; c.epi.stats_ld = sld;
+            c.epi.topk_k = KB; c.epi.topk_v = tk_v; c.epi.topk_i = tk_i;
+          } else {
+            c.C = logits.p; c.epi.out_f32 = 1;
+          }
           OK(gemm<T>(gc, c));
         }
         prof.mark("dec.out_proj_vocab", rs);
         // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
-        beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
-                  score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
-                  d_trace.as<int>() + (size_t)step * R * 2);
+        if (kFusedTopk)
+          beam_step_partials(lc, n_groups, sld, st_m, st_s, tk_v, tk_i, KB, V, B, beam, step, Ti, cfg.padding_idx,
+                             cfg.stop_idx, finish, score[cur], score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok,
+                             src, d_beam.p, d_trace.as<int>() + (size_t)step * R * 2);
+        else
+          beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
+                    score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
+                    d_trace.as<int>() + (size_t)step * R * 2);
         prof.mark("dec.beam_topk", rs);
         if (step + 1 < Ti)
           beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
@@ -926,7 +950,10 @@ template <typename T> class Decoder : public DecoderBase {
     // Small batches are launch-latency bound (14 dependent launches per step, ~9 us each at one image): the step loop
     // is captured once into a CUDA graph per (images, beam, finish) and replayed.  The first call of a shape runs
     // eagerly (it allocates the workspace and warms the tensor-map cache), the second captures.
-    const bool want_graph = R <= 96 && !prof.on;
+#ifndef CAPDEC_DECODE_GRAPH_MAX_ROWS
+#define CAPDEC_DECODE_GRAPH_MAX_ROWS 96   // build-time: larger decodes keep programmatic dependent launch instead
+#endif
+    const bool want_graph = R <= CAPDEC_DECODE_GRAPH_MAX_ROWS && !prof.on;
     bool done = false;
     if (want_graph) {
       const unsigned long key_epoch = g_ws_epoch;
@@ -995,7 +1022,7 @@ template <typename T> class Decoder : public DecoderBase {
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
-            &d_state, &d_beam, &d_trace, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
+            &d_state, &d_beam, &d_trace, &dec_stats, &dec_topk, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
             &dHhead_c, &dHprev_c, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
@@ -1034,7 +1061,7 @@ template <typename T> class Decoder : public DecoderBase {
   long head_rows = 0;
   DevBuf row_steps, row_prow, row_pm, hprev_c, hcur_c, actx_p, dactx_p, dsg_c, dHhead_c, dHprev_c;
   // decode state
-  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace;
+  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace, dec_stats, dec_topk;
   int trace_B = 0, trace_beam = 0;
   // feature adaptor (capdec_img2feature)
   capdec_adaptor_params aprm{};

@@ -254,6 +254,73 @@ __device__ __forceinline__ void epilogue_stats32(uint32_t tmem_addr, const float
   }
 }
 
+// ACT_ROWSTATS with GemmEpi::topk_k > 0: additionally the KB largest x of the 64-column group with their column indices,
+// ties towards the lower column (strict > insertion while scanning the columns in ascending order).  With the group
+// statistics this is everything a soft-max top-k needs (the beam search of capdec_decode): the [M, N] logits are never
+// written.  Records: topk_v / topk_i [M, stats_ld, KB] at (row, group); unused slots hold -inf / INT_MAX.
+template <int KB>
+__device__ __forceinline__ void topk_insert(float (&tv)[KB], int (&ti)[KB], float x, int n) {
+  if (x > tv[KB - 1]) {
+    tv[KB - 1] = x; ti[KB - 1] = n;
+#pragma unroll
+    for (int r = KB - 1; r > 0; --r) {
+      if (tv[r] > tv[r - 1]) {
+        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
+        const int iv = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = iv;
+      }
+    }
+  }
+}
+template <int KB>
+__device__ __forceinline__ void epilogue_stats_topk32(uint32_t tmem_addr, const float* bias_t, int left, int n_base, float& m,
+                                                      float& s, float (&tv)[KB], int (&ti)[KB]) {
+  uint32_t r[32];
+  __syncwarp();
+  tmem_ld32(tmem_addr, r);
+  tmem_ld_wait();
+  float x[32];
+  float cm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    x[i] = (i < left) ? __uint_as_float(r[i]) + (bias_t ? bias_t[i] : 0.f) : -INFINITY;
+    cm = fmaxf(cm, x[i]);
+  }
+  if (cm > m) { s *= __expf(m - cm); m = cm; }
+  if (m > -INFINITY) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += __expf(x[i] - m);
+  }
+  if (cm > tv[KB - 1]) {   // nothing in these 32 columns beats the current KB-th best: skip the insertion scan
+#pragma unroll
+    for (int i = 0; i < 32; ++i) topk_insert<KB>(tv, ti, x[i], n_base + i);
+  }
+}
+template <int KB>
+__device__ __forceinline__ void rowstats_topk_group(uint32_t tmem_addr, const float* bsp, int left, int n_base, bool row_ok,
+                                                    long row, const GemmEpi& epi) {
+  float rm = -INFINITY, rs = 0.f;
+  float tv[KB];
+  int ti[KB];
+#pragma unroll
+  for (int j = 0; j < KB; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  epilogue_stats_topk32<KB>(tmem_addr, bsp, left, n_base, rm, rs, tv, ti);
+  epilogue_stats_topk32<KB>(tmem_addr + 32u, bsp ? bsp + 32 : nullptr, left - 32, n_base + 32, rm, rs, tv, ti);
+  if (row_ok && left > 0) {
+    const long o = row * epi.stats_ld + (n_base >> 6);
+    epi.stats_m[o] = rm;
+    epi.stats_s[o] = rs;
+    float* ov = epi.topk_v + o * KB;
+    int* oi = epi.topk_i + o * KB;
+    if (KB == 4) {
+      *reinterpret_cast<float4*>(ov) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+      *reinterpret_cast<int4*>(oi) = make_int4(ti[0], ti[1], ti[2], ti[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KB; ++j) { ov[j] = tv[j]; oi[j] = ti[j]; }
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -452,13 +519,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bf16* ap = add_p ? add_p + c0 : nullptr;
             const bf16* yp = y_p ? y_p + c0 : nullptr;
             if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
-              float rm = -INFINITY, rs = 0.f;
-              epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
-              epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
-              if (row_ok && left > 0) {
-                const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
-                epi.stats_m[o] = rm;
-                epi.stats_s[o] = rs;
+              if (epi.topk_k > 4) {
+                rowstats_topk_group<8>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
+              } else if (epi.topk_k > 0) {
+                rowstats_topk_group<4>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
+              } else {
+                float rm = -INFINITY, rs = 0.f;
+                epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+                epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+                if (row_ok && left > 0) {
+                  const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+                  epi.stats_m[o] = rm;
+                  epi.stats_s[o] = rs;
+                }
               }
               if (ps == my_last && last_block) {
                 tc_fence_before();
@@ -826,13 +899,19 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bf16* ap = add_p ? add_p + c0 : nullptr;
         const bf16* yp = y_p ? y_p + c0 : nullptr;
         if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
-          float rm = -INFINITY, rs = 0.f;
-          epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
-          epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
-          if (row_ok && left > 0) {
-            const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
-            epi.stats_m[o] = rm;
-            epi.stats_s[o] = rs;
+          if (epi.topk_k > 4) {
+            rowstats_topk_group<8>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
+          } else if (epi.topk_k > 0) {
+            rowstats_topk_group<4>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
+          } else {
+            float rm = -INFINITY, rs = 0.f;
+            epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+            epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+            if (row_ok && left > 0) {
+              const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+              epi.stats_m[o] = rm;
+              epi.stats_s[o] = rs;
+            }
           }
           if (ps == my_last) {
             tc_fence_before();
@@ -1107,7 +1186,8 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
     const GemmEpi& e = c.epi;
     const bool ok = !e.out_f32 && !e.atomic && c.batch <= 1 && !e.addend && !e.dact_y && (!e.bias || e.aux_padded) &&
                     (((uintptr_t)c.C & 15) == 0) && ((c.ldc * 2) % 16 == 0) && e.stats_m && e.stats_s &&
-                    e.stats_ld >= (c.N + 63) / 64;
+                    e.stats_ld >= (c.N + 63) / 64 && e.topk_k >= 0 && e.topk_k <= 8 &&
+                    (e.topk_k == 0 || (e.topk_v && e.topk_i && ((uintptr_t)e.topk_v & 15) == 0 && ((uintptr_t)e.topk_i & 15) == 0));
     if (!ok) { set_error("gemm_tc: unsupported arguments for the row-statistics epilogue"); return -1; }
   }
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }

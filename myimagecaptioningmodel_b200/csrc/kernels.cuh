@@ -59,6 +59,11 @@ void lstm_cell_fwd(LaunchCtx c, int R, int H, const float* gpre, long ld_gpre, c
 template <typename T>
 void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* xe, long ld_xe, const float* g5,
                   long ld_g5, int g5_mod, int g5_div, const float* cc, T* sgate, T* s_out, const int* rowmap = nullptr);
+// inference step: cell + sentinel from one fp32 pre-activation row gpre5 [R, 5H] = [gates i,f,o,g | sentinel gate] and the
+// per-image term g5 [R / beam, 5H] (model:87-92); h_out, s_out [R, H] (T), c_out [R, H] fp32
+template <typename T>
+void lstm_cell_sentinel_fwd(LaunchCtx c, int R, int H, const float* gpre5, const float* g5, int beam, const float* c_prev,
+                            T* h_out, float* c_out, T* s_out);
 // ---- packed rows of the time-batched head (see pointwise.cu) ----
 //   out: steps [B] live steps per sample (from the captions); prow [T*B] padded -> packed row or -1; pm [Mp] packed ->
 //   padded row (zero it first: entries the captions do not fill must stay valid rows).  Mp = the host's row count.
@@ -212,6 +217,12 @@ int beam_max_vocab();
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
                const int* hist_in, int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace);
+// the same step from the per-64-column-group statistics and top-KB candidates left by the vocabulary GEMM's epilogue
+// (gemm.cuh ACT_ROWSTATS + topk_k; KB = 4 or 8 >= beam): st_m, st_s [rows, ld]; tk_v, tk_i [rows, ld, KB]; S = groups
+void beam_step_partials(LaunchCtx c, int S, long ld, const float* st_m, const float* st_s, const float* tk_v, const int* tk_i,
+                        int KB, int V, int n_img, int beam, int step, int T_total, int pad, int stop, int finish_on_stop,
+                        const float* score_in, float* score_out, const int* fin_in, int* fin_out, const int* hist_in,
+                        int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace);
 // initial beam state: score = 0 for prefix 0 of every image, -inf for the others; tok = start; src = r % beam
 void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src);
 // next-step operands: xin[r] = [emb[tok[r]] | h_new[src_row(r)]], c_next[r] = c_new[src_row(r)]

@@ -115,6 +115,49 @@ __global__ void lstm_cell_fwd_kernel(int R, int H, const float* __restrict__ gpr
   }
 }
 
+// Inference step: the LSTM cell and the visual sentinel from ONE fp32 pre-activation row [gates i,f,o,g | sentinel gate]
+// (model:87-92): pre = gpre5[r] + g5[r / beam];  c = sig(f) c_prev + sig(i) tanh(g);  h = sig(o) tanh(c);
+// s = sig(pre[4H:5H]) tanh(c).  (Was two kernels behind two GEMMs; the [R, 5H] product is one GEMM now.)
+template <typename T>
+__global__ void lstm_cell_sentinel_kernel(int R, int H, const float* __restrict__ gpre5, const float* __restrict__ g5,
+                                          int beam, const float* __restrict__ c_prev, T* __restrict__ h_out,
+                                          float* __restrict__ c_out, T* __restrict__ s_out) {
+  pdl_trigger();
+  constexpr bool F = fast_math<T>::value;
+  const int vec_per_row = H / 8;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x, n = (long)R * vec_per_row;
+  for (; i < n; i += stride) {
+    const long r = i / vec_per_row;
+    const int h0 = (int)(i % vec_per_row) * 8;
+    const float* pr = gpre5 + r * 5 * H + h0;
+    const float* gr = g5 + (r / beam) * 5 * H + h0;
+    float pre[5][8];
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      float x[8];
+      load8(pr + (long)g * H, pre[g]);
+      load8(gr + (long)g * H, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[g][j] += x[j];
+    }
+    float cp[8], cn[8], hn[8], sn[8];
+    load8(c_prev + r * H + h0, cp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ig = sigmoid_t<F>(pre[0][j]), fg = sigmoid_t<F>(pre[1][j]), og = sigmoid_t<F>(pre[2][j]);
+      const float gg = tanh_t<F>(pre[3][j]);
+      cn[j] = fg * cp[j] + ig * gg;
+      const float tc = tanh_t<F>(cn[j]);
+      hn[j] = og * tc;
+      sn[j] = sigmoid_t<F>(pre[4][j]) * tc;
+    }
+    store8(c_out + r * H + h0, cn);
+    store8(h_out + r * H + h0, hn);
+    store8(s_out + r * H + h0, sn);
+  }
+}
+
 // rowmap (packed rows, see row_map_kernel): row r of ph / sgate / s_out is row rowmap[r] of xe / g5 / cc
 template <typename T>
 __global__ void sentinel_fwd_kernel(long R, int H, const T* __restrict__ ph, long ld_ph, const T* __restrict__ xe,
@@ -704,6 +747,14 @@ void sentinel_fwd(LaunchCtx c, long R, int H, const T* ph, long ld_ph, const T* 
   BUMP(c);
 }
 template <typename T>
+void lstm_cell_sentinel_fwd(LaunchCtx c, int R, int H, const float* gpre5, const float* g5, int beam, const float* c_prev,
+                            T* h_out, float* c_out, T* s_out) {
+  if (R <= 0) return;
+  lstm_cell_sentinel_kernel<T><<<grid_for((long)R * (H / 8), 128), 128, 0, c.stream>>>(R, H, gpre5, g5, beam, c_prev, h_out,
+                                                                                     c_out, s_out);
+  BUMP(c);
+}
+template <typename T>
 void sentinel_bwd_packed(LaunchCtx c, long M, int H, const int* prow, const T* dS, const T* sgate, const float* cc,
                          T* dsg_pre, long ld_dsg, float* dC_head, T* dsg_packed) {
   if (M <= 0) return;
@@ -818,6 +869,8 @@ template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
                                  int, const float*, T*, long, float*, T*);                                             \
   template void sentinel_fwd<T>(LaunchCtx, long, int, const T*, long, const T*, long, const float*, long, int, int,    \
                                 const float*, T*, T*, const int*);                                                     \
+  template void lstm_cell_sentinel_fwd<T>(LaunchCtx, int, int, const float*, const float*, int, const float*, T*,      \
+                                          float*, T*);                                                                 \
   template void sentinel_bwd_packed<T>(LaunchCtx, long, int, const int*, const T*, const T*, const float*, T*, long,   \
                                        float*, T*);                                                                    \
   template void gather_rows<T>(LaunchCtx, const T*, const T*, long, const int*, long, int, T*, T*, long);              \
