@@ -846,7 +846,10 @@ template <typename T> class Decoder : public DecoderBase {
     OK(proj.ensure(e * (size_t)R * E, &ws_bytes));
     // bf16 storage: the vocabulary GEMM's epilogue leaves per-group soft-max statistics and top-k candidates (ACT_ROWSTATS +
     // topk_k) and the logits are never written; fp32 storage (SIMT GEMM): logits + the full-row top-k kernel
-    constexpr bool kFusedTopk = std::is_same<T, bf16>::value;
+#ifndef CAPDEC_DECODE_FUSED_TOPK
+#define CAPDEC_DECODE_FUSED_TOPK 0   // measured on B200: 144 us per step against 62 (GEMM) + 38 (top-k kernel): the K = 256
+#endif                               // GEMM is epilogue-bound, selection logic in its epilogue costs more than the round trip
+    constexpr bool kFusedTopk = CAPDEC_DECODE_FUSED_TOPK && std::is_same<T, bf16>::value;
     const int n_groups = (V + 63) / 64;
     const long sld = (n_groups + 7) & ~7;
     const int KB = beam <= 4 ? 4 : 8;
