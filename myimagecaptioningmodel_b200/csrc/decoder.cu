@@ -844,21 +844,10 @@ template <typename T> class Decoder : public DecoderBase {
     OK(actx.ensure(e * (size_t)R * H, &ws_bytes));
     OK(outv.ensure(e * (size_t)R * H, &ws_bytes));
     OK(proj.ensure(e * (size_t)R * E, &ws_bytes));
-    // bf16 storage: the vocabulary GEMM's epilogue leaves per-group soft-max statistics and top-k candidates (ACT_ROWSTATS +
-    // topk_k) and the logits are never written; fp32 storage (SIMT GEMM): logits + the full-row top-k kernel
-#ifndef CAPDEC_DECODE_FUSED_TOPK
-#define CAPDEC_DECODE_FUSED_TOPK 0   // measured on B200: 144 us per step against 62 (GEMM) + 38 (top-k kernel): the K = 256
-#endif                               // GEMM is epilogue-bound, selection logic in its epilogue costs more than the round trip
-    constexpr bool kFusedTopk = CAPDEC_DECODE_FUSED_TOPK && std::is_same<T, bf16>::value;
-    const int n_groups = (V + 63) / 64;
-    const long sld = (n_groups + 7) & ~7;
-    const int KB = beam <= 4 ? 4 : 8;
-    if (kFusedTopk) {
-      OK(dec_stats.ensure(2 * 4 * (size_t)R * sld + 256, &ws_bytes));
-      OK(dec_topk.ensure(2 * 4 * (size_t)R * sld * KB + 256, &ws_bytes));
-    } else {
-      OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
-    }
+    // (Measured and dropped: soft-max statistics + top-k candidates emitted by the vocabulary GEMM's epilogue instead of the
+    // fp32 logits -- 144 us per step against 62 (GEMM) + 38 (top-k kernel): the K = 256 GEMM is epilogue-bound and selection
+    // logic in its register-capped epilogue costs more than the 76 MB round trip.)
+    OK(logits.ensure(4 * (size_t)R * Vp, &ws_bytes));
     OK(d_state.ensure((size_t)R * (2 * 4 + 2 * 4 + 2 * 4 * Ti + 8) + 256, &ws_bytes));
     OK(d_beam.ensure(beam_scratch_bytes(B, beam), &ws_bytes));
     OK(d_trace.ensure(8 * (size_t)R * Ti, &ws_bytes));
@@ -915,33 +904,17 @@ template <typename T> class Decoder : public DecoderBase {
         prof.mark("dec.attention", rs);
         OK(fc(gc, actx.p, H, w_o_n.as<T>(), H, prm.fc_o_b, outv.p, H, R, H, H, ACT_TANH));
         OK(fc(gc, outv.p, H, w_e_n.as<T>(), E, prm.fc_e_b, proj.p, E, R, E, H, ACT_NONE));
-        float* st_m = dec_stats.as<float>();
-        float* st_s = st_m + (size_t)R * sld;
-        float* tk_v = dec_topk.as<float>();
-        int* tk_i = reinterpret_cast<int*>(tk_v + (size_t)R * sld * KB);
         {
           GemmCall c;                                                                                 // model:25
-          c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
-          c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1;
-          if (kFusedTopk) {
-            c.C = dec_stats.p;   // never written: the epilogue only leaves the group records
-            c.epi.act = ACT_ROWSTATS; c.epi.stats_m = st_m; c.epi.stats_s = st_s; c.epi.stats_ld = sld;
-            c.epi.topk_k = KB; c.epi.topk_v = tk_v; c.epi.topk_i = tk_i;
-          } else {
-            c.C = logits.p; c.epi.out_f32 = 1;
-          }
+          c.A = proj.p; c.lda = E; c.B = emb.p; c.ldb = E; c.C = logits.p; c.ldc = Vp; c.M = R; c.N = V; c.K = E;
+          c.epi.bias = b_vocab.as<float>(); c.epi.aux_padded = 1; c.epi.out_f32 = 1;
           OK(gemm<T>(gc, c));
         }
         prof.mark("dec.out_proj_vocab", rs);
         // top-k + back-pointers (model:119-123 generalised), then reorder the recurrent state for the next step
-        if (kFusedTopk)
-          beam_step_partials(lc, n_groups, sld, st_m, st_s, tk_v, tk_i, KB, V, B, beam, step, Ti, cfg.padding_idx,
-                             cfg.stop_idx, finish, score[cur], score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok,
-                             src, d_beam.p, d_trace.as<int>() + (size_t)step * R * 2);
-        else
-          beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
-                    score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
-                    d_trace.as<int>() + (size_t)step * R * 2);
+        beam_step(lc, logits.as<float>(), Vp, V, B, beam, step, Ti, cfg.padding_idx, cfg.stop_idx, finish, score[cur],
+                  score[nxt], fin[cur], fin[nxt], hist[cur], hist[nxt], tok, src, d_beam.p,
+                  d_trace.as<int>() + (size_t)step * R * 2);
         prof.mark("dec.beam_topk", rs);
         if (step + 1 < Ti)
           beam_reorder<T>(lc, B, beam, E, H, cfg.padding_idx, emb.as<T>(), tok, src, d_hnew.as<T>(), d_cnew.as<float>(),
@@ -1025,7 +998,7 @@ template <typename T> class Decoder : public DecoderBase {
             &keys, &vals, &embx, &xe, &g5, &hs, &cs, &gact, &gpre, &ph, &sgate, &sent, &phid, &hemb, &semb, &alpha, &actx,
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
-            &d_state, &d_beam, &d_trace, &dec_stats, &dec_topk, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
+            &d_state, &d_beam, &d_trace, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
             &dHhead_c, &dHprev_c, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
@@ -1064,7 +1037,7 @@ template <typename T> class Decoder : public DecoderBase {
   long head_rows = 0;
   DevBuf row_steps, row_prow, row_pm, hprev_c, hcur_c, actx_p, dactx_p, dsg_c, dHhead_c, dHprev_c;
   // decode state
-  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace, dec_stats, dec_topk;
+  DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace;
   int trace_B = 0, trace_beam = 0;
   // feature adaptor (capdec_img2feature)
   capdec_adaptor_params aprm{};

@@ -15,8 +15,7 @@
 namespace capdec {
 
 //   ACT_ROWSTATS     (tensor-core kernels only) no C output; per (row, 64-column group g) the partial max and
-//                    sum exp(x - max) of x = acc + bias go to stats_m / stats_s [M, stats_ld] at column g; with topk_k > 0
-//                    also the group's largest entries (the beam search of capdec_decode never writes its logits)
+//                    sum exp(x - max) of x = acc + bias go to stats_m / stats_s [M, stats_ld] at column g
 //   ACT_RELU         max(x, 0)            (the feature adaptor, model:196-198)
 //   ACT_DRELU        x * [y > 0] with y = dact_y, the ReLU output
 enum { ACT_NONE = 0, ACT_TANH = 1, ACT_DTANH = 2, ACT_ROWSTATS = 3, ACT_RELU = 5, ACT_DRELU = 6 };
@@ -39,9 +38,6 @@ struct GemmEpi {
   float* stats_m = nullptr;      // ACT_ROWSTATS outputs
   float* stats_s = nullptr;
   long stats_ld = 0;
-  int topk_k = 0;                // ACT_ROWSTATS: > 0 also emits the top 4 (topk_k <= 4) or top 8 entries of every 64-column
-  float* topk_v = nullptr;       //   group: topk_v / topk_i [M, stats_ld, 4 or 8] (16-byte aligned)
-  int* topk_i = nullptr;
 };
 
 struct GemmCall {

@@ -135,8 +135,6 @@ struct TcShape {
   int vec_ok;
   int rotate_k;  // start every CTA's k-loop at a different k-block (spreads L2 hot lines among CTAs sharing a tile)
   int tma_out;   // epilogue writes through shared memory + TMA tensor stores (needs an aligned C)
-  int direct_out;  // pair kernel, short-K variant: the epilogue writes C with per-thread 128-bit global stores (see below)
-  void* c_ptr;     // C (direct_out)
   unsigned long long* trace;  // debug timeline (capdec_debug_gemm_trace), 32 slots per CTA, or nullptr
 };
 __device__ __forceinline__ unsigned long long gtime() {
@@ -236,99 +234,6 @@ __device__ __forceinline__ void epilogue_cols32(uint32_t tmem_addr, uint32_t bia
   }
 }
 
-// The same 32 columns written straight to global memory: every thread owns one output row, so its 32 columns are 128 (fp32)
-// or 64 (bf16) contiguous bytes = 8 or 4 stores of 16 bytes.  For the short-K, many-tile forward problems (fp32 logits,
-// x-part pre-activations: K <= 512) the epilogue IS the kernel, and the staged path costs ~2 us per 4 KB pass and warp
-// (tcgen05.ld -> st.shared -> fence.proxy.async -> tensor store, waiting for the store before last to drain): 16 GB/s per
-// SM = 2.4 TB/s chip-wide.  Direct stores are fire-and-forget; the L2 merges the 16-byte pieces of a line before eviction.
-// `left` = valid columns from this chunk on; `c_row` = &C[row][first column of the chunk] (nullptr: row past M).
-template <bool OUT_F32>
-__device__ __forceinline__ void epilogue_cols32_direct(uint32_t tmem_addr, uint32_t bias_t, const bf16* add_p,
-                                                       const bf16* y_p, int fact, float alpha, int left, void* c_row) {
-  uint32_t r[32];
-  uint4 aq[4], yq[4];
-  __syncwarp();  // tcgen05.ld is .sync.aligned
-  tmem_ld32(tmem_addr, r);
-  if (add_p) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g * 8 < left) aq[g] = *reinterpret_cast<const uint4*>(add_p + g * 8);
-  }
-  if (y_p) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g * 8 < left) yq[g] = *reinterpret_cast<const uint4*>(y_p + g * 8);
-  }
-  tmem_ld_wait();
-  if (!c_row) return;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g * 8 < left) {
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * alpha;
-      if (bias_t) {
-        const float4 b0 = lds_f4(bias_t + (uint32_t)(g * 32));
-        const float4 b1 = lds_f4(bias_t + (uint32_t)(g * 32 + 16));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
-      if (add_p) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aq[g]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          v[2 * i] += f.x; v[2 * i + 1] += f.y;
-        }
-      }
-      if (fact & 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = tanh_t<true>(v[i]);
-      } else if (fact & 2) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (y_p) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yq[g]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          if (fact & 4) {
-            v[2 * i] = f.x > 0.f ? v[2 * i] : 0.f; v[2 * i + 1] = f.y > 0.f ? v[2 * i + 1] : 0.f;
-          } else {
-            v[2 * i] *= (1.f - f.x * f.x); v[2 * i + 1] *= (1.f - f.y * f.y);
-          }
-        }
-      }
-      const int nv = left - g * 8;   // valid columns of this group of 8 (> 0)
-      if (OUT_F32) {
-        float* o = reinterpret_cast<float*>(c_row) + g * 8;
-        if (nv >= 8) {
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) o[i] = v[i];
-        }
-      } else {
-        bf16* o = reinterpret_cast<bf16*>(c_row) + g * 8;
-        if (nv >= 8) {
-          uint4 u;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          *reinterpret_cast<uint4*>(o) = u;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nv) o[i] = __float2bfloat16_rn(v[i]);
-        }
-      }
-    }
-  }
-}
-
 // ACT_ROWSTATS: running (max, sum exp(x - max)) of x = acc + bias over 32 accumulator columns of this thread's row
 __device__ __forceinline__ void epilogue_stats32(uint32_t tmem_addr, const float* bias_t, int left, float& m, float& s) {
   uint32_t r[32];
@@ -346,73 +251,6 @@ __device__ __forceinline__ void epilogue_stats32(uint32_t tmem_addr, const float
   if (m > -INFINITY) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) s += __expf(x[i] - m);
-  }
-}
-
-// ACT_ROWSTATS with GemmEpi::topk_k > 0: additionally the KB largest x of the 64-column group with their column indices,
-// ties towards the lower column (strict > insertion while scanning the columns in ascending order).  With the group
-// statistics this is everything a soft-max top-k needs (the beam search of capdec_decode): the [M, N] logits are never
-// written.  Records: topk_v / topk_i [M, stats_ld, KB] at (row, group); unused slots hold -inf / INT_MAX.
-template <int KB>
-__device__ __forceinline__ void topk_insert(float (&tv)[KB], int (&ti)[KB], float x, int n) {
-  if (x > tv[KB - 1]) {
-    tv[KB - 1] = x; ti[KB - 1] = n;
-#pragma unroll
-    for (int r = KB - 1; r > 0; --r) {
-      if (tv[r] > tv[r - 1]) {
-        const float fv = tv[r]; tv[r] = tv[r - 1]; tv[r - 1] = fv;
-        const int iv = ti[r]; ti[r] = ti[r - 1]; ti[r - 1] = iv;
-      }
-    }
-  }
-}
-template <int KB>
-__device__ __forceinline__ void epilogue_stats_topk32(uint32_t tmem_addr, const float* bias_t, int left, int n_base, float& m,
-                                                      float& s, float (&tv)[KB], int (&ti)[KB]) {
-  uint32_t r[32];
-  __syncwarp();
-  tmem_ld32(tmem_addr, r);
-  tmem_ld_wait();
-  float x[32];
-  float cm = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    x[i] = (i < left) ? __uint_as_float(r[i]) + (bias_t ? bias_t[i] : 0.f) : -INFINITY;
-    cm = fmaxf(cm, x[i]);
-  }
-  if (cm > m) { s *= __expf(m - cm); m = cm; }
-  if (m > -INFINITY) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += __expf(x[i] - m);
-  }
-  if (cm > tv[KB - 1]) {   // nothing in these 32 columns beats the current KB-th best: skip the insertion scan
-#pragma unroll
-    for (int i = 0; i < 32; ++i) topk_insert<KB>(tv, ti, x[i], n_base + i);
-  }
-}
-template <int KB>
-__device__ __forceinline__ void rowstats_topk_group(uint32_t tmem_addr, const float* bsp, int left, int n_base, bool row_ok,
-                                                    long row, const GemmEpi& epi) {
-  float rm = -INFINITY, rs = 0.f;
-  float tv[KB];
-  int ti[KB];
-#pragma unroll
-  for (int j = 0; j < KB; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  epilogue_stats_topk32<KB>(tmem_addr, bsp, left, n_base, rm, rs, tv, ti);
-  epilogue_stats_topk32<KB>(tmem_addr + 32u, bsp ? bsp + 32 : nullptr, left - 32, n_base + 32, rm, rs, tv, ti);
-  if (row_ok && left > 0) {
-    const long o = row * epi.stats_ld + (n_base >> 6);
-    epi.stats_m[o] = rm;
-    epi.stats_s[o] = rs;
-    float* ov = epi.topk_v + o * KB;
-    int* oi = epi.topk_i + o * KB;
-    if (KB == 4) {
-      *reinterpret_cast<float4*>(ov) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-      *reinterpret_cast<int4*>(oi) = make_int4(ti[0], ti[1], ti[2], ti[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < KB; ++j) { ov[j] = tv[j]; oi[j] = ti[j]; }
-    }
   }
 }
 
@@ -614,19 +452,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bf16* ap = add_p ? add_p + c0 : nullptr;
             const bf16* yp = y_p ? y_p + c0 : nullptr;
             if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
-              if (epi.topk_k > 4) {
-                rowstats_topk_group<8>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
-              } else if (epi.topk_k > 0) {
-                rowstats_topk_group<4>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
-              } else {
-                float rm = -INFINITY, rs = 0.f;
-                epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
-                epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
-                if (row_ok && left > 0) {
-                  const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
-                  epi.stats_m[o] = rm;
-                  epi.stats_s[o] = rs;
-                }
+              float rm = -INFINITY, rs = 0.f;
+              epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+              epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+              if (row_ok && left > 0) {
+                const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+                epi.stats_m[o] = rm;
+                epi.stats_s[o] = rs;
               }
               if (ps == my_last && last_block) {
                 tc_fence_before();
@@ -984,31 +816,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ps = warp_empty ? n_pass : half; ps < n_pass; ps += 2) {
         const int c0 = ps * pw;
         const int left = sh.N - (n0 + c0);
-        if (EPI2 && sh.direct_out) {
-          // ---- registers -> global memory, 16 bytes per store (see epilogue_cols32_direct) ----
-          const uint32_t bsa_d = has_bias ? bias_sa + (uint32_t)((buf * BN + c0) * 4) : 0u;
-          const bf16* ap_d = add_p ? add_p + c0 : nullptr;
-          const bf16* yp_d = y_p ? y_p + c0 : nullptr;
-          if (f32_out) {
-            float* crow = row_ok ? reinterpret_cast<float*>(sh.c_ptr) + bt * sh.batch_c + (long)row * sh.ldc + n0 + c0 : nullptr;
-            epilogue_cols32_direct<true>(tmem_d + (uint32_t)c0, bsa_d, ap_d, yp_d, do_tanh, alpha, left, crow);
-          } else {
-            bf16* crow = row_ok ? reinterpret_cast<bf16*>(sh.c_ptr) + bt * sh.batch_c + (long)row * sh.ldc + n0 + c0 : nullptr;
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-              const int o = sub * 32;
-              epilogue_cols32_direct<false>(tmem_d + (uint32_t)(c0 + o), bsa_d ? bsa_d + (uint32_t)(o * 4) : 0u,
-                                            ap_d ? ap_d + o : nullptr, yp_d ? yp_d + o : nullptr, do_tanh, alpha, left - o,
-                                            crow ? crow + o : nullptr);
-            }
-          }
-          if (ps == my_last) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(empty_leader);
-          }
-          continue;
-        }
         // EPI2: two staging tiles per warp, used alternately: only the store before the previous one must have drained
         const uint32_t my_stage = staging_sa + (uint32_t)((EPI2 ? ew * kEpiDepth + (int)(stage_flip % kEpiDepth) : ew) * 4096);
         const uint32_t my_row = my_stage + (uint32_t)(lane * 128);
@@ -1019,19 +826,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bf16* ap = add_p ? add_p + c0 : nullptr;
         const bf16* yp = y_p ? y_p + c0 : nullptr;
         if (epi.act == ACT_ROWSTATS) {  // pw == 64: one 64-column group per pass, nothing is stored
-          if (epi.topk_k > 4) {
-            rowstats_topk_group<8>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
-          } else if (epi.topk_k > 0) {
-            rowstats_topk_group<4>(tmem_d + (uint32_t)c0, bsp, left, n0 + c0, row_ok, row, epi);
-          } else {
-            float rm = -INFINITY, rs = 0.f;
-            epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
-            epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
-            if (row_ok && left > 0) {
-              const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
-              epi.stats_m[o] = rm;
-              epi.stats_s[o] = rs;
-            }
+          float rm = -INFINITY, rs = 0.f;
+          epilogue_stats32(tmem_d + (uint32_t)c0, bsp, left, rm, rs);
+          epilogue_stats32(tmem_d + (uint32_t)(c0 + 32), bsp ? bsp + 32 : nullptr, left - 32, rm, rs);
+          if (row_ok && left > 0) {
+            const long o = (long)row * epi.stats_ld + ((n0 + c0) >> 6);
+            epi.stats_m[o] = rm;
+            epi.stats_s[o] = rs;
           }
           if (ps == my_last) {
             tc_fence_before();
@@ -1200,8 +1001,6 @@ int launch(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   }
   TcShape sh;
   sh.tma_out = out_mode;
-  sh.direct_out = 0;
-  sh.c_ptr = c.C;
   sh.trace = g_trace;
   sh.M = c.M; sh.N = c.N; sh.K = c.K;
   sh.tiles_m = (c.M + BM * MT - 1) / (BM * MT); sh.tiles_n = (c.N + BN - 1) / BN;
@@ -1254,12 +1053,6 @@ int launch_pair(GemmContext& ctx, const GemmCall& c, int splits, int kbps) {
   TcShape sh;
   sh.tma_out = 1;
   sh.trace = nullptr;
-#ifndef CAPDEC_GEMM_DIRECT_OUT
-#define CAPDEC_GEMM_DIRECT_OUT 1   // build-time A/B switch of the direct-store epilogue (profiling)
-#endif
-  // direct stores need whole 16-byte vectors inside a row: the C pitch / base alignment pair_eligible() already demands
-  sh.direct_out = (CAPDEC_GEMM_DIRECT_OUT && EPI2 && !e.atomic && e.act != ACT_ROWSTATS) ? 1 : 0;
-  sh.c_ptr = c.C;
   sh.M = c.M; sh.N = c.N; sh.K = c.K;
   sh.tiles_m = (c.M + 2 * BM - 1) / (2 * BM); sh.tiles_n = (c.N + kPairBN - 1) / kPairBN;
   sh.splits = splits; sh.kb_per_split = kbps; sh.ldc = c.ldc; sh.vec_ok = 1;
@@ -1314,8 +1107,7 @@ int gemm_bf16_tc(GemmContext& ctx, const GemmCall& c) {
     const GemmEpi& e = c.epi;
     const bool ok = !e.out_f32 && !e.atomic && c.batch <= 1 && !e.addend && !e.dact_y && (!e.bias || e.aux_padded) &&
                     (((uintptr_t)c.C & 15) == 0) && ((c.ldc * 2) % 16 == 0) && e.stats_m && e.stats_s &&
-                    e.stats_ld >= (c.N + 63) / 64 && e.topk_k >= 0 && e.topk_k <= 8 &&
-                    (e.topk_k == 0 || (e.topk_v && e.topk_i && ((uintptr_t)e.topk_v & 15) == 0 && ((uintptr_t)e.topk_i & 15) == 0));
+                    e.stats_ld >= (c.N + 63) / 64;
     if (!ok) { set_error("gemm_tc: unsupported arguments for the row-statistics epilogue"); return -1; }
   }
   if (c.splits > 1 && !c.epi.atomic) { set_error("gemm_tc: split-K needs an atomic epilogue"); return -1; }

@@ -217,12 +217,6 @@ int beam_max_vocab();
 void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int beam, int step, int T_total, int pad,
                int stop, int finish_on_stop, const float* score_in, float* score_out, const int* fin_in, int* fin_out,
                const int* hist_in, int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace);
-// the same step from the per-64-column-group statistics and top-KB candidates left by the vocabulary GEMM's epilogue
-// (gemm.cuh ACT_ROWSTATS + topk_k; KB = 4 or 8 >= beam): st_m, st_s [rows, ld]; tk_v, tk_i [rows, ld, KB]; S = groups
-void beam_step_partials(LaunchCtx c, int S, long ld, const float* st_m, const float* st_s, const float* tk_v, const int* tk_i,
-                        int KB, int V, int n_img, int beam, int step, int T_total, int pad, int stop, int finish_on_stop,
-                        const float* score_in, float* score_out, const int* fin_in, int* fin_out, const int* hist_in,
-                        int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace);
 // initial beam state: score = 0 for prefix 0 of every image, -inf for the others; tok = start; src = r % beam
 void beam_init(LaunchCtx c, int R, int beam, int start, float* score, int* tok, int* src);
 // next-step operands: xin[r] = [emb[tok[r]] | h_new[src_row(r)]], c_next[r] = c_new[src_row(r)]

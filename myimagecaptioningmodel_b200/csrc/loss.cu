@@ -190,83 +190,6 @@ beam_rows_kernel(const float* __restrict__ logits, long ldl, int V, int beam, in
   }
 }
 
-// The same per-row result from the PARTIAL statistics and candidates the vocabulary GEMM's epilogue leaves per 64-column
-// group (gemm.cuh ACT_ROWSTATS with topk_k: max, sum exp, and the KB largest logits with their token ids) -- the [rows, V]
-// logits are never written (76 MB per decode step at 512 images x beam 3) nor read back.  One warp per row: lane l owns
-// the groups l, l + 32, ..; every comparison uses (logit desc, token asc), so ties resolve like the full-row kernel.
-template <int KB>
-__global__ void __launch_bounds__(256)
-beam_rows_partial_kernel(long rows, int S, long ld, const float* __restrict__ st_m, const float* __restrict__ st_s,
-                         const float* __restrict__ tk_v, const int* __restrict__ tk_i, int V, int beam, int pad,
-                         int finish_on_stop, const float* __restrict__ score_in, const int* __restrict__ fin_in,
-                         float* __restrict__ cand_v, int* __restrict__ cand_i, float* __restrict__ gscore) {
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long r = (long)blockIdx.x * 8 + warp;
-  if (r >= rows) return;
-  const int p = (int)(r % beam);
-  const int INT_BIG = 0x7fffffff;
-  const bool greedy = (beam == 1 && !finish_on_stop);
-  float* cv = cand_v + r * kMaxBeam;
-  int* ci = cand_i + r * kMaxBeam;
-  const float sc = score_in[r];
-  if (!(sc > -INFINITY)) {  // dead prefix: no candidates
-    if (lane < beam) { cv[lane] = -INFINITY; ci[lane] = INT_BIG; }
-    return;
-  }
-  if (finish_on_stop && fin_in[r]) {  // finished: one candidate, itself + pad, score unchanged
-    if (lane < beam) { cv[lane] = lane == 0 ? sc : -INFINITY; ci[lane] = lane == 0 ? p * V + pad : INT_BIG; }
-    return;
-  }
-  const float* gm = st_m + r * ld;
-  const float* gs = st_s + r * ld;
-  float m = -INFINITY;
-  for (int g = lane; g < S; g += 32) m = fmaxf(m, gm[g]);
-  m = warp_max(m);
-  float sum = 0.f;
-  for (int g = lane; g < S; g += 32) sum += gs[g] * __expf(gm[g] - m);
-  sum = warp_sum(sum);
-  const float lse = m + logf(sum);
-  // this lane's best candidates, sorted by (logit desc, token asc)
-  float lv[kMaxBeam];
-  int li[kMaxBeam];
-#pragma unroll
-  for (int j = 0; j < kMaxBeam; ++j) { lv[j] = -INFINITY; li[j] = INT_BIG; }
-  for (int g = lane; g < S; g += 32) {
-    const float* v = tk_v + (r * ld + g) * KB;
-    const int* ix = tk_i + (r * ld + g) * KB;
-#pragma unroll
-    for (int j = 0; j < KB; ++j) {
-      const float x = v[j];
-      const int n = ix[j];
-      if (n != INT_BIG && better(x, n, lv[kMaxBeam - 1], li[kMaxBeam - 1])) {
-        lv[kMaxBeam - 1] = x; li[kMaxBeam - 1] = n;
-#pragma unroll
-        for (int q = kMaxBeam - 1; q > 0; --q) {
-          if (better(lv[q], li[q], lv[q - 1], li[q - 1])) {
-            const float fv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = fv;
-            const int iv = li[q]; li[q] = li[q - 1]; li[q - 1] = iv;
-          }
-        }
-      }
-    }
-  }
-  for (int rr = 0; rr < beam; ++rr) {
-    const Cand wb = warp_best(Cand{lv[0], li[0]});   // every lane offers the head of its list
-    if (lane == 0) {
-      // greedy ranks the raw logits exactly like layers.argmax (model:120); the score is still accumulated
-      cv[rr] = (wb.idx == INT_BIG) ? -INFINITY : (greedy ? wb.v : sc + (wb.v - lse));
-      ci[rr] = (wb.idx == INT_BIG) ? INT_BIG : p * V + wb.idx;
-      if (greedy) gscore[r] = sc + (wb.v - lse);
-    }
-    if (wb.idx != INT_BIG && li[0] == wb.idx) {   // token ids are unique within a row: exactly one lane pops
-#pragma unroll
-      for (int q = 0; q + 1 < kMaxBeam; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
-      lv[kMaxBeam - 1] = -INFINITY; li[kMaxBeam - 1] = INT_BIG;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(128)
 beam_merge_kernel(int n_img, int V, int beam, int step, int T_total, int pad, int stop, int finish_on_stop,
                   const float* __restrict__ cand_v, const int* __restrict__ cand_i, const float* __restrict__ gscore,
@@ -416,28 +339,6 @@ void beam_step(LaunchCtx c, const float* logits, long ldl, int V, int n_img, int
   else if (V <= kRowThreads * 49) LAUNCH_ROWS(49);      // config.py:55 (12295)
   else LAUNCH_ROWS(64);                                  // up to beam_max_vocab()
 #undef LAUNCH_ROWS
-  beam_merge_kernel<<<(n_img + 3) / 4, 128, 0, c.stream>>>(n_img, V, beam, step, T_total, pad, stop, finish_on_stop, cv, ci,
-                                                          gs, score_out, fin_in, fin_out, hist_in, hist_out, tok_out,
-                                                          src_out, trace);
-  if (c.launches) *c.launches += 2;
-}
-void beam_step_partials(LaunchCtx c, int S, long ld, const float* st_m, const float* st_s, const float* tk_v, const int* tk_i,
-                        int KB, int V, int n_img, int beam, int step, int T_total, int pad, int stop, int finish_on_stop,
-                        const float* score_in, float* score_out, const int* fin_in, int* fin_out, const int* hist_in,
-                        int* hist_out, int* tok_out, int* src_out, void* scratch, int* trace) {
-  if (n_img <= 0) return;
-  const long rows = (long)n_img * beam;
-  char* sp = static_cast<char*>(scratch);
-  float* cv = reinterpret_cast<float*>(sp);
-  int* ci = reinterpret_cast<int*>(sp + (size_t)rows * kMaxBeam * 4);
-  float* gs = reinterpret_cast<float*>(sp + (size_t)rows * kMaxBeam * 8);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (KB == 4)
-    beam_rows_partial_kernel<4><<<grid, 256, 0, c.stream>>>(rows, S, ld, st_m, st_s, tk_v, tk_i, V, beam, pad, finish_on_stop,
-                                                           score_in, fin_in, cv, ci, gs);
-  else
-    beam_rows_partial_kernel<8><<<grid, 256, 0, c.stream>>>(rows, S, ld, st_m, st_s, tk_v, tk_i, V, beam, pad, finish_on_stop,
-                                                           score_in, fin_in, cv, ci, gs);
   beam_merge_kernel<<<(n_img + 3) / 4, 128, 0, c.stream>>>(n_img, V, beam, step, T_total, pad, stop, finish_on_stop, cv, ci,
                                                           gs, score_out, fin_in, fin_out, hist_in, hist_out, tok_out,
                                                           src_out, trace);
