@@ -153,11 +153,12 @@ int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_de
 /* Data-parallel callers (the reference's ParallelExecutor wrapper, train.py:119-127): up to five
  * cudaEvent_t (as void*; n = 0 switches the marks off) that every following capdec_train_bwd records on its stream as
  * soon as a group of gradients is final, so that the caller can all-reduce that group while the rest of the backward pass
- * still runs.  Groups, in the order they become final (rows refer to lstm_w [E+2H, 4H]):
+ * still runs.  Groups (rows refer to lstm_w [E+2H, 4H]) -- they become final in the order 0, 2, 3, 1, 4: after the BPTT
+ * kernel the largest ranges come first, so that their exchange has the most work left to hide behind:
  *   events[0]  fc_hs_w .. fc_e_b (fc_hs, fc_p, fc_g, fc_s, fc_a, fc_o, fc_e) and fc_v_w .. fc_k_b  -- before the BPTT kernel
- *   events[1]  word_embedding, out_fc_bias                                                         -- first work after it
- *   events[2]  lstm_w rows [E+H, E+2H)  (hidden-state rows)
+ *   events[2]  lstm_w rows [E+H, E+2H)  (hidden-state rows)                                        -- first work after it
  *   events[3]  lstm_w rows [E, E+H)     (global-image rows)
+ *   events[1]  word_embedding, out_fc_bias
  *   events[4]  lstm_b, fc_xs_w, fc_xs_b, lstm_w rows [0, E) (word rows)                            -- last work of the call */
 int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n);
 
@@ -206,6 +207,12 @@ int capdec_img2feature_bwd(capdec_handle h, float* d_enc_map, const capdec_adapt
  * clip_value > 0 applies GradientClipByValue(clip_value) to g first (train.py:41-42); 0 = off (config.py:36). */
 int capdec_adam_step(float* param, const float* grad, float* moment1, float* moment2, int64_t n, float lr, float beta1,
                      float beta2, float epsilon, float beta1_pow, float beta2_pow, float clip_value, void* stream);
+
+/* Data-parallel gradient exchange in bf16 (train.py:119-127 is the wrapper being replaced): a range of the
+ * flat fp32 gradient buffer is rounded to bf16 (round to nearest even) for the NCCL all-reduce and widened back, so
+ * that half the bytes cross NVLink.  n % 8 == 0, 16-byte aligned pointers.  to_bf16 != 0: src fp32 -> dst bf16;
+ * to_bf16 == 0: src bf16 -> dst fp32. */
+int capdec_cast_bf16(int32_t to_bf16, const void* src, void* dst, int64_t n, void* stream);
 
 /* ---- kernel-level entry points (parity tests and micro-benchmarks) ------------------------------------------ */
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "capdec_gemm", "capdec_attention_fwd", "capdec_attention_bwd", "capdec_lstm_cell_fwd", "capdec_beam_step",
     "capdec_profile", "capdec_profile_report", "capdec_set_grad_ready_events",
     "capdec_bind_adaptor", "capdec_img2feature", "capdec_img2feature_bwd", "capdec_adam_step", "capdec_decode_trace",
-    "capdec_status",
+    "capdec_status", "capdec_cast_bf16",
 ]
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
@@ -93,6 +93,7 @@ def load_library(build_if_missing: bool = True):
     lib.capdec_decode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.capdec_decode_trace.argtypes = [vp, vp, vp]
     lib.capdec_status.argtypes = [vp, vp]
+    lib.capdec_cast_bf16.argtypes = [i32, vp, vp, i64, vp]
     lib.capdec_bind_adaptor.argtypes = [vp, i32, C.POINTER(CapdecAdaptorParams), vp]
     lib.capdec_img2feature.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.capdec_img2feature_bwd.argtypes = [vp, vp, C.POINTER(CapdecAdaptorGrads), vp]

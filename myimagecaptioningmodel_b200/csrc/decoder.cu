@@ -777,6 +777,12 @@ template <typename T> class Decoder : public DecoderBase {
     // After the BPTT everything left is independent; it is ordered so that the gradients become final in large groups
     // early and a small one last (capdec_set_grad_ready_events): each group's all-reduce runs behind the remaining work.
     const T* HprevFull = hs.as<T>();   // h_{t-1} of ALL rows: the recurrence ran on every (step, sample)
+    // weight gradients of the gate GEMM, batched over all steps
+    OK(wgrad(gc, HprevFull, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
+    mark_ready(2, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
+    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
+    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
+    mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
     {
       GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
       c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
@@ -785,12 +791,6 @@ template <typename T> class Decoder : public DecoderBase {
     }
     embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
     mark_ready(1, s);  // word_embedding, out_fc_bias are final
-    // weight gradients of the gate GEMM, batched over all steps
-    OK(wgrad(gc, HprevFull, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
-    mark_ready(2, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
-    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
-    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
-    mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
     if (dg) {
       GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
@@ -1266,6 +1266,19 @@ int capdec_adam_step(float* param, const float* grad, float* moment1, float* mom
                 beta2_pow, clip_value)) {
     set_error("capdec_adam_step: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -1;
   }
+  return 0;
+}
+
+int capdec_cast_bf16(int32_t to_bf16, const void* src, void* dst, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst))) { set_error("capdec_cast_bf16: null buffer"); return -1; }
+  if (n % 8 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) {
+    set_error("capdec_cast_bf16: n must be a multiple of 8 and the buffers 16-byte aligned"); return -1;
+  }
+  LaunchCtx lc{(cudaStream_t)stream, nullptr};
+  if (to_bf16) convert_from_f32<bf16>(lc, static_cast<const float*>(src), static_cast<bf16*>(dst), (long)n);
+  else convert_to_f32<bf16>(lc, static_cast<const bf16*>(src), static_cast<float*>(dst), (long)n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("capdec_cast_bf16: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 

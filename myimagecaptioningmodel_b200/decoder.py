@@ -436,9 +436,9 @@ class CaptionDecoderEngine:
         lw = st.offsets["lstm_w"]
         row = 4 * H
         out = [(0,) + span("fc_hs_w", "fc_k_b"),                         # head parameters and fc_v, fc_k
-               (1,) + span("word_embedding", "out_fc_bias"),
                (2, lw + (E + H) * row, lw + (E + 2 * H) * row),          # lstm_w hidden-state rows
                (3, lw + E * row, lw + (E + H) * row),                    # lstm_w global-image rows
+               (1,) + span("word_embedding", "out_fc_bias"),
                (4, st.offsets["lstm_b"], lw + E * row)]                  # lstm_b, fc_xs_* and the lstm_w word rows
         return out
 
