@@ -42,12 +42,14 @@ BEAM = 3
 SOFTMAX_AXIS = "position"     # the full attention arithmetic; the parity gate also covers 'feature'
 
 
-def workload_config(n_gpus):
-    return {"workload": "teacher_forced_train_step_B256_per_gpu_T34_H1024_E256_V12295_k49", "global_batch": B_PER_GPU * n_gpus,
-            "batch_per_gpu": B_PER_GPU, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
+def workload_config(n_gpus, b_per_gpu=B_PER_GPU):
+    return {"workload": "teacher_forced_train_step_B%d_per_gpu_T34_H1024_E256_V12295_k49" % b_per_gpu,
+            "global_batch": b_per_gpu * n_gpus,
+            "batch_per_gpu": b_per_gpu, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
             "lengths": "host token counts passed (captions L ~ U{5..33} words: 57 % of the B x 34 rows carry a target; the "
                        "head skips the others, loss and gradients unchanged); tokens/s counts all B x 34 positions",
-            "parallelism": "dp%d" % n_gpus, "step": "bind_params+train_fwd+train_bwd(+allreduce)+adam(paddle-1.8 rule, lr 5e-5)",
+            "parallelism": "dp%d" % n_gpus, "grad_exchange": "bf16 on the wire (fp32 buffers), one all-reduce per gradient range",
+            "step": "bind_params+train_fwd+train_bwd(+allreduce)+adam(paddle-1.8 rule, lr 5e-5)",
             "e2e": "pinned host buffers, H2D of the next batch prefetched on a copy stream, loss D2H every step (read by the "
                    "host one step later)",
             "l2": "per-step working set ~1.5 GB >> 126 MB L2 (no flush needed)"}
@@ -276,8 +278,8 @@ def main_ours(args):
 
     cfg = M.DecoderConfig(dtype="bf16", softmax_axis=SOFTMAX_AXIS)
     eng = M.CaptionDecoderEngine(cfg, seed=0)           # same weights on every rank (replicated)
-    trainer = M.DataParallelTrainer(eng)
-    B = B_PER_GPU
+    trainer = M.DataParallelTrainer(eng, grad_exchange=args.grad_exchange)
+    B = args.batch_per_gpu      # 256 = BASELINE.json configs[1]; configs[2] at 2 / 4 GPUs (global 2048) is --batch-per-gpu 1024 / 512
     g_h, P_h, cap_h = synth.make_batch(cfg, B, 20260 + rank)
     g_h, P_h, cap_h = g_h.pin_memory(), P_h.pin_memory(), cap_h.pin_memory()
     g_d, P_d, cap_d = g_h.cuda(), P_h.cuda(), cap_h.cuda()
@@ -594,7 +596,7 @@ def main_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world, B),
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps, "h2d_alone_ms_per_step": ms_h2d,
@@ -639,6 +641,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-per-gpu", type=int, default=B_PER_GPU,
+                    help="captions per GPU and step (default 256 = BASELINE.json configs[1]; configs[2] keeps the global batch at "
+                         "2048: 1024 at 2 GPUs, 512 at 4, 256 at 8)")
+    ap.add_argument("--grad-exchange", default=None, choices=["fp32", "bf16"],
+                    help="wire type of the data-parallel gradient all-reduce (default: bf16 for the bf16 engine)")
     ap.add_argument("--reference-batch", type=int, default=B_PER_GPU,
                     help="batch of the --impl reference arm (default: the bench's own 256; the CPU contract test uses a smaller one)")
     args = ap.parse_args()

@@ -18,7 +18,9 @@ cfg = M.DecoderConfig(dtype="bf16", softmax_axis="position")
 eng = M.CaptionDecoderEngine(cfg, seed=0)
 trainer = M.DataParallelTrainer(eng)
 g, P, cap = synth.make_batch(cfg, 256, 20260 + rank)
+lengths = M.caption_lengths(cap)
 g, P, cap = g.cuda(), P.cuda(), cap.cuda()
+opt = M.Adam([(eng.store.flat, eng.store.flat_grad)], 0.00005)      # the bench's step: Adam per gradient range
 REPS = 10
 e_bwd_end = [torch.cuda.Event(enable_timing=True) for _ in range(REPS)]
 e_step_end = [torch.cuda.Event(enable_timing=True) for _ in range(REPS)]
@@ -36,7 +38,7 @@ def bwd_marked(*a, **k):
 eng.train_backward = bwd_marked
 for i in range(5):
     eng.bind_params()
-    trainer.forward_backward(g, P, cap)
+    trainer.forward_backward(g, P, cap, optimizer=opt, lengths=lengths)
 torch.cuda.synchronize()
 dist.barrier()
 eng.profile(True)
@@ -44,7 +46,7 @@ for i in range(REPS):
     cur["i"] = i
     e_step_start[i].record()
     eng.bind_params()
-    trainer.forward_backward(g, P, cap)
+    trainer.forward_backward(g, P, cap, optimizer=opt, lengths=lengths)
     e_step_end[i].record()
 torch.cuda.synchronize()
 rep = eng.profile_report()
