@@ -48,7 +48,7 @@ def workload_config(n_gpus, b_per_gpu=B_PER_GPU):
             "batch_per_gpu": b_per_gpu, "steps_per_caption": 34, "softmax_axis": SOFTMAX_AXIS,
             "lengths": "host token counts passed (captions L ~ U{5..33} words: 57 % of the B x 34 rows carry a target; the "
                        "head skips the others, loss and gradients unchanged); tokens/s counts all B x 34 positions",
-            "parallelism": "dp%d" % n_gpus, "grad_exchange": "bf16 on the wire (fp32 buffers), one all-reduce per gradient range",
+            "parallelism": "dp%d" % n_gpus, "grad_exchange": "fp32, one all-reduce per gradient range as the backward pass finalises it",
             "step": "bind_params+train_fwd+train_bwd(+allreduce)+adam(paddle-1.8 rule, lr 5e-5)",
             "e2e": "pinned host buffers, H2D of the next batch prefetched on a copy stream, loss D2H every step (read by the "
                    "host one step later)",
@@ -645,7 +645,7 @@ def main():
                     help="captions per GPU and step (default 256 = BASELINE.json configs[1]; configs[2] keeps the global batch at "
                          "2048: 1024 at 2 GPUs, 512 at 4, 256 at 8)")
     ap.add_argument("--grad-exchange", default=None, choices=["fp32", "bf16"],
-                    help="wire type of the data-parallel gradient all-reduce (default: bf16 for the bf16 engine)")
+                    help="wire type of the data-parallel gradient all-reduce (default fp32)")
     ap.add_argument("--reference-batch", type=int, default=B_PER_GPU,
                     help="batch of the --impl reference arm (default: the bench's own 256; the CPU contract test uses a smaller one)")
     args = ap.parse_args()

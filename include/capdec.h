@@ -150,16 +150,19 @@ int capdec_train_fwd(capdec_handle h, const float* global_img_feat, const float*
 int capdec_train_bwd(capdec_handle h, float loss_scale, const float* inv_ntok_dev, float* d_global_img_feat,
                      float* d_p_img_feat, const capdec_grads* g, void* stream);
 
-/* Data-parallel callers (the reference's ParallelExecutor wrapper, train.py:119-127): up to five
+/* Data-parallel callers (the reference's ParallelExecutor wrapper, train.py:119-127): up to six
  * cudaEvent_t (as void*; n = 0 switches the marks off) that every following capdec_train_bwd records on its stream as
  * soon as a group of gradients is final, so that the caller can all-reduce that group while the rest of the backward pass
- * still runs.  Groups (rows refer to lstm_w [E+2H, 4H]) -- they become final in the order 0, 2, 3, 1, 4: after the BPTT
- * kernel the largest ranges come first, so that their exchange has the most work left to hide behind:
- *   events[0]  fc_hs_w .. fc_e_b (fc_hs, fc_p, fc_g, fc_s, fc_a, fc_o, fc_e) and fc_v_w .. fc_k_b  -- before the BPTT kernel
+ * still runs.  Groups (rows refer to lstm_w [E+2H, 4H]), in the order they become final: 0, 2, 3, 4, 1, 5.  Only the
+ * weight gradients of the head are final before the BPTT kernel; the gate-weight gradients, which exist only after it,
+ * come next (largest first) and the vocabulary-side and per-image weight gradients -- independent of the recurrence -- are
+ * computed last, so that every exchange but the last small one has work to hide behind:
+ *   events[0]  fc_hs_w .. fc_e_b (fc_hs, fc_p, fc_g, fc_s, fc_a, fc_o, fc_e)                      -- before the BPTT kernel
  *   events[2]  lstm_w rows [E+H, E+2H)  (hidden-state rows)                                        -- first work after it
  *   events[3]  lstm_w rows [E, E+H)     (global-image rows)
+ *   events[4]  lstm_b, fc_xs_w, fc_xs_b, lstm_w rows [0, E) (word rows)
  *   events[1]  word_embedding, out_fc_bias
- *   events[4]  lstm_b, fc_xs_w, fc_xs_b, lstm_w rows [0, E) (word rows)                            -- last work of the call */
+ *   events[5]  fc_v_w .. fc_k_b                                                                    -- last work of the call */
 int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n);
 
 /* Inference: Decoder(mode='eval').call (model:55-58, 66-69, 119-123, 132-133) generalised to beam search

@@ -133,7 +133,7 @@ class DecoderBase {
     return e;
   }
   // caller-owned events recorded by train_bwd when a group of gradients is final (capdec_set_grad_ready_events)
-  cudaEvent_t grad_ready[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t grad_ready[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void mark_ready(int i, cudaStream_t s) {
     if (grad_ready[i]) cudaEventRecord(grad_ready[i], s);
   }
@@ -629,15 +629,17 @@ template <typename T> class Decoder : public DecoderBase {
     // (softmax_with_cross_entropy_grad + the mask/scale ops) is applied by its three consumers
     float* gscale = acc.as<float>() + 4;
     scale_scalar(lc, inv_ntok ? inv_ntok : acc.as<float>() + 3, loss_scale, gscale);
-    colsum_add<T>(lc, dlogits.as<T>(), Vp, Mp, V, G.out_fc_bias, gscale);
-    // tied output projection (model:24-25): d proj, d Emb (output side), d fc_e
+    // Only what the BPTT kernel needs (the data-gradient chain down to d h, d c) and the weight gradients that are final
+    // with it run before that kernel; the vocabulary-side and per-image weight gradients are independent of the recurrence
+    // and run at the END of the pass, so that the gate-weight gradients -- which exist only after the BPTT -- are exchanged
+    // behind them instead of behind nothing (data-parallel: the exposed tail was 334 us at 8 GPUs).
+    // tied output projection (model:24-25): d proj, d fc_e
     {
       GemmCall c;
       c.A = dlogits.p; c.lda = Vp; c.B = emb.p; c.ldb = E; c.b_mn = true; c.C = dproj.p; c.ldc = E; c.M = Mh; c.N = E;
       c.K = V; c.epi.alpha_dev = gscale;
       OK(gemm<T>(gc, c));
     }
-    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, Mh, G.word_embedding, E, gscale));
     ColsumTable bias_sums;  // the bias gradients of the time-batched head: one launch, just before their group is marked
     bias_sums.add(dproj.p, E, Mp, E, G.fc_e_b);
     OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, Mh, G.fc_e_w, E));
@@ -719,32 +721,10 @@ template <typename T> class Decoder : public DecoderBase {
     if (packed)   // the BPTT kernel reads both by (step, sample): back to padded rows, zeros where no target exists
       scatter_rows_zero<T>(lc, dHhead_c.as<T>(), dHprev_c.as<T>(), d_prow, M, H, dHhead.as<T>(), dHprev.as<T>());
     prof.mark("bwd.head_fc", s);
-    // once-per-image projections (model:52-53)
-    bias_sums.add(dkv.p, 2 * H, (long)B * k, H, G.fc_v_b);
-    bias_sums.add(dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
-    OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
-    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
-    if (dP) {
-      GemmCall c;  // d p_img_feat
-      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
-      c.epi.out_f32 = 1;
-      OK(gemm<T>(gc, c));
-    }
-    if (fwd_staged) {
-      // the features came from the adaptor (capdec_img2feature): leave d(pre-ReLU img_embed) = d p_img_feat * [P > 0]
-      // in the handle for capdec_img2feature_bwd (model:197)
-      OK(dzp.ensure(e * (size_t)B * k * H, &ws_bytes));
-      GemmCall c;
-      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dzp.p; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
-      c.epi.act = ACT_DRELU; c.epi.dact_y = PT.p; c.epi.ld_y = H;
-      OK(gemm<T>(gc, c));
-    }
     colsum_multi<T>(lc, bias_sums);
     CUDA_OK(cudaMemcpyAsync(G.fc_xs_b, G.fc_hs_b, 4 * H, cudaMemcpyDeviceToDevice, s));  // same pre-activation
-    prof.mark("bwd.image_kv", s);
-    // fc_hs .. fc_e (incl. fc_a) and fc_v, fc_k are final: their all-reduce overlaps the BPTT.  (The per-image
-    // projections depend on the attention gradients only, so they run here rather than at the end of the pass, where
-    // their gradients would be exchanged with nothing left to hide behind.)
+    prof.mark("bwd.head_bias", s);
+    // fc_hs .. fc_e (incl. fc_a) are final: their all-reduce overlaps the BPTT
     mark_ready(0, s);
     // BPTT through the recurrent core (while_grad of model:87-88, 94-95)
     bool persistent = false;
@@ -783,14 +763,6 @@ template <typename T> class Decoder : public DecoderBase {
     sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
     OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
     mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
-    {
-      GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
-      c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
-      c.K = 5 * H;
-      OK(gemm<T>(gc, c));
-    }
-    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
-    mark_ready(1, s);  // word_embedding, out_fc_bias are final
     if (dg) {
       GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
@@ -809,8 +781,44 @@ template <typename T> class Decoder : public DecoderBase {
     OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
     colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
     OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
-    mark_ready(4, s);  // lstm_b, fc_xs_w, fc_xs_b and the lstm_w word rows: everything is final
-    prof.mark("bwd.gate_wgrad_embed", s);
+    mark_ready(4, s);  // lstm_b, fc_xs_w, fc_xs_b and the lstm_w word rows are final
+    prof.mark("bwd.gate_wgrad", s);
+    // the tied table: lookup side (needs d gates) + output side (deferred from the start of the pass), out_fc_bias
+    {
+      GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
+      c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
+      c.K = 5 * H;
+      OK(gemm<T>(gc, c));
+    }
+    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
+    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, Mh, G.word_embedding, E, gscale));
+    colsum_add<T>(lc, dlogits.as<T>(), Vp, Mp, V, G.out_fc_bias, gscale);
+    mark_ready(1, s);  // word_embedding, out_fc_bias are final
+    prof.mark("bwd.embedding", s);
+    ColsumTable kv_sums;
+    // once-per-image projections (model:52-53)
+    kv_sums.add(dkv.p, 2 * H, (long)B * k, H, G.fc_v_b);
+    kv_sums.add(dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
+    OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
+    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
+    if (dP) {
+      GemmCall c;  // d p_img_feat
+      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
+      c.epi.out_f32 = 1;
+      OK(gemm<T>(gc, c));
+    }
+    if (fwd_staged) {
+      // the features came from the adaptor (capdec_img2feature): leave d(pre-ReLU img_embed) = d p_img_feat * [P > 0]
+      // in the handle for capdec_img2feature_bwd (model:197)
+      OK(dzp.ensure(e * (size_t)B * k * H, &ws_bytes));
+      GemmCall c;
+      c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dzp.p; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
+      c.epi.act = ACT_DRELU; c.epi.dact_y = PT.p; c.epi.ld_y = H;
+      OK(gemm<T>(gc, c));
+    }
+    colsum_multi<T>(lc, kv_sums);
+    mark_ready(5, s);  // fc_v, fc_k: everything is final
+    prof.mark("bwd.image_kv", s);
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1171,8 +1179,8 @@ int capdec_destroy(capdec_handle h) {
 
 int capdec_set_grad_ready_events(capdec_handle h, void* const* events, int32_t n) {
   if (!h || !h->impl) { set_error("null capdec handle"); return -1; }
-  if (n < 0 || n > 5 || (n > 0 && !events)) { set_error("capdec_set_grad_ready_events: need 0 <= n <= 5 events"); return -1; }
-  for (int i = 0; i < 5; ++i) h->impl->grad_ready[i] = (i < n) ? (cudaEvent_t)events[i] : nullptr;
+  if (n < 0 || n > 6 || (n > 0 && !events)) { set_error("capdec_set_grad_ready_events: need 0 <= n <= 6 events"); return -1; }
+  for (int i = 0; i < 6; ++i) h->impl->grad_ready[i] = (i < n) ? (cudaEvent_t)events[i] : nullptr;
   return 0;
 }
 

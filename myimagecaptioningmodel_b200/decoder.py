@@ -422,7 +422,7 @@ class CaptionDecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self.handle))
 
-    N_GRAD_EVENTS = 5
+    N_GRAD_EVENTS = 6
 
     def grad_group_slices(self):
         """[(event index, lo, hi)]: element ranges of store.flat_grad in the order capdec_train_bwd finalises them
@@ -435,11 +435,12 @@ class CaptionDecoderEngine:
 
         lw = st.offsets["lstm_w"]
         row = 4 * H
-        out = [(0,) + span("fc_hs_w", "fc_k_b"),                         # head parameters and fc_v, fc_k
+        out = [(0,) + span("fc_hs_w", "fc_e_b"),                         # head parameters: final before the BPTT kernel
                (2, lw + (E + H) * row, lw + (E + 2 * H) * row),          # lstm_w hidden-state rows
                (3, lw + E * row, lw + (E + H) * row),                    # lstm_w global-image rows
+               (4, st.offsets["lstm_b"], lw + E * row),                  # lstm_b, fc_xs_* and the lstm_w word rows
                (1,) + span("word_embedding", "out_fc_bias"),
-               (4, st.offsets["lstm_b"], lw + E * row)]                  # lstm_b, fc_xs_* and the lstm_w word rows
+               (5,) + span("fc_v_w", "fc_k_b")]                          # per-image projections: last work of the pass
         return out
 
     def set_grad_ready_events(self, events) -> None:

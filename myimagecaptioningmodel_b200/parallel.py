@@ -6,8 +6,8 @@ Training shards along the batch; the only exchange steps are
       (model:169, 182), not ParallelExecutor's per-device averaging (offered as `pe_semantics=True`); the loss value
       sum(ce*mask) is all-reduced beside the backward pass;
   (2) the all-reduce (sum) of the flat gradient buffer over NCCL / NVLink, one call per gradient range as the backward
-      pass finalises it; with `grad_exchange="bf16"` (the default for a bf16 engine) every range is rounded to bf16 for the
-      wire (43 MB instead of 86 MB, libcapdec's cast kernels) and widened back into the fp32 buffer.
+      pass finalises it; with `grad_exchange="bf16"` every range is rounded to bf16 for the wire (43 MB instead of 86 MB,
+      libcapdec's cast kernels) and widened back into the fp32 buffer.
 Inference shards by image with no collective on the data path.
 
 The class is written against a small engine protocol (train_forward / train_backward / store.flat_grad) so the
@@ -33,16 +33,15 @@ def shard_range(n_global: int, rank: int, world: int) -> Tuple[int, int]:
 class DataParallelTrainer:
     def __init__(self, engine, group: Optional["dist.ProcessGroup"] = None, pe_semantics: bool = False,
                  grad_exchange: Optional[str] = None):
-        """grad_exchange: "fp32" = all-reduce the fp32 gradient ranges as they are; "bf16" = round every range to bf16 for
-        the all-reduce (half the NVLink bytes; the sum of N bf16 addends carries ~2^-9 relative rounding per element, inside
-        the bf16 storage mode's 2e-2 tolerance) and widen it back; None = "bf16" for a bf16-storage engine on GPUs, else "fp32"."""
+        """grad_exchange: "fp32" (default) = all-reduce the fp32 gradient ranges as they are; "bf16" = round every range to
+        bf16 for the all-reduce (half the NVLink bytes; the sum of N bf16 addends carries ~2^-9 relative rounding per
+        element, inside the bf16 storage mode's 2e-2 tolerance) and widen it back."""
         self.engine = engine
         self.group = group
         self.pe_semantics = pe_semantics
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if grad_exchange is None:
-            cfg = getattr(engine, "cfg", None)
-            grad_exchange = "bf16" if (getattr(cfg, "dtype", None) == "bf16" and hasattr(engine, "lib")) else "fp32"
+            grad_exchange = "fp32"
         if grad_exchange not in ("fp32", "bf16"):
             raise ValueError("grad_exchange must be 'fp32' or 'bf16'")
         self.grad_exchange = grad_exchange
@@ -156,7 +155,9 @@ class DataParallelTrainer:
         if not hasattr(eng, "set_grad_ready_events") or not torch.cuda.is_available():
             return
         self._comm = torch.cuda.Stream()
-        self._events = [torch.cuda.Event() for _ in range(getattr(eng, "N_GRAD_EVENTS", 5))]
+        self._upd = torch.cuda.Stream()      # parameter updates: the next range's all-reduce does not wait for Adam
+        self._events = [torch.cuda.Event() for _ in range(getattr(eng, "N_GRAD_EVENTS", 6))]
+        self._reduced = [torch.cuda.Event() for _ in self._events]
         for e in self._events:
             e.record()                      # creates the underlying cudaEvent_t
         eng.set_grad_ready_events(self._events)
@@ -184,6 +185,7 @@ class DataParallelTrainer:
             return
         main = torch.cuda.current_stream()
         lr = optimizer.current_lr() if optimizer is not None else None
+        upd = self._upd if (reduce and optimizer is not None) else self._comm
         with torch.cuda.stream(self._comm):
             for ev, lo, hi in self._slices:
                 # every group waits for its own event, recorded by capdec_train_bwd in the middle of the backward pass
@@ -191,7 +193,15 @@ class DataParallelTrainer:
                 if reduce:
                     self._all_reduce(flat, lo, hi)
                 if optimizer is not None:
-                    optimizer.step_range(0, lo, hi, lr)
+                    if upd is not self._comm:
+                        self._reduced[ev].record(self._comm)
+                        with torch.cuda.stream(upd):
+                            upd.wait_event(self._reduced[ev])
+                            optimizer.step_range(0, lo, hi, lr, stream=upd)
+                    else:
+                        optimizer.step_range(0, lo, hi, lr)
+            if upd is not self._comm:
+                self._comm.wait_stream(upd)
             if extra:
                 self._comm.wait_stream(main)                 # the adaptor backward runs after capdec_train_bwd
                 for i, t in enumerate(extra):

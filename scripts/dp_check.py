@@ -27,7 +27,7 @@ g, P, cap = synth.make_batch(cfg, B, 4242)            # the same global batch on
 g, P, cap = g.cuda(), P.cuda(), cap.cuda()
 eng = M.CaptionDecoderEngine(cfg, seed=0)
 ref = M.CaptionDecoderEngine(cfg, seed=0)
-trainer = M.DataParallelTrainer(eng)
+trainer = M.DataParallelTrainer(eng, grad_exchange=os.environ.get("DP_CHECK_EXCHANGE", "fp32"))
 lo, hi = shard_range(B, rank, world)
 for it in range(3):                                    # repeated: the events / comm stream are reused
     eng.bind_params()

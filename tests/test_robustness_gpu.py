@@ -124,12 +124,13 @@ def test_trainer_loss_is_not_a_view_of_the_live_buffer():
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_two_gpu_data_parallel_equals_single_process(dtype):
+@pytest.mark.parametrize("dtype,exchange", [("fp32", "fp32"), ("bf16", "fp32"), ("bf16", "bf16")])
+def test_two_gpu_data_parallel_equals_single_process(dtype, exchange):
     """scripts/dp_check.py under torch.distributed.run on 2 ranks (NCCL): all-reduced shard gradients == a local
-    full-batch step (fp32: every tensor to 1e-4; bf16: the flat gradient to 1e-2), features and encoder-map entry points."""
-    env = dict(os.environ, DP_CHECK_DTYPE=dtype)
+    full-batch step (fp32: every tensor to 1e-4; bf16: the flat gradient to 1e-2), features and encoder-map entry points;
+    gradient ranges all-reduced in fp32 or rounded to bf16 for the wire."""
+    env = dict(os.environ, DP_CHECK_DTYPE=dtype, DP_CHECK_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541" if dtype == "fp32" else "29542",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29541 + len(dtype + exchange) % 7 + (3 if exchange == "bf16" else 0)),
                         os.path.join(ROOT, "scripts", "dp_check.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DP CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
