@@ -131,6 +131,6 @@ def test_two_gpu_data_parallel_equals_single_process(dtype, exchange):
     gradient ranges all-reduced in fp32 or rounded to bf16 for the wire."""
     env = dict(os.environ, DP_CHECK_DTYPE=dtype, DP_CHECK_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(29541 + len(dtype + exchange) % 7 + (3 if exchange == "bf16" else 0)),
+                        "--master-addr", "127.0.0.1", "--master-port", {"fp32fp32": "29541", "bf16fp32": "29542", "bf16bf16": "29543"}[dtype + exchange],
                         os.path.join(ROOT, "scripts", "dp_check.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DP CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
