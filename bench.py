@@ -257,8 +257,18 @@ def timed_region(fn, steps, sync, barrier):
     return e0.elapsed_time(e1)
 
 
+def stage(msg):
+    """progress on stderr (stdout carries the one JSON line)"""
+    print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - T0, msg), file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
 def main_ours(args):
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, repeat=True, file=sys.stderr)   # a stuck run says where (stderr)
     import myimagecaptioningmodel_b200 as M
     from myimagecaptioningmodel_b200 import _capi
     from myimagecaptioningmodel_b200 import synth
@@ -359,17 +369,21 @@ def main_ours(args):
         c.record()
     # rank 0 prints the line and samples its own GPU; N polling nvidia-smi processes would only contend for the driver
     with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:   # started before the warm-up: nvidia-smi needs a moment
+        stage("warm-up")
         for i in range(args.warmup):
             step_resident(i)
         sync()
+        stage("timed region")
         l0 = eng.launch_count
         with clocks.window():
             ms = timed_region(step_resident, args.steps, sync, barrier)
         launches = eng.launch_count - l0 + args.steps * eng.N_GRAD_EVENTS     # + one capdec_adam_step launch per gradient group
+        stage("all-rows leg")
         for i in range(3):
             step_resident_all_rows(i)
         sync()
         ms_all_rows = timed_region(step_resident_all_rows, args.steps, sync, barrier)
+        stage("e2e leg")
         for i in range(max(2, args.warmup // 2)):
             step_e2e(i)
         sync()
@@ -394,6 +408,7 @@ def main_ours(args):
     sync()
     ms_h2d = pe0.elapsed_time(pe1) / 4
 
+    stage("beam search")
     # ---- beam search (BASELINE.json configs[3], 512 images per GPU, beam 3, 35 steps): secondary number ----
     gi, Pi, _ = synth.make_batch(cfg, BEAM_IMAGES_PER_GPU, 777 + rank)
     gi, Pi = gi.cuda(), Pi.cuda()
@@ -421,6 +436,7 @@ def main_ours(args):
     # ---- widened path (SURVEY.md 8f N1 + N2): encoder map in, parameters updated -- secondary numbers ----
     # step = bind (decoder + adaptor) + capdec_img2feature + train_fwd + train_bwd + capdec_img2feature_bwd
     #        (+ the data-parallel exchanges) + capdec_adam_step over both flat buffers (PaddlePaddle 1.8 rule)
+    stage("widened step")
     X_ENC = 1280
     eng.attach_adaptor(X_ENC, seed=0)
     opt, _ = M.get_optimizer(eng)
@@ -485,6 +501,7 @@ def main_ours(args):
         eng.profile(False)
         return {k: 1e3 * v / reps for k, v in rep_ms.items()}      # us per step
 
+    stage("phase profile")
     ph = phase_profile(step_resident)
     ph_dec = phase_profile(lambda i: eng.decode(gi, Pi, beam=BEAM, finish_on_stop=True), reps=2)
     Hh, Ee, Vv, kk, Tt = cfg.hidden_dim, cfg.embedding_size, cfg.vocab_size, cfg.num_positions, cfg.train_steps
@@ -540,6 +557,7 @@ def main_ours(args):
 
     # ---- sustained: >= 5 s of back-to-back steps (the timed region above lasts tens of milliseconds: a burst), with the
     # clocks sampled inside it ----
+    stage("sustained leg")
     n_sus = int(5500.0 / (ms / args.steps)) + 1
     with ClockSampler(local_rank, enabled=(rank == 0)) as clocks_s:
         for i in range(3):
@@ -552,6 +570,7 @@ def main_ours(args):
     # computed locally on rank 0 from the gathered shards (train.py:119-127 is what the
     # data-parallel wrapper replaces) ----
     dp_parity = None
+    stage("dp parity")
     if world > 1:
         eng.store.init_reference(0)
         eng.bind_params()
@@ -629,6 +648,7 @@ def main_ours(args):
                                          "algorithmic_bytes_per_parameter": 28},
                            "workspace_gb": eng.workspace_bytes / 1e9, "last_loss": losses[-1] if losses else None}}
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
     return 0
