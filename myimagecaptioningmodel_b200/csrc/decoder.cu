@@ -150,6 +150,9 @@ template <typename T> class Decoder : public DecoderBase {
   ~Decoder() override {
     dgraph.reset();
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (DevBuf* b : all_bufs()) b->release();
   }
 
@@ -872,6 +875,12 @@ template <typename T> class Decoder : public DecoderBase {
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
     as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
+    if (!side_stream) {
+      if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) side_stream = nullptr;
+      if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) ev_fork = nullptr;
+      if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) ev_join = nullptr;
+      cudaGetLastError();
+    }
     // everything from here to the end of the step loop touches handle-owned memory only
     cudaStream_t rs = s;  // stream the step loop is enqueued on (a private stream while it is being captured)
     auto run_steps = [&]() -> int {
@@ -893,9 +902,21 @@ template <typename T> class Decoder : public DecoderBase {
         lstm_cell_sentinel_fwd<T>(lc, R, H, gpre.as<float>(), g5.as<float>(), beam, d_ccur.as<float>(), d_hnew.as<T>(),
                                   d_cnew.as<float>(), sent.as<T>());
         prof.mark("dec.gates_cell", rs);
+        // sentinel_emb = fc(sentinel) (model:104) does not depend on p_hid / hid_emb (model:99-102): it runs on the side
+        // stream beside them (M = rows is small: each of these GEMMs leaves a third of the SMs idle and is latency-bound)
+        const bool fork = side_stream && ev_fork && ev_join;
+        if (fork) {
+          CUDA_OK(cudaEventRecord(ev_fork, rs));
+          CUDA_OK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+          GemmContext gs; gs.stream = side_stream;
+          OK(fc(gs, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+          gc.launches += gs.launches;
+          CUDA_OK(cudaEventRecord(ev_join, side_stream));
+        }
         OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
         OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
-        OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+        if (fork) CUDA_OK(cudaStreamWaitEvent(rs, ev_join, 0));
+        else OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
         prof.mark("dec.head_fc", rs);
         bool attn_small = false;
         if constexpr (std::is_same<T, bf16>::value) {
@@ -1025,6 +1046,8 @@ template <typename T> class Decoder : public DecoderBase {
     }
   } dgraph;
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t side_stream = nullptr;                 // decode: independent GEMMs of a step run beside each other
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   capdec_config cfg;
   capdec_params prm{};
