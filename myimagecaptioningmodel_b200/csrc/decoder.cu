@@ -156,6 +156,32 @@ template <typename T> class Decoder : public DecoderBase {
     for (DevBuf* b : all_bufs()) b->release();
   }
 
+  // A second, handle-owned stream: independent kernel chains of one schedule run beside each other.  Most GEMMs of the
+  // time-batched head are 80 tiles on 74 CTA pairs (two waves, the second almost empty) and the weight gradients use 128
+  // of the 148 SMs: a neighbour on the other stream fills what they leave idle.  fork(): the side stream waits for
+  // everything enqueued on `s` so far; join(): `s` waits for the side stream.  Without the stream both are no-ops and the
+  // side chain runs in order on `s`.  (Inside a stream capture the side stream joins the capture.)
+  cudaStream_t fork(cudaStream_t s) {
+    if (!side_stream) {
+      if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) side_stream = nullptr;
+      if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) ev_fork = nullptr;
+      if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) ev_join = nullptr;
+      cudaGetLastError();
+    }
+    if (!side_stream || !ev_fork || !ev_join) return s;
+    if (cudaEventRecord(ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(side_stream, ev_fork, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return s;
+    }
+    return side_stream;
+  }
+  int join(cudaStream_t s, cudaStream_t side) {
+    if (side == s) return 0;
+    CUDA_OK(cudaEventRecord(ev_join, side));
+    CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
+    return 0;
+  }
+
   // ------------------------------------------------------------------------------------------------------------
   int bind(const capdec_params* p, cudaStream_t s) override {
     prm = *p;
@@ -496,12 +522,21 @@ template <typename T> class Decoder : public DecoderBase {
       Hprev = hprev_c.as<T>(); Hcur = hcur_c.as<T>();
     }
     const int Mh = (int)Mp;   // rows of the time-batched head
-    OK(fc(gc, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, Mh, H, H, ACT_NONE));                           // model:90
-    sentinel_fwd<T>(lc, Mp, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H, persistent ? nullptr : g5.as<float>() + 4 * H,
-                    5 * H, B, 1, Ccur, sgate.as<T>(), sent.as<T>(), d_pm);                            // model:91-92
-    OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, Mh, H, H, ACT_TANH));                            // model:99
-    OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, Mh, H, H, ACT_NONE));                         // model:102
-    OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, Mh, H, H, ACT_NONE));                          // model:104
+    {
+      // the sentinel chain (h_{t-1} -> p_hidden -> sentinel -> sentinel_emb) beside the hidden chain (h_t -> p_hid -> hid_emb)
+      cudaStream_t s2 = fork(s);
+      GemmContext g2; g2.stream = s2;
+      LaunchCtx l2{s2, &launches};
+      OK(fc(g2, Hprev, H, w_hs_n.as<T>(), H, prm.fc_hs_b, ph.p, H, Mh, H, H, ACT_NONE));                         // model:90
+      OK(fc(gc, Hcur, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, Mh, H, H, ACT_TANH));                          // model:99
+      sentinel_fwd<T>(l2, Mp, H, ph.as<T>(), H, xe.as<T>() + 4 * H, 5 * H,
+                      persistent ? nullptr : g5.as<float>() + 4 * H, 5 * H, B, 1, Ccur, sgate.as<T>(), sent.as<T>(),
+                      d_pm);                                                                          // model:91-92
+      OK(fc(g2, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, Mh, H, H, ACT_NONE));                        // model:104
+      OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, Mh, H, H, ACT_NONE));                       // model:102
+      OK(join(s, s2));
+      gc.launches += g2.launches;
+    }
     prof.mark("fwd.head_fc", s);
     AttnShape as = train_shape(B);
     as.prow = d_prow; as.pm = d_pm; as.nq = d_steps; as.packed_rows = packed ? Mp : 0;
@@ -645,7 +680,6 @@ template <typename T> class Decoder : public DecoderBase {
     }
     ColsumTable bias_sums;  // the bias gradients of the time-batched head: one launch, just before their group is marked
     bias_sums.add(dproj.p, E, Mp, E, G.fc_e_b);
-    OK(wgrad(gc, outv.p, H, H, dproj.p, E, E, Mh, G.fc_e_w, E));
     prof.mark("bwd.vocab_proj", s);
     // out = tanh(fc_o(ctx + p_hid))   (model:115)
     {
@@ -655,7 +689,14 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     bias_sums.add(doutp.p, H, Mp, H, G.fc_o_b);
-    OK(wgrad(gc, actx.p, H, H, doutp.p, H, H, Mh, G.fc_o_w, H));
+    // The data-gradient chain (d proj -> d out -> d ctx -> attention -> .. -> d h) is what the BPTT kernel waits for; the
+    // weight gradients of the head only have to be final when group 0 is marked: they run on the side stream beside it.
+    GemmContext g2;
+    cudaStream_t s2 = fork(s);
+    g2.stream = s2;
+    LaunchCtx l2{s2, &launches};
+    OK(wgrad(g2, outv.p, H, H, dproj.p, E, E, Mh, G.fc_e_w, E));
+    OK(wgrad(g2, actx.p, H, H, doutp.p, H, H, Mh, G.fc_o_w, H));
     {
       GemmCall c;  // d(ctx + p_hid)
       c.A = doutp.p; c.lda = H; c.B = w_o_n.p; c.ldb = H; c.C = dactx.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
@@ -678,10 +719,19 @@ template <typename T> class Decoder : public DecoderBase {
                         alpha.as<float>(), dctx_att, dal.as<float>(), alpha_t.as<T>(), de.as<float>(),
                         dsctx.as<T>(), dkv.as<T>(), dhemb.as<T>(), dsemb.as<T>(), G.fc_a_w, G.fc_a_b));
     prof.mark("bwd.attention", s);
+    // two independent chains down to the BPTT kernel: hid_emb -> p_hid -> d h_t on the caller's stream,
+    // sentinel_emb -> sentinel -> p_hidden -> d h_{t-1} on the side stream (behind the two weight gradients queued above)
+    s2 = fork(s);
+    g2.stream = s2;
+    l2.stream = s2;
     bias_sums.add(dhemb.p, H, Mp, H, G.fc_g_b);
-    OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, Mh, G.fc_g_w, H));
     bias_sums.add(dsemb.p, H, Mp, H, G.fc_s_b);
-    OK(wgrad(gc, sent.p, H, H, dsemb.p, H, H, Mh, G.fc_s_w, H));
+    {
+      GemmCall c;  // d sentinel = alpha_k d ctx / (k+1) + d sentinel_emb . fc_s^T                (model:104, 111)
+      c.A = dsemb.p; c.lda = H; c.B = w_s_n.p; c.ldb = H; c.C = dS.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
+      c.epi.addend = dsctx.p; c.epi.ld_add = H;
+      OK(gemm<T>(g2, c));
+    }
     {
       GemmCall c;  // d p_hid (pre-tanh) = (d actx + d hid_emb . fc_g^T) * (1 - p_hid^2)      (model:99, 102)
       c.A = dhemb.p; c.lda = H; c.B = w_g2_n.p; c.ldb = H; c.C = dphp.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
@@ -689,26 +739,18 @@ template <typename T> class Decoder : public DecoderBase {
       OK(gemm<T>(gc, c));
     }
     bias_sums.add(dphp.p, H, Mp, H, G.fc_p_b);
-    OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, Mh, G.fc_p_w, H));
-    {
-      GemmCall c;  // d sentinel = alpha_k d ctx / (k+1) + d sentinel_emb . fc_s^T                (model:104, 111)
-      c.A = dsemb.p; c.lda = H; c.B = w_s_n.p; c.ldb = H; c.C = dS.p; c.ldc = H; c.M = Mh; c.N = H; c.K = H;
-      c.epi.addend = dsctx.p; c.epi.ld_add = H;
-      OK(gemm<T>(gc, c));
-    }
     // sentinel = sigmoid(p_word_emb + p_hidden) * tanh(c)     (model:89-92); d(gate pre-activation) is one column block
     // of dG [M, 5H] (padded rows: the BPTT kernel and the x-side weight gradients read it), d c goes to dChead
     const T* dsg = dG.as<T>() + 4 * H;   // d(sentinel gate pre-activation) of the head's rows, and its pitch
     long ld_dsg = 5 * H;
     if (packed) {
-      sentinel_bwd_packed<T>(lc, M, H, d_prow, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H,
+      sentinel_bwd_packed<T>(l2, M, H, d_prow, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H,
                              dChead.as<float>(), dsg_c.as<T>());
       dsg = dsg_c.as<T>(); ld_dsg = H;
     } else {
-      sentinel_bwd<T>(lc, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
+      sentinel_bwd<T>(l2, M, H, dS.as<T>(), sgate.as<T>(), Ccur, dG.as<T>() + 4 * H, 5 * H, dChead.as<float>());
     }
     bias_sums.add(dsg, ld_dsg, Mp, H, G.fc_hs_b);
-    OK(wgrad(gc, Hprev, H, H, dsg, ld_dsg, H, Mh, G.fc_hs_w, H));
     {
       GemmCall c;  // d h_t from p_hid
       c.A = dphp.p; c.lda = H; c.B = w_p_n.p; c.ldb = H; c.C = packed ? dHhead_c.p : dHhead.p; c.ldc = H; c.M = Mh;
@@ -719,8 +761,16 @@ template <typename T> class Decoder : public DecoderBase {
       GemmCall c;  // d h_{t-1} from p_hidden
       c.A = dsg; c.lda = ld_dsg; c.B = w_hs_n.p; c.ldb = H; c.C = packed ? dHprev_c.p : dHprev.p; c.ldc = H; c.M = Mh;
       c.N = H; c.K = H;
-      OK(gemm<T>(gc, c));
+      OK(gemm<T>(g2, c));
     }
+    // the four weight gradients of these chains, two per stream, behind the data gradients
+    OK(wgrad(gc, phid.p, H, H, dhemb.p, H, H, Mh, G.fc_g_w, H));
+    OK(wgrad(g2, sent.p, H, H, dsemb.p, H, H, Mh, G.fc_s_w, H));
+    OK(wgrad(gc, Hcur, H, H, dphp.p, H, H, Mh, G.fc_p_w, H));
+    OK(wgrad(g2, Hprev, H, H, dsg, ld_dsg, H, Mh, G.fc_hs_w, H));
+    OK(join(s, s2));
+    gc.launches += g2.launches;
+    g2.launches = 0;
     if (packed)   // the BPTT kernel reads both by (step, sample): back to padded rows, zeros where no target exists
       scatter_rows_zero<T>(lc, dHhead_c.as<T>(), dHprev_c.as<T>(), d_prow, M, H, dHhead.as<T>(), dHprev.as<T>());
     prof.mark("bwd.head_fc", s);
@@ -759,51 +809,79 @@ template <typename T> class Decoder : public DecoderBase {
     prof.mark("bwd.recurrence", s);
     // After the BPTT everything left is independent; it is ordered so that the gradients become final in large groups
     // early and a small one last (capdec_set_grad_ready_events): each group's all-reduce runs behind the remaining work.
-    const T* HprevFull = hs.as<T>();   // h_{t-1} of ALL rows: the recurrence ran on every (step, sample)
+    // Rows without a target have d gates == 0 exactly (nothing flows into them), so with packed rows the contractions over
+    // (step, sample) run on the live rows only: d gates and the word embeddings are gathered once, h_{t-1} already is.
+    const T* HprevW = hs.as<T>();       // h_{t-1} of the rows the weight gradients contract over
+    const T* dGw = dG.as<T>();          // d [gates | sentinel gate] of the same rows, pitch 5H
+    const T* embW = embx.as<T>();
+    const int Mw = packed ? Mh : (int)M;
+    // (the per-image terms need only the sum over steps of d gates: they run on the side stream beside the large
+    // hidden-state gradient)
+    s2 = fork(s);
+    g2.stream = s2;
+    l2.stream = s2;
+    if (packed) {
+      OK(dG_c.ensure(e * Mp * 5 * H, &ws_bytes));
+      OK(embx_c.ensure(e * Mp * E, &ws_bytes));
+      gather_rows<T>(lc, dG.as<T>(), nullptr, 5 * H, d_pm, Mp, 5 * H, dG_c.as<T>(), nullptr, 5 * H);
+      gather_rows<T>(lc, embx.as<T>(), nullptr, E, d_pm, Mp, E, embx_c.as<T>(), nullptr, E);
+      HprevW = hprev_c.as<T>(); dGw = dG_c.as<T>(); embW = embx_c.as<T>();
+    }
     // weight gradients of the gate GEMM, batched over all steps
-    OK(wgrad(gc, HprevFull, H, H, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w + (size_t)X * 4 * H, 4 * H));
+    OK(wgrad(gc, HprevW, H, H, dGw, 5 * H, 4 * H, Mw, G.lstm_w + (size_t)X * 4 * H, 4 * H));
     mark_ready(2, s);  // lstm_w rows [E+H, E+2H) (hidden-state rows) are final
-    sum_over_steps<T>(lc, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H);
-    OK(wgrad(gc, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
-    mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
+    sum_over_steps<T>(l2, dG.as<T>(), 5 * H, B, Tt, 5 * H, dGsum.as<T>(), 5 * H, d_steps);
+    OK(wgrad(g2, gT.p, H, H, dGsum.p, 5 * H, 4 * H, B, G.lstm_w + (size_t)E * 4 * H, 4 * H));
     if (dg) {
       GemmCall c;  // gradient handed back to the encoder side: d global_img_feat
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dg; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
       c.epi.out_f32 = 1;
-      OK(gemm<T>(gc, c));
+      OK(gemm<T>(g2, c));
     }
     if (fwd_staged) {  // d(pre-ReLU img_global) for capdec_img2feature_bwd (model:199)
       OK(dzg.ensure(e * (size_t)B * H, &ws_bytes));
       GemmCall c;
       c.A = dGsum.p; c.lda = 5 * H; c.B = w_g_n.p; c.ldb = 5 * H; c.C = dzg.p; c.ldc = H; c.M = B; c.N = H; c.K = 5 * H;
       c.epi.act = ACT_DRELU; c.epi.dact_y = gT.p; c.epi.ld_y = H;
-      OK(gemm<T>(gc, c));
+      OK(gemm<T>(g2, c));
       have_dz = true;
     }
-    OK(wgrad(gc, embx.p, E, E, dG.as<T>() + 4 * H, 5 * H, H, (int)M, G.fc_xs_w, H));
-    OK(wgrad(gc, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
-    colsum_add<T>(lc, dG.as<T>(), 5 * H, M, 4 * H, G.lstm_b);
-    OK(wgrad(gc, embx.p, E, E, dG.p, 5 * H, 4 * H, (int)M, G.lstm_w, 4 * H));
+    OK(wgrad(g2, gT.p, H, H, dGsum.as<T>() + 4 * H, 5 * H, H, B, G.fc_xs_w + (size_t)E * H, H));
+    OK(join(s, s2));
+    mark_ready(3, s);  // lstm_w rows [E, E+H) (global-image rows) are final
+    // the vocabulary side of the tied table (deferred from the start of the pass; 49 tiles: a third of the SMs idle) beside
+    // the word-row gradients
+    s2 = fork(s);
+    g2.stream = s2;
+    l2.stream = s2;
+    OK(wgrad(g2, dlogits.p, Vp, V, proj.p, E, E, Mh, G.word_embedding, E, gscale));
+    colsum_add<T>(l2, dlogits.as<T>(), Vp, Mp, V, G.out_fc_bias, gscale);
+    OK(wgrad(gc, embW, E, E, dGw + 4 * H, 5 * H, H, Mw, G.fc_xs_w, H));
+    colsum_add<T>(lc, dGw, 5 * H, Mw, 4 * H, G.lstm_b);
+    OK(wgrad(gc, embW, E, E, dGw, 5 * H, 4 * H, Mw, G.lstm_w, 4 * H));
     mark_ready(4, s);  // lstm_b, fc_xs_w, fc_xs_b and the lstm_w word rows are final
     prof.mark("bwd.gate_wgrad", s);
-    // the tied table: lookup side (needs d gates) + output side (deferred from the start of the pass), out_fc_bias
+    // the tied table, lookup side (needs d gates): d word_emb -> scatter-add, padding_idx skipped
     {
-      GemmCall c;  // d word_emb -> scatter-add into the tied table (lookup side, padding_idx skipped)
-      c.A = dG.p; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = (int)M; c.N = E;
+      GemmCall c;
+      c.A = dGw; c.lda = 5 * H; c.B = w_x_n.p; c.ldb = 5 * H; c.C = dembx.p; c.ldc = E; c.M = Mw; c.N = E;
       c.K = 5 * H;
       OK(gemm<T>(gc, c));
     }
-    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding);
-    OK(wgrad(gc, dlogits.p, Vp, V, proj.p, E, E, Mh, G.word_embedding, E, gscale));
-    colsum_add<T>(lc, dlogits.as<T>(), Vp, Mp, V, G.out_fc_bias, gscale);
+    OK(join(s, s2));   // the scatter-add and the vocabulary-side product add into the same table: one after the other
+    embed_scatter_add<T>(lc, dembx.as<T>(), E, E, V, cap, S, B, Tt, cfg.padding_idx, G.word_embedding, d_pm, Mw);
     mark_ready(1, s);  // word_embedding, out_fc_bias are final
     prof.mark("bwd.embedding", s);
     ColsumTable kv_sums;
     // once-per-image projections (model:52-53)
     kv_sums.add(dkv.p, 2 * H, (long)B * k, H, G.fc_v_b);
     kv_sums.add(dkv.as<T>() + H, 2 * H, (long)B * k, H, G.fc_k_b);
+    s2 = fork(s);
+    g2.stream = s2;
+    l2.stream = s2;
     OK(wgrad(gc, PT.p, H, H, dkv.p, 2 * H, H, B * k, G.fc_v_w, H));
-    OK(wgrad(gc, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
+    OK(wgrad(g2, PT.p, H, H, dkv.as<T>() + H, 2 * H, H, B * k, G.fc_k_w, H));
+    colsum_multi<T>(l2, kv_sums);
     if (dP) {
       GemmCall c;  // d p_img_feat
       c.A = dkv.p; c.lda = 2 * H; c.B = w_kv_n.p; c.ldb = 2 * H; c.C = dP; c.ldc = H; c.M = B * k; c.N = H; c.K = 2 * H;
@@ -819,9 +897,10 @@ template <typename T> class Decoder : public DecoderBase {
       c.epi.act = ACT_DRELU; c.epi.dact_y = PT.p; c.epi.ld_y = H;
       OK(gemm<T>(gc, c));
     }
-    colsum_multi<T>(lc, kv_sums);
+    OK(join(s, s2));
     mark_ready(5, s);  // fc_v, fc_k: everything is final
     prof.mark("bwd.image_kv", s);
+    launches += g2.launches;
     launches += gc.launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -875,12 +954,6 @@ template <typename T> class Decoder : public DecoderBase {
     AttnShape as;
     as.H = H; as.k = k; as.n_img = B; as.q_per_img = beam; as.row0_stride = beam; as.q_stride = 1;
     as.position_softmax = cfg.softmax_axis == CAPDEC_SOFTMAX_POSITION;
-    if (!side_stream) {
-      if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) side_stream = nullptr;
-      if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) ev_fork = nullptr;
-      if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) ev_join = nullptr;
-      cudaGetLastError();
-    }
     // everything from here to the end of the step loop touches handle-owned memory only
     cudaStream_t rs = s;  // stream the step loop is enqueued on (a private stream while it is being captured)
     auto run_steps = [&]() -> int {
@@ -904,19 +977,13 @@ template <typename T> class Decoder : public DecoderBase {
         prof.mark("dec.gates_cell", rs);
         // sentinel_emb = fc(sentinel) (model:104) does not depend on p_hid / hid_emb (model:99-102): it runs on the side
         // stream beside them (M = rows is small: each of these GEMMs leaves a third of the SMs idle and is latency-bound)
-        const bool fork = side_stream && ev_fork && ev_join;
-        if (fork) {
-          CUDA_OK(cudaEventRecord(ev_fork, rs));
-          CUDA_OK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
-          GemmContext gs; gs.stream = side_stream;
-          OK(fc(gs, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
-          gc.launches += gs.launches;
-          CUDA_OK(cudaEventRecord(ev_join, side_stream));
-        }
+        cudaStream_t s2 = fork(rs);
+        GemmContext gs; gs.stream = s2;
+        OK(fc(gs, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+        gc.launches += gs.launches;
         OK(fc(gc, d_hnew.p, H, w_p_n.as<T>(), H, prm.fc_p_b, phid.p, H, R, H, H, ACT_TANH));
         OK(fc(gc, phid.p, H, w_g2_n.as<T>(), H, prm.fc_g_b, hemb.p, H, R, H, H, ACT_NONE));
-        if (fork) CUDA_OK(cudaStreamWaitEvent(rs, ev_join, 0));
-        else OK(fc(gc, sent.p, H, w_s_n.as<T>(), H, prm.fc_s_b, semb.p, H, R, H, H, ACT_NONE));
+        OK(join(rs, s2));
         prof.mark("dec.head_fc", rs);
         bool attn_small = false;
         if constexpr (std::is_same<T, bf16>::value) {
@@ -1028,7 +1095,7 @@ template <typename T> class Decoder : public DecoderBase {
             &outv, &proj, &logits, &lse, &acc, &dlogits, &dproj, &doutp, &dactx, &de, &dsctx, &dkv, &dhemb, &dsemb, &dphp,
             &dS, &dG, &dChead, &dHhead, &dHprev, &dhrec, &dcrec, &dGsum, &dembx, &dal, &alpha_t, &w_hh_perm, &rec_ctr, &w_x_p, &w_g_p, &b5p, &g5b, &sadd, &xin, &d_hnew, &d_cnew, &d_ccur,
             &d_state, &d_beam, &d_trace, &row_steps, &row_prow, &row_pm, &hprev_c, &hcur_c, &actx_p, &dactx_p, &dsg_c,
-            &dHhead_c, &dHprev_c, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
+            &dHhead_c, &dHprev_c, &dG_c, &embx_c, &w_img_n, &w_glob_n, &imgT, &meanT, &dzp, &dzg, &dimg, &dmean};
   }
 
   // captured step loop of capdec_decode for small batches
@@ -1066,7 +1133,7 @@ template <typename T> class Decoder : public DecoderBase {
   // packed rows of the time-batched head (train_fwd with lengths)
   bool packed = false;
   long head_rows = 0;
-  DevBuf row_steps, row_prow, row_pm, hprev_c, hcur_c, actx_p, dactx_p, dsg_c, dHhead_c, dHprev_c;
+  DevBuf row_steps, row_prow, row_pm, hprev_c, hcur_c, actx_p, dactx_p, dsg_c, dHhead_c, dHprev_c, dG_c, embx_c;
   // decode state
   DevBuf xin, d_hnew, d_cnew, d_ccur, d_state, d_beam, d_trace;
   int trace_B = 0, trace_beam = 0;

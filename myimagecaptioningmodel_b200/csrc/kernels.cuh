@@ -89,8 +89,9 @@ template <typename T>
 void lstm_cell_bwd(LaunchCtx c, int B, int H, const T* dH_head, const T* dHprev_head, const float* dh_rec,
                    const float* dC_head, float* dc_rec, const T* gates_act, const float* c_t, const float* c_prev,
                    T* dgates, long ld_dg);
-// out[b, :] = sum_t x[(t*B+b), :]
-template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo);
+// out[b, :] = sum_t x[(t*B+b), :]   (live [B] optional: only the first live[b] steps of sample b are read, the rest are zero)
+template <typename T>
+void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo, const int* live = nullptr);
 // out[n] += sum_m x[m, n]    (fp32 atomics)
 // out[n] += scale * sum_m x[m, n]   (fp32 atomics; scale read from a device scalar, or 1)
 template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out, const float* scale_dev = nullptr);
@@ -115,9 +116,10 @@ struct BiasBind {
 };
 void bind_biases(LaunchCtx c, const BiasBind& a);
 // dEmb[id] += dX[(t*B+b)]  for id != pad        (lookup_table_v2_grad, padding_idx)
+// pm (optional): dX holds `rows` packed rows, row r belongs to (t, b) = pm[r] / B, pm[r] % B
 template <typename T>
 void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, int V, const int64_t* ids, long ids_ld, int B, int steps,
-                       int pad, float* dEmb);
+                       int pad, float* dEmb, const int* pm = nullptr, long rows = 0);
 
 // ---- adaptor.cu ----------------------------------------------------------------------------------
 // feature adaptor layout kernels (model:193-199): enc_map [B,X,k] fp32 -> rows [B*k,X], mean [B,X]; and the backward

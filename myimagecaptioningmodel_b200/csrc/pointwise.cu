@@ -445,7 +445,7 @@ __global__ void lstm_cell_bwd_kernel(int B, int H, const T* __restrict__ dH_head
 
 template <typename T>
 __global__ void sum_over_steps_kernel(const T* __restrict__ x, long ld, int B, int steps, int N, T* __restrict__ out,
-                                      long ldo) {
+                                      long ldo, const int* __restrict__ live) {
   pdl_trigger();
   const int vec_per_row = N / 8;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,7 +454,8 @@ __global__ void sum_over_steps_kernel(const T* __restrict__ x, long ld, int B, i
     const long b = i / vec_per_row;
     const int n0 = (int)(i % vec_per_row) * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < steps; ++t) {
+    const int nt = live ? min(max(live[b], 0), steps) : steps;
+    for (int t = 0; t < nt; ++t) {
       float v[8];
       load8(x + ((long)t * B + b) * ld + n0, v);
 #pragma unroll
@@ -591,14 +592,16 @@ __global__ void __launch_bounds__(512) colsum_multi_kernel(ColsumTable tab) {
 
 template <typename T>
 __global__ void embed_scatter_kernel(const T* __restrict__ dX, long ld, int E, int V, const int64_t* __restrict__ ids,
-                                     long ids_ld, int B, int steps, int pad, float* __restrict__ dEmb) {
+                                     long ids_ld, int B, long rows, int pad, float* __restrict__ dEmb,
+                                     const int* __restrict__ pm) {
   pdl_trigger();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x, n = (long)B * steps * E;
+  const long stride = (long)gridDim.x * blockDim.x, n = rows * E;
   for (; i < n; i += stride) {
-    const long m = i / E;
+    const long m = i / E;                         // row of dX
     const int e = (int)(i % E);
-    const int t = (int)(m / B), b = (int)(m % B);
+    const long mp = pm ? pm[m] : m;               // its (step, sample)
+    const int t = (int)(mp / B), b = (int)(mp % B);
     const long id = ids[(long)b * ids_ld + t];
     // ids outside [0, V) were reported by the forward gather and read as padding there: no gradient either
     if (id != pad && (unsigned long)id < (unsigned long)V) atomicAdd(dEmb + id * E + e, to_f(dX[m * ld + e]));
@@ -797,8 +800,9 @@ void lstm_cell_bwd(LaunchCtx c, int B, int H, const T* dH_head, const T* dHprev_
       B, H, dH_head, dHprev_head, dh_rec, dC_head, dc_rec, gates_act, c_t, c_prev, dgates, ld_dg);
   BUMP(c);
 }
-template <typename T> void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo) {
-  sum_over_steps_kernel<T><<<grid_for((long)B * (N / 8), 128), 128, 0, c.stream>>>(x, ld, B, steps, N, out, ldo);
+template <typename T>
+void sum_over_steps(LaunchCtx c, const T* x, long ld, int B, int steps, int N, T* out, long ldo, const int* live) {
+  sum_over_steps_kernel<T><<<grid_for((long)B * (N / 8), 128), 128, 0, c.stream>>>(x, ld, B, steps, N, out, ldo, live);
   BUMP(c);
 }
 template <typename T> void colsum_add(LaunchCtx c, const T* x, long ld, long M, int N, float* out, const float* scale_dev) {
@@ -848,9 +852,10 @@ template <typename T> void colsum_multi(LaunchCtx c, ColsumTable& tab) {
 }
 template <typename T>
 void embed_scatter_add(LaunchCtx c, const T* dX, long ld, int E, int V, const int64_t* ids, long ids_ld, int B, int steps,
-                       int pad, float* dEmb) {
-  embed_scatter_kernel<T><<<grid_for((long)B * steps * E), 256, 0, c.stream>>>(dX, ld, E, V, ids, ids_ld, B, steps, pad,
-                                                                             dEmb);
+                       int pad, float* dEmb, const int* pm, long rows) {
+  if (!pm) rows = (long)B * steps;
+  if (rows <= 0) return;
+  embed_scatter_kernel<T><<<grid_for(rows * E), 256, 0, c.stream>>>(dX, ld, E, V, ids, ids_ld, B, rows, pad, dEmb, pm);
   BUMP(c);
 }
 void bind_biases(LaunchCtx c, const BiasBind& a) {
@@ -878,10 +883,11 @@ template int multi_convert<bf16>(LaunchCtx, ConvertTable&);
   template void sentinel_bwd<T>(LaunchCtx, long, int, const T*, const T*, const float*, T*, long, float*);             \
   template void lstm_cell_bwd<T>(LaunchCtx, int, int, const T*, const T*, const float*, const float*, float*,          \
                                  const T*, const float*, const float*, T*, long);                                      \
-  template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long);                                 \
+  template void sum_over_steps<T>(LaunchCtx, const T*, long, int, int, int, T*, long, const int*);                          \
   template void colsum_add<T>(LaunchCtx, const T*, long, long, int, float*, const float*);                                           \
   template void colsum_multi<T>(LaunchCtx, ColsumTable&);                                           \
-  template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, int, const int64_t*, long, int, int, int, float*);
+  template void embed_scatter_add<T>(LaunchCtx, const T*, long, int, int, const int64_t*, long, int, int, int, float*, \
+                                     const int*, long);
 
 INSTANTIATE(float)
 INSTANTIATE(bf16)
