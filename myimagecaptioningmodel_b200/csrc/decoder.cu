@@ -160,7 +160,8 @@ template <typename T> class Decoder : public DecoderBase {
   // time-batched head are 80 tiles on 74 CTA pairs (two waves, the second almost empty) and the weight gradients use 128
   // of the 148 SMs: a neighbour on the other stream fills what they leave idle.  fork(): the side stream waits for
   // everything enqueued on `s` so far; join(): `s` waits for the side stream.  Without the stream both are no-ops and the
-  // side chain runs in order on `s`.  (Inside a stream capture the side stream joins the capture.)
+  // side chain runs in order on `s`.  (Inside a stream capture the side stream joins the capture.)  Measured: switching
+  // programmatic dependent launch off between fork and join changes nothing (2.429 vs 2.431 ms per step).
   cudaStream_t fork(cudaStream_t s) {
     if (!side_stream) {
       if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) side_stream = nullptr;

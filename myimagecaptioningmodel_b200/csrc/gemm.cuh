@@ -101,5 +101,6 @@ template <> inline int gemm<bf16>(GemmContext& ctx, const GemmCall& c) {
 void set_error(const char* fmt, ...);
 // programmatic dependent launch of the tensor-core GEMMs on / off for the calling thread (off while a CUDA graph is captured)
 void set_gemm_pdl(bool on);
+bool gemm_pdl();
 
 }  // namespace capdec

@@ -1094,6 +1094,7 @@ bool pair_eligible(const GemmCall& c) {
 
 void set_gemm_trace(unsigned long long* buf) { g_trace = buf; }
 void set_gemm_pdl(bool on) { t_pdl_on = on; }
+bool gemm_pdl() { return t_pdl_on; }
 
 // the tensor-map cache, for the other TMA kernels of the library (recurrent.cu)
 int tma_map_3d(const void* p, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo, CUtensorMap* out,
