@@ -558,7 +558,12 @@ def main_ours(args):
     # ---- sustained: >= 5 s of back-to-back steps (the timed region above lasts tens of milliseconds: a burst), with the
     # clocks sampled inside it ----
     stage("sustained leg")
-    n_sus = int(5500.0 / (ms / args.steps)) + 1
+    # the step count must be the SAME on every rank (each step is a set of collectives): derive it from the slowest rank's
+    # time, not from the local one (a count that differed by one between ranks left them waiting for each other forever)
+    t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    n_sus = int(5500.0 / (float(t_ms.cpu()) / args.steps)) + 1
     with ClockSampler(local_rank, enabled=(rank == 0)) as clocks_s:
         for i in range(3):
             step_resident(i)
