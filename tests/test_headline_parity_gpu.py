@@ -27,8 +27,8 @@ from oracle import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-3, "bf16": 2e-2}
-MAX_TOL = {"fp32": 5e-3, "bf16": 6e-2}
+TOL = {"fp32": 1e-3, "bf16": 2e-2}        # north_star: rel 1e-3 fp32, 2e-2 bf16 (measured: 4e-6 / 1.3e-2, profiles/r02_parity_b256.txt)
+MAX_TOL = {"fp32": 1e-3, "bf16": 6e-2}    # max|a-b| / max|b| per tensor (measured: 6e-6 / 1.4e-2)
 
 
 def _engine(dims, axis, dtype, params):
