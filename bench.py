@@ -266,6 +266,17 @@ def timed_region(fn, steps, sync, barrier):
     return e0.elapsed_time(e1)
 
 
+def agreed_step_count(budget_ms, local_ms_per_step, world, device):
+    """Number of steps that fill `budget_ms`, IDENTICAL on every rank: each data-parallel step is a set of collectives, so
+    a count derived from the local step time (ranks differ in the last digits) can differ by one between ranks and leave
+    them waiting for each other forever -- it is derived from the slowest rank's time instead."""
+    t = torch.tensor([local_ms_per_step], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(budget_ms / float(t.cpu())) + 1
+
+
 def stage(msg):
     """progress on stderr (stdout carries the one JSON line)"""
     print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - T0, msg), file=sys.stderr, flush=True)
@@ -567,12 +578,7 @@ def main_ours(args):
     # ---- sustained: >= 5 s of back-to-back steps (the timed region above lasts tens of milliseconds: a burst), with the
     # clocks sampled inside it ----
     stage("sustained leg")
-    # the step count must be the SAME on every rank (each step is a set of collectives): derive it from the slowest rank's
-    # time, not from the local one (a count that differed by one between ranks left them waiting for each other forever)
-    t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    n_sus = int(5500.0 / (float(t_ms.cpu()) / args.steps)) + 1
+    n_sus = agreed_step_count(5500.0, ms / args.steps, world, "cuda")
     with ClockSampler(local_rank, enabled=(rank == 0)) as clocks_s:
         for i in range(3):
             step_resident(i)
