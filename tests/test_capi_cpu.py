@@ -174,3 +174,40 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     assert int(n) == len(syms)
     if not torch.cuda.is_available():
         assert int(rc) != 0 and ("CUDA" in msg or "no CPU fallback" in msg)
+
+
+def test_caption_lengths_is_the_position_after_the_last_token():
+    """`lengths` of capdec_train_fwd (include/capdec.h): [start, w_1 .. w_L, stop, pad ..] -> L + 2
+    (preprocess/ai_challenge_tokenizer.py:81-86); rows t >= lengths - 1 carry no target (model:163-171)."""
+    import numpy as np
+    cap = torch.tensor([[2, 7, 9, 3, 0, 0],      # L = 2
+                        [2, 3, 0, 0, 0, 0],      # empty sentence
+                        [2, 5, 6, 7, 8, 3],      # fills the row
+                        [0, 0, 0, 0, 0, 0],      # fully padded sample
+                        [2, 5, 0, 6, 3, 0]])     # a hole inside the caption stays inside
+    ln = M.caption_lengths(cap, 0)
+    assert ln.dtype == np.int32 and ln.tolist() == [4, 2, 6, 0, 5]
+    assert M.caption_lengths(cap.numpy(), 0).tolist() == [4, 2, 6, 0, 5]
+    # on captions without holes the live rows of the packed head are exactly the rows the loss mask keeps
+    cfg = M.DecoderConfig()
+    caps = M.synth.make_captions(cfg, 256, 20260)
+    T = cfg.sentence_length - 1
+    live = np.clip(M.caption_lengths(caps, cfg.padding_idx).astype(np.int64) - 1, 0, T).sum()
+    assert live == int((caps[:, 1:] != cfg.padding_idx).sum())
+    assert 0.5 < live / (256 * T) < 0.65          # bench.py: "57 % of the B x 34 rows carry a target"
+
+
+def test_parameter_versions_follow_in_place_updates():
+    """The engine re-binds its operand copies when the flat parameter buffer's version moved: the registry is
+    keyed by the buffer, bumped by Adam / ParamStore.load / checkpoint loads."""
+    from myimagecaptioningmodel_b200 import _capi
+    a, b = torch.zeros(8), torch.zeros(8)
+    va, vb = _capi.version_of(a), _capi.version_of(b)
+    _capi.bump_version(a)
+    assert _capi.version_of(a) == va + 1 and _capi.version_of(b) == vb
+    _capi.bump_version(a)
+    _capi.bump_version(b)
+    assert _capi.version_of(a) == va + 2 and _capi.version_of(b) == vb + 1
+    # the product's optimizer refuses host buffers (there is no CPU path to update)
+    with pytest.raises(ValueError):
+        M.Adam([(a, torch.zeros(8))], 1e-3)
