@@ -198,3 +198,42 @@ def test_golden_fixture(axis, golden_dir):
     pn = {k: v.numpy() for k, v in p.items()}
     loss2, _ = N.training_loss(pn, g.numpy(), P.numpy(), cap.numpy(), hid_size=cfg.hidden_dim, softmax_axis=axis)
     assert abs(float(loss2) - float(z["loss"])) < 1e-9
+
+
+def test_lstm_step_equals_the_library_lstm_cell_with_paddles_gate_order():
+    """model:87-88 layers.lstm_unit: gate column blocks i, f, o, g over concat([x, h]).  torch.nn.LSTMCell is an independent
+    library implementation of the same cell with gate ROWS i, f, g, o and separate input / hidden weights: with the columns
+    re-ordered and split, its (h', c') must equal the oracle's, step after step."""
+    cfg, p, g, P, cap = _setup(SMALL, "position", B=5)
+    H, E = cfg.hidden_dim, cfg.embedding_size
+    X = E + H
+    W, b = p["lstm_w"], p["lstm_b"]                                     # [X + H, 4H], [4H]: i | f | o | g
+    perm = torch.cat([torch.arange(0, 2 * H), torch.arange(3 * H, 4 * H), torch.arange(2 * H, 3 * H)])   # -> i, f, g, o
+    cell = torch.nn.LSTMCell(X, H, bias=True).double()
+    with torch.no_grad():
+        cell.weight_ih.copy_(W[:X, perm].t())
+        cell.weight_hh.copy_(W[X:, perm].t())
+        cell.bias_ih.copy_(b[perm])
+        cell.bias_hh.zero_()
+    img_feat, img_feat_emb = R.image_projections(p, P)
+    hid = torch.zeros(5, H, dtype=torch.float64)
+    c = torch.zeros(5, H, dtype=torch.float64)
+    h_lib, c_lib = hid.clone(), c.clone()
+    for t in range(cfg.sentence_length - 1):
+        word = cap[:, t]
+        xt = torch.cat([R.embedding_function(p, word, cfg), g], dim=-1)
+        h_lib, c_lib = cell(xt, (h_lib, c_lib))
+        _, hid, c, _, _ = R.decoder_step(p, cfg, word, g, img_feat, img_feat_emb, hid, c)
+        assert torch.allclose(hid, h_lib, atol=1e-12) and torch.allclose(c, c_lib, atol=1e-12)
+
+
+def test_masked_loss_equals_the_library_ignore_index_cross_entropy():
+    """model:163-171, 180-183, 205-212: sum(ce * [target != pad]) / sum([target != pad]) is what
+    torch.nn.functional.cross_entropy(ignore_index=pad, reduction='mean') computes."""
+    cfg, p, g, P, cap = _setup(SMALL, "position", B=6)
+    logits, _ = R.decoder_train(p, cfg, g, P, cap[:, :-1])
+    loss, loss_sum, ntok = R.masked_loss(cfg, logits, cap)
+    ref = torch.nn.functional.cross_entropy(logits.reshape(-1, cfg.vocab_size), cap[:, 1:].reshape(-1),
+                                            ignore_index=cfg.padding_idx, reduction="mean")
+    assert torch.allclose(loss, ref, atol=1e-12)
+    assert int(ntok) == int((cap[:, 1:] != cfg.padding_idx).sum())
